@@ -1,0 +1,216 @@
+"""ctypes binding of libcpm_b200.so (the C ABI declared in include/cpm_b200.h).
+
+PyTorch is used only as the owner of device memory: every function takes CUDA tensors and
+passes ``data_ptr()`` through.  There is no CPU path here -- if the shared library is missing
+or no B200 is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+ROOT = _HERE.parent
+LIB_PATH = _HERE / "libcpm_b200.so"
+HEADER = ROOT / "include" / "cpm_b200.h"
+
+CPM_FMT_U8, CPM_FMT_U16, CPM_FMT_F32 = 0, 1, 2
+CPM_VOLUME_LINEAR, CPM_VOLUME_TEXTURE = 0, 1
+CPM_TRACE_PROGRESSIVE, CPM_TRACE_NO_SINGLE_SCATTERING = 1, 2
+CPM_PHASE_ISOTROPIC, CPM_PHASE_HENYEY_GREENSTEIN = 0, 1
+FLT_MAX = 3.4028234663852886e38
+
+
+class CpmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cpm error {code}: {msg}")
+        self.code = code
+
+
+class TraceParams(C.Structure):
+    _fields_ = [
+        ("aabb_min", C.c_float * 3),
+        ("aabb_max", C.c_float * 3),
+        ("material", C.c_float * 4),
+        ("phase_function", C.c_int32),
+        ("step_size", C.c_float),
+        ("max_interactions", C.c_int32),
+        ("photon_offset", C.c_int32),
+        ("total_photons", C.c_int32),
+        ("n_light_samples", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def declared_symbols() -> list[str]:
+    """Every CPM_API function name declared in include/cpm_b200.h."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"CPM_API\s+[\w\s\*]+?\b(cpm_\w+)\s*\(", text)))
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.cpm_last_error.restype = C.c_char_p
+        _lib.cpm_last_error.argtypes = [C.c_void_p]
+        _lib.cpm_version.restype = C.c_char_p
+        _lib.cpm_ctx_stream.restype = C.c_void_p
+        _lib.cpm_ctx_stream.argtypes = [C.c_void_p]
+        _lib.cpm_ctx_launch_count.restype = C.c_uint64
+        _lib.cpm_ctx_launch_count.argtypes = [C.c_void_p, C.c_int]
+        _lib.cpm_ctx_destroy.restype = None
+        _lib.cpm_ctx_destroy.argtypes = [C.c_void_p]
+        _lib.cpm_volume_destroy.restype = None
+        _lib.cpm_volume_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(t):
+    """device (or host) pointer of a tensor / None"""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Volume:
+    def __init__(self, ctx, handle, data, dims, fmt, layout):
+        self.ctx, self.handle, self.data, self.dims, self.fmt, self.layout = ctx, handle, data, dims, fmt, layout
+
+    def update(self, data):
+        self.ctx._check(lib().cpm_volume_update(self.ctx.h, self.handle, _p(data)))
+        self.data = data
+
+    def destroy(self):
+        if self.handle:
+            lib().cpm_volume_destroy(self.ctx.h, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per GPU.  Mirrors the role of OpenCL::getPtr()->getQueue() in the reference."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self.h = C.c_void_p()
+        rc = lib().cpm_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(self.h))
+        if rc != 0:
+            raise CpmError(rc, lib().cpm_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().cpm_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CpmError(rc, lib().cpm_last_error(self.h).decode())
+
+    def sync(self):
+        self._check(lib().cpm_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().cpm_ctx_stream(self.h)
+
+    def launch_count(self, reset=False):
+        return int(lib().cpm_ctx_launch_count(self.h, int(reset)))
+
+    # -- RNG ---------------------------------------------------------------------------
+    def rng_seed_streams(self, state, n=None, gap=1 << 40, first_stream=0):
+        n = state.numel() // 2 if n is None else n
+        self._check(lib().cpm_rng_seed_streams(self.h, _p(state), C.c_size_t(n), C.c_uint64(gap), C.c_uint64(first_stream)))
+
+    def rng_uniform(self, state, out, per_stream=1):
+        n = state.numel() // 2
+        self._check(lib().cpm_rng_uniform(self.h, _p(state), C.c_size_t(n), int(per_stream), _p(out)))
+
+    # -- emission ----------------------------------------------------------------------
+    def sample_uniform2d(self, nx, ny, n, out):
+        self._check(lib().cpm_sample_uniform2d(self.h, C.c_float(nx), C.c_float(ny), int(n), _p(out)))
+
+    def light_sample_directional(self, samples, radiance, direction, origin, u, v, area, n, out):
+        self._check(lib().cpm_light_sample_directional(self.h, _p(samples), _f3(radiance), _f3(direction), _f3(origin),
+                                                       _f3(u), _f3(v), C.c_float(area), int(n), _p(out)))
+
+    def light_sample_point(self, samples, radiance, position, n, out):
+        self._check(lib().cpm_light_sample_point(self.h, _p(samples), _f3(radiance), _f3(position), int(n), _p(out)))
+
+    def light_mesh_intersect(self, vertices, indices, n_indices, light_samples, n, out):
+        self._check(lib().cpm_light_mesh_intersect(self.h, _p(vertices), _p(indices), int(n_indices), _p(light_samples),
+                                                   int(n), _p(out)))
+
+    # -- volumes -----------------------------------------------------------------------
+    def volume_create(self, data, dims, fmt, scale=1.0, offset=0.0, layout=CPM_VOLUME_LINEAR) -> Volume:
+        h = C.c_void_p()
+        d = (C.c_int * 3)(*[int(x) for x in dims])
+        self._check(lib().cpm_volume_create(self.h, _p(data), d, int(fmt), C.c_float(scale), C.c_float(offset),
+                                            int(layout), C.byref(h)))
+        return Volume(self, h, data, tuple(dims), fmt, layout)
+
+    # -- tracer ------------------------------------------------------------------------
+    def trace_photons(self, vol: Volume, tf_rgba, params: TraceParams, light_samples, intersections, photons,
+                      rng_state, recompute_index=None, n_recompute=0, collision_tests=None):
+        self._check(lib().cpm_trace_photons(self.h, vol.handle, _p(tf_rgba), int(tf_rgba.numel() // 4), C.byref(params),
+                                            _p(light_samples), _p(intersections), _p(recompute_index),
+                                            int(n_recompute), _p(photons), _p(rng_state), _p(collision_tests)))
+
+
+def rng_host_base_offsets(seed: int, n: int):
+    """glibc srand(seed)/rand() base offsets as a (n,2) uint32 numpy array (host, synchronous)."""
+    import numpy as np
+    out = np.zeros((n, 2), dtype=np.uint32)
+    rc = lib().cpm_rng_host_base_offsets(C.c_uint32(seed), out.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    if rc != 0:
+        raise CpmError(rc, "cpm_rng_host_base_offsets")
+    return out
+
+
+def make_trace_params(n_light_samples, total_photons=None, photon_offset=0, max_interactions=1, step_size=1.0 / 256,
+                      aabb_min=(0, 0, 0), aabb_max=(1, 1, 1), phase=CPM_PHASE_ISOTROPIC, material=(0, 0, 0, 0),
+                      flags=0) -> TraceParams:
+    p = TraceParams()
+    p.aabb_min[:] = [float(x) for x in aabb_min]
+    p.aabb_max[:] = [float(x) for x in aabb_max]
+    p.material[:] = [float(x) for x in material]
+    p.phase_function = phase
+    p.step_size = step_size
+    p.max_interactions = max_interactions
+    p.photon_offset = photon_offset
+    p.total_photons = n_light_samples if total_photons is None else total_photons
+    p.n_light_samples = n_light_samples
+    p.flags = flags
+    return p
+
+
+def _selftest_math(self, fn, x, y, out):
+    self._check(lib().cpm_selftest_math(self.h, int(fn), _p(x), _p(y), _p(out), C.c_size_t(x.numel())))
+
+
+Context.selftest_math = _selftest_math

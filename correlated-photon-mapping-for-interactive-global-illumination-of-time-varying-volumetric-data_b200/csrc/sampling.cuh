@@ -1,0 +1,192 @@
+// sampling.cuh -- exact (bit-reproducible) volume / transfer-function sampling and the small
+// geometric helpers of the photon path, device side.
+//
+// Restates what the reference pulls from un-vendored Inviwo OpenCL headers (samplers.cl,
+// transformations.cl, intersection/rayboxintersection.cl, shading/shading.cl), following the
+// OpenCL 1.2 specification section 8.2 for CLK_NORMALIZED_COORDS_TRUE |
+// CLK_ADDRESS_CLAMP_TO_EDGE | CLK_FILTER_LINEAR.  The operation order here is the contract
+// that oracle/cpm_oracle.c follows op for op; do not reorder without changing both.
+#pragma once
+#include "common.cuh"
+
+struct VolumeView {
+    const void* lin;
+    cudaTextureObject_t tex;
+    int nx, ny, nz;
+    float fx, fy, fz;  // dims as float
+    float scale, offset;
+};
+
+static inline VolumeView make_view(const cpm_volume* v) {
+    VolumeView w;
+    w.lin = v->linear;
+    w.tex = v->tex;
+    w.nx = v->dims[0];
+    w.ny = v->dims[1];
+    w.nz = v->dims[2];
+    w.fx = (float)v->dims[0];
+    w.fy = (float)v->dims[1];
+    w.fz = (float)v->dims[2];
+    w.scale = v->scale;
+    w.offset = v->offset;
+    return w;
+}
+
+// v/255 and v/65535, correctly rounded, as one FMUL + one FFMA.  Equality with the IEEE
+// division for every u8/u16 input is checked in tests (tools/fit_detmath.py documents why:
+// the quotients are never within 2^-40 of a rounding boundary).
+__device__ __forceinline__ float unorm8(float v) { return fmaf(v, 0x1.010102p-8f, v * -0x1.fdfdfep-33f); }
+__device__ __forceinline__ float unorm16(float v) { return fmaf(v, 0x1.0001p-16f, v * 0x1.0001p-48f); }
+
+template <int FMT>
+__device__ __forceinline__ float load_linear(const void* base, size_t idx) {
+    if (FMT == CPM_FMT_U8) return unorm8((float)__ldg((const unsigned char*)base + idx));
+    if (FMT == CPM_FMT_U16) return unorm16((float)__ldg((const unsigned short*)base + idx));
+    return __ldg((const float*)base + idx);
+}
+
+// Four texels of the bilinear footprint {i0,i0+1} x {j0,j0+1} of layer k, unfiltered, with
+// clamp-to-edge addressing done by the texture unit.  The coordinate (i0+1, j0+1) sits exactly
+// in the middle of the footprint, far from the 1/256 fixed-point selection boundaries.
+// Result order (PTX tld4): x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0).
+template <int FMT>
+__device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int k, float cx, float cy) {
+    float4 r;
+    if (FMT == CPM_FMT_F32) {
+        asm("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+            : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+            : "l"(tex), "r"(k), "f"(cx), "f"(cy));
+    } else {
+        unsigned a, b, c, d;
+        asm("tld4.r.a2d.v4.u32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+            : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+            : "l"(tex), "r"(k), "f"(cx), "f"(cy));
+        if (FMT == CPM_FMT_U8) {
+            r.x = unorm8((float)a); r.y = unorm8((float)b); r.z = unorm8((float)c); r.w = unorm8((float)d);
+        } else {
+            r.x = unorm16((float)a); r.y = unorm16((float)b); r.z = unorm16((float)c); r.w = unorm16((float)d);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ float lerpf(float p, float q, float a) { return fmaf(a, q - p, p); }
+
+// getNormalizedVoxel(volume, params, pos).x  -- trilinear, normalised coordinates.
+template <int FMT, int LAYOUT>
+__device__ __forceinline__ float sample_volume(const VolumeView& V, float px, float py, float pz) {
+    float u = fmaf(px, V.fx, -0.5f);
+    float v = fmaf(py, V.fy, -0.5f);
+    float w = fmaf(pz, V.fz, -0.5f);
+    float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+    float a = u - fu, b = v - fv, c = w - fw;
+    // NaN/inf safe conversion: clamp in float first (NaN -> -1)
+    int i0 = (int)cpm_clamp(fu, -1.0f, V.fx - 1.0f);
+    int j0 = (int)cpm_clamp(fv, -1.0f, V.fy - 1.0f);
+    int k0 = (int)cpm_clamp(fw, -1.0f, V.fz - 1.0f);
+    int k1 = min(k0 + 1, V.nz - 1);
+    k0 = max(k0, 0);
+    float t000, t100, t010, t110, t001, t101, t011, t111;
+    if (LAYOUT == CPM_VOLUME_TEXTURE) {
+        float cx = (float)(i0 + 1), cy = (float)(j0 + 1);
+        float4 g0 = gather_layer<FMT>(V.tex, k0, cx, cy);
+        float4 g1 = gather_layer<FMT>(V.tex, k1, cx, cy);
+        t000 = g0.w; t100 = g0.z; t010 = g0.x; t110 = g0.y;
+        t001 = g1.w; t101 = g1.z; t011 = g1.x; t111 = g1.y;
+    } else {
+        int i1 = min(i0 + 1, V.nx - 1);
+        int j1 = min(j0 + 1, V.ny - 1);
+        i0 = max(i0, 0);
+        j0 = max(j0, 0);
+        size_t sy = (size_t)V.nx, sz = (size_t)V.nx * V.ny;
+        size_t b00 = (size_t)k0 * sz + (size_t)j0 * sy, b10 = (size_t)k0 * sz + (size_t)j1 * sy;
+        size_t b01 = (size_t)k1 * sz + (size_t)j0 * sy, b11 = (size_t)k1 * sz + (size_t)j1 * sy;
+        t000 = load_linear<FMT>(V.lin, b00 + i0); t100 = load_linear<FMT>(V.lin, b00 + i1);
+        t010 = load_linear<FMT>(V.lin, b10 + i0); t110 = load_linear<FMT>(V.lin, b10 + i1);
+        t001 = load_linear<FMT>(V.lin, b01 + i0); t101 = load_linear<FMT>(V.lin, b01 + i1);
+        t011 = load_linear<FMT>(V.lin, b11 + i0); t111 = load_linear<FMT>(V.lin, b11 + i1);
+    }
+    float x00 = lerpf(t000, t100, a), x10 = lerpf(t010, t110, a);
+    float x01 = lerpf(t001, t101, a), x11 = lerpf(t011, t111, a);
+    float y0 = lerpf(x00, x10, b), y1 = lerpf(x01, x11, b);
+    float val = lerpf(y0, y1, c);
+    return (val + V.offset) * V.scale;
+}
+
+// read_imagef(tf, smpNormClampEdgeLinear, (v, 0.5)).w on a width x 1 image: 1-D linear.
+__device__ __forceinline__ float sample_tf_alpha(const float* __restrict__ alpha, int width, float fwidth, float v) {
+    float u = fmaf(v, fwidth, -0.5f);
+    float fu = floorf(u);
+    float a = u - fu;
+    int i0 = (int)cpm_clamp(fu, -1.0f, fwidth - 1.0f);
+    int i1 = min(i0 + 1, width - 1);
+    i0 = max(i0, 0);
+    return lerpf(alpha[i0], alpha[i1], a);
+}
+
+struct float3_ {
+    float x, y, z;
+};
+
+// decodeDirection / encodeDirection (Inviwo transformations.cl; host twin
+// ppm/photondata.cpp:100-117): theta = acos(clamp(z)), phi = atan2(y, x).
+__device__ __forceinline__ float3_ decode_direction(float theta, float phi) {
+    float st, ct, sp, cp;
+    cpm_sincosf(theta, &st, &ct);
+    cpm_sincosf(phi, &sp, &cp);
+    return {st * cp, st * sp, ct};
+}
+__device__ __forceinline__ float2 encode_direction(float3_ d) {
+    return make_float2(cpm_acosf(cpm_clamp(d.z, -1.0f, 1.0f)), cpm_atan2f(d.y, d.x));
+}
+
+// rayBoxIntersection (Inviwo intersection/rayboxintersection.cl): slab test, tightens [t0,t1].
+__device__ __forceinline__ bool ray_box(const float* bmin, const float* bmax, float3_ o, float3_ d, float& t0, float& t1) {
+    float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+    float ax = (bmin[0] - o.x) * ix, bx = (bmax[0] - o.x) * ix;
+    float ay = (bmin[1] - o.y) * iy, by = (bmax[1] - o.y) * iy;
+    float az = (bmin[2] - o.z) * iz, bz = (bmax[2] - o.z) * iz;
+    float n = cpm_fmax(cpm_fmax(cpm_fmin(ax, bx), cpm_fmin(ay, by)), cpm_fmin(az, bz));
+    float f = cpm_fmin(cpm_fmin(cpm_fmax(ax, bx), cpm_fmax(ay, by)), cpm_fmax(az, bz));
+    t0 = cpm_fmax(t0, n);
+    t1 = cpm_fmin(t1, f);
+    return t0 < t1;
+}
+
+// uniformSampleSphere (Inviwo shading/shadingmath.cl, pbrt form): z = 1-2u, phi = 2 pi v.
+__device__ __forceinline__ float3_ uniform_sample_sphere(float u1, float u2) {
+    float z = fmaf(-2.0f, u1, 1.0f);
+    float r = sqrtf(cpm_fmax(0.0f, fmaf(-z, z, 1.0f)));
+    float s, c;
+    cpm_sincosf(CPM_2PI_F * u2, &s, &c);
+    return {r * c, r * s, z};
+}
+
+// Henyey-Greenstein sampling around the incoming direction `wi` (restated; the reference's
+// version lives in un-vendored shading.cl -- parity unpinned, benchmarks run isotropic).
+__device__ __forceinline__ float3_ sample_henyey_greenstein(float3_ wi, float g, float u1, float u2) {
+    float ct;
+    if (fabsf(g) < 1e-3f) {
+        ct = fmaf(-2.0f, u1, 1.0f);
+    } else {
+        float q = (1.0f - g * g) / fmaf(2.0f * g, u1, 1.0f - g);
+        ct = (1.0f + g * g - q * q) / (2.0f * g);
+    }
+    ct = cpm_clamp(ct, -1.0f, 1.0f);
+    float st = sqrtf(cpm_fmax(0.0f, fmaf(-ct, ct, 1.0f)));
+    float sp, cp;
+    cpm_sincosf(CPM_2PI_F * u2, &sp, &cp);
+    // orthonormal basis (pbrt coordinateSystem)
+    float3_ v2;
+    if (fabsf(wi.x) > fabsf(wi.y)) {
+        float inv = 1.0f / sqrtf(fmaf(wi.x, wi.x, wi.z * wi.z));
+        v2 = {-wi.z * inv, 0.0f, wi.x * inv};
+    } else {
+        float inv = 1.0f / sqrtf(fmaf(wi.y, wi.y, wi.z * wi.z));
+        v2 = {0.0f, wi.z * inv, -wi.y * inv};
+    }
+    float3_ v3 = {fmaf(wi.y, v2.z, -(wi.z * v2.y)), fmaf(wi.z, v2.x, -(wi.x * v2.z)), fmaf(wi.x, v2.y, -(wi.y * v2.x))};
+    float a = st * cp, b = st * sp;
+    return {fmaf(a, v2.x, fmaf(b, v3.x, ct * wi.x)), fmaf(a, v2.y, fmaf(b, v3.y, ct * wi.y)),
+            fmaf(a, v2.z, fmaf(b, v3.z, ct * wi.z))};
+}

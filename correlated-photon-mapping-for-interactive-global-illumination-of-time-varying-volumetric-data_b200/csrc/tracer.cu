@@ -1,0 +1,207 @@
+// tracer.cu -- delta-tracking photon tracer (north-star subsystem 3 and the re-trace half of 4).
+//
+// Replaces photonTracerKernel (ppm/cl/photontracer.cl:69-216) with woodcockTracking
+// (ppm/cl/transmittance.cl:126-144) and nextInteraction (photontracer.cl:50-58).
+//
+// B200 design
+//  * Each photon owns MWC64X stream `photon_offset + i`, so the result of a photon does not
+//    depend on which lane, warp or GPU traces it.  That freedom is used for scheduling.
+//  * The woodcock loop needs only the ALPHA channel of the transfer function (colour is never
+//    read on this path: photontracer.cl:171-176 use color.w / scattering.w only).  The alpha
+//    column (tf_width floats) is staged once per CTA in shared memory; every collision test
+//    then costs two LDS instead of two RGBA texture fetches.
+//  * Volume taps: exact fp32 trilinear (OpenCL 1.2 section 8.2 arithmetic) over unfiltered
+//    texels.  TEXTURE layout: 2 x tld4 on a 2-D layered array (the texture unit does the
+//    clamping and fetches a 2x2 footprint per instruction, block-linear layout keeps the
+//    footprint in one sector).  LINEAR layout: 8 x LDG from the caller's buffer.
+//    Hardware-filtered taps are not used: their 1.8 fixed-point weights flip accept/reject
+//    decisions, which breaks the replay property the correlated re-trace depends on.
+//  * Photon records are 32 B: written as two 16 B stores (STG.128).
+#include "sampling.cuh"
+
+namespace {
+
+struct TraceArgs {
+    cpm_trace_params p;
+    VolumeView vol;
+    const float4* tf;
+    int tf_width;
+    const float4* light_samples;  // float8 as 2 x float4
+    const float2* isect;
+    const uint32_t* recompute;
+    int n_work;  // n_light_samples or n_recompute
+    float4* photons;
+    uint2* rng;
+    unsigned long long* tests;
+};
+
+__device__ __forceinline__ void store_photon(float4* photons, size_t id, float x, float y, float z, float pr, float pg,
+                                             float pb, float th, float ph) {
+    photons[2 * id] = make_float4(x, y, z, pr);
+    photons[2 * id + 1] = make_float4(pg, pb, th, ph);
+}
+
+#define CPM_FLT_MAX 3.402823466e+38f
+
+template <int FMT, int LAYOUT>
+__device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_alpha, int tfw, float ftfw, float3_ o,
+                                          float3_ d, float tStart, float tEnd, cpm_rng& rng, unsigned& tests) {
+    // tauMax = 1 (photontracer.cl:160): invTauMaxSampleBaseInterval = 1/(1*150), invTauMax = 1
+    const float inv = 1.0f / 150.0f;
+    float t = tStart;
+    float opacity;
+    float u2;
+    do {
+        t = fmaf(-cpm_logf(cpm_rng_01(rng)), inv, t);
+        float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
+        float vs = sample_volume<FMT, LAYOUT>(V, px, py, pz);
+        opacity = sample_tf_alpha(s_alpha, tfw, ftfw, vs);
+        u2 = cpm_rng_01(rng);
+        ++tests;
+    } while (u2 >= opacity && t <= tEnd);
+    return t;
+}
+
+template <int FMT, int LAYOUT>
+__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
+    extern __shared__ float s_alpha[];
+    for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
+    __syncthreads();
+
+    const cpm_trace_params& P = A.p;
+    unsigned tests = 0;
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int tid = -1;
+    if (gid < A.n_work) {
+        if (A.recompute) {
+            int t = (int)A.recompute[gid] - P.photon_offset;
+            if (t >= 0 && t < P.n_light_samples) tid = t;
+        } else {
+            tid = gid;
+        }
+    }
+    if (tid >= 0) {
+        const int tfw = A.tf_width;
+        const float ftfw = (float)tfw;
+        uint2 st = A.rng[P.photon_offset + tid];
+        cpm_rng rng{st.x, st.y};
+        float4 l0 = A.light_samples[2 * (size_t)tid], l1 = A.light_samples[2 * (size_t)tid + 1];
+        float3_ o = {l0.x, l0.y, l0.z};
+        float fmaxi = (float)P.max_interactions;
+        float pr = l0.w / fmaxi, pg = l1.x / fmaxi, pb = l1.y / fmaxi;
+        float3_ d = decode_direction(l1.z, l1.w);
+        float2 ip = A.isect[tid];
+        float tStart = ip.x, tEnd = ip.y;
+        bool scatter = tStart < tEnd;
+        unsigned n = 0;
+        const unsigned maxI = (unsigned)P.max_interactions;
+
+        if (P.flags & CPM_TRACE_NO_SINGLE_SCATTERING) {
+            // photontracer.cl:143-157: the walk is executed even when the ray misses
+            float t = woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            if (scatter) {
+                o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+                tStart = 0.0f;
+                tEnd = CPM_FLT_MAX;
+                float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
+                d = (P.phase_function == CPM_PHASE_HENYEY_GREENSTEIN)
+                        ? sample_henyey_greenstein(d, P.material[0], u1, u2)
+                        : uniform_sample_sphere(u1, u2);
+                scatter = ray_box(P.aabb_min, P.aabb_max, o, d, tStart, tEnd);
+                // power /= pdf, isotropic pdf = 1/(4 pi); HG restated with the same constant
+                pr = pr / CPM_INV_4PI_F; pg = pg / CPM_INV_4PI_F; pb = pb / CPM_INV_4PI_F;
+                tStart += 0.5f * P.step_size;
+            }
+        }
+        while (scatter) {
+            float t = woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            scatter = t <= tEnd;
+            if (scatter) {
+                o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+                size_t pid = (size_t)P.photon_offset + (size_t)n * P.total_photons + tid;
+                float2 ang = encode_direction(d);
+                float vs = sample_volume<FMT, LAYOUT>(A.vol, o.x, o.y, o.z);
+                float ca = sample_tf_alpha(s_alpha, tfw, ftfw, vs);  // color.w == scattering.w
+                float albedo = ca / (ca + ca);                      // 0.5, or NaN when alpha == 0
+                float den = cpm_fmax(ca, 0.01f);
+                pr = pr / den; pg = pg / den; pb = pb / den;
+                ++n;
+                // short-circuit: the random number is drawn only when n < maxInteractions
+                if (n < maxI && cpm_rng_01(rng) < albedo) {
+                    pr *= albedo; pg *= albedo; pb *= albedo;
+                    store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+                    tStart = 0.0f;
+                    tEnd = CPM_FLT_MAX;
+                    float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
+                    d = (P.phase_function == CPM_PHASE_HENYEY_GREENSTEIN)
+                            ? sample_henyey_greenstein(d, P.material[0], u1, u2)
+                            : uniform_sample_sphere(u1, u2);
+                    scatter = ray_box(P.aabb_min, P.aabb_max, o, d, tStart, tEnd);
+                    tStart += 0.5f * P.step_size;
+                } else {
+                    store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+                    pr = pg = pb = CPM_FLT_MAX;  // "absorbed" marker read by the detector
+                    scatter = false;
+                }
+            }
+        }
+        float2 ang = encode_direction(d);
+        for (unsigned i = n; i < maxI; ++i) {
+            size_t pid = (size_t)P.photon_offset + (size_t)i * P.total_photons + tid;
+            store_photon(A.photons, pid, CPM_FLT_MAX, CPM_FLT_MAX, CPM_FLT_MAX, pr, CPM_FLT_MAX, CPM_FLT_MAX, ang.x, ang.y);
+        }
+        if (P.flags & CPM_TRACE_PROGRESSIVE) A.rng[P.photon_offset + tid] = make_uint2(rng.x, rng.c);
+    }
+    if (A.tests) {
+        unsigned long long v = tests;
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(A.tests, v);
+    }
+}
+
+template <int FMT, int LAYOUT>
+int launch(cpm_ctx* ctx, const TraceArgs& a) {
+    size_t smem = (size_t)a.tf_width * sizeof(float);
+    if (smem > 48 * 1024)
+        CPM_CUDA(ctx, cudaFuncSetAttribute(trace_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT>), cpm_div_up(a.n_work, 128), 128, smem, a);
+    return CPM_OK;
+}
+
+}  // namespace
+
+extern "C" int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgba, int tf_width,
+                                 const cpm_trace_params* params, const float* light_samples, const float* intersections,
+                                 const uint32_t* recompute_index, int n_recompute, float* photons, uint32_t* rng_state,
+                                 unsigned long long* collision_tests) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, vol && tf_rgba && params && light_samples && intersections && photons && rng_state, "null argument");
+    CPM_REQUIRE(ctx, tf_width >= 1 && tf_width <= 32768, "tf_width out of range");
+    CPM_REQUIRE(ctx, params->max_interactions >= 1, "max_interactions must be >= 1");
+    CPM_REQUIRE(ctx, params->n_light_samples >= 0 && params->photon_offset >= 0, "negative size");
+    CPM_REQUIRE(ctx, params->total_photons >= params->photon_offset + params->n_light_samples,
+                "total_photons smaller than photon_offset + n_light_samples");
+    CPM_REQUIRE(ctx, recompute_index == nullptr || n_recompute >= 0, "negative n_recompute");
+    TraceArgs a;
+    a.p = *params;
+    a.vol = make_view(vol);
+    a.tf = (const float4*)tf_rgba;
+    a.tf_width = tf_width;
+    a.light_samples = (const float4*)light_samples;
+    a.isect = (const float2*)intersections;
+    a.recompute = recompute_index;
+    a.n_work = recompute_index ? n_recompute : params->n_light_samples;
+    a.photons = (float4*)photons;
+    a.rng = (uint2*)rng_state;
+    a.tests = collision_tests;
+    if (a.n_work == 0) return CPM_OK;
+#define CPM_DISPATCH(F)                                                                  \
+    return vol->layout == CPM_VOLUME_TEXTURE ? launch<F, CPM_VOLUME_TEXTURE>(ctx, a)      \
+                                             : launch<F, CPM_VOLUME_LINEAR>(ctx, a);
+    switch (vol->format) {
+        case CPM_FMT_U8: CPM_DISPATCH(CPM_FMT_U8)
+        case CPM_FMT_U16: CPM_DISPATCH(CPM_FMT_U16)
+        default: CPM_DISPATCH(CPM_FMT_F32)
+    }
+#undef CPM_DISPATCH
+}

@@ -1,0 +1,187 @@
+/*
+ * cpm_b200.h -- C ABI of libcpm_b200.so: the B200-native (sm_100a) implementation of the
+ * correlated progressive photon-mapping hot path.
+ *
+ * The reference has no C ABI of its own (it is six Inviwo C++/OpenCL modules); the natural
+ * cut is its layer of kernel-launcher classes, whose methods take raw device buffers and
+ * plain scalars.  Every entry point below names the launcher method (and the OpenCL kernel
+ * behind it) that it replaces.  Paths are relative to /modules of the reference:
+ *   ppm/ = progressivephotonmapping/   lcl/ = lightcl/   isc/ = importancesamplingcl/
+ *   ugc/ = uniformgridcl/   rsc/ = radixsortcl/   rng/ = rndgenmwc64x/
+ *
+ * Conventions
+ *  - Every pointer argument is a DEVICE pointer owned by the caller unless its name ends
+ *    in `_host`.  Nothing is retained after the call returns unless documented.
+ *  - Calls are asynchronous on the context's CUDA stream (like enqueueNDRangeKernel on the
+ *    reference's in-order queue) except the ones documented as synchronous.
+ *  - Return value: 0 (CPM_OK) or a negative CPM_E_* code; cpm_last_error() gives the text.
+ *    No exception crosses the ABI.
+ *  - One context per GPU; a context is not thread-safe (the reference runs on Inviwo's
+ *    single evaluation thread).
+ *  - There is no CPU fallback: without a CUDA device cpm_ctx_create fails with
+ *    CPM_E_NO_DEVICE.
+ */
+#ifndef CPM_B200_H
+#define CPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CPM_API
+#else
+#define CPM_API __attribute__((visibility("default")))
+#endif
+
+/* ---- error codes ------------------------------------------------------------------- */
+enum {
+    CPM_OK = 0,
+    CPM_E_INVALID = -1,     /* bad argument (mirrors cl::Error CL_INVALID_VALUE) */
+    CPM_E_NO_DEVICE = -2,   /* no CUDA device / wrong architecture */
+    CPM_E_CUDA = -3,        /* a CUDA runtime call failed */
+    CPM_E_NOMEM = -4,       /* device allocation failed */
+    CPM_E_UNSUPPORTED = -5, /* valid in the reference but not built here */
+    CPM_E_COMM = -6         /* NCCL failure */
+};
+
+typedef struct cpm_ctx cpm_ctx;
+typedef struct cpm_volume cpm_volume;
+
+/* ---- context ----------------------------------------------------------------------- */
+/* stream: a cudaStream_t cast to void*, or NULL to let the context create its own
+ * non-blocking stream.  Replaces OpenCL::getPtr()->getQueue(). */
+CPM_API int cpm_ctx_create(int device, void* stream, cpm_ctx** out);
+CPM_API void cpm_ctx_destroy(cpm_ctx* ctx);
+CPM_API void* cpm_ctx_stream(cpm_ctx* ctx);
+CPM_API int cpm_ctx_sync(cpm_ctx* ctx); /* cudaStreamSynchronize */
+CPM_API const char* cpm_last_error(cpm_ctx* ctx);
+CPM_API const char* cpm_version(void);
+/* number of kernel launches issued through this context since creation / last reset */
+CPM_API uint64_t cpm_ctx_launch_count(cpm_ctx* ctx, int reset);
+
+/* ---- (1) MWC64X per-photon RNG streams -------------------------------------------- */
+/* Fill the per-stream base offsets exactly as MWC64XSeedGenerator::generateRandomSeeds
+ * does on the host (rng/mwc64xseedgenerator.cpp:56-64): srand(seed); state[i].x = rand().
+ * Only .x is written by the reference; we also zero .y.  Host-side, synchronous.
+ * glibc's rand() is reproduced bit-exactly (TYPE_3 additive feedback generator). */
+CPM_API int cpm_rng_host_base_offsets(uint32_t seed, uint32_t* state_host /* 2*n */, size_t n);
+
+/* MWC64X_GenerateRandomState (rng/cl/randstategen.cl:39-47): in place,
+ * state[i] = SeedStreams(baseOffset = state[i].x, perStreamOffset = stream_gap) for stream
+ * index first_stream + i.  stream_gap = 2^40 reproduces the reference kernel;
+ * MWC64X_GeneratePerStreamRandomState (:52-60) is the same with a caller-supplied gap.
+ * first_stream lets a GPU seed its own shard of a larger stream set. */
+CPM_API int cpm_rng_seed_streams(cpm_ctx* ctx, uint32_t* state /* uint2[n] */, size_t n,
+                                 uint64_t stream_gap, uint64_t first_stream);
+
+/* randomNumberGeneratorKernel (rng/cl/randomnumbergenerator.cl:34-49): one random_01 per
+ * stream, state advanced and saved.  samples_per_stream generalises N_NUMBERS_PER_THREAD. */
+CPM_API int cpm_rng_uniform(cpm_ctx* ctx, uint32_t* state, size_t n, int samples_per_stream,
+                            float* out /* n*samples_per_stream */);
+
+/* ---- (2) emission ------------------------------------------------------------------ */
+/* uniformSampleGenerator2DKernel (isc/cl/uniformsamplegenerator2d.cl:35-52).
+ * out[i] = ((0.5 + fmod(i, nx)) / nx, (0.5 + i / nx) / ny, 0, 1)  (y is NOT floored). */
+CPM_API int cpm_sample_uniform2d(cpm_ctx* ctx, float nx, float ny, int n_elements,
+                                 float* out /* float4[n] */);
+
+/* directionalLightSamplerKernel (lcl/cl/directionallightsampler.cl:38-63), host side
+ * DirectionalLightSamplerCL::sampleLightSource (lcl/directionallightsamplercl.cpp:114-130).
+ * light_samples is the StoredLightSample float8 buffer {origin.xyz, power.rgb, theta, phi}. */
+CPM_API int cpm_light_sample_directional(cpm_ctx* ctx, const float* samples /* float4[n] */,
+                                         const float radiance[3], const float direction[3],
+                                         const float plane_origin[3], const float plane_u[3],
+                                         const float plane_v[3], float plane_area, int n,
+                                         float* light_samples /* float8[n] */);
+
+/* Point-light emission restated from sampleLight's LIGHT_POINT branch
+ * (isc/cl/light/light.cl:84-92): origin = position, wi = -uniformSampleSphere(uv),
+ * power = radiance / (1/4pi).  No reference processor launches it ("parity unpinned"). */
+CPM_API int cpm_light_sample_point(cpm_ctx* ctx, const float* samples /* float4[n] */,
+                                   const float radiance[3], const float position[3], int n,
+                                   float* light_samples /* float8[n] */);
+
+/* lightSampleMeshIntersectionKernel (lcl/cl/intersection/lightsamplemeshintersection.cl:37-59),
+ * host side LightSampleMeshIntersectionCL::meshSampleIntersection
+ * (lcl/lightsamplemeshintersectioncl.cpp:87-99).  Miss -> (0, -1). */
+CPM_API int cpm_light_mesh_intersect(cpm_ctx* ctx, const float* vertices /* float3 packed */,
+                                     const int32_t* indices, int n_indices,
+                                     const float* light_samples, int n,
+                                     float* intersections /* float2[n] */);
+
+/* ---- volumes ----------------------------------------------------------------------- */
+enum { CPM_FMT_U8 = 0, CPM_FMT_U16 = 1, CPM_FMT_F32 = 2 };
+enum {
+    CPM_VOLUME_LINEAR = 0, /* sample straight from the caller's x-fastest linear buffer */
+    CPM_VOLUME_TEXTURE = 1 /* copy into a 2-D layered CUDA array; the tracer then fetches
+                              bilinear footprints with tld4 (unfiltered texels) */
+};
+/* Replaces Volume::getRepresentation<VolumeCL>() + VolumeCLBase::getVolumeStruct
+ * (ppm/photontracercl.cpp:108-119).  A voxel read returns
+ *   (normalise(v) + format_offset) * format_scale
+ * where normalise is v/255, v/65535 or identity ("Scaling for 12-bit data",
+ * ugc/processors/volumeminmaxclprocessor.cpp:134-136).  The LINEAR layout keeps a pointer
+ * to `data`; the caller must keep it alive.  TEXTURE copies. */
+CPM_API int cpm_volume_create(cpm_ctx* ctx, const void* data, const int dims[3], int format,
+                              float format_scale, float format_offset, int layout,
+                              cpm_volume** out);
+/* new voxel data, same dims/format (a time step change) */
+CPM_API int cpm_volume_update(cpm_ctx* ctx, cpm_volume* vol, const void* data);
+CPM_API void cpm_volume_destroy(cpm_ctx* ctx, cpm_volume* vol);
+
+/* ---- (3) photon tracer -------------------------------------------------------------- */
+enum {
+    CPM_TRACE_PROGRESSIVE = 1,         /* -D PROGRESSIVE_PHOTON_MAPPING: save RNG state */
+    CPM_TRACE_NO_SINGLE_SCATTERING = 2 /* -D NO_SINGLE_SCATTERING */
+};
+enum { CPM_PHASE_ISOTROPIC = 0, CPM_PHASE_HENYEY_GREENSTEIN = 1 };
+
+typedef struct cpm_trace_params {
+    float aabb_min[3];     /* clip box in texture space (axisAlignedBoundingBoxCL_,       */
+    float aabb_max[3];     /*   ppm/processor/progressivephotontracercl.cpp:192-195,678-684) */
+    float material[4];     /* AdvancedMaterialProperty::getCombinedMaterialParameters();
+                              [0] = anisotropy g for Henyey-Greenstein */
+    int32_t phase_function; /* CPM_PHASE_* (material.getPhaseFunctionEnum()) */
+    float step_size;       /* samplingRate * min voxel spacing (:236-239) */
+    int32_t max_interactions; /* maxScatteringEvents, 1..16 */
+    int32_t photon_offset; /* first photon id of this light source */
+    int32_t total_photons; /* photonData->getNumberOfPhotons(): stride between interactions */
+    int32_t n_light_samples;
+    uint32_t flags;        /* CPM_TRACE_* */
+} cpm_trace_params;
+
+/* photonTracerKernel (ppm/cl/photontracer.cl:69-216) incl. woodcockTracking
+ * (ppm/cl/transmittance.cl:126-144); host side PhotonTracerCL::tracePhotons
+ * (ppm/photontracercl.cpp:136-174).
+ *  tf_rgba         the transfer function rasterised to tf_width RGBA float texels (both
+ *                  tfData and tfScattering, as the reference binds the same layer twice,
+ *                  ppm/photontracercl.cpp:150-151)
+ *  recompute_index NULL for the plain kernel; otherwise the -D PHOTON_RECOMPUTATION build:
+ *                  n_recompute photon ids, ids outside [photon_offset,
+ *                  photon_offset + n_light_samples) are skipped (photontracer.cl:99-106)
+ *  photons         float8 records, index photon_offset + k*total_photons + i
+ *  rng_state       uint2 per photon of the WHOLE photon set (indexed photon_offset + i)
+ *  collision_tests optional device uint64 counter (may be NULL): incremented by the number
+ *                  of delta-tracking collision tests executed -- the benchmark's
+ *                  "photon-interaction" unit.  Not in the reference. */
+CPM_API int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgba,
+                              int tf_width, const cpm_trace_params* params,
+                              const float* light_samples, const float* intersections,
+                              const uint32_t* recompute_index, int n_recompute, float* photons,
+                              uint32_t* rng_state, unsigned long long* collision_tests);
+
+/* ---- self test ----------------------------------------------------------------------- */
+/* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,
+ * 3 acos, 4 atan2(x, y), 5 v/255, 6 v/65535 (x holds the integer value as float).  Lets the
+ * tests prove that the host and sm_100a compilations of the math layer agree bit for bit. */
+CPM_API int cpm_selftest_math(cpm_ctx* ctx, int fn, const float* x, const float* y, float* out,
+                              size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPM_B200_H */

@@ -1,0 +1,199 @@
+/*
+ * cpm_detmath.h -- deterministic fp32 elementary functions shared by the CUDA kernels
+ * and by the CPU oracle.
+ *
+ * Why this exists: the reference tracer calls OpenCL `native_log`, `native_sin/cos`,
+ * `acos`, `atan2` (ppm/cl/transmittance.cl:135, Inviwo shading/transformations headers,
+ * ppm/photondata.cpp:100-117).  Those are implementation-defined, and one flipped
+ * accept/reject in Woodcock tracking sends a photon down a different path.  To make
+ * "same seed -> same photon" a bit-exact statement between the sm_100a kernels and the
+ * CPU oracle, every transcendental on the path is defined HERE, once, in terms of IEEE-754
+ * correctly rounded fp32 operations only (+, -, *, /, sqrt, fma, floor/rint, int<->float
+ * conversions and bit casts).  Those operations give identical bits on an x86 host
+ * (gcc -ffp-contract=off, fmaf -> vfmadd with -mfma) and on the GPU (nvcc -fmad=false,
+ * default -prec-div=true -prec-sqrt=true -ftz=false).
+ *
+ * Accuracy (checked in tests/test_detmath.py against float64 libm): <= 2 ulp on the
+ * argument ranges the path uses.  Coefficients: Taylor for log/sin/cos (error bound in
+ * comments), least-squares Chebyshev fits from tools/fit_detmath.py for asin/atan.
+ *
+ * Everything is `static inline` and usable from C99, C++ and CUDA.
+ */
+#ifndef CPM_DETMATH_H
+#define CPM_DETMATH_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define CPM_HD __host__ __device__ __forceinline__
+#else
+#define CPM_HD static inline
+#endif
+
+#define CPM_PI_F 3.14159274101257324219f      /* float(pi)            0x1.921fb6p+1 */
+#define CPM_2PI_F 6.28318548202514648438f     /* float(2*pi)          0x1.921fb6p+2 */
+#define CPM_PIO2_HI 1.57079637050628662109f   /* float(pi/2)          0x1.921fb6p+0 */
+#define CPM_PIO2_LO -4.37113882867379118e-8f  /* float(pi/2 - PIO2_HI) */
+#define CPM_PIO4_F 0.78539818525314331055f    /* float(pi/4) */
+#define CPM_2OPI_F 0.63661974668502807617f    /* float(2/pi) */
+#define CPM_LN2_HI 0.693145751953125f         /* 0x1.62e3p-1, 16 significant bits */
+#define CPM_LN2_LO 1.42860677e-06f            /* ln2 - LN2_HI */
+#define CPM_INV_4PI_F 0.07957747154594767f    /* 1/(4 pi) */
+
+CPM_HD uint32_t cpm_f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+CPM_HD float cpm_u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+/* min/max with the IEEE "return the non-NaN operand" rule, written with compares so the
+ * host and the device agree bit for bit (fminf/fmaxf may differ in the sign of zero). */
+CPM_HD float cpm_fmin(float a, float b) { return (a != a) ? b : ((b < a) ? b : a); }
+CPM_HD float cpm_fmax(float a, float b) { return (a != a) ? b : ((b > a) ? b : a); }
+/* clamp that maps NaN to lo */
+CPM_HD float cpm_clamp(float x, float lo, float hi) {
+    if (!(x >= lo)) x = lo;
+    if (x > hi) x = hi;
+    return x;
+}
+
+/* Natural logarithm for x >= 0.  x == 0 -> -inf, x == 1 -> 0 exactly.
+ * x = 2^e * m, m in [sqrt(1/2), sqrt(2)); s = (m-1)/(m+1), |s| <= 0.1716;
+ * log m = 2 atanh s = 2s + 2s^3/3 + ... ; truncation after s^11 is < 3e-10 relative. */
+CPM_HD float cpm_logf(float x) {
+    uint32_t ix = cpm_f2u(x);
+    int e = 0;
+    if (ix == 0u) return cpm_u2f(0xff800000u); /* -inf */
+    if (ix < 0x00800000u) {                    /* subnormal: scale by 2^25 */
+        x = x * 33554432.0f;
+        ix = cpm_f2u(x);
+        e = -25;
+    }
+    if (ix >= 0x7f800000u) return x; /* inf or nan (not reached on the path) */
+    /* bring mantissa into [sqrt(1/2), sqrt(2)) */
+    ix += 0x3f800000u - 0x3f3504f3u;
+    e += (int)(ix >> 23) - 127;
+    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+    float m = cpm_u2f(ix);
+    float f = m - 1.0f;
+    float s = f / (2.0f + f);
+    float z = s * s;
+    float p = 0.18181818181818182f;                 /* 2/11 */
+    p = fmaf(p, z, 0.22222222222222222f);          /* 2/9  */
+    p = fmaf(p, z, 0.28571428571428571f);          /* 2/7  */
+    p = fmaf(p, z, 0.4f);                          /* 2/5  */
+    p = fmaf(p, z, 0.66666666666666667f);          /* 2/3  */
+    float r = fmaf(s * z, p, s + s);               /* log(m) */
+    float fe = (float)e;
+    return fmaf(fe, CPM_LN2_HI, fmaf(fe, CPM_LN2_LO, r));
+}
+
+/* sin and cos for |x| <= ~16 (path uses [-pi, 2pi]).  Cody-Waite reduction with two fma
+ * steps, Taylor kernels on [-pi/4, pi/4] (next omitted term < 2.3e-9 relative). */
+CPM_HD void cpm_sincosf(float x, float* sn, float* cs) {
+    float kf = rintf(x * CPM_2OPI_F);
+    float r = fmaf(-kf, CPM_PIO2_HI, x);
+    r = fmaf(-kf, CPM_PIO2_LO, r);
+    int k = (int)kf;
+    float z = r * r;
+    float ps = 2.7557319223985893e-06f;            /*  1/9! */
+    ps = fmaf(ps, z, -1.9841269841269841e-04f);    /* -1/7! */
+    ps = fmaf(ps, z, 8.3333333333333333e-03f);     /*  1/5! */
+    ps = fmaf(ps, z, -1.6666666666666667e-01f);    /* -1/3! */
+    float s = fmaf(r * z, ps, r);
+    float pc = -2.7557319223985888e-07f;           /* -1/10! */
+    pc = fmaf(pc, z, 2.4801587301587302e-05f);     /*  1/8!  */
+    pc = fmaf(pc, z, -1.3888888888888889e-03f);    /* -1/6!  */
+    pc = fmaf(pc, z, 4.1666666666666667e-02f);     /*  1/4!  */
+    float c = fmaf(z * z, pc, fmaf(-0.5f, z, 1.0f));
+    float so = (k & 1) ? c : s;
+    float co = (k & 1) ? s : c;
+    if (k & 2) so = -so;
+    if ((k + 1) & 2) co = -co;
+    *sn = so;
+    *cs = co;
+}
+
+/* asin on [0, 0.5]: x + x z Q(z).  Coefficients: tools/fit_detmath.py (max rel err 2.7e-9). */
+CPM_HD float cpm_asin_core(float x) {
+    float z = x * x;
+    float q = 0x1.14f3d2p-5f;
+    q = fmaf(q, z, 0x1.17c832p-6f);
+    q = fmaf(q, z, 0x1.fdd000p-6f);
+    q = fmaf(q, z, 0x1.6d58c6p-5f);
+    q = fmaf(q, z, 0x1.33343cp-4f);
+    q = fmaf(q, z, 0x1.555554p-3f);
+    return fmaf(x * z, q, x);
+}
+
+/* acos for x in [-1, 1] (callers clamp first, as ppm/photondata.cpp:109 does). */
+CPM_HD float cpm_acosf(float x) {
+    float ax = fabsf(x);
+    if (ax <= 0.5f) {
+        float a = cpm_asin_core(ax);
+        a = (x < 0.0f) ? -a : a;
+        return (CPM_PIO2_HI - a) + CPM_PIO2_LO;
+    }
+    float h = (1.0f - ax) * 0.5f;
+    float r = sqrtf(h);
+    float a2 = 2.0f * cpm_asin_core(r);
+    return (x < 0.0f) ? (CPM_PI_F - a2) : a2;
+}
+
+/* atan for t >= 0, result in [0, pi/2]. */
+CPM_HD float cpm_atan_pos(float t) {
+    /* reduce to |u| <= tan(pi/8) */
+    float base = 0.0f;
+    float u = t;
+    if (t > 2.41421356237309515f) { /* tan(3pi/8) */
+        base = CPM_PIO2_HI;
+        u = -1.0f / t;
+    } else if (t > 0.41421356237309503f) { /* tan(pi/8) */
+        base = CPM_PIO4_F;
+        u = (t - 1.0f) / (t + 1.0f);
+    }
+    float z = u * u;
+    float p = 0x1.9dffb4p-5f;
+    p = fmaf(p, z, -0x1.615d26p-4f);
+    p = fmaf(p, z, 0x1.c57f60p-4f);
+    p = fmaf(p, z, -0x1.248a34p-3f);
+    p = fmaf(p, z, 0x1.99997cp-3f);
+    p = fmaf(p, z, -0x1.555556p-2f);
+    float a = fmaf(u * z, p, u);
+    return base + a;
+}
+
+/* atan2(y, x) with the C99 special cases that can occur for finite inputs. */
+CPM_HD float cpm_atan2f(float y, float x) {
+    float ay = fabsf(y), ax = fabsf(x);
+    float a;
+    if (ax == 0.0f && ay == 0.0f) {
+        /* atan2(+-0, +0) = +-0 ; atan2(+-0, -0) = +-pi */
+        a = (cpm_f2u(x) >> 31) ? CPM_PI_F : 0.0f;
+        return (cpm_f2u(y) >> 31) ? -a : a;
+    }
+    if (ax == 0.0f) {
+        a = CPM_PIO2_HI;
+    } else {
+        a = cpm_atan_pos(ay / ax);
+        if (cpm_f2u(x) >> 31) a = CPM_PI_F - a;
+    }
+    return (cpm_f2u(y) >> 31) ? -a : a;
+}
+
+#endif /* CPM_DETMATH_H */

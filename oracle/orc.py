@@ -1,0 +1,161 @@
+"""ctypes loader of the CPU oracle (oracle/liboracle.so) and of the reference-derived MWC64X
+checker (oracle/_ref/libmwc64x_ref.so).  TEST INFRASTRUCTURE: imported only by tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_lib = None
+_ref = None
+
+
+class OrcVolume(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dims", C.c_int * 3), ("format", C.c_int), ("scale", C.c_float),
+                ("offset", C.c_float)]
+
+
+class OrcTraceParams(C.Structure):
+    _fields_ = [
+        ("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("material", C.c_float * 4),
+        ("phase_function", C.c_int32), ("step_size", C.c_float), ("max_interactions", C.c_int32),
+        ("photon_offset", C.c_int32), ("total_photons", C.c_int32), ("n_light_samples", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+def build():
+    subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        so = HERE / "liboracle.so"
+        if not so.exists():
+            build()
+        _lib = C.CDLL(str(so))
+        _lib.orc_sample_volume.restype = C.c_float
+        _lib.orc_sample_tf_alpha.restype = C.c_float
+        _lib.orc_trace_photons.restype = C.c_ulonglong
+    return _lib
+
+
+def ref():
+    """The reference's own MWC64X kernels compiled for the host, or None when not built."""
+    global _ref
+    if _ref is None:
+        so = HERE / "_ref" / "libmwc64x_ref.so"
+        if not so.exists():
+            return None
+        _ref = C.CDLL(str(so))
+    return _ref
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def volume(data: np.ndarray, scale=1.0, offset=0.0) -> OrcVolume:
+    """data: (nz, ny, nx) C-contiguous array of uint8 / uint16 / float32"""
+    fmt = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[data.dtype]
+    v = OrcVolume()
+    v.data = data.ctypes.data
+    v.dims[:] = [data.shape[2], data.shape[1], data.shape[0]]
+    v.format = fmt
+    v.scale = scale
+    v.offset = offset
+    v._keep = data
+    return v
+
+
+def rng_host_base_offsets(seed, n):
+    out = np.zeros((n, 2), np.uint32)
+    lib().orc_rng_host_base_offsets(C.c_uint32(seed), _ptr(out), C.c_size_t(n))
+    return out
+
+
+def rng_seed_streams(state, gap=1 << 40, first_stream=0):
+    lib().orc_rng_seed_streams(_ptr(state), C.c_size_t(state.shape[0]), C.c_uint64(gap), C.c_uint64(first_stream))
+    return state
+
+
+def rng_uniform(state, per_stream=1):
+    out = np.empty((state.shape[0], per_stream), np.float32)
+    lib().orc_rng_uniform(_ptr(state), C.c_size_t(state.shape[0]), int(per_stream), _ptr(out))
+    return out
+
+
+def sample_uniform2d(nx, ny, n):
+    out = np.empty((n, 4), np.float32)
+    lib().orc_sample_uniform2d(C.c_float(nx), C.c_float(ny), int(n), _ptr(out))
+    return out
+
+
+def light_sample_directional(samples, radiance, direction, origin, u, v, area):
+    n = samples.shape[0]
+    out = np.empty((n, 8), np.float32)
+    lib().orc_light_sample_directional(_ptr(samples), _f3(radiance), _f3(direction), _f3(origin), _f3(u), _f3(v),
+                                       C.c_float(area), n, _ptr(out))
+    return out
+
+
+def light_sample_point(samples, radiance, pos):
+    n = samples.shape[0]
+    out = np.empty((n, 8), np.float32)
+    lib().orc_light_sample_point(_ptr(samples), _f3(radiance), _f3(pos), n, _ptr(out))
+    return out
+
+
+def light_mesh_intersect(vertices, indices, light_samples):
+    n = light_samples.shape[0]
+    out = np.empty((n, 2), np.float32)
+    lib().orc_light_mesh_intersect(_ptr(vertices), _ptr(indices), int(indices.size), _ptr(light_samples), n, _ptr(out))
+    return out
+
+
+def fit_light_plane(points, plane_point, plane_normal):
+    out = np.empty(9, np.float32)
+    pts = np.ascontiguousarray(points, np.float32)
+    lib().orc_fit_light_plane(_ptr(pts), int(pts.shape[0]), _f3(plane_point), _f3(plane_normal), _ptr(out))
+    return out[0:3].copy(), out[3:6].copy(), out[6:9].copy()
+
+
+def trace_params(**kw) -> OrcTraceParams:
+    p = OrcTraceParams()
+    p.aabb_min[:] = [float(x) for x in kw.get("aabb_min", (0, 0, 0))]
+    p.aabb_max[:] = [float(x) for x in kw.get("aabb_max", (1, 1, 1))]
+    p.material[:] = [float(x) for x in kw.get("material", (0, 0, 0, 0))]
+    p.phase_function = kw.get("phase", 0)
+    p.step_size = kw.get("step_size", 1.0 / 256)
+    p.max_interactions = kw.get("max_interactions", 1)
+    p.photon_offset = kw.get("photon_offset", 0)
+    p.n_light_samples = kw["n_light_samples"]
+    p.total_photons = kw.get("total_photons", None) or kw["n_light_samples"]
+    p.flags = kw.get("flags", 0)
+    return p
+
+
+def trace_photons(vol: OrcVolume, tf_rgba, params: OrcTraceParams, light_samples, isect, photons, rng,
+                  recompute=None, n_recompute=0, n_threads=0) -> int:
+    return int(lib().orc_trace_photons(C.byref(vol), _ptr(tf_rgba), int(tf_rgba.shape[0]), C.byref(params),
+                                       _ptr(light_samples), _ptr(isect), _ptr(recompute), int(n_recompute),
+                                       _ptr(photons), _ptr(rng), int(n_threads)))
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def selftest_math(fn, x, y=None):
+    out = np.empty_like(x)
+    lib().orc_selftest_math(int(fn), _ptr(x), _ptr(y), _ptr(out), C.c_size_t(x.size))
+    return out
