@@ -1,0 +1,383 @@
+// radixsort.cu -- hand-written onesweep LSD radix sort (north-star subsystem 5), no CUB.
+//
+// Replaces clogs::Radixsort::enqueue (rsc/ext/clogs/src/radixsort.cpp:169-259) and its three
+// kernels radixsortReduce / radixsortScan / radixsortScatter (clogs/kernels/radixsort.cl:248,
+// 323, 893).  Same contract (clogs/radixsort.h:227-229): ascending, STABLE, keys (and values)
+// sorted in place, `max_bits` bounds the significant key bits (0 = all 32).
+//
+// Traffic: clogs reads the keys twice and moves key+value once per 4-bit pass: 8 x (4+8+8) =
+// 160 B per (u32,u32) pair.  Onesweep with 8-bit digits reads the keys once for all digit
+// histograms and then moves each element exactly once per pass with a single-pass chained scan
+// (decoupled look-back): 4 + 4 x 2 x (4+4) = 68 B per pair, 36 B per key for keys only.
+//
+// Kernel structure per pass (one CTA = one tile of TILE elements, tiles taken in order from an
+// atomic ticket so that look-back never waits on a CTA that has not started):
+//   1. warp-striped coalesced load of ITEMS keys (and values) per thread
+//   2. stable ranking inside each warp with MATCH.ANY on the digit + warp-private digit counters
+//      in shared memory (no atomics); items are ranked in load order, so the order of equal
+//      digits is the input order
+//   3. thread d owns digit d: sums the warp counters, publishes the tile's count for d
+//      (FLAG_AGGREGATE), walks back over predecessor tiles until it meets an inclusive prefix
+//      (FLAG_PREFIX), publishes its own inclusive prefix
+//   4. keys/values are permuted through shared memory into tile-sorted order and written out in
+//      runs of equal digit (coalesced stores)
+#include "common.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int MAX_PASSES = 4;
+
+constexpr uint32_t FLAG_AGGREGATE = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+
+// ---- pass 0: all digit histograms in one read of the keys -----------------------------------
+// 4 B/key of HBM traffic.  Shared-memory atomics; a warp whose 32 keys share a digit (the
+// importance keys are ~90 % 0x7FFFFFFF) adds 32 once instead of serialising on one bank.
+__global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restrict__ keys, size_t n, int passes,
+                                                        uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const size_t n4 = n / 4;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    const unsigned lane = threadIdx.x & 31;
+    auto add = [&](uint32_t k) {
+        // all lanes of the warp are active here (uniform loop trip count per warp is enforced below)
+        uint32_t k0 = __shfl_sync(0xffffffffu, k, 0);
+        bool same = __all_sync(0xffffffffu, k == k0);
+        if (same) {
+            if (lane < (unsigned)passes) atomicAdd(&s_hist[lane * RADIX + ((k0 >> (lane * RADIX_BITS)) & (RADIX - 1))], 32u);
+        } else {
+#pragma unroll
+            for (int p = 0; p < MAX_PASSES; ++p)
+                if (p < passes) atomicAdd(&s_hist[p * RADIX + ((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        }
+    };
+    // warp-uniform trip count: iterate over whole-warp chunks, tail handled separately
+    size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    size_t n_warps = ((size_t)gridDim.x * blockDim.x) / 32;
+    size_t full_chunks = n4 / 32;  // chunks of 32 uint4
+    for (size_t c = warp_global; c < full_chunks; c += n_warps) {
+        uint4 v = k4[c * 32 + lane];
+        add(v.x); add(v.y); add(v.z); add(v.w);
+    }
+    // tail: remaining keys one by one (fewer than 128 + 3), done by block 0
+    if (blockIdx.x == 0) {
+        for (size_t i = full_chunks * 128 + threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t k = keys[i];
+            for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p * RADIX + ((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+struct SortSmem {
+    uint32_t warp_count[SORT_WARPS][RADIX];  // per-warp digit counters, later exclusive warp offsets
+    uint32_t gbase[RADIX];                   // global index of local position 0 of each digit run
+    uint32_t keys[SORT_TILE];
+    uint32_t vals[SORT_TILE];
+    uint32_t scan_tmp[SORT_WARPS];
+    uint32_t tile;
+};
+
+template <bool HAS_VALUES>
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out,
+                                                                uint32_t* __restrict__ vals_out, size_t n, int shift,
+                                                                const uint32_t* __restrict__ hist,  // this pass
+                                                                volatile uint32_t* status,          // [tiles][RADIX]
+                                                                uint32_t* ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) S.warp_count[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const size_t tile_base = (size_t)tile * SORT_TILE;
+    const uint32_t n_valid = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
+
+    // 1. load (warp-striped): warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+    const uint32_t warp_base = warp * 32 * SORT_ITEMS;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        uint32_t local = warp_base + j * 32 + lane;
+        bool ok = local < n_valid;
+        key[j] = ok ? keys_in[tile_base + local] : 0xffffffffu;
+        if (HAS_VALUES) val[j] = ok ? vals_in[tile_base + local] : 0u;
+    }
+
+    // 2. stable in-warp ranking
+    uint32_t* wc = S.warp_count[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        uint32_t d = (key[j] >> shift) & (RADIX - 1);
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if ((int)lane == leader) {
+            before = wc[d];
+            wc[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rank[j] = before + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // 3. thread `tid` owns digit `tid`: warp-exclusive offsets, tile total
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+        uint32_t c = S.warp_count[w][tid];
+        S.warp_count[w][tid] = total;
+        total += c;
+    }
+    // padding of the last tile sits in digit 255, after every real key
+    uint32_t real_total = total;
+    if (tid == RADIX - 1) real_total -= (SORT_TILE - n_valid);
+
+    // publish + decoupled look-back (value and flag travel in one 32-bit word)
+    uint32_t exclusive = 0;
+    if (tile == 0) {
+        status[(size_t)tile * RADIX + tid] = FLAG_PREFIX | real_total;
+    } else {
+        status[(size_t)tile * RADIX + tid] = FLAG_AGGREGATE | real_total;
+        int64_t t = (int64_t)tile - 1;
+        while (true) {
+            uint32_t s = status[(size_t)t * RADIX + tid];
+            uint32_t f = s & FLAG_MASK;
+            if (f == FLAG_PREFIX) {
+                exclusive += s & VALUE_MASK;
+                break;
+            }
+            if (f == FLAG_AGGREGATE) {
+                exclusive += s & VALUE_MASK;
+                --t;
+            }
+            // else: not published yet, poll again
+        }
+        status[(size_t)tile * RADIX + tid] = FLAG_PREFIX | (exclusive + real_total);
+    }
+
+    // exclusive scan of the tile totals over the 256 digits (tile-local start of each digit run)
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    if (lane == 31) S.scan_tmp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w)
+        if (w < (int)warp) woff += S.scan_tmp[w];
+    const uint32_t digit_start = woff + incl - total;
+
+    // global digit base = exclusive scan of the global histogram (256 values: recomputed per CTA)
+    uint32_t h = hist[tid];
+    uint32_t hincl = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, hincl, o);
+        if (lane >= (unsigned)o) hincl += v;
+    }
+    __syncthreads();  // scan_tmp reuse
+    if (lane == 31) S.scan_tmp[warp] = hincl;
+    __syncthreads();
+    uint32_t hoff = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w)
+        if (w < (int)warp) hoff += S.scan_tmp[w];
+    const uint32_t digit_base = hoff + hincl - h;
+
+    // local position p of digit d goes to global index gbase[d] + p
+    S.gbase[tid] = digit_base + exclusive - digit_start;
+    // fold the tile-local digit start into the warp offsets: local pos = warp_count[w][d] + rank
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) S.warp_count[w][tid] += digit_start;
+    __syncthreads();
+
+    // 4. permute through shared memory, then coalesced stores
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        uint32_t d = (key[j] >> shift) & (RADIX - 1);
+        uint32_t pos = wc[d] + rank[j];
+        S.keys[pos] = key[j];
+        if (HAS_VALUES) S.vals[pos] = val[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        uint32_t p = j * SORT_THREADS + tid;
+        if (p < n_valid) {
+            uint32_t k = S.keys[p];
+            uint32_t d = (k >> shift) & (RADIX - 1);
+            size_t g = (size_t)S.gbase[d] + p;
+            keys_out[g] = k;
+            if (HAS_VALUES) vals_out[g] = S.vals[p];
+        }
+    }
+}
+
+// ---- small stream kernels of the selection stage ----------------------------------------------
+__global__ void __launch_bounds__(256) threshold_kernel(const uint32_t* __restrict__ data, uint32_t threshold, size_t n,
+                                                        uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = data[i] < threshold ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+// sum of ints (clogs Reduce with TYPE_INT) / fused count(data < threshold) + optional iota
+template <bool COUNT_BELOW>
+__global__ void __launch_bounds__(256) reduce_kernel(const uint32_t* __restrict__ data, uint32_t threshold, size_t n,
+                                                     uint32_t* __restrict__ iota_out, unsigned long long* __restrict__ result) {
+    unsigned long long acc = 0;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t v = data[i];
+        if (COUNT_BELOW) {
+            acc += v < threshold ? 1u : 0u;
+            if (iota_out) iota_out[i] = (uint32_t)i;
+        } else {
+            acc += (unsigned long long)(long long)(int32_t)v;
+        }
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ unsigned long long s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        if (t) atomicAdd(result, t);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t cpm_radix_sort_scratch_bytes(size_t n) {
+    size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    return 4096 /*hist*/ + 256 /*tickets*/ + (size_t)MAX_PASSES * tiles * RADIX * sizeof(uint32_t);
+}
+
+int cpm_radix_sort_u32(cpm_ctx* ctx, uint32_t* keys, uint32_t* values, size_t n, unsigned max_bits, uint32_t* tmp_keys,
+                       uint32_t* tmp_values) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, n > 0, "elements is zero");                       // clogs: CL_INVALID_GLOBAL_WORK_SIZE
+    CPM_REQUIRE(ctx, max_bits <= 32, "maxBits is too large");          // clogs: CL_INVALID_VALUE
+    CPM_REQUIRE(ctx, keys && tmp_keys, "keys / temporary key buffer is NULL");
+    CPM_REQUIRE(ctx, !values || tmp_values, "temporary value buffer is NULL");
+    if (n >= (1ull << 30)) return cpm_fail(ctx, CPM_E_UNSUPPORTED, "cpm_radix_sort_u32: n must be < 2^30");
+    if (max_bits == 0) max_bits = 32;
+    const int passes = (int)((max_bits + RADIX_BITS - 1) / RADIX_BITS);
+    const size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    void* scratch;
+    size_t status_bytes = (size_t)passes * tiles * RADIX * sizeof(uint32_t);
+    int rc = cpm_scratch(ctx, 4096 + 256 + status_bytes, &scratch);
+    if (rc != CPM_OK) return rc;
+    uint32_t* hist = (uint32_t*)scratch;
+    uint32_t* tickets = (uint32_t*)((char*)scratch + 4096);
+    uint32_t* status = (uint32_t*)((char*)scratch + 4096 + 256);
+    CPM_CUDA(ctx, cudaMemsetAsync(scratch, 0, 4096 + 256 + status_bytes, ctx->stream));
+
+    unsigned hgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, std::max<size_t>(1, n / (512 * 4)));
+    CPM_LAUNCH(ctx, histogram_kernel, hgrid, 512, 0, keys, n, passes, hist);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+        attr_set = true;
+    }
+    uint32_t *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_values;
+    for (int p = 0; p < passes; ++p) {
+        if (values) {
+            CPM_LAUNCH(ctx, onesweep_kernel<true>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem), kin, vin, kout, vout, n,
+                       p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+        } else {
+            CPM_LAUNCH(ctx, onesweep_kernel<false>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem), kin, nullptr, kout, nullptr,
+                       n, p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+        }
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    if (kin != keys) {  // odd number of passes: copy back, as clogs does (radixsort.cpp:241-256)
+        CPM_CUDA(ctx, cudaMemcpyAsync(keys, kin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (values) CPM_CUDA(ctx, cudaMemcpyAsync(values, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return CPM_OK;
+}
+
+int cpm_threshold_u32(cpm_ctx* ctx, const uint32_t* data, uint32_t threshold, size_t n, uint32_t* out) {
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, data && out, "null buffer");
+    CPM_LAUNCH(ctx, threshold_kernel, cpm_div_up(n, 256), 256, 0, data, threshold, n, out);
+    return CPM_OK;
+}
+
+int cpm_iota_u32(cpm_ctx* ctx, uint32_t* out, size_t n) {
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, out != nullptr, "null buffer");
+    CPM_LAUNCH(ctx, iota_kernel, cpm_div_up(n, 256), 256, 0, out, n);
+    return CPM_OK;
+}
+
+static int reduce_common(cpm_ctx* ctx, bool count_below, const uint32_t* data, uint32_t threshold, size_t n,
+                         uint32_t* iota_out, long long* result_host) {
+    CPM_REQUIRE(ctx, result_host != nullptr, "result pointer is NULL");
+    *result_host = 0;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, data != nullptr, "null buffer");
+    void* scratch;
+    int rc = cpm_scratch(ctx, 4096, &scratch);
+    if (rc != CPM_OK) return rc;
+    unsigned long long* acc = (unsigned long long*)((char*)scratch + 2048);  // away from the sort's histogram words
+    CPM_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(*acc), ctx->stream));
+    unsigned grid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, cpm_div_up(n, 256));
+    if (count_below)
+        CPM_LAUNCH(ctx, reduce_kernel<true>, grid, 256, 0, data, threshold, n, iota_out, acc);
+    else
+        CPM_LAUNCH(ctx, reduce_kernel<false>, grid, 256, 0, data, threshold, n, nullptr, acc);
+    unsigned long long* pinned = (unsigned long long*)ctx->pinned;
+    CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
+    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *result_host = (long long)*pinned;
+    return CPM_OK;
+}
+
+int cpm_reduce_sum_i32(cpm_ctx* ctx, const int32_t* data, size_t n, long long* result_host) {
+    if (!ctx) return CPM_E_INVALID;
+    return reduce_common(ctx, false, (const uint32_t*)data, 0, n, nullptr, result_host);
+}
+
+int cpm_count_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* iota_out,
+                    long long* count_host) {
+    if (!ctx) return CPM_E_INVALID;
+    return reduce_common(ctx, true, data, threshold, n, iota_out, count_host);
+}
+
+}  // extern "C"
