@@ -214,3 +214,116 @@ def _selftest_math(self, fn, x, y, out):
 
 
 Context.selftest_math = _selftest_math
+
+
+# -- selection / sort --------------------------------------------------------------------------
+def _threshold(self, data, threshold, out):
+    self._check(lib().cpm_threshold_u32(self.h, _p(data), C.c_uint32(threshold), C.c_size_t(data.numel()), _p(out)))
+
+
+def _iota(self, out):
+    self._check(lib().cpm_iota_u32(self.h, _p(out), C.c_size_t(out.numel())))
+
+
+def _reduce_sum_i32(self, data):
+    r = C.c_longlong(0)
+    self._check(lib().cpm_reduce_sum_i32(self.h, _p(data), C.c_size_t(data.numel()), C.byref(r)))
+    return r.value
+
+
+def _count_below(self, data, threshold, iota_out=None, n=None):
+    r = C.c_longlong(0)
+    n = data.numel() if n is None else n
+    self._check(lib().cpm_count_below(self.h, _p(data), C.c_size_t(n), C.c_uint32(threshold), _p(iota_out), C.byref(r)))
+    return r.value
+
+
+def _radix_sort(self, keys, values, tmp_keys, tmp_values, n=None, max_bits=0):
+    n = keys.numel() if n is None else n
+    self._check(lib().cpm_radix_sort_u32(self.h, _p(keys), _p(values), C.c_size_t(n), C.c_uint(max_bits), _p(tmp_keys),
+                                         _p(tmp_values)))
+
+
+Context.threshold = _threshold
+Context.iota = _iota
+Context.reduce_sum_i32 = _reduce_sum_i32
+Context.count_below = _count_below
+Context.radix_sort = _radix_sort
+
+
+# -- detector / grids / splat ------------------------------------------------------------------
+CPM_DETECT_FIX_EXIT = 1
+
+
+def _fN(v, n):
+    return (C.c_float * n)(*[float(x) for x in v])
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def texture_to_index_matrix(dims):
+    """column-major 4x4: index = tex * dim - 0.5 (Inviwo StructuredCoordinateTransformer)"""
+    m = [0.0] * 16
+    m[0], m[5], m[10], m[15] = float(dims[0]), float(dims[1]), float(dims[2]), 1.0
+    m[12] = m[13] = m[14] = -0.5
+    return m
+
+
+def index_to_texture_matrix(dims):
+    m = [0.0] * 16
+    m[0], m[5], m[10], m[15] = 1.0 / dims[0], 1.0 / dims[1], 1.0 / dims[2], 1.0
+    m[12], m[13], m[14] = 0.5 / dims[0], 0.5 / dims[1], 0.5 / dims[2]
+    import numpy as np
+    return [float(np.float32(x)) for x in m]
+
+
+def _detect_invalid(self, grid, grid_dims, cell_size, tex2idx, photons, photon_offset, light_samples, intersections,
+                    n_light_samples, max_interactions, total_photons, importances, equal_importance=False,
+                    percentage=100, iteration=0, flags=0):
+    self._check(lib().cpm_detect_invalid(self.h, _p(grid), _i3(grid_dims), _f3(cell_size), _fN(tex2idx, 16), _p(photons),
+                                         int(photon_offset), _p(light_samples), _p(intersections), int(n_light_samples),
+                                         int(max_interactions), int(total_photons), _p(importances),
+                                         int(bool(equal_importance)), int(percentage), int(iteration), C.c_uint32(flags)))
+
+
+def _volume_minmax(self, vol, region, out):
+    od = (C.c_int * 3)()
+    self._check(lib().cpm_volume_minmax(self.h, vol.handle, int(region), _p(out), od))
+    return tuple(od)
+
+
+def _volume_diff_bricks(self, a, b, region, scaling, rmin, rmax, out):
+    self._check(lib().cpm_volume_diff_bricks(self.h, a.handle, b.handle, int(region), C.c_double(scaling),
+                                             C.c_double(rmin), C.c_double(rmax), _p(out)))
+
+
+def _classify_importance(self, minmax, n, positions, colors, n_points, weights, incremental, out, prev=None, diff=None):
+    self._check(lib().cpm_classify_importance(self.h, _p(minmax), _p(prev), _p(diff), int(n), _p(positions), _p(colors),
+                                              int(n_points), _fN(weights, 4), int(bool(incremental)), _p(out)))
+
+
+def _hash_light_samples(self, light_samples, intersections, n_src, ids, n_ids, cell_size, n_blocks, out, out_offset=0):
+    self._check(lib().cpm_hash_light_samples(self.h, _p(light_samples), _p(intersections), int(n_src), _p(ids), int(n_ids),
+                                             _f3(cell_size), _i3(n_blocks), _p(out), int(out_offset)))
+
+
+def _build_cell_ranges(self, keys, n, n_cells, start, end):
+    self._check(lib().cpm_build_cell_ranges(self.h, _p(keys), C.c_size_t(n), C.c_uint32(n_cells), _p(start), _p(end)))
+
+
+def _splat_photons(self, light_volume, channels, tex2idx, idx2tex, out_dims, photons, indices, n, per_interaction,
+                   n_interactions, radius, scale, multiplier=1.0):
+    self._check(lib().cpm_splat_photons(self.h, _p(light_volume), int(channels), _fN(tex2idx, 16), _fN(idx2tex, 16),
+                                        _i3(out_dims), _p(photons), _p(indices), int(n), int(per_interaction),
+                                        int(n_interactions), C.c_float(radius), C.c_float(scale), C.c_float(multiplier)))
+
+
+Context.detect_invalid = _detect_invalid
+Context.volume_minmax = _volume_minmax
+Context.volume_diff_bricks = _volume_diff_bricks
+Context.classify_importance = _classify_importance
+Context.hash_light_samples = _hash_light_samples
+Context.build_cell_ranges = _build_cell_ranges
+Context.splat_photons = _splat_photons

@@ -1,0 +1,196 @@
+// detector.cu -- temporal-correlation pass: which stored photon paths cross changed bricks
+// (north-star subsystem 4, detection half).
+//
+// Replaces photonRecomputationDetectorKernel / ...EqualImportanceKernel
+// (ppm/cl/photonrecomputationdetector.cl:92-157, :160-194) and the DDA library they use
+// (ugc/cl/uniformgrid/uniformgrid.cl:38-69, :147-197, OPTIMIZE_STEP_FOR_SIMD branch).
+//
+// B200 notes: one thread per photon path; the streams (light sample 32 B, intersection 8 B,
+// photon 32 B per interaction, key 4 B RMW) are read with 16 B vector loads; the importance grid
+// (1-8 MB) is read through the read-only path and stays L2 resident.  The DDA loop is
+// divergent by nature (3*dim/8 cells at most).
+#include <string.h>
+
+#include "sampling.cuh"
+
+namespace {
+
+#define CPM_FLT_MAX 3.402823466e+38f
+
+struct Mat4 {
+    float m[16];
+};
+
+__device__ __forceinline__ float3_ transform_point(const Mat4& M, float3_ p) {
+    return {fmaf(M.m[8], p.z, fmaf(M.m[4], p.y, fmaf(M.m[0], p.x, M.m[12]))),
+            fmaf(M.m[9], p.z, fmaf(M.m[5], p.y, fmaf(M.m[1], p.x, M.m[13]))),
+            fmaf(M.m[10], p.z, fmaf(M.m[6], p.y, fmaf(M.m[2], p.x, M.m[14])))};
+}
+
+struct GridArgs {
+    const float* grid;
+    int dims[3];
+    float cell[3];
+};
+
+__device__ float uniform_grid_importance(const GridArgs& G, float3_ x1, float3_ x2) {
+    float a1[3] = {x1.x, x1.y, x1.z}, a2[3] = {x2.x, x2.y, x2.z};
+    float dt[3], deltatx[3];
+    int cell[3], cell_end[3], di[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float mx = (float)(G.dims[k] - 1);
+        float cf = cpm_clamp(floorf(a1[k] / G.cell[k]), 0.0f, mx);
+        cell[k] = (int)cf;
+        cell_end[k] = (int)cpm_clamp(truncf(a2[k] / G.cell[k]), 0.0f, mx);
+        di[k] = (a1[k] < a2[k]) ? 1 : ((a1[k] > a2[k]) ? -1 : 0);
+        float inv_abs = 1.0f / fabsf(a2[k] - a1[k]);
+        float minx = G.cell[k] * cf;
+        float maxx = minx + G.cell[k];
+        dt[k] = ((a1[k] > a2[k]) ? (a1[k] - minx) : (maxx - a1[k])) * inv_abs;
+        deltatx[k] = G.cell[k] * inv_abs;
+    }
+    bool go = true;
+    float importance = 0.0f, dt1 = 0.0f;
+    const int sy = G.dims[0], sz = G.dims[0] * G.dims[1];
+    while (go) {
+        float val = __ldg(G.grid + cell[0] + cell[1] * sy + cell[2] * sz);
+        float dt0 = dt1;
+        bool ax = (dt[0] <= dt[1] && dt[0] <= dt[2]);
+        bool ay = !ax && (dt[0] > dt[1] && dt[1] <= dt[2]);
+        // select the axis without dynamic register indexing
+        float dsel = ax ? dt[0] : (ay ? dt[1] : dt[2]);
+        int csel = ax ? cell[0] : (ay ? cell[1] : cell[2]);
+        int esel = ax ? cell_end[0] : (ay ? cell_end[1] : cell_end[2]);
+        dt1 = dsel;
+        if (csel == esel) {
+            go = false;
+        } else if (ax) {
+            dt[0] += deltatx[0]; cell[0] += di[0];
+        } else if (ay) {
+            dt[1] += deltatx[1]; cell[1] += di[1];
+        } else {
+            dt[2] += deltatx[2]; cell[2] += di[2];
+        }
+        importance += val * (cpm_fmin(1.0f, dt1) - dt0);
+    }
+    float dx = x2.x - x1.x, dy = x2.y - x1.y, dz = x2.z - x1.z;
+    float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    return importance * len;
+}
+
+__device__ __forceinline__ uint32_t convert_uint_sat_rtp(float v) {
+    if (!(v > 0.0f)) return 0u;
+    float c = ceilf(v);
+    if (c >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)c;
+}
+
+struct DetectArgs {
+    GridArgs grid;
+    Mat4 tex2idx;
+    const float4* photons;
+    int photon_offset;
+    const float4* light_samples;
+    const float2* isect;
+    int n_light_samples;
+    int max_interactions;
+    int total_photons;
+    uint32_t* importances;
+    int equal_importance, percentage, iteration, fix_exit;
+};
+
+__global__ void __launch_bounds__(128) detect_kernel(const DetectArgs A) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= A.n_light_samples) return;
+    float imp = 0.0f;
+    if (A.equal_importance) {
+        int pid = A.photon_offset + tid;
+        int div = (A.percentage > 0 && A.percentage <= 100) ? 100 / A.percentage : 1;
+        if ((pid + A.iteration) % div == 0) imp = 1.0f;
+    } else {
+        float4 l0 = A.light_samples[2 * (size_t)tid], l1 = A.light_samples[2 * (size_t)tid + 1];
+        float3_ origin = {l0.x, l0.y, l0.z};
+        float3_ dir = decode_direction(l1.z, l1.w);
+        float2 ip = A.isect[tid];
+        float tStart = ip.x, tEnd = ip.y;
+        if (tStart < tEnd) {
+            float3_ entry = {fmaf(tStart, dir.x, origin.x), fmaf(tStart, dir.y, origin.y), fmaf(tStart, dir.z, origin.z)};
+            for (int k = 0; k < A.max_interactions; ++k) {
+                size_t pid = (size_t)A.photon_offset + (size_t)k * A.total_photons + tid;
+                float4 p0 = A.photons[2 * pid], p1 = A.photons[2 * pid + 1];
+                float3_ exit = {p0.x, p0.y, p0.z};
+                if (p0.x == CPM_FLT_MAX || p0.y == CPM_FLT_MAX || p0.z == CPM_FLT_MAX) {
+                    if (k == 0) {
+                        if (A.fix_exit)
+                            exit = {fmaf(tEnd, dir.x, origin.x), fmaf(tEnd, dir.y, origin.y), fmaf(tEnd, dir.z, origin.z)};
+                        else
+                            exit = {tEnd * dir.x, tEnd * dir.y, tEnd * dir.z};  // reference quirk (:128)
+                    } else if (entry.x == CPM_FLT_MAX || entry.y == CPM_FLT_MAX || entry.z == CPM_FLT_MAX) {
+                        break;
+                    } else {
+                        const float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {1.f, 1.f, 1.f};
+                        float t0 = 0.0f, t1 = CPM_FLT_MAX;
+                        float3_ pd = decode_direction(p1.z, p1.w);
+                        if (p0.w != CPM_FLT_MAX && ray_box(bmin, bmax, entry, pd, t0, t1)) {
+                            exit = {fmaf(t1, pd.x, entry.x), fmaf(t1, pd.y, entry.y), fmaf(t1, pd.z, entry.z)};
+                        } else {
+                            break;
+                        }
+                    }
+                }
+                float3_ x1 = transform_point(A.tex2idx, entry), x2 = transform_point(A.tex2idx, exit);
+                x1 = {x1.x + 0.5f, x1.y + 0.5f, x1.z + 0.5f};
+                x2 = {x2.x + 0.5f, x2.y + 0.5f, x2.z + 0.5f};
+                imp += uniform_grid_importance(A.grid, x1, x2);
+                entry = {p0.x, p0.y, p0.z};
+            }
+        }
+    }
+    uint32_t v = convert_uint_sat_rtp(100.0f * imp);
+    if (v > 2147483647u) v = 2147483647u;
+    A.importances[A.photon_offset + tid] -= v;
+}
+
+}  // namespace
+
+extern "C" int cpm_detect_invalid(cpm_ctx* ctx, const float* importance_grid, const int grid_dims[3],
+                                  const float cell_size[3], const float texture_to_index[16], const float* photons,
+                                  int photon_offset, const float* light_samples, const float* intersections,
+                                  int n_light_samples, int max_interactions, int total_photons, uint32_t* importances,
+                                  int equal_importance, int percentage, int iteration, uint32_t flags) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, n_light_samples >= 0, "negative n_light_samples");
+    if (n_light_samples == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, importances != nullptr, "importances is NULL");
+    CPM_REQUIRE(ctx, equal_importance || (importance_grid && grid_dims && cell_size && texture_to_index && photons &&
+                                          light_samples && intersections),
+                "null argument");
+    CPM_REQUIRE(ctx, max_interactions >= 1 && photon_offset >= 0 && total_photons >= photon_offset + n_light_samples,
+                "inconsistent photon counts");
+    DetectArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!equal_importance) {
+        CPM_REQUIRE(ctx, grid_dims[0] > 0 && grid_dims[1] > 0 && grid_dims[2] > 0, "grid dims must be positive");
+        a.grid.grid = importance_grid;
+        for (int k = 0; k < 3; ++k) {
+            a.grid.dims[k] = grid_dims[k];
+            a.grid.cell[k] = cell_size[k];
+        }
+        for (int k = 0; k < 16; ++k) a.tex2idx.m[k] = texture_to_index[k];
+    }
+    a.photons = (const float4*)photons;
+    a.photon_offset = photon_offset;
+    a.light_samples = (const float4*)light_samples;
+    a.isect = (const float2*)intersections;
+    a.n_light_samples = n_light_samples;
+    a.max_interactions = max_interactions;
+    a.total_photons = total_photons;
+    a.importances = importances;
+    a.equal_importance = equal_importance;
+    a.percentage = percentage;
+    a.iteration = iteration;
+    a.fix_exit = (flags & CPM_DETECT_FIX_EXIT) ? 1 : 0;
+    CPM_LAUNCH(ctx, detect_kernel, cpm_div_up(n_light_samples, 128), 128, 0, a);
+    return CPM_OK;
+}

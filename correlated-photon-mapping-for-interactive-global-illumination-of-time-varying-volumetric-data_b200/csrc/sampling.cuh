@@ -124,6 +124,8 @@ __device__ __forceinline__ float sample_tf_alpha(const float* __restrict__ alpha
     return lerpf(alpha[i0], alpha[i1], a);
 }
 
+#define CPM_FLT_MAX_ 3.402823466e+38f
+
 struct float3_ {
     float x, y, z;
 };

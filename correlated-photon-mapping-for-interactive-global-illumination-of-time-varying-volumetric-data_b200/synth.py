@@ -51,7 +51,7 @@ def volume_field(dims, seed: int, t: float = 0.0, n_blobs: int = 12, noise_res: 
         cx = 0.15 + 0.7 * cx + 0.12 * orad * np.cos(ang)
         cy = 0.15 + 0.7 * cy + 0.12 * orad * np.sin(ang)
         cz = 0.15 + 0.7 * cz
-        s = 0.05 + 0.12 * rad
+        s = 0.04 + 0.08 * rad
         gx[k] = np.exp(-0.5 * ((xs - cx) / s) ** 2)
         gy[k] = np.exp(-0.5 * ((ys - cy) / s) ** 2)
         gz[k] = np.exp(-0.5 * ((zs - cz) / s) ** 2)
@@ -59,7 +59,7 @@ def volume_field(dims, seed: int, t: float = 0.0, n_blobs: int = 12, noise_res: 
     f = np.einsum("k,kz,ky,kx->zyx", amp, gz, gy, gx, optimize=True).astype(np.float32)
     mz, my, mx = _interp_matrix(nz, noise_res), _interp_matrix(ny, noise_res), _interp_matrix(nx, noise_res)
     nfield = np.einsum("zc,yb,xa,cba->zyx", mz, my, mx, noise, optimize=True)
-    f = 0.85 * np.minimum(f, 1.0) + 0.15 * nfield
+    f = 0.93 * np.minimum(f, 1.0) + 0.07 * nfield
     return np.clip(f, 0.0, 1.0).astype(np.float32)
 
 

@@ -174,6 +174,99 @@ CPM_API int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const float* 
                               const uint32_t* recompute_index, int n_recompute, float* photons,
                               uint32_t* rng_state, unsigned long long* collision_tests);
 
+/* ---- (5) selection: threshold / count / iota / radix sort --------------------------- */
+/* thresholdKernel (ppm/cl/threshold.cl:33-40): out[i] = data[i] < threshold. */
+CPM_API int cpm_threshold_u32(cpm_ctx* ctx, const uint32_t* data, uint32_t threshold, size_t n,
+                              uint32_t* out);
+/* indexToBufferKernel (ppm/cl/indextobuffer.cl:33-40): out[i] = i. */
+CPM_API int cpm_iota_u32(cpm_ctx* ctx, uint32_t* out, size_t n);
+/* clogs::Reduce::enqueue with TYPE_INT (rsc/ext/clogs/src/reduce.cpp:262-345) as called by
+ * ProgressivePhotonTracerCL::reduceInts (ppm/processor/progressivephotontracercl.cpp:727-741).
+ * SYNCHRONOUS: returns the exact sum in *result_host (the reference reads its result before
+ * the read-back event completes, :342-345,374 -- fixed here). */
+CPM_API int cpm_reduce_sum_i32(cpm_ctx* ctx, const int32_t* data, size_t n, long long* result_host);
+/* Fused replacement of threshold + reduce + iota for the re-trace selection
+ * (ppm/processor/progressivephotontracercl.cpp:318-356): one 4 B/photon pass that counts
+ * data[i] < threshold and, if iota_out != NULL, writes iota_out[i] = i.  SYNCHRONOUS. */
+CPM_API int cpm_count_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold,
+                            uint32_t* iota_out, long long* count_host);
+
+/* clogs::Radixsort::enqueue (rsc/ext/clogs/radixsort.h:227-262, src/radixsort.cpp:169-259) for
+ * TYPE_UINT keys with TYPE_UINT values (values == NULL: keys only, as recomputationIndexSorter_).
+ * Ascending, stable, in place; max_bits = 0 means all 32 bits; tmp_* are the ping-pong buffers
+ * of setTemporaryBuffers (same sizes as keys / values).  Errors as clogs: n == 0 and
+ * max_bits > 32 -> CPM_E_INVALID.  Hand-written onesweep (8-bit digits, decoupled look-back). */
+CPM_API int cpm_radix_sort_u32(cpm_ctx* ctx, uint32_t* keys, uint32_t* values, size_t n,
+                               unsigned max_bits, uint32_t* tmp_keys, uint32_t* tmp_values);
+/* bytes of context scratch a sort of n elements uses (status words of the chained scan) */
+CPM_API size_t cpm_radix_sort_scratch_bytes(size_t n);
+
+/* ---- (4) temporal-correlation detector ---------------------------------------------- */
+enum { CPM_DETECT_FIX_EXIT = 1 /* use origin + tEnd*direction where the reference has
+                                  `exit = tEnd*direction` (photonrecomputationdetector.cl:128) */ };
+/* photonRecomputationDetectorKernel / ...EqualImportanceKernel
+ * (ppm/cl/photonrecomputationdetector.cl:92-157, 160-194); host side
+ * PhotonRecomputationDetector::photonRecomputationImportance
+ * (ppm/photonrecomputationdetector.cpp:93-121).  importances[photon_offset + i] -=
+ * min(2^31-1, ceil(100 * sum over path segments of DDA(importance grid))).
+ *  importance_grid   float per cell, id = x + y*dx + z*dx*dy (ugc/uniformgrid3d.h:56-62)
+ *  cell_size         UniformGrid3DBase::getCellDimension() as floats
+ *  texture_to_index  column-major 4x4 of the ORIGINAL volume (getTextureToIndexMatrix) */
+CPM_API int cpm_detect_invalid(cpm_ctx* ctx, const float* importance_grid, const int grid_dims[3],
+                               const float cell_size[3], const float texture_to_index[16],
+                               const float* photons, int photon_offset, const float* light_samples,
+                               const float* intersections, int n_light_samples, int max_interactions,
+                               int total_photons, uint32_t* importances, int equal_importance,
+                               int percentage, int iteration, uint32_t flags);
+
+/* ---- (6) uniform grids ---------------------------------------------------------------- */
+/* volumeMinMaxKernel (ugc/cl/uniformgrid/volumeminmax.cl:33-61), host side
+ * VolumeMinMaxCLProcessor::compute (ugc/processors/volumeminmaxclprocessor.cpp:149-184).
+ * out: ushort2 (min, max) * 65535 per brick, out_dims = ceil(dims / region) (may be NULL).
+ * Needs a LINEAR volume. */
+CPM_API int cpm_volume_minmax(cpm_ctx* ctx, const cpm_volume* vol, int region, uint16_t* out,
+                              int out_dims[3]);
+/* DynamicVolumeDifferenceAnalysis (ugc/processors/dynamicvolumedifferenceanalysis.h:96-151,
+ * .cpp:60-104) -- a CPU loop in the reference -- on the GPU: per brick
+ * (sum |data_scaling*(b - a)| / region^3 - range_min) / (range_max - range_min). */
+CPM_API int cpm_volume_diff_bricks(cpm_ctx* ctx, const cpm_volume* a, const cpm_volume* b, int region,
+                                   double data_scaling, double range_min, double range_max,
+                                   float* out);
+/* classifyMinMaxUniformGrid3DImportanceKernel (prev_minmax == NULL) and
+ * classifyTimeVaryingMinMaxUniformGrid3DImportanceKernel
+ * (isc/cl/minmaxuniformgrid3dimportance.cl:269-330); host side computeImportance
+ * (isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:218-297).
+ * weights = {colorWeight, colorDiffWeight, opacityDiffWeight, opacityWeight} already
+ * normalised by the host; incremental != 0 selects -D INCREMENTAL_TF_IMPORTANCE. */
+CPM_API int cpm_classify_importance(cpm_ctx* ctx, const uint16_t* minmax, const uint16_t* prev_minmax,
+                                    const float* volume_diff, int n, const float* tf_positions,
+                                    const float* tf_colors /* float4[n_points] */, int n_points,
+                                    const float weights[4], int incremental, float* out);
+/* hashLightSampleKernel (ppm/cl/hashlightsample.cl:38-66): cell index of each listed light
+ * sample's entry point, the spatial sort key of the HASH_SORT_PHOTONS build. */
+CPM_API int cpm_hash_light_samples(cpm_ctx* ctx, const float* light_samples, const float* intersections,
+                                   int n_light_source_samples, const uint32_t* ids, int n_ids,
+                                   const float cell_size[3], const int n_blocks[3],
+                                   uint32_t* which_bucket, int out_offset);
+/* Cell ranges over ascending keys: cell_start[c] = lower_bound(c), cell_end[c] = upper_bound(c)
+ * for every c < n_cells (keys >= n_cells are ignored).  Not in the reference;
+ * parity is against the oracle's restatement. */
+CPM_API int cpm_build_cell_ranges(cpm_ctx* ctx, const uint32_t* sorted_keys, size_t n, uint32_t n_cells,
+                                  uint32_t* cell_start, uint32_t* cell_end);
+
+/* ---- (7) density estimation: splat to the light volume ---------------------------------- */
+/* splatPhotonsToLightVolumeKernel (indices == NULL; photon ids [0, n)) and
+ * splatSelectedPhotonsToLightVolumeKernel (n indices, every interaction, times multiplier)
+ * (ppm/cl/photonstolightvolume.cl:139-202); host side executeVolumeOperation /
+ * photonsToLightVolume (ppm/processor/photontolightvolumeprocessorcl.cpp:356-472).
+ * light_volume: float[dims] (channels = 1) or float4[dims] (channels = 4, alpha untouched).
+ * Adds are L2 reductions (red.global.add.f32) in unspecified order, like the reference's CAS adds. */
+CPM_API int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels,
+                              const float texture_to_index[16], const float index_to_texture[16],
+                              const int out_dims[3], const float* photons, const uint32_t* indices,
+                              int n, int photons_per_interaction, int n_interactions, float radius,
+                              float relative_irradiance_scale, float multiplier);
+
 /* ---- self test ----------------------------------------------------------------------- */
 /* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,
  * 3 acos, 4 atan2(x, y), 5 v/255, 6 v/65535 (x holds the integer value as float).  Lets the

@@ -77,6 +77,32 @@ unsigned long long orc_trace_photons(const orc_volume* vol, const float* tf_rgba
                                      const float* isect, const uint32_t* recompute, int n_recompute,
                                      float* photons, uint32_t* rng, int n_threads);
 
+/* --- selection stage: clogs radix sort semantics, threshold + reduce ------------------------- */
+void orc_radix_sort_u32(uint32_t* keys, uint32_t* values, size_t n, unsigned max_bits);
+void orc_merge_sort_u32(uint32_t* keys, uint32_t* values, size_t n);
+long long orc_count_below(const uint32_t* data, size_t n, uint32_t threshold);
+
+/* --- uniform grids, detector, hash, cell ranges (orc_grid.c) ---------------------------------- */
+void orc_volume_minmax(const orc_volume* vol, int region, uint16_t* out);
+void orc_volume_diff_bricks(const orc_volume* a, const orc_volume* b, int region, double data_scaling,
+                            double range_min, double range_max, float* out);
+void orc_classify_importance(const uint16_t* minmax, const uint16_t* prev_minmax, const float* diff, int n,
+                             const float* positions, const float* colors, int n_points, const float weights[4],
+                             int incremental, float* out);
+void orc_detect_invalid(const float* grid, const int grid_dims[3], const float cell_size[3], const float tex2idx[16],
+                        const float* photons, int photon_offset, const float* light_samples, const float* isect,
+                        int n_light_samples, int max_interactions, int total_photons, uint32_t* importances,
+                        int equal_importance, int percentage, int iteration, int fix_exit);
+void orc_hash_light_samples(const float* light_samples, const float* isect, int n_light_source_samples,
+                            const uint32_t* ids, int n_ids, const float cell_size[3], const int n_blocks[3],
+                            uint32_t* which_bucket, int out_offset);
+void orc_build_cell_ranges(const uint32_t* sorted_keys, size_t n, uint32_t n_cells, uint32_t* cell_start,
+                           uint32_t* cell_end);
+/* --- splat density estimation (orc_splat.c), double accumulation ------------------------------ */
+void orc_splat(double* vol, int channels, const float tex2idx[16], const float idx2tex[16], const int outDim[3],
+               const float* photons, const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
+               float radius, float relative_irradiance_scale, float multiplier);
+
 void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_t n);
 int orc_num_threads(void);
 

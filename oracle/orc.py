@@ -159,3 +159,78 @@ def selftest_math(fn, x, y=None):
     out = np.empty_like(x)
     lib().orc_selftest_math(int(fn), _ptr(x), _ptr(y), _ptr(out), C.c_size_t(x.size))
     return out
+
+
+def radix_sort(keys, values=None, max_bits=0):
+    lib().orc_radix_sort_u32(_ptr(keys), _ptr(values), C.c_size_t(keys.size), C.c_uint(max_bits))
+
+
+def merge_sort(keys, values=None):
+    lib().orc_merge_sort_u32(_ptr(keys), _ptr(values), C.c_size_t(keys.size))
+
+
+def count_below(data, threshold):
+    lib().orc_count_below.restype = C.c_longlong
+    return int(lib().orc_count_below(_ptr(data), C.c_size_t(data.size), C.c_uint32(threshold)))
+
+
+def _fN(v, n):
+    return (C.c_float * n)(*[float(x) for x in v])
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def volume_minmax(vol_np, region, scale=1.0, offset=0.0):
+    nz, ny, nx = vol_np.shape
+    od = [-(-nx // region), -(-ny // region), -(-nz // region)]
+    out = np.empty((od[2], od[1], od[0], 2), np.uint16)
+    v = volume(vol_np, scale, offset)
+    lib().orc_volume_minmax(C.byref(v), int(region), _ptr(out))
+    return out
+
+
+def volume_diff_bricks(a_np, b_np, region, scaling=1.0, rmin=0.0, rmax=1.0):
+    nz, ny, nx = a_np.shape
+    od = [-(-nx // region), -(-ny // region), -(-nz // region)]
+    out = np.empty((od[2], od[1], od[0]), np.float32)
+    va, vb = volume(a_np), volume(b_np)
+    lib().orc_volume_diff_bricks(C.byref(va), C.byref(vb), int(region), C.c_double(scaling), C.c_double(rmin),
+                                 C.c_double(rmax), _ptr(out))
+    return out
+
+
+def classify_importance(minmax, positions, colors, weights, incremental, prev=None, diff=None):
+    n = minmax.size // 2
+    out = np.empty(n, np.float32)
+    lib().orc_classify_importance(_ptr(minmax), _ptr(prev), _ptr(diff), n, _ptr(positions), _ptr(colors),
+                                  int(positions.size), _fN(weights, 4), int(bool(incremental)), _ptr(out))
+    return out
+
+
+def detect_invalid(grid, grid_dims, cell_size, tex2idx, photons, photon_offset, light_samples, isect, n_light_samples,
+                   max_interactions, total_photons, importances, equal_importance=False, percentage=100, iteration=0,
+                   fix_exit=False):
+    lib().orc_detect_invalid(_ptr(grid), _i3(grid_dims), _f3(cell_size), _fN(tex2idx, 16), _ptr(photons),
+                             int(photon_offset), _ptr(light_samples), _ptr(isect), int(n_light_samples),
+                             int(max_interactions), int(total_photons), _ptr(importances), int(bool(equal_importance)),
+                             int(percentage), int(iteration), int(bool(fix_exit)))
+
+
+def hash_light_samples(light_samples, isect, n_src, ids, cell_size, n_blocks, out, out_offset=0):
+    lib().orc_hash_light_samples(_ptr(light_samples), _ptr(isect), int(n_src), _ptr(ids), int(ids.size), _f3(cell_size),
+                                 _i3(n_blocks), _ptr(out), int(out_offset))
+
+
+def build_cell_ranges(keys, n_cells):
+    s, e = np.empty(n_cells, np.uint32), np.empty(n_cells, np.uint32)
+    lib().orc_build_cell_ranges(_ptr(keys), C.c_size_t(keys.size), C.c_uint32(n_cells), _ptr(s), _ptr(e))
+    return s, e
+
+
+def splat(vol64, channels, tex2idx, idx2tex, out_dims, photons, indices, n, per_interaction, n_interactions, radius,
+          scale, multiplier=1.0):
+    lib().orc_splat(_ptr(vol64), int(channels), _fN(tex2idx, 16), _fN(idx2tex, 16), _i3(out_dims), _ptr(photons),
+                    _ptr(indices), int(n), int(per_interaction), int(n_interactions), C.c_float(radius), C.c_float(scale),
+                    C.c_float(multiplier))

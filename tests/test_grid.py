@@ -1,0 +1,164 @@
+"""Uniform-grid operators: min/max bricks, inter-step difference, importance classification,
+light-sample hash, cell ranges."""
+import numpy as np
+import pytest
+
+import scenes
+
+
+def _dev_vol(cpm, ctx, torch, vol_np):
+    fmt = {np.dtype(np.uint8): cpm.CPM_FMT_U8, np.dtype(np.uint16): cpm.CPM_FMT_U16,
+           np.dtype(np.float32): cpm.CPM_FMT_F32}[vol_np.dtype]
+    raw = vol_np.view(np.int16) if vol_np.dtype == np.uint16 else vol_np
+    d = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+    return ctx.volume_create(d, (vol_np.shape[2], vol_np.shape[1], vol_np.shape[0]), fmt), d
+
+
+def tf_points(synth):
+    """host TF point list as updateTransferFunctionData builds it
+    (isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:304-362): end points added at 0 and 1"""
+    pts = synth.WS_TF_POINTS
+    pos = [0.0] + [p[0] for p in pts] + [1.0]
+    col = [pts[0][1]] + [p[1] for p in pts] + [pts[-1][1]]
+    return np.array(pos, np.float32), np.ascontiguousarray(np.array(col, np.float32))
+
+
+# ------------------------------------------------------------------------------- CPU ---------
+def test_oracle_minmax_against_numpy(orc, synth):
+    vol = synth.volume_u8((40, 24, 19), 5)          # ragged: not multiples of the region
+    mm = orc.volume_minmax(vol, 8)
+    assert mm.shape == (3, 3, 5, 2)
+    for (gz, gy, gx) in [(0, 0, 0), (2, 2, 4), (1, 2, 3)]:
+        blk = vol[gz * 8:(gz + 1) * 8, gy * 8:(gy + 1) * 8, gx * 8:(gx + 1) * 8].astype(np.float64) / 255.0
+        assert mm[gz, gy, gx, 0] == int(np.rint(np.float32(blk.min()) * np.float32(65535)))
+        assert mm[gz, gy, gx, 1] == int(np.rint(np.float32(blk.max()) * np.float32(65535)))
+
+
+def test_oracle_diff_bricks_edge_divides_by_full_region(orc, synth):
+    """ugc/processors/dynamicvolumedifferenceanalysis.h:147"""
+    a = np.zeros((4, 4, 12), np.uint8)
+    b = np.full((4, 4, 12), 10, np.uint8)
+    d = orc.volume_diff_bricks(a, b, 8, 1.0, 0.0, 255.0)
+    assert d.shape == (1, 1, 2)
+    assert np.isclose(d[0, 0, 0], 10.0 * (8 * 4 * 4) / 512 / 255)
+    assert np.isclose(d[0, 0, 1], 10.0 * (4 * 4 * 4) / 512 / 255)
+
+
+def test_oracle_cell_ranges(orc):
+    keys = np.array([1, 1, 3, 3, 3, 7], np.uint32)
+    s, e = orc.build_cell_ranges(keys, 9)
+    assert s.tolist() == [0, 0, 2, 2, 5, 5, 5, 5, 6]
+    assert e.tolist() == [0, 2, 2, 5, 5, 5, 5, 6, 6]
+    s, e = orc.build_cell_ranges(np.zeros(0, np.uint32), 3)
+    assert s.tolist() == [0, 0, 0] and e.tolist() == [0, 0, 0]
+
+
+def test_oracle_classify_incremental_is_sum_of_max_colour(orc, synth):
+    pos, col = tf_points(synth)
+    mm = np.array([[0, 65535], [0, 100], [30000, 30000]], np.uint16)
+    imp = orc.classify_importance(mm, pos, col, (0, 0, 0, 1), True)
+    assert np.isclose(imp[0], col.max(axis=0).sum(), rtol=1e-6)
+    assert imp[1] == np.float32(col[0].sum())          # range entirely left of the first real point
+    assert imp[2] > 0
+
+
+# ------------------------------------------------------------------------------- GPU ---------
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["u8", "u16", "f32"])
+@pytest.mark.parametrize("dims,region", [((64, 48, 40), 8), ((50, 33, 17), 8), ((64, 64, 64), 5), ((32, 32, 32), 1)])
+def test_cuda_minmax_bit_exact(cpm, orc, ctx, torch_cuda, fmt, dims, region):
+    torch = torch_cuda
+    vol = scenes.make_volume(dims, fmt, 9)
+    want = orc.volume_minmax(vol, region)
+    V, keep = _dev_vol(cpm, ctx, torch, vol)
+    out = torch.zeros(want.size, dtype=torch.int16, device="cuda")
+    od = ctx.volume_minmax(V, region, out)
+    ctx.sync()
+    assert od == (want.shape[2], want.shape[1], want.shape[0])
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), want.reshape(-1))
+    V.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["u8", "f32"])
+def test_cuda_diff_bricks(cpm, orc, ctx, torch_cuda, synth, fmt):
+    torch = torch_cuda
+    dims = (72, 40, 36)
+    if fmt == "u8":
+        a, b = synth.volume_u8(dims, 1), synth.volume_u8(dims, 2)
+        rng = (1.0, 0.0, 255.0)
+    else:
+        a, b = synth.volume_f32(dims, 4, 0.0), synth.volume_f32(dims, 4, 1.0 / 32)
+        rng = (1.0, 0.0, 1.0)
+    want = orc.volume_diff_bricks(a, b, 8, *rng)
+    Va, ka = _dev_vol(cpm, ctx, torch, a)
+    Vb, kb = _dev_vol(cpm, ctx, torch, b)
+    out = torch.zeros(want.size, dtype=torch.float32, device="cuda")
+    ctx.volume_diff_bricks(Va, Vb, 8, *rng, out)
+    ctx.sync()
+    got = out.cpu().numpy()
+    if fmt == "u8":
+        assert np.array_equal(got.view(np.uint32), want.reshape(-1).view(np.uint32))   # integer sums: exact
+    else:
+        # double sums in a different order: at most one float ulp
+        assert np.allclose(got, want.reshape(-1), rtol=2e-7, atol=1e-12)
+    Va.destroy(); Vb.destroy()
+
+
+@pytest.mark.gpu
+def test_cuda_classify_importance(cpm, orc, ctx, torch_cuda, synth):
+    torch = torch_cuda
+    vol_a, vol_b = synth.volume_u8((64, 64, 64), 1), synth.volume_u8((64, 64, 64), 2)
+    mm, prev = orc.volume_minmax(vol_a, 8), orc.volume_minmax(vol_b, 8)
+    diff = orc.volume_diff_bricks(vol_b, vol_a, 8, 1.0, 0.0, 255.0)
+    pos, col = tf_points(synth)
+    n = mm.size // 2
+    dmm = torch.from_numpy(mm.reshape(-1).view(np.int16)).cuda()
+    dprev = torch.from_numpy(prev.reshape(-1).view(np.int16)).cuda()
+    ddiff = torch.from_numpy(diff.reshape(-1)).cuda()
+    dpos, dcol = torch.from_numpy(pos).cuda(), torch.from_numpy(col).cuda()
+    out = torch.zeros(n, dtype=torch.float32, device="cuda")
+    # static, incremental formula: pure fp32 arithmetic -> bit exact
+    w = (0.0, 0.0, 0.0, 1.0)
+    ctx.classify_importance(dmm, n, dpos, dcol, len(pos), w, True, out)
+    ctx.sync()
+    want = orc.classify_importance(mm, pos, col, w, True)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # time-varying, Lab formula (powf/cbrtf from two different libms): tolerance
+    norm = 1.0 / np.sqrt(100.0 ** 2 + 500.0 ** 2 + 400.0 ** 2)
+    w = (0.5 * norm / 2.0, 0.5 * norm / 2.0, 0.5 / 2.0, 0.5 / 2.0)   # ws:472-483, normalised as the host does
+    ctx.classify_importance(dmm, n, dpos, dcol, len(pos), w, False, out, prev=dprev, diff=ddiff)
+    ctx.sync()
+    want = orc.classify_importance(mm, pos, col, w, False, prev=prev, diff=diff.reshape(-1))
+    assert np.allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-9)
+    assert want.max() > 0
+
+
+@pytest.mark.gpu
+def test_cuda_hash_and_cell_ranges(cpm, orc, ctx, torch_cuda, synth):
+    torch = torch_cuda
+    L = scenes.directional_light(96)
+    n = L["n"]
+    ids = (synth.splitmix64(3, 5000) % np.uint64(n + 50)).astype(np.uint32)   # some ids out of range
+    nb = (32, 32, 32)
+    want = np.full(5000, 0xDEADBEEF, np.uint32)
+    orc.hash_light_samples(L["light_samples"], L["isect"], n, ids, nb, nb, want)
+    dls, dis = torch.from_numpy(L["light_samples"]).cuda(), torch.from_numpy(L["isect"]).cuda()
+    dids = torch.from_numpy(ids.view(np.int32)).cuda()
+    out = torch.from_numpy(np.full(5000, 0xDEADBEEF, np.uint32).view(np.int32)).cuda()
+    ctx.hash_light_samples(dls, dis, n, dids, 5000, nb, nb, out)
+    ctx.sync()
+    got = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want)
+    # cell ranges over the sorted valid keys
+    keys = np.sort(got[got != 0xDEADBEEF])
+    ncell = nb[0] * nb[1] * nb[2]
+    for kk, nc in ((keys, ncell), (keys[:1], ncell), (np.zeros(0, np.uint32), 7), (keys, 100)):
+        ws, we = orc.build_cell_ranges(kk, nc)
+        dk = torch.from_numpy(kk.view(np.int32)).cuda() if kk.size else None
+        s = torch.full((nc,), -1, dtype=torch.int32, device="cuda")
+        e = torch.full((nc,), -1, dtype=torch.int32, device="cuda")
+        ctx.build_cell_ranges(dk, kk.size, nc, s, e)
+        ctx.sync()
+        assert np.array_equal(s.cpu().numpy().view(np.uint32), ws)
+        assert np.array_equal(e.cpu().numpy().view(np.uint32), we)
