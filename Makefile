@@ -10,8 +10,17 @@ HDRS := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard include/*.h)
 NCCL_INC ?= $(shell python -c "import nvidia.nccl, os; print(os.path.join(os.path.dirname(nvidia.nccl.__file__), 'include'))" 2>/dev/null)
 
 LIB := $(PKG)/libcpm_b200.so
+HOSTLIB := $(PKG)/libcpm_host.so
+HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
+HOST_HDRS := $(wildcard $(PKG)/host/*.h)
+HOST_CXX ?= $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 
-all: $(LIB) oracle
+all: $(LIB) $(HOSTLIB) oracle
+
+# Host mirror of the reference's Inviwo processors: plain C++17 on top of the C ABI only.
+$(HOSTLIB): $(HOST_SRCS) $(HOST_HDRS) $(LIB) include/cpm_b200.h
+	$(HOST_CXX) -std=c++17 -O2 -fPIC -fvisibility=hidden -Wall -shared -Iinclude -I$(PKG)/host \
+	    -o $@ $(HOST_SRCS) -L$(PKG) -lcpm_b200 -Wl,-rpath,'$$ORIGIN'
 
 build/%.o: $(PKG)/csrc/%.cu $(HDRS)
 	@mkdir -p build
@@ -24,7 +33,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(HOSTLIB)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

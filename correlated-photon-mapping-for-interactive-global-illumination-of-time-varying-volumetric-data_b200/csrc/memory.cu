@@ -1,0 +1,109 @@
+// memory.cu -- device memory and transfer entry points, so that host code above the C ABI
+// (the Inviwo processor mirror in host/) needs no CUDA headers.  Counterparts of cl::Buffer,
+// enqueueWriteBuffer / enqueueReadBuffer / enqueueCopyBuffer / enqueueFillBuffer.
+#include "common.cuh"
+
+extern "C" {
+
+int cpm_mem_alloc(cpm_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, out != nullptr, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return CPM_OK;
+    CPM_CUDA(ctx, cudaMalloc(out, bytes));
+    return CPM_OK;
+}
+
+int cpm_mem_free(cpm_ctx* ctx, void* ptr) {
+    if (!ctx) return CPM_E_INVALID;
+    if (!ptr) return CPM_OK;
+    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CPM_CUDA(ctx, cudaFree(ptr));
+    return CPM_OK;
+}
+
+int cpm_host_alloc(cpm_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, out != nullptr, "out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return CPM_OK;
+    CPM_CUDA(ctx, cudaMallocHost(out, bytes));
+    return CPM_OK;
+}
+
+int cpm_host_free(cpm_ctx* ctx, void* ptr) {
+    if (!ctx) return CPM_E_INVALID;
+    if (!ptr) return CPM_OK;
+    CPM_CUDA(ctx, cudaFreeHost(ptr));
+    return CPM_OK;
+}
+
+int cpm_mem_copy_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
+    if (!ctx) return CPM_E_INVALID;
+    if (bytes == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, dst && src_host, "null pointer");
+    CPM_CUDA(ctx, cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return CPM_OK;
+}
+
+int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes) {
+    if (!ctx) return CPM_E_INVALID;
+    if (bytes == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, dst_host && src, "null pointer");
+    CPM_CUDA(ctx, cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return CPM_OK;
+}
+
+int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return CPM_E_INVALID;
+    if (bytes == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, dst && src, "null pointer");
+    // memmove semantics are what the reference's chunked self-copy of the index list emulates
+    // (ppm/processor/progressivephotontracercl.cpp:389-419); cudaMemcpyAsync D2D needs disjoint ranges
+    const char *d = (const char*)dst, *s = (const char*)src;
+    if (d < s + bytes && s < d + bytes) {
+        size_t gap = d < s ? (size_t)(s - d) : (size_t)(d - s);
+        CPM_REQUIRE(ctx, d < s && gap > 0, "overlapping copy must move data toward lower addresses");
+        for (size_t off = 0; off < bytes; off += gap) {
+            size_t len = bytes - off < gap ? bytes - off : gap;
+            CPM_CUDA(ctx, cudaMemcpyAsync((char*)dst + off, s + off, len, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        return CPM_OK;
+    }
+    CPM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CPM_OK;
+}
+
+namespace {
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void scatter_fill_u32_kernel(uint32_t* p, const uint32_t* idx, size_t n, uint32_t v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[idx[i]] = v;
+}
+}  // namespace
+
+int cpm_mem_scatter_fill_u32(cpm_ctx* ctx, void* dst, const uint32_t* indices, size_t n, uint32_t value) {
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, dst && indices, "null pointer");
+    CPM_LAUNCH(ctx, scatter_fill_u32_kernel, cpm_div_up(n, 256), 256, 0, (uint32_t*)dst, indices, n, value);
+    return CPM_OK;
+}
+
+int cpm_mem_fill_u32(cpm_ctx* ctx, void* dst, uint32_t value, size_t count) {
+    if (!ctx) return CPM_E_INVALID;
+    if (count == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, dst != nullptr, "null pointer");
+    uint8_t b = (uint8_t)value;
+    if (value == (0x01010101u * b)) {
+        CPM_CUDA(ctx, cudaMemsetAsync(dst, b, count * 4, ctx->stream));
+    } else {
+        CPM_LAUNCH(ctx, fill_u32_kernel, cpm_div_up(count, 256), 256, 0, (uint32_t*)dst, value, count);
+    }
+    return CPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+"""ctypes binding of libcpm_host.so: the headless driver of the drop-in Inviwo processor network
+(host/host_capi.h).  This is the reference-facing call path: host buffers in, host buffers out."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+HOST_LIB_PATH = _HERE / "libcpm_host.so"
+_lib = None
+
+
+class HostConfig(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("dims", C.c_int32 * 3), ("format", C.c_int32), ("samples_per_side", C.c_int32),
+        ("n_lights", C.c_int32), ("light_directions", (C.c_float * 3) * 8), ("light_intensity", (C.c_float * 3) * 8),
+        ("max_scattering_events", C.c_int32), ("light_volume_option", C.c_int32), ("light_volume_channels", C.c_int32),
+        ("with_importance_grid", C.c_int32), ("volume_layout", C.c_int32), ("photon_radius_voxels", C.c_float),
+        ("max_incremental_percent", C.c_float), ("clip", C.c_int32 * 6), ("reference_full_splat_bound", C.c_int32),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not HOST_LIB_PATH.exists():
+            raise FileNotFoundError(f"{HOST_LIB_PATH} missing: run __graft_entry__.build()")
+        _lib = C.CDLL(str(HOST_LIB_PATH))
+        _lib.cpmh_last_error.restype = C.c_char_p
+        _lib.cpmh_network_last_splat_path.restype = C.c_char_p
+        _lib.cpmh_network_last_splat_path.argtypes = [C.c_void_p]
+        _lib.cpmh_network_stage_ms.restype = C.c_float
+        _lib.cpmh_network_stage_ms.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.cpmh_network_launch_count.restype = C.c_uint64
+        _lib.cpmh_network_launch_count.argtypes = [C.c_void_p, C.c_int]
+        _lib.cpmh_describe_processors.restype = C.c_char_p
+        _lib.cpmh_network_ctx.restype = C.c_void_p
+        _lib.cpmh_network_ctx.argtypes = [C.c_void_p]
+        _lib.cpmh_network_destroy.argtypes = [C.c_void_p]
+        _lib.cpmh_network_destroy.restype = None
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def describe_processors() -> dict:
+    """{classIdentifier: (set(port ids), set(property ids))} of the drop-in processors"""
+    out = {}
+    for line in lib().cpmh_describe_processors().decode().strip().split("\n"):
+        cid, ports, props = line.split("|")
+        out[cid] = (set(filter(None, ports.split(","))), set(filter(None, props.split(","))))
+    return out
+
+
+class Network:
+    """The workspace network of the reference (ws:1178-1271), evaluated headless."""
+
+    def __init__(self, dims, fmt, samples_per_side, light_directions, max_scattering_events=1, light_volume_option=2,
+                 light_volume_channels=1, with_importance_grid=False, volume_layout=1, photon_radius_voxels=1.0,
+                 max_incremental_percent=100.0, clip=None, device=0, light_intensity=None,
+                 reference_full_splat_bound=True):
+        cfg = HostConfig()
+        cfg.device = device
+        cfg.dims[:] = [int(d) for d in dims]
+        cfg.format = fmt
+        cfg.samples_per_side = samples_per_side
+        cfg.n_lights = len(light_directions)
+        for i, d in enumerate(light_directions):
+            cfg.light_directions[i][:] = [float(x) for x in d]
+            it = (1.0, 1.0, 1.0) if light_intensity is None else light_intensity[i]
+            cfg.light_intensity[i][:] = [float(x) for x in it]
+        cfg.max_scattering_events = max_scattering_events
+        cfg.light_volume_option = light_volume_option
+        cfg.light_volume_channels = light_volume_channels
+        cfg.with_importance_grid = int(with_importance_grid)
+        cfg.volume_layout = volume_layout
+        cfg.photon_radius_voxels = photon_radius_voxels
+        cfg.max_incremental_percent = max_incremental_percent
+        if clip:
+            cfg.clip[:] = [int(c) for c in clip]
+        cfg.reference_full_splat_bound = int(reference_full_splat_bound)
+        self.h = C.c_void_p()
+        self._keep = []
+        self._check(lib().cpmh_network_create(C.byref(cfg), C.byref(self.h)))
+        self.cfg = cfg
+
+    def _check(self, rc):
+        if rc < 0:
+            raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if self.h:
+            lib().cpmh_network_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_transfer_function(self, points):
+        """points: iterable of (pos, (r, g, b, a))"""
+        flat = np.array([[p, *c] for p, c in points], np.float32)
+        self._check(lib().cpmh_network_set_transfer_function(self.h, flat.ctypes.data_as(C.c_void_p), len(flat)))
+
+    def set_volume_host(self, ptr_or_array):
+        if isinstance(ptr_or_array, np.ndarray):
+            self._keep = [ptr_or_array]
+            ptr = ptr_or_array.ctypes.data
+        elif hasattr(ptr_or_array, "data_ptr"):
+            self._keep = [ptr_or_array]
+            ptr = ptr_or_array.data_ptr()
+        else:
+            ptr = int(ptr_or_array)
+        self._check(lib().cpmh_network_set_volume_host(self.h, C.c_void_p(ptr)))
+
+    def set_sequence_host(self, arrays):
+        self._seq = list(arrays)
+        ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data for a in arrays])
+        self._check(lib().cpmh_network_set_sequence_host(self.h, ptrs, len(arrays)))
+
+    def set_timestep(self, t):
+        self._check(lib().cpmh_network_set_timestep(self.h, int(t)))
+
+    def evaluate(self) -> int:
+        return self._check(lib().cpmh_network_evaluate(self.h))
+
+    @property
+    def remaining_photons(self):
+        return lib().cpmh_network_remaining_photons(self.h)
+
+    @property
+    def n_photons(self):
+        return lib().cpmh_network_n_photons(self.h)
+
+    @property
+    def n_recomputed(self):
+        return lib().cpmh_network_n_recomputed(self.h)
+
+    @property
+    def light_volume_dims(self):
+        d = (C.c_int * 3)()
+        self._check(lib().cpmh_network_light_volume_dims(self.h, d))
+        return tuple(d)
+
+    def read_light_volume(self, out=None):
+        d = self.light_volume_dims
+        n = d[0] * d[1] * d[2] * self.cfg.light_volume_channels
+        if out is None:
+            out = np.empty(n, np.float32)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._check(lib().cpmh_network_read_light_volume(self.h, C.c_void_p(ptr), C.c_size_t(n)))
+        return out
+
+    def read_photons(self, max_interactions):
+        n = self.n_photons * max_interactions * 8
+        out = np.empty(n, np.float32)
+        self._check(lib().cpmh_network_read_photons(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+        return out.reshape(-1, 8)
+
+    @property
+    def last_splat_path(self):
+        return lib().cpmh_network_last_splat_path(self.h).decode()
+
+    def set_profile(self, on=True):
+        lib().cpmh_network_set_profile(self.h, int(on))
+
+    def stage_ms(self, stage):
+        return float(lib().cpmh_network_stage_ms(self.h, stage.encode()))
+
+    def launch_count(self, reset=False):
+        return int(lib().cpmh_network_launch_count(self.h, int(reset)))
+
+    @staticmethod
+    def transfer_bytes(reset=False):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().cpmh_transfer_bytes(C.byref(a), C.byref(b), int(reset))
+        return a.value, b.value

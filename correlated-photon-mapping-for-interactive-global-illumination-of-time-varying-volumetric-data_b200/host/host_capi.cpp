@@ -1,0 +1,275 @@
+// host_capi.cpp -- headless driver of the drop-in processor network (see host_capi.h).
+#include "host_capi.h"
+
+#include <sstream>
+
+#include "processors.h"
+
+using namespace inviwo;
+
+static thread_local std::string g_err;
+
+struct cpmh_network {
+    cpmh_config cfg;
+    std::shared_ptr<Volume> volume;
+    DataOutport<Volume> volumeSource{"data"};
+    std::shared_ptr<Mesh> proxy;
+    DataOutport<Mesh> meshSource{"geometry"};
+    std::vector<std::shared_ptr<DirectionalLight>> lights;
+    std::vector<std::unique_ptr<DataOutport<LightSource>>> lightSources;
+    UniformSampleGenerator2DProcessorCL sampleGen;
+    std::vector<std::unique_ptr<DirectionalLightSamplerCLProcessor>> lightSamplers;
+    VolumeMinMaxCLProcessor minMax;
+    MinMaxUniformGrid3DImportanceCLProcessor importance;
+    ProgressivePhotonTracerCL tracer;
+    PhotonToLightVolumeProcessorCL toLightVolume;
+    // time series plumbing (the reference's sequence players / selectors are GUI processors)
+    std::shared_ptr<VolumeSequence> sequence;
+    std::vector<std::shared_ptr<UniformGrid3DBase>> seqMinMax, seqDiff;
+    DataOutport<UniformGrid3DBase> minMaxSelector{"selectedMinMax"}, diffSelector{"selectedDiff"};
+    bool useSequence = false;
+};
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        return f();
+    } catch (CpmError& e) {
+        g_err = e.what();
+        return e.code();
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return CPM_E_INVALID;
+    }
+}
+
+extern "C" {
+
+const char* cpmh_last_error(void) { return g_err.c_str(); }
+
+int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
+    return guarded([&]() {
+        if (!cfg || !out) throw std::invalid_argument("null argument");
+        if (cfg->n_lights < 1 || cfg->n_lights > 8) throw std::invalid_argument("n_lights must be 1..8");
+        CpmRuntime::init(cfg->device);
+        auto* n = new cpmh_network();
+        n->cfg = *cfg;
+        DataFormatId fid = cfg->format == CPM_FMT_U8 ? DataFormatId::UInt8 : (cfg->format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
+        n->volume = std::make_shared<Volume>(size3_t(cfg->dims[0], cfg->dims[1], cfg->dims[2]), DataFormatBase::get(fid));
+        n->proxy = Mesh::unitCube();
+        n->meshSource.setData(n->proxy);
+        n->sampleGen.nSamples_.set(ivec2{cfg->samples_per_side, cfg->samples_per_side});
+        for (int l = 0; l < cfg->n_lights; ++l) {
+            auto light = std::make_shared<DirectionalLight>();
+            vec3 d = normalize(vec3(cfg->light_directions[l][0], cfg->light_directions[l][1], cfg->light_directions[l][2]));
+            light->set(vec3(0.5f, 0.5f, 0.5f) - 2.f * d, d);
+            light->setIntensity(vec3(cfg->light_intensity[l][0], cfg->light_intensity[l][1], cfg->light_intensity[l][2]));
+            n->lights.push_back(light);
+            n->lightSources.emplace_back(new DataOutport<LightSource>("light"));
+            n->lightSamplers.emplace_back(new DirectionalLightSamplerCLProcessor());
+            auto& ls = *n->lightSamplers.back();
+            ls.boundingVolumeInport_.connectTo(&n->meshSource);
+            ls.samplesInport_.connectTo(&n->sampleGen.samplesPort_);
+            ls.lightInport_.connectTo(n->lightSources.back().get());
+            n->lightSources.back()->setData(std::shared_ptr<const LightSource>(light));
+            n->tracer.lightSamples_.connectTo(&ls.lightSamplesOutport_);
+        }
+        n->tracer.volumePort_.connectTo(&n->volumeSource);
+        n->tracer.maxScatteringEvents_.set(cfg->max_scattering_events);
+        n->tracer.radius_.set(cfg->photon_radius_voxels > 0 ? cfg->photon_radius_voxels : 1.f);
+        if (cfg->max_incremental_percent > 0) n->tracer.maxIncrementalPhotonsToUpdate_.set(cfg->max_incremental_percent);
+        n->tracer.tracer().volumeLayout = cfg->volume_layout;
+        n->toLightVolume.volumeInport_.connectTo(&n->volumeSource);
+        n->toLightVolume.photons_.connectTo(&n->tracer.outport_);
+        n->toLightVolume.recomputedPhotonIndicesPort_.connectTo(&n->tracer.recomputedIndicesPort_);
+        n->toLightVolume.referenceFullSplatBound = cfg->reference_full_splat_bound != 0;
+        if (cfg->light_volume_channels == 4) n->toLightVolume.volumeDataTypeOption_.setSelectedIdentifier("4xfloat32");
+        const char* opt = cfg->light_volume_option == 1 ? "1" : (cfg->light_volume_option == 2 ? "1/2" : (cfg->light_volume_option == 4 ? "1/4" : "radius"));
+        n->toLightVolume.volumeSizeOption_.setSelectedIdentifier(opt);
+        if (cfg->with_importance_grid) {
+            n->minMax.inport_.connectTo(&n->volumeSource);
+            n->importance.minMaxUniformGrid3DInport_.connectTo(&n->minMax.outport_);
+            n->tracer.recomputationImportanceGrid_.connectTo(&n->importance.importanceUniformGrid3DOutport_);
+        }
+        n->volumeSource.setData(n->volume);
+        bool anyClip = false;
+        for (int k = 0; k < 6; ++k) anyClip |= cfg->clip[k] != 0;
+        if (anyClip) {
+            n->tracer.clipX_.set(ivec2{cfg->clip[0], cfg->clip[1]});
+            n->tracer.clipY_.set(ivec2{cfg->clip[2], cfg->clip[3]});
+            n->tracer.clipZ_.set(ivec2{cfg->clip[4], cfg->clip[5]});
+        }
+        *out = n;
+        return (int)CPM_OK;
+    });
+}
+
+void cpmh_network_destroy(cpmh_network* net) {
+    if (!net) return;
+    try {
+        CpmRuntime::get().sync();
+    } catch (...) {
+    }
+    delete net;
+}
+
+int cpmh_network_set_transfer_function(cpmh_network* net, const float* pts, int n) {
+    return guarded([&]() {
+        TransferFunction tf;
+        for (int i = 0; i < n; ++i) tf.add(pts[5 * i], vec4(pts[5 * i + 1], pts[5 * i + 2], pts[5 * i + 3], pts[5 * i + 4]));
+        net->tracer.transferFunction_.set(tf);
+        net->importance.transferFunction_.set(tf);
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_set_volume_host(cpmh_network* net, const void* voxels) {
+    return guarded([&]() {
+        net->useSequence = false;
+        net->volume->setExternalRAMData(const_cast<void*>(voxels));
+        net->volumeSource.setData(net->volume);   // notifies connected inports: Volume invalidation
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels, int T) {
+    return guarded([&]() {
+        auto seq = std::make_shared<VolumeSequence>();
+        const cpmh_config& c = net->cfg;
+        DataFormatId fid = c.format == CPM_FMT_U8 ? DataFormatId::UInt8 : (c.format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
+        for (int t = 0; t < T; ++t) {
+            auto v = std::make_shared<Volume>(size3_t(c.dims[0], c.dims[1], c.dims[2]), DataFormatBase::get(fid));
+            v->setExternalRAMData(const_cast<void*>(voxels[t]));
+            v->deviceRead();   // keep the whole series resident in HBM
+            seq->push_back(v);
+        }
+        CpmRuntime::get().sync();
+        net->sequence = seq;
+        net->seqMinMax.clear();
+        net->seqDiff.clear();
+        // VolumeMinMaxCLProcessor on every step and DynamicVolumeDifferenceAnalysis between steps
+        for (int t = 0; t < T; ++t) net->seqMinMax.emplace_back(std::shared_ptr<UniformGrid3DBase>(net->minMax.compute((*seq)[t].get()).release()));
+        DynamicVolumeDifferenceAnalysis diff;
+        DataOutport<VolumeSequence> src("data");
+        diff.inport_.connectTo(&src);
+        src.setData(std::shared_ptr<const VolumeSequence>(seq));
+        diff.process();
+        net->seqDiff = *diff.outport_.getData();
+        // re-route the importance processor to the selected step's grids
+        net->importance.minMaxUniformGrid3DInport_.connectTo(&net->minMaxSelector);
+        net->importance.volumeDifferenceInfoInport_.connectTo(&net->diffSelector);
+        net->useSequence = true;
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_set_timestep(cpmh_network* net, int t) {
+    return guarded([&]() {
+        if (!net->useSequence || !net->sequence || t < 0 || t >= (int)net->sequence->size()) throw std::invalid_argument("bad time step");
+        const int T = (int)net->sequence->size();
+        // difference between the previous step and this one is stored at index of the earlier step
+        net->diffSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->seqDiff[(t + T - 1) % T]));
+        net->minMaxSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->seqMinMax[t]));
+        net->volumeSource.setData((*net->sequence)[t]);
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_evaluate(cpmh_network* net) {
+    int ran = 0;
+    int rc = guarded([&]() {
+        ran += net->sampleGen.evaluate();
+        for (auto& ls : net->lightSamplers) ran += ls->evaluate();
+        if (net->cfg.with_importance_grid) {
+            if (!net->useSequence) ran += net->minMax.evaluate();
+            ran += net->importance.evaluate();
+        }
+        ran += net->tracer.evaluate();
+        ran += net->toLightVolume.evaluate();
+        return (int)CPM_OK;
+    });
+    return rc == CPM_OK ? ran : rc;
+}
+
+int cpmh_network_remaining_photons(cpmh_network* net) { return net->tracer.remainingPhotonsToUpdate(); }
+int cpmh_network_n_photons(cpmh_network* net) {
+    auto d = net->tracer.outport_.getData();
+    return d ? (int)d->getNumberOfPhotons() : 0;
+}
+int cpmh_network_n_recomputed(cpmh_network* net) {
+    auto d = net->tracer.recomputedIndicesPort_.getData();
+    return d ? d->nRecomputedPhotons : -1;
+}
+int cpmh_network_light_volume_dims(cpmh_network* net, int dims[3]) {
+    auto v = net->toLightVolume.outport_.getData();
+    if (!v) return CPM_E_INVALID;
+    size3_t d = v->getDimensions();
+    dims[0] = (int)d.x; dims[1] = (int)d.y; dims[2] = (int)d.z;
+    return CPM_OK;
+}
+int cpmh_network_read_light_volume(cpmh_network* net, float* out, size_t n) {
+    return guarded([&]() {
+        auto v = std::const_pointer_cast<Volume>(net->toLightVolume.outport_.getData());
+        if (!v || v->getSizeInBytes() != n * sizeof(float)) throw std::invalid_argument("light volume size mismatch");
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, v->deviceRead(), n * sizeof(float)));
+        rt.sync();
+        BufferBase::d2hBytes() += n * sizeof(float);
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_read_photons(cpmh_network* net, float* out, size_t n) {
+    return guarded([&]() {
+        auto p = std::const_pointer_cast<PhotonData>(net->tracer.outport_.getData());
+        if (!p || p->photons_.getSizeInBytes() != n * sizeof(float)) throw std::invalid_argument("photon buffer size mismatch");
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, p->photons_.deviceRead(), n * sizeof(float)));
+        rt.sync();
+        BufferBase::d2hBytes() += n * sizeof(float);
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_read_importance_keys(cpmh_network*, uint32_t*, size_t) { return CPM_E_UNSUPPORTED; }
+const char* cpmh_network_last_splat_path(cpmh_network* net) { return net->toLightVolume.lastPath.c_str(); }
+int cpmh_network_set_profile(cpmh_network* net, int on) {
+    net->tracer.profile = on != 0;
+    return CPM_OK;
+}
+float cpmh_network_stage_ms(cpmh_network* net, const char* stage) {
+    auto it = net->tracer.lastStageMs.find(stage);
+    return it == net->tracer.lastStageMs.end() ? 0.f : it->second;
+}
+uint64_t cpmh_network_launch_count(cpmh_network*, int reset) { return cpm_ctx_launch_count(CpmRuntime::get().ctx(), reset); }
+void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
+    if (h2d) *h2d = BufferBase::h2dBytes();
+    if (d2h) *d2h = BufferBase::d2hBytes();
+    if (reset) BufferBase::h2dBytes() = BufferBase::d2hBytes() = 0;
+}
+void* cpmh_network_ctx(cpmh_network*) { return CpmRuntime::get().ctx(); }
+
+const char* cpmh_describe_processors(void) {
+    static std::string s;
+    std::ostringstream os;
+    auto dump = [&](Processor& p) {
+        os << p.getProcessorInfo().classIdentifier << "|";
+        bool first = true;
+        for (auto& id : p.getPortIdentifiers()) { os << (first ? "" : ",") << id; first = false; }
+        os << "|";
+        first = true;
+        for (auto& id : p.getPropertyIdentifiers()) { os << (first ? "" : ",") << id; first = false; }
+        os << "\n";
+    };
+    { UniformSampleGenerator2DProcessorCL p; dump(p); }
+    { DirectionalLightSamplerCLProcessor p; dump(p); }
+    { ProgressivePhotonTracerCL p; dump(p); }
+    { PhotonToLightVolumeProcessorCL p; dump(p); }
+    { VolumeMinMaxCLProcessor p; dump(p); }
+    { DynamicVolumeDifferenceAnalysis p; dump(p); }
+    { MinMaxUniformGrid3DImportanceCLProcessor p; dump(p); }
+    { RadixSortCL p; dump(p); }
+    { RandomNumberGeneratorCL p; dump(p); }
+    s = os.str();
+    return s.c_str();
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+/* host_capi.h -- C entry points that drive the drop-in processor network headless (what Inviwo's
+ * ProcessorNetworkEvaluator does when the reference workspace is open).  Used by bench.py (the
+ * `e2e` leg: host buffers in, host buffers out) and by the host-layer tests.  The network is the
+ * one of workspaces/CorrelatedPhotonMappingSingleVolume.inv (ws:1178-1271):
+ *   VolumeSource -> VolumeMinMaxCL -> MinMaxUniformGrid3DImportance -> (importance grid) --+
+ *   UniformSampleGenerator2D -> DirectionalLightSamplerCL (x n_lights) -> ProgressivePhotonTracerCL
+ *                                                                      -> PhotonToLightVolumeProcessorCL
+ */
+#ifndef CPM_HOST_CAPI_H
+#define CPM_HOST_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define CPMH_API __attribute__((visibility("default")))
+
+typedef struct cpmh_network cpmh_network;
+
+typedef struct cpmh_config {
+    int32_t device;
+    int32_t dims[3];
+    int32_t format;              /* CPM_FMT_* */
+    int32_t samples_per_side;    /* UniformSampleGenerator2D nSamples = (s, s) per light */
+    int32_t n_lights;
+    float light_directions[8][3];
+    float light_intensity[8][3];
+    int32_t max_scattering_events;
+    int32_t light_volume_option; /* volumeSizeOption: 0 radius, 1, 2, 4 */
+    int32_t light_volume_channels; /* 1 or 4 */
+    int32_t with_importance_grid;  /* connect VolumeMinMax + importance grid => correlated re-tracing */
+    int32_t volume_layout;       /* CPM_VOLUME_* used by the tracer */
+    float photon_radius_voxels;  /* `radius` property */
+    float max_incremental_percent; /* `maxIncrementalPhotonsToUpdate` */
+    int32_t clip[6];             /* clipX.min,max, clipY.., clipZ..; all zero = no clipping */
+    int32_t reference_full_splat_bound;
+} cpmh_config;
+
+CPMH_API int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out);
+CPMH_API void cpmh_network_destroy(cpmh_network* net);
+CPMH_API const char* cpmh_last_error(void);
+/* transfer function of the tracer AND of the importance processor: n points of (pos, r, g, b, a) */
+CPMH_API int cpmh_network_set_transfer_function(cpmh_network* net, const float* points, int n);
+/* new voxel data from a HOST buffer (kept by reference until the next evaluate: use pinned memory for
+ * asynchronous upload).  Marks the volume port changed, as VolumeSource / a sequence player would. */
+CPMH_API int cpmh_network_set_volume_host(cpmh_network* net, const void* voxels_host);
+/* a time series: T host buffers; min-max grids and inter-step difference grids are computed on the
+ * device for all steps (VolumeMinMaxCL on the sequence + DynamicVolumeDifferenceAnalysis) */
+CPMH_API int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels_host, int n_steps);
+CPMH_API int cpmh_network_set_timestep(cpmh_network* net, int t);
+/* evaluate every invalid processor in network order; returns the number of processors that ran */
+CPMH_API int cpmh_network_evaluate(cpmh_network* net);
+/* progressive work left (budgeted re-trace batches): call evaluate again while > 0 */
+CPMH_API int cpmh_network_remaining_photons(cpmh_network* net);
+CPMH_API int cpmh_network_n_photons(cpmh_network* net);
+CPMH_API int cpmh_network_n_recomputed(cpmh_network* net);
+CPMH_API int cpmh_network_light_volume_dims(cpmh_network* net, int dims[3]);
+/* device -> host reads (synchronous) */
+CPMH_API int cpmh_network_read_light_volume(cpmh_network* net, float* out_host, size_t n_floats);
+CPMH_API int cpmh_network_read_photons(cpmh_network* net, float* out_host, size_t n_floats);
+CPMH_API int cpmh_network_read_importance_keys(cpmh_network* net, uint32_t* out_host, size_t n);
+CPMH_API const char* cpmh_network_last_splat_path(cpmh_network* net);
+/* stage timing of the tracer's last process(): "detector","count+iota","sort","indexsort","trace" */
+CPMH_API int cpmh_network_set_profile(cpmh_network* net, int on);
+CPMH_API float cpmh_network_stage_ms(cpmh_network* net, const char* stage);
+CPMH_API uint64_t cpmh_network_launch_count(cpmh_network* net, int reset);
+CPMH_API void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset);
+CPMH_API void* cpmh_network_ctx(cpmh_network* net);
+/* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */
+CPMH_API const char* cpmh_describe_processors(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

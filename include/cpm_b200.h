@@ -267,6 +267,27 @@ CPM_API int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels,
                               int n, int photons_per_interaction, int n_interactions, float radius,
                               float relative_irradiance_scale, float multiplier);
 
+/* ---- device memory (cl::Buffer, enqueueWrite/Read/Copy/FillBuffer) -------------------- */
+/* Lets host code above this ABI (host/: the Inviwo processor mirror) stay free of CUDA headers.
+ * Copies and fills are asynchronous on the context stream; use cpm_ctx_sync before reading a
+ * d2h destination.  cpm_host_alloc returns page-locked memory (true async copies). */
+CPM_API int cpm_mem_alloc(cpm_ctx* ctx, size_t bytes, void** out);
+CPM_API int cpm_mem_free(cpm_ctx* ctx, void* ptr);
+CPM_API int cpm_host_alloc(cpm_ctx* ctx, size_t bytes, void** out);
+CPM_API int cpm_host_free(cpm_ctx* ctx, void* ptr);
+CPM_API int cpm_mem_copy_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+CPM_API int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes);
+/* overlapping ranges are allowed when dst < src (the index-list slide-down of
+ * ppm/processor/progressivephotontracercl.cpp:389-419) */
+CPM_API int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* enqueueFillBuffer<unsigned int> (resetPhotonImportance, :607-611) */
+CPM_API int cpm_mem_fill_u32(cpm_ctx* ctx, void* dst, uint32_t value, size_t count);
+/* dst[indices[i]] = value for i < n: resets the importance keys of the photons just re-traced.
+ * (The reference resets a slice of its in-place sorted key array, :529; here keys stay in photon
+ * order and are addressed through the sorted id list.) */
+CPM_API int cpm_mem_scatter_fill_u32(cpm_ctx* ctx, void* dst, const uint32_t* indices, size_t n,
+                                     uint32_t value);
+
 /* ---- self test ----------------------------------------------------------------------- */
 /* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,
  * 3 acos, 4 atan2(x, y), 5 v/255, 6 v/65535 (x holds the integer value as float).  Lets the

@@ -1,0 +1,142 @@
+"""Drop-in host layer: processor identifiers / ports / properties of the reference, and the network
+evaluated headless (full trace, correlated re-trace, incremental light-volume update)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import scenes
+from conftest import PKG_NAME
+from test_tracer import oracle_trace
+
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+# class id -> (ports, properties that the reference adds)
+CONTRACT = {
+    "org.inviwo.ProgressivePhotonTracerCL": (
+        {"volume", "recomputationImportance", "LightSamples", "photons", "recomputedIndices"},
+        {"samplingRate", "radius", "maxScatteringEvents", "noSingleScattering", "alpha", "material", "transferFunction",
+         "wgsize", "glsharing", "camera", "maxIncrementalPhotonsToUpdate", "equalImportance", "spatialSorting",
+         "invalidate", "enableRefinement", "enableProgressiveRecomputation", "clipX", "clipY", "clipZ"}),
+    "org.inviwo.PhotonToLightVolumeProcessorCL": (
+        {"volume", "photons", "recomputedPhotonIndices", "lightvolume"},
+        {"incrementalRecomputationThreshold", "volumeSizeOption", "volumeDataType", "alignChangedPhotons", "wgsize",
+         "glsharing"}),
+    "org.inviwo.DirectionalLightSamplerCL": ({"SceneGeometry", "samples", "light", "LightSamples"}, {"wgsize"}),
+    "org.inviwo.UniformSampleGenerator2DCL": ({"samples", "DirectionalSamples"}, {"nSamples", "wgsize", "glsharing"}),
+    "org.inviwo.MinMaxUniformGrid3DImportanceCLProcessor": (
+        {"minMaxUniformGrid3D", "volumeDifferenceInfo", "importanceUniformGrid3D"},
+        {"incrementalImportance", "constantWeight", "opacityDiffWeight", "colorWeight", "colorDiffWeight",
+         "useAssociatedColor", "TFPointEpsilon", "transferfunction", "wgsize", "glsharing"}),
+    "org.inviwo.VolumeMinMaxCLProcessor": ({"volume", "VolumeSequenceInput", "output", "UniformGrid3DVectorOut"},
+                                           {"region", "wgsize", "glsharing"}),
+    "org.inviwo.DynamicVolumeDifferenceAnalysis": ({"data", "DynamicDataInfo"}, {"region"}),
+    "org.inviwo.RadixSortCL": ({"unsortedKeys", "unsortedData", "sortedData"}, set()),
+    "org.inviwo.RandomNumberGeneratorCL": ({"samples"}, {"nSamples", "genRnd", "seed", "wgsize", "glsharing"}),
+}
+
+
+@pytest.fixture(scope="module")
+def host():
+    return importlib.import_module(PKG_NAME + ".host")
+
+
+def test_processor_contract(host):
+    got = host.describe_processors()
+    for cid, (ports, props) in CONTRACT.items():
+        assert cid in got, cid
+        assert got[cid][0] == ports, (cid, got[cid][0] ^ ports)
+        assert props <= got[cid][1], (cid, props - got[cid][1])
+
+
+@pytest.mark.gpu
+def test_network_full_trace_matches_oracle(host, cpm, orc, synth, torch_cuda):
+    dims, ns, I = (64, 64, 64), 96, 2
+    d = (0.3, -0.5, 0.8)
+    vol = synth.volume_u8(dims, 8)
+    net = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], max_scattering_events=I, light_volume_option=2)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_volume_host(vol)
+    assert net.evaluate() >= 4
+    ph = net.read_photons(I)
+    # the oracle with the same set-up (light plane fit done by the oracle's own CPU geometry)
+    L = scenes.directional_light(ns, d)
+    tf = synth.rasterise_tf(width=1024)
+    want, _, _ = oracle_trace(orc, vol, tf, L, max_interactions=I, step_size=1.0 / 64)
+    stored = want[:, 0] != FLT_MAX
+    assert stored.sum() > 1000
+    # the host layer fits the light plane in its own float arithmetic: positions agree to fp32 noise,
+    # and wherever the light samples are bit-identical the photons are too
+    same = np.all(ph.view(np.uint32) == want.view(np.uint32), axis=1)
+    assert same.mean() > 0.99, same.mean()
+    assert net.last_splat_path == "full"
+    lv = net.read_light_volume()
+    assert lv.shape[0] == 32 * 32 * 32 and lv.sum() > 0 and np.isfinite(lv).all()
+    assert net.evaluate() == 0          # nothing invalid: nothing runs
+    net.close()
+
+
+@pytest.mark.gpu
+def test_network_correlated_retrace(host, cpm, orc, synth, torch_cuda):
+    """TF change with the importance grid connected: only photons whose paths cross changed cells are
+    re-traced, the light volume is updated by -old/+new splats and equals a from-scratch result."""
+    dims, ns, I = (64, 64, 64), 128, 2
+    d = (0.2, 0.3, 0.9)
+    vol = synth.volume_u8(dims, 8)
+    kw = dict(max_scattering_events=I, light_volume_option=2, with_importance_grid=True, reference_full_splat_bound=False)
+    net = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], **kw)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_volume_host(vol)
+    net.evaluate()
+    assert net.n_recomputed == -1 and net.last_splat_path == "full"
+    before = net.read_photons(I).copy()
+    # change only the top of the transfer function (dense material): few cells are affected
+    pts = list(synth.WS_TF_POINTS)
+    pts[-1] = (pts[-1][0], (0.1, 0.6, 0.65, 0.9))
+    net.set_transfer_function(pts)
+    net.evaluate()
+    n = net.n_photons
+    nrec = net.n_recomputed
+    assert 0 < nrec < n, nrec
+    assert net.last_splat_path == "incremental"
+    after = net.read_photons(I)
+    changed = np.any(before.view(np.uint32) != after.view(np.uint32), axis=1).reshape(I, n).any(axis=0)
+    assert changed.sum() <= nrec
+    lv_inc = net.read_light_volume().astype(np.float64)
+    # from-scratch network with the new transfer function
+    ref = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], **kw)
+    ref.set_transfer_function(pts)
+    ref.set_volume_host(vol)
+    ref.evaluate()
+    full = ref.read_photons(I)
+    # replay property: every photon equals the from-scratch trace (re-traced ones are new, the others
+    # were provably unaffected) unless the detector's conservative grid missed nothing
+    same = np.all(full.view(np.uint32) == after.view(np.uint32), axis=1)
+    assert same.mean() > 0.999, same.mean()
+    lv_full = ref.read_light_volume().astype(np.float64)
+    rmse = np.sqrt(((lv_inc - lv_full) ** 2).mean()) / np.sqrt((lv_full ** 2).mean())
+    assert rmse < 2e-3, rmse
+    net.close(); ref.close()
+
+
+@pytest.mark.gpu
+def test_network_budgeted_batches(host, cpm, synth, torch_cuda):
+    """maxIncrementalPhotonsToUpdate < 100: the re-trace is spread over several evaluations"""
+    dims, ns = (48, 48, 48), 64
+    vol = synth.volume_u8(dims, 8)
+    net = host.Network(dims, cpm.CPM_FMT_U8, ns, [(0, 0, 1)], with_importance_grid=True, max_incremental_percent=10.0)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_volume_host(vol)
+    net.evaluate()
+    pts = [(p, (c[0], c[1], c[2], min(1.0, c[3] * 1.5))) for p, c in synth.WS_TF_POINTS]
+    net.set_transfer_function(pts)
+    total, rounds = 0, 0
+    net.evaluate()
+    total += max(net.n_recomputed, 0)
+    while net.remaining_photons > 0 and rounds < 50:
+        assert net.evaluate() >= 1
+        total += max(net.n_recomputed, 0)
+        rounds += 1
+    assert rounds >= 1 and total > 0
+    assert net.n_recomputed <= int(0.10 * net.n_photons)
+    net.close()
