@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the correlated photon-mapping hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[3], "C4" of SURVEY.md section 8d): a synthetic 512^3 float32 time-varying
+volume with 32 time steps, 2048^2 = 4 194 304 photons from one directional light, correlated re-tracing.
+A *step* is one time-step change handled the way the reference handles it (call stack D):
+importance classify -> photon re-computation detector -> count -> key/value radix sort -> index sort ->
+re-trace of the invalidated photons -> -old/+new splat into the light volume.  Everything goes through the
+reference-facing host layer (libcpm_host.so, the drop-in Inviwo processor mirror) on top of the C ABI.
+
+  value     photons (re)traced per second, whole job, the time series resident in HBM
+  e2e       the same metric with the volume of every step uploaded from pinned HOST memory inside the timed
+            region (its min-max and difference grids computed on the device) and the light volume read back
+  roofline  the dominant kernel (trace) against the HBM peak, SURVEY.md section 8(d) byte accounting
+  cpu_baseline / --impl reference
+            the CPU oracle (oracle/, a restatement of the reference's OpenCL kernels; the reference itself
+            needs Inviwo + an OpenCL device, neither exists here) on all host cores, on a bounded photon sample
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- every GPU traces its own 4 Mi photons on disjoint MWC64X
+substreams against the replicated volume and the per-GPU light volumes are summed with an NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+PKG = "correlated-photon-mapping-for-interactive-global-illumination-of-time-varying-volumetric-data_b200"
+FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md, used when MEASURED_PEAKS.json is absent
+LIGHT_DIR = (0.3, -0.5, 0.8)
+METRIC = "photons_traced_per_sec"
+UNIT = "photons/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dims", type=int, default=512)
+    ap.add_argument("--photons-side", type=int, default=2048)
+    ap.add_argument("--timesteps", type=int, default=32)
+    ap.add_argument("--max-interactions", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="budget of the whole --impl reference run")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C4: synthetic {a.dims}^3 float32 time-varying volume, {a.timesteps} time steps, "
+            f"{a.photons_side}^2 photons per GPU, correlated re-tracing, maxScatteringEvents={a.max_interactions}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBs"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's correlated frame on a photon sample
+class CpuArm:
+    """The reference's per-frame algorithm executed by the CPU oracle with OpenMP."""
+
+    def __init__(self, a, volumes, n_side):
+        from oracle import orc
+        self.orc, self.a, self.vols = orc, a, volumes
+        synth = importlib.import_module(PKG + ".synth")
+        self.synth = synth
+        self.dims = (a.dims,) * 3
+        self.I = a.max_interactions
+        self.tf = synth.rasterise_tf(width=1024)
+        d = synth.normalize(LIGHT_DIR)
+        o, u, v = orc.fit_light_plane(synth.CUBE_VERTICES, np.float32([0.5, 0.5, 0.5]) - 2 * d, d)
+        area = float(np.float32(np.linalg.norm(u)) * np.float32(np.linalg.norm(v)))
+        n = n_side * n_side
+        s = orc.sample_uniform2d(n_side, n_side, n)
+        self.ls = orc.light_sample_directional(s, (1, 1, 1), d, o, u, v, area)
+        self.isect = orc.light_mesh_intersect(synth.CUBE_VERTICES, synth.CUBE_INDICES, self.ls)
+        self.n = n
+        self.rng = orc.rng_seed_streams(orc.rng_host_base_offsets(0, n))
+        self.photons = np.zeros((n * self.I, 8), np.float32)
+        self.prev = np.zeros_like(self.photons)
+        self.keys = np.full(n, 0x7FFFFFFF, np.uint32)
+        pts = synth.WS_TF_POINTS
+        self.tfpos = np.array([0.0] + [p[0] for p in pts] + [1.0], np.float32)
+        self.tfcol = np.ascontiguousarray(np.array([pts[0][1]] + [p[1] for p in pts] + [pts[-1][1]], np.float32))
+        self.region = 8
+        self.gd = tuple(-(-x // self.region) for x in self.dims)
+        lv = a.dims // 2
+        self.lvdims = (lv, lv, lv)
+        self.lightvol = np.zeros(lv * lv * lv, np.float64)
+        cpm = importlib.import_module(PKG)
+        self.t2i_vol = cpm.capi.texture_to_index_matrix(self.dims)
+        self.t2i_lv = cpm.capi.texture_to_index_matrix(self.lvdims)
+        self.i2t_lv = cpm.capi.index_to_texture_matrix(self.lvdims)
+        self.radius = float(np.float32(np.sqrt(3.0) / a.dims))   # |indexToTexture * (1,1,1)| for radius = 1 voxel
+        self.mm, self.diff = {}, {}
+
+    def params(self):
+        return self.orc.trace_params(n_light_samples=self.n, max_interactions=self.I, step_size=1.0 / self.a.dims)
+
+    def scale(self):
+        vol = 4.0 / 3.0 * np.pi * self.radius ** 3
+        return float((1.0 / np.pi) / (vol * self.n))
+
+    def prepare(self, t):
+        """untimed, as in the GPU arm's resident mode: min-max grid of step t and difference grid (t-1 -> t)"""
+        T = len(self.vols)
+        if t % T not in self.mm:
+            self.mm[t % T] = self.orc.volume_minmax(self.vols[t % T], self.region)
+        if (t - 1) % T not in self.mm:
+            self.mm[(t - 1) % T] = self.orc.volume_minmax(self.vols[(t - 1) % T], self.region)
+        if (t - 1) % T not in self.diff:
+            self.diff[(t - 1) % T] = self.orc.volume_diff_bricks(self.vols[(t - 1) % T], self.vols[t % T], self.region)
+
+    def first_frame(self, t=0):
+        orc = self.orc
+        self.tests = orc.trace_photons(orc.volume(self.vols[t]), self.tf, self.params(), self.ls, self.isect,
+                                       self.photons, self.rng.copy())
+        self.lightvol[:] = 0
+        orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, None, self.n, self.n, self.I,
+                  self.radius, self.scale())
+        self.prev[:] = self.photons
+
+    def frame(self, t):
+        """one time-step change; returns (photons re-traced, collision tests)"""
+        orc, T = self.orc, len(self.vols)
+        imp = orc.classify_importance(self.mm[t % T], self.tfpos, self.tfcol, (0, 0, 0, 1), False,
+                                      prev=self.mm[(t - 1) % T], diff=self.diff[(t - 1) % T].reshape(-1))
+        orc.detect_invalid(imp, self.gd, (self.region,) * 3, self.t2i_vol, self.photons, 0, self.ls, self.isect, self.n,
+                           self.I, self.n, self.keys)
+        n_inv = orc.count_below(self.keys, 0x7FFFFFFF)
+        ids = np.arange(self.n, dtype=np.uint32)
+        sk = self.keys.copy()
+        orc.radix_sort(sk, ids)
+        sel = np.ascontiguousarray(ids[:n_inv])
+        tests = 0
+        if n_inv:
+            orc.radix_sort(sel, None)
+            tests = orc.trace_photons(orc.volume(self.vols[t % T]), self.tf, self.params(), self.ls, self.isect,
+                                      self.photons, self.rng.copy(), recompute=sel, n_recompute=n_inv)
+            self.keys[sel] = 0x7FFFFFFF
+            if n_inv < 0.5 * self.n:      # incrementalRecomputationThreshold = 50 %: remove old, add new
+                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.prev, sel, n_inv, self.n, self.I,
+                          self.radius, self.scale(), -1.0)
+                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, sel, n_inv, self.n,
+                          self.I, self.radius, self.scale(), 1.0)
+            else:                         # above the threshold the reference clears and splats everything
+                self.lightvol[:] = 0
+                allp = np.arange(self.n, dtype=np.uint32)
+                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, allp, self.n, self.n,
+                          self.I, self.radius, self.scale(), 1.0)
+            self.prev[:] = self.photons
+        return n_inv, tests
+
+
+def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False):
+    """times `steps` CPU frames after `warmup`, the photon sample sized to fit budget_s"""
+    from oracle import orc
+    cores = orc.num_threads()
+    # calibrate: trace rate on a 128^2 sample
+    cal = CpuArm(a, volumes, 256)
+    cal.first_frame(0)
+    cal.prepare(1)
+    t0 = time.perf_counter()
+    cal.frame(1)
+    rate = cal.n / max(time.perf_counter() - t0, 1e-6)          # photons in the map per second of frame time
+    frames = steps + warmup + 1
+    side = int(np.sqrt(max(rate * budget_s / frames, 64.0 * 64.0)))
+    side = int(min(a.photons_side, max(64, side // 32 * 32)))
+    if side == a.photons_side and grow_steps:
+        # the whole photon set fits the budget: spend the rest of it on more frames (at most one period)
+        steps = int(min(max(steps, rate * budget_s / (side * side) - warmup - 1), a.timesteps, len(volumes) - warmup - 2))
+    arm = CpuArm(a, volumes, side)
+    arm.first_frame(0)
+    for t in range(1, warmup + 1):
+        arm.prepare(t)
+        arm.frame(t)
+    traced = tests = 0
+    elapsed = 0.0
+    for t in range(warmup + 1, warmup + 1 + steps):
+        arm.prepare(t)
+        t0 = time.perf_counter()
+        n_inv, nt = arm.frame(t)
+        elapsed += time.perf_counter() - t0
+        traced += n_inv
+        tests += nt
+    return {"value": traced / elapsed if elapsed > 0 else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{side}x{side} = {side * side} photons of the {a.photons_side}^2 light-sample grid, {steps} correlated "
+                      f"frames ({elapsed:.2f} s CPU) on the full {a.dims}^3 volumes; min-max / difference grids "
+                      f"precomputed untimed as in the resident GPU run",
+            "ms_per_step": elapsed / steps * 1e3, "retrace_fraction": traced / (steps * arm.n),
+            "collision_tests_per_sec": tests / elapsed if elapsed > 0 else 0.0, "frames_per_sec": steps / elapsed}
+
+
+def make_volumes_numpy(a, n_steps, device):
+    synth = importlib.import_module(PKG + ".synth")
+    T = a.timesteps
+    return [synth.volume_field_torch((a.dims,) * 3, 4, t / T, device=device).cpu().numpy() for t in range(min(n_steps, T))]
+
+
+def run_reference(a):
+    """--impl reference: the CPU oracle on this box's host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    vols = make_volumes_numpy(a, a.steps + a.warmup + 2, dev)
+    r = cpu_run(a, vols, a.steps, a.warmup, a.ref_seconds)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU oracle restatement of the reference's OpenCL kernels "
+                       "(reference needs Inviwo + OpenCL: unbuildable here), OpenMP over photons"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "frames_per_sec": r["frames_per_sec"], "retrace_fraction": r["retrace_fraction"],
+            "collision_tests_per_sec": r["collision_tests_per_sec"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class DevTensorView:
+    """__cuda_array_interface__ over a raw device pointer (the light volume owned by the host layer)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def run_b200(a):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a B200 (there is no CPU fallback; use --impl reference for the CPU arm)"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cpm = importlib.import_module(PKG)
+    host = importlib.import_module(PKG + ".host")
+    synth = importlib.import_module(PKG + ".synth")
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)
+    T, D, I = a.timesteps, a.dims, a.max_interactions
+    n_photons = a.photons_side ** 2
+    host.runtime_init(local, stream.cuda_stream, rank * n_photons)
+
+    # ---- the time series: generated on the device, staged in pinned host memory (the e2e source) ----
+    pinned = []
+    for t in range(T):
+        v = synth.volume_field_torch((D, D, D), 4, t / T, device=dev)
+        h = torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+        h.copy_(v)
+        pinned.append(h)
+        del v
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_loop(net, n_steps, first_t, step_fn):
+        """barrier + sync, CUDA events on the launch stream around n_steps, max over ranks"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        traced = 0
+        for k in range(n_steps):
+            traced += step_fn(first_t + k)
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        tr = torch.tensor([traced], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+        return float(t[0]), float(t[1]), float(tr[0])
+
+    with torch.cuda.stream(stream):
+        net = host.Network((D, D, D), cpm.CPM_FMT_F32, a.photons_side, [LIGHT_DIR], max_scattering_events=I,
+                           light_volume_option=2, with_importance_grid=True, volume_layout=cpm.CPM_VOLUME_TEXTURE,
+                           reference_full_splat_bound=False, device=local)
+        net.set_transfer_function(synth.WS_TF_POINTS)
+        net.count_collision_tests(True)
+        lv_view = {}
+
+        def allreduce_light_volume():
+            if world == 1:
+                return
+            ptr, n = net.light_volume_device()
+            if lv_view.get("ptr") != ptr:
+                lv_view["ptr"], lv_view["t"] = ptr, torch.as_tensor(DevTensorView(ptr, n), device=dev)
+            dist.all_reduce(lv_view["t"], op=dist.ReduceOp.SUM)
+
+        # ---------------- resident leg (value) ----------------
+        net.set_sequence_host(pinned)          # uploads all T steps once, min-max + difference grids on the device
+        net.set_timestep(0)
+        net.evaluate()                         # first frame: full trace + full splat
+
+        def step_resident(t):
+            net.set_timestep(t % T)
+            net.evaluate()
+            allreduce_light_volume()
+            return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
+
+        for k in range(a.warmup):
+            step_resident(1 + k)
+        net.read_collision_tests(reset=True)
+        host.profile_enable(True)
+        host.profile_reset()
+        net.launch_count(reset=True)
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ms, wall_ms, traced = time_loop(net, a.steps, 1 + a.warmup, step_resident)
+        clk = clocks.stop() if rank == 0 else None
+        launches = net.launch_count()
+        tests = net.read_collision_tests(reset=True)
+        stages = {s: (host.profile_total_ms(s), host.profile_count(s)) for s in host.profile_stages()}
+        host.profile_enable(False)
+        tests_t = torch.tensor([float(tests)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tests_t, op=dist.ReduceOp.SUM)
+        value = traced / (ms * 1e-3)
+
+        # ---------------- e2e leg: host volume in, light volume out, every step ----------------
+        e2e = None
+        if not a.no_e2e:
+            lvd = net.light_volume_dims
+            out_host = torch.empty(lvd[0] * lvd[1] * lvd[2], dtype=torch.float32, pin_memory=True)
+
+            def step_e2e(t):
+                net.stream_timestep_host(pinned[t % T])
+                net.evaluate()
+                allreduce_light_volume()
+                net.read_light_volume(out_host)
+                return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
+
+            first = 1 + a.warmup + a.steps
+            for k in range(max(a.warmup, 2)):
+                step_e2e(first + k)
+            first += max(a.warmup, 2)
+            host.Network.transfer_bytes(reset=True)
+            ms_e, wall_e, traced_e = time_loop(net, a.steps, first, step_e2e)
+            h2d, d2h = host.Network.transfer_bytes()
+            e2e = {"value": traced_e / (wall_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
+                   "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": wall_e / a.steps,
+                   "frames_per_sec": a.steps / (wall_e * 1e-3),
+                   "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume) -> "
+                           "cpmh_network_evaluate -> cpmh_network_read_light_volume(pinned host buffer)"}
+        net.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = hbm_peak()
+    trace_ms, trace_n = stages.get("trace", (0.0, 0))
+    dom = max(stages.items(), key=lambda kv: kv[1][0])[0] if stages else "trace"
+    tests_rank0 = float(tests)
+    traced_rank0 = traced / world
+    # stream part 48 + 32 I + 4 (index) B per traced photon, sampling part 8 * sizeof(voxel)
+    # per collision test (+ the 2 x 4 B transfer-function taps are served from shared memory: not counted)
+    alg_bytes = traced_rank0 * (48 + 32 * I + 4) + tests_rank0 * 8 * 4
+    roof = {"bound": "hbm", "kernel": "trace_kernel (photonTracerKernel -D PHOTON_RECOMPUTATION)",
+            "achieved": alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None, "peak": peak, "unit": "GB/s",
+            "frac": (alg_bytes / (trace_ms * 1e-3) / 1e9 / peak) if trace_ms > 0 else None, "peak_source": peak_src,
+            "traffic": None, "launches": trace_n, "avg_launch_ms": trace_ms / trace_n if trace_n else None,
+            "algorithmic_bytes_per_launch": alg_bytes / trace_n if trace_n else None,
+            "dominant_stage_by_time": dom,
+            "note": "algorithmic bytes = 84 B/photon stream + 32 B per collision test (8 f32 taps); taps are mostly "
+                    "texture-cache/L2 hits, so DRAM traffic is far below this and frac can exceed what HBM alone allows"}
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        try:
+            roof["traffic"] = json.loads(tp.read_text()).get("trace_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        vols = [p.numpy() for p in pinned]
+        r = cpu_run(a, vols, 3, 1, a.cpu_seconds, grow_steps=True)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "photons_total": n_photons * world,
+                       "light_volume": f"{D // 2}^3 f32", "volume_layout": "2-D layered CUDA array (tld4)",
+                       "l2": "inputs larger than L2: a different 512 MB volume every step, 128 MB photon records",
+                       "parallelism": f"photon shards x{world}, NCCL all-reduce of the light volume" if world > 1 else "1 GPU"},
+            "frames_per_sec": a.steps / (ms * 1e-3), "retrace_fraction": traced / (a.steps * n_photons * world),
+            "collision_tests_per_sec": float(tests_t[0]) / (ms * 1e-3),
+            "wall_ms_per_step": wall_ms / a.steps,
+            "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(stages.items())},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

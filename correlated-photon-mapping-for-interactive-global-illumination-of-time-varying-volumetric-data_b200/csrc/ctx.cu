@@ -71,6 +71,14 @@ int cpm_ctx_create(int device, void* stream, cpm_ctx** out) {
         }
         c->own_stream = true;
     }
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     if ((e = cudaMallocHost((void**)&c->pinned, 256)) != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
         delete c;
@@ -105,6 +113,46 @@ uint64_t cpm_ctx_launch_count(cpm_ctx* ctx, int reset) {
     uint64_t n = ctx->launches;
     if (reset) ctx->launches = 0;
     return n;
+}
+
+// ---- events ----------------------------------------------------------------------------
+struct cpm_event {
+    cudaEvent_t ev;
+};
+
+int cpm_event_create(cpm_ctx* ctx, cpm_event** out) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, out, "null argument");
+    cpm_event* e = new cpm_event();
+    cudaError_t rc = cudaEventCreate(&e->ev);
+    if (rc != cudaSuccess) {
+        delete e;
+        return cpm_fail(ctx, CPM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(rc));
+    }
+    *out = e;
+    return CPM_OK;
+}
+
+int cpm_event_record(cpm_ctx* ctx, cpm_event* ev) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, ev, "null argument");
+    CPM_CUDA(ctx, cudaEventRecord(ev->ev, ctx->stream));
+    return CPM_OK;
+}
+
+int cpm_event_elapsed_ms(cpm_ctx* ctx, cpm_event* begin, cpm_event* end, float* ms_host) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, begin && end && ms_host, "null argument");
+    CPM_CUDA(ctx, cudaEventSynchronize(end->ev));
+    CPM_CUDA(ctx, cudaEventElapsedTime(ms_host, begin->ev, end->ev));
+    return CPM_OK;
+}
+
+void cpm_event_destroy(cpm_ctx* ctx, cpm_event* ev) {
+    (void)ctx;
+    if (!ev) return;
+    cudaEventDestroy(ev->ev);
+    delete ev;
 }
 
 // ---- volumes ---------------------------------------------------------------------------

@@ -10,15 +10,16 @@ int cpm_mem_alloc(cpm_ctx* ctx, size_t bytes, void** out) {
     CPM_REQUIRE(ctx, out != nullptr, "out is NULL");
     *out = nullptr;
     if (bytes == 0) return CPM_OK;
-    CPM_CUDA(ctx, cudaMalloc(out, bytes));
+    // stream-ordered allocation from the device's default pool (release threshold raised in
+    // cpm_ctx_create): per-frame buffers of the host layer are recycled without a device sync
+    CPM_CUDA(ctx, cudaMallocAsync(out, bytes, ctx->stream));
     return CPM_OK;
 }
 
 int cpm_mem_free(cpm_ctx* ctx, void* ptr) {
     if (!ctx) return CPM_E_INVALID;
     if (!ptr) return CPM_OK;
-    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    CPM_CUDA(ctx, cudaFree(ptr));
+    CPM_CUDA(ctx, cudaFreeAsync(ptr, ctx->stream));
     return CPM_OK;
 }
 

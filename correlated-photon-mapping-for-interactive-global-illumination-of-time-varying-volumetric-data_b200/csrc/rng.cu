@@ -116,6 +116,18 @@ int cpm_rng_host_base_offsets(uint32_t seed, uint32_t* state_host, size_t n) {
     return CPM_OK;
 }
 
+int cpm_rng_host_base_offsets_range(uint32_t seed, uint64_t first, uint32_t* state_host, size_t n) {
+    if (!state_host && n) return CPM_E_INVALID;
+    glibc_rand g;
+    g.seed(seed);
+    for (uint64_t i = 0; i < first; ++i) g.next();
+    for (size_t i = 0; i < n; ++i) {
+        state_host[2 * i] = g.next();
+        state_host[2 * i + 1] = 0;
+    }
+    return CPM_OK;
+}
+
 int cpm_rng_seed_streams(cpm_ctx* ctx, uint32_t* state, size_t n, uint64_t stream_gap, uint64_t first_stream) {
     if (!ctx) return CPM_E_INVALID;
     if (n == 0) return CPM_OK;

@@ -19,6 +19,7 @@ class HostConfig(C.Structure):
         ("max_scattering_events", C.c_int32), ("light_volume_option", C.c_int32), ("light_volume_channels", C.c_int32),
         ("with_importance_grid", C.c_int32), ("volume_layout", C.c_int32), ("photon_radius_voxels", C.c_float),
         ("max_incremental_percent", C.c_float), ("clip", C.c_int32 * 6), ("reference_full_splat_bound", C.c_int32),
+        ("incremental_threshold_percent", C.c_float),
     ]
 
 
@@ -40,7 +41,49 @@ def lib():
         _lib.cpmh_network_ctx.argtypes = [C.c_void_p]
         _lib.cpmh_network_destroy.argtypes = [C.c_void_p]
         _lib.cpmh_network_destroy.restype = None
+        _lib.cpmh_runtime_init.argtypes = [C.c_int, C.c_void_p, C.c_uint64]
+        _lib.cpmh_network_stream_timestep_host.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.cpmh_network_sync.argtypes = [C.c_void_p]
+        _lib.cpmh_network_light_volume_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        _lib.cpmh_network_count_collision_tests.argtypes = [C.c_void_p, C.c_int]
+        _lib.cpmh_network_read_collision_tests.argtypes = [C.c_void_p, C.c_int]
+        _lib.cpmh_network_read_collision_tests.restype = C.c_ulonglong
+        _lib.cpmh_profile_enable.argtypes = [C.c_int]
+        _lib.cpmh_profile_enable.restype = None
+        _lib.cpmh_profile_reset.restype = None
+        _lib.cpmh_profile_total_ms.argtypes = [C.c_char_p]
+        _lib.cpmh_profile_total_ms.restype = C.c_double
+        _lib.cpmh_profile_count.argtypes = [C.c_char_p]
+        _lib.cpmh_profile_stages.restype = C.c_char_p
     return _lib
+
+
+def runtime_init(device=0, stream=None, photon_shard_offset=0):
+    """one context per process; stream = cudaStream_t handle (int) or None; see cpmh_runtime_init"""
+    rc = lib().cpmh_runtime_init(int(device), C.c_void_p(stream or 0), C.c_uint64(photon_shard_offset))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+
+
+def profile_enable(on=True):
+    lib().cpmh_profile_enable(int(on))
+
+
+def profile_reset():
+    lib().cpmh_profile_reset()
+
+
+def profile_total_ms(stage):
+    return float(lib().cpmh_profile_total_ms(stage.encode()))
+
+
+def profile_count(stage):
+    return int(lib().cpmh_profile_count(stage.encode()))
+
+
+def profile_stages():
+    s = lib().cpmh_profile_stages().decode()
+    return [x for x in s.split(",") if x]
 
 
 class HostError(RuntimeError):
@@ -62,7 +105,7 @@ class Network:
     def __init__(self, dims, fmt, samples_per_side, light_directions, max_scattering_events=1, light_volume_option=2,
                  light_volume_channels=1, with_importance_grid=False, volume_layout=1, photon_radius_voxels=1.0,
                  max_incremental_percent=100.0, clip=None, device=0, light_intensity=None,
-                 reference_full_splat_bound=True):
+                 reference_full_splat_bound=True, incremental_threshold=0.0):
         cfg = HostConfig()
         cfg.device = device
         cfg.dims[:] = [int(d) for d in dims]
@@ -83,6 +126,7 @@ class Network:
         if clip:
             cfg.clip[:] = [int(c) for c in clip]
         cfg.reference_full_splat_bound = int(reference_full_splat_bound)
+        cfg.incremental_threshold_percent = incremental_threshold
         self.h = C.c_void_p()
         self._keep = []
         self._check(lib().cpmh_network_create(C.byref(cfg), C.byref(self.h)))
@@ -121,6 +165,27 @@ class Network:
 
     def set_timestep(self, t):
         self._check(lib().cpmh_network_set_timestep(self.h, int(t)))
+
+    def stream_timestep_host(self, array):
+        """upload the next time step from a (pinned) host array / tensor; see cpmh_network_stream_timestep_host"""
+        ptr = array.data_ptr() if hasattr(array, "data_ptr") else array.ctypes.data
+        self._stream_keep = array
+        self._check(lib().cpmh_network_stream_timestep_host(self.h, C.c_void_p(ptr)))
+
+    def sync(self):
+        self._check(lib().cpmh_network_sync(self.h))
+
+    def light_volume_device(self):
+        """(device pointer, number of floats) of the light volume"""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(lib().cpmh_network_light_volume_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def count_collision_tests(self, on=True):
+        self._check(lib().cpmh_network_count_collision_tests(self.h, int(on)))
+
+    def read_collision_tests(self, reset=False):
+        return int(lib().cpmh_network_read_collision_tests(self.h, int(reset)))
 
     def evaluate(self) -> int:
         return self._check(lib().cpmh_network_evaluate(self.h))

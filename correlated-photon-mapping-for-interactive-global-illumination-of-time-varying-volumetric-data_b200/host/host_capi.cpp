@@ -28,6 +28,12 @@ struct cpmh_network {
     std::vector<std::shared_ptr<UniformGrid3DBase>> seqMinMax, seqDiff;
     DataOutport<UniformGrid3DBase> minMaxSelector{"selectedMinMax"}, diffSelector{"selectedDiff"};
     bool useSequence = false;
+    // streaming time steps (cpmh_network_stream_timestep_host): two volumes / min-max grids in ping-pong
+    std::shared_ptr<Volume> streamVol[2];
+    std::shared_ptr<MinMaxUniformGrid3D> streamMinMax[2];
+    std::shared_ptr<DynamicVolumeInfoUniformGrid3D> streamDiff[2];
+    int streamSlot = -1;
+    unsigned long long* collisionCounter = nullptr;
 };
 
 template <typename F>
@@ -46,6 +52,14 @@ static int guarded(F&& f) {
 extern "C" {
 
 const char* cpmh_last_error(void) { return g_err.c_str(); }
+
+int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset) {
+    return guarded([&]() {
+        CpmRuntime::init(device, stream);
+        CpmRuntime::get().photonShardOffset = photon_shard_offset;
+        return (int)CPM_OK;
+    });
+}
 
 int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
     return guarded([&]() {
@@ -83,6 +97,7 @@ int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
         n->toLightVolume.photons_.connectTo(&n->tracer.outport_);
         n->toLightVolume.recomputedPhotonIndicesPort_.connectTo(&n->tracer.recomputedIndicesPort_);
         n->toLightVolume.referenceFullSplatBound = cfg->reference_full_splat_bound != 0;
+        if (cfg->incremental_threshold_percent > 0) n->toLightVolume.incrementalRecomputationThreshold_.set(cfg->incremental_threshold_percent);
         if (cfg->light_volume_channels == 4) n->toLightVolume.volumeDataTypeOption_.setSelectedIdentifier("4xfloat32");
         const char* opt = cfg->light_volume_option == 1 ? "1" : (cfg->light_volume_option == 2 ? "1/2" : (cfg->light_volume_option == 4 ? "1/4" : "radius"));
         n->toLightVolume.volumeSizeOption_.setSelectedIdentifier(opt);
@@ -140,7 +155,8 @@ int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels,
         for (int t = 0; t < T; ++t) {
             auto v = std::make_shared<Volume>(size3_t(c.dims[0], c.dims[1], c.dims[2]), DataFormatBase::get(fid));
             v->setExternalRAMData(const_cast<void*>(voxels[t]));
-            v->deviceRead();   // keep the whole series resident in HBM
+            v->deviceRead();   // keep the whole series resident in HBM ...
+            v->handle(net->tracer.tracer().volumeLayout);   // ... in the layout the tracer samples (no allocation inside a frame)
             seq->push_back(v);
         }
         CpmRuntime::get().sync();
@@ -173,6 +189,88 @@ int cpmh_network_set_timestep(cpmh_network* net, int t) {
         net->volumeSource.setData((*net->sequence)[t]);
         return (int)CPM_OK;
     });
+}
+
+int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
+    return guarded([&]() {
+        if (!voxels) throw std::invalid_argument("null voxel buffer");
+        const cpmh_config& c = net->cfg;
+        auto& rt = CpmRuntime::get();
+        DataFormatId fid = c.format == CPM_FMT_U8 ? DataFormatId::UInt8 : (c.format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
+        const int prev = net->streamSlot;
+        const int cur = prev < 0 ? 0 : 1 - prev;
+        if (!net->streamVol[cur]) net->streamVol[cur] = std::make_shared<Volume>(size3_t(c.dims[0], c.dims[1], c.dims[2]), DataFormatBase::get(fid));
+        Volume* v = net->streamVol[cur].get();
+        v->setExternalRAMData(const_cast<void*>(voxels));
+        const size_t r = (size_t)net->minMax.volumeRegionSize_.get();
+        if (c.with_importance_grid) {
+            if (!net->streamMinMax[cur]) {
+                net->streamMinMax[cur] = std::shared_ptr<MinMaxUniformGrid3D>(net->minMax.compute(v).release());
+            } else {
+                const cpm_volume* vh = v->handle(CPM_VOLUME_LINEAR);
+                ScopedStage st("minmax");
+                rt.check(cpm_volume_minmax(rt.ctx(), vh, (int)r, static_cast<uint16_t*>(net->streamMinMax[cur]->data.deviceWrite()), nullptr));
+            }
+            if (prev >= 0) {
+                // difference grid prev -> cur; a fresh grid object every step would churn the allocator, so two are kept
+                net->streamDiff[cur] = DynamicVolumeDifferenceAnalysis::difference(net->streamVol[prev].get(), v, r);
+                net->diffSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->streamDiff[cur]));
+                net->importance.volumeDifferenceInfoInport_.connectTo(&net->diffSelector);
+            }
+            net->importance.minMaxUniformGrid3DInport_.connectTo(&net->minMaxSelector);
+            net->minMaxSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->streamMinMax[cur]));
+        }
+        net->useSequence = true;
+        net->streamSlot = cur;
+        net->volumeSource.setData(net->streamVol[cur]);
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_sync(cpmh_network*) {
+    return guarded([&]() {
+        CpmRuntime::get().sync();
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_floats) {
+    return guarded([&]() {
+        auto v = std::const_pointer_cast<Volume>(net->toLightVolume.outport_.getData());
+        if (!v || !ptr) throw std::invalid_argument("no light volume yet");
+        const void* p = v->deviceRead();
+        *ptr = v->deviceWrite();
+        (void)p;
+        if (n_floats) *n_floats = v->getSizeInBytes() / sizeof(float);
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_count_collision_tests(cpmh_network* net, int on) {
+    return guarded([&]() {
+        auto& rt = CpmRuntime::get();
+        if (on && !net->collisionCounter) {
+            void* p = nullptr;
+            rt.check(cpm_mem_alloc(rt.ctx(), sizeof(unsigned long long), &p));
+            rt.check(cpm_mem_fill_u32(rt.ctx(), p, 0u, 2));
+            net->collisionCounter = static_cast<unsigned long long*>(p);
+        }
+        net->tracer.tracer().collisionCounter = on ? net->collisionCounter : nullptr;
+        return (int)CPM_OK;
+    });
+}
+
+unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset) {
+    unsigned long long v = 0;
+    guarded([&]() {
+        if (!net->collisionCounter) return (int)CPM_OK;
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), &v, net->collisionCounter, sizeof(v)));
+        rt.sync();
+        if (reset) rt.check(cpm_mem_fill_u32(rt.ctx(), net->collisionCounter, 0u, 2));
+        return (int)CPM_OK;
+    });
+    return v;
 }
 
 int cpmh_network_evaluate(cpmh_network* net) {
@@ -231,13 +329,31 @@ int cpmh_network_read_photons(cpmh_network* net, float* out, size_t n) {
 }
 int cpmh_network_read_importance_keys(cpmh_network*, uint32_t*, size_t) { return CPM_E_UNSUPPORTED; }
 const char* cpmh_network_last_splat_path(cpmh_network* net) { return net->toLightVolume.lastPath.c_str(); }
-int cpmh_network_set_profile(cpmh_network* net, int on) {
-    net->tracer.profile = on != 0;
+int cpmh_network_set_profile(cpmh_network*, int on) {
+    StageProfiler::get().enabled = on != 0;
     return CPM_OK;
 }
-float cpmh_network_stage_ms(cpmh_network* net, const char* stage) {
-    auto it = net->tracer.lastStageMs.find(stage);
-    return it == net->tracer.lastStageMs.end() ? 0.f : it->second;
+float cpmh_network_stage_ms(cpmh_network*, const char* stage) {
+    float v = 0.f;
+    guarded([&]() { v = (float)StageProfiler::get().lastMs(stage); return (int)CPM_OK; });
+    return v;
+}
+void cpmh_profile_enable(int on) { StageProfiler::get().enabled = on != 0; }
+void cpmh_profile_reset(void) { guarded([&]() { StageProfiler::get().reset(); return (int)CPM_OK; }); }
+double cpmh_profile_total_ms(const char* stage) {
+    double v = 0;
+    guarded([&]() { v = StageProfiler::get().totalMs(stage); return (int)CPM_OK; });
+    return v;
+}
+int cpmh_profile_count(const char* stage) {
+    int v = 0;
+    guarded([&]() { v = StageProfiler::get().count(stage); return (int)CPM_OK; });
+    return v;
+}
+const char* cpmh_profile_stages(void) {
+    static std::string s;
+    guarded([&]() { s = StageProfiler::get().stages(); return (int)CPM_OK; });
+    return s.c_str();
 }
 uint64_t cpmh_network_launch_count(cpmh_network*, int reset) { return cpm_ctx_launch_count(CpmRuntime::get().ctx(), reset); }
 void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
@@ -246,6 +362,17 @@ void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
     if (reset) BufferBase::h2dBytes() = BufferBase::d2hBytes() = 0;
 }
 void* cpmh_network_ctx(cpmh_network*) { return CpmRuntime::get().ctx(); }
+
+int cpmh_fit_light_plane(const float* points, int n, const float P[3], const float N[3], float out[9]) {
+    return guarded([&]() {
+        std::vector<vec3> pts;
+        for (int i = 0; i < n; ++i) pts.push_back(vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+        auto f = geometry::fitPlaneAlignedOrientedBoundingBox2D(pts, vec3(P[0], P[1], P[2]), vec3(N[0], N[1], N[2]));
+        const vec3 v[3] = {f.origin, f.u, f.v};
+        for (int k = 0; k < 3; ++k) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
+        return (int)CPM_OK;
+    });
+}
 
 const char* cpmh_describe_processors(void) {
     static std::string s;

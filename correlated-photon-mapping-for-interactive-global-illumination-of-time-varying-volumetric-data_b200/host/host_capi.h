@@ -34,8 +34,13 @@ typedef struct cpmh_config {
     float max_incremental_percent; /* `maxIncrementalPhotonsToUpdate` */
     int32_t clip[6];             /* clipX.min,max, clipY.., clipZ..; all zero = no clipping */
     int32_t reference_full_splat_bound;
+    float incremental_threshold_percent; /* `incrementalRecomputationThreshold`; 0 = the reference's default 50 */
 } cpmh_config;
 
+/* One context per process.  Optional: call before the first network is created to choose the CUDA
+ * stream (a cudaStream_t, NULL = own stream) and this process's photon shard: photon i of this process
+ * is photon photon_shard_offset + i of the global photon set (MWC64X stream and host base offset). */
+CPMH_API int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset);
 CPMH_API int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out);
 CPMH_API void cpmh_network_destroy(cpmh_network* net);
 CPMH_API const char* cpmh_last_error(void);
@@ -48,6 +53,18 @@ CPMH_API int cpmh_network_set_volume_host(cpmh_network* net, const void* voxels_
  * device for all steps (VolumeMinMaxCL on the sequence + DynamicVolumeDifferenceAnalysis) */
 CPMH_API int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels_host, int n_steps);
 CPMH_API int cpmh_network_set_timestep(cpmh_network* net, int t);
+/* Streaming variant for data that does not stay resident: upload the next time step from a HOST buffer
+ * (pinned memory: asynchronous), compute its min-max grid and the per-brick difference to the previously
+ * streamed step on the device, and mark volume / grids changed.  The buffer must stay valid until the
+ * next evaluate has been synchronised (cpmh_network_read_* or cpmh_network_sync). */
+CPMH_API int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels_host);
+CPMH_API int cpmh_network_sync(cpmh_network* net);
+/* device pointer of the light volume (float[dims] or float4[dims]) for zero-copy consumers, e.g. an
+ * NCCL all-reduce across the GPUs that each splatted their photon shard */
+CPMH_API int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_floats);
+/* count delta-tracking collision tests of every trace from now on (device counter); read = sync */
+CPMH_API int cpmh_network_count_collision_tests(cpmh_network* net, int on);
+CPMH_API unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset);
 /* evaluate every invalid processor in network order; returns the number of processors that ran */
 CPMH_API int cpmh_network_evaluate(cpmh_network* net);
 /* progressive work left (budgeted re-trace batches): call evaluate again while > 0 */
@@ -63,9 +80,21 @@ CPMH_API const char* cpmh_network_last_splat_path(cpmh_network* net);
 /* stage timing of the tracer's last process(): "detector","count+iota","sort","indexsort","trace" */
 CPMH_API int cpmh_network_set_profile(cpmh_network* net, int on);
 CPMH_API float cpmh_network_stage_ms(cpmh_network* net, const char* stage);
+/* accumulated device time per stage (CUDA events on the context stream) since the last reset:
+ * "seed","emission","h2d","texcopy","minmax","voldiff","classify","detector","count+iota","sort",
+ * "indexsort","trace","splat","copyprev" */
+CPMH_API void cpmh_profile_enable(int on);
+CPMH_API void cpmh_profile_reset(void);
+CPMH_API double cpmh_profile_total_ms(const char* stage);
+CPMH_API int cpmh_profile_count(const char* stage);
+CPMH_API const char* cpmh_profile_stages(void);
 CPMH_API uint64_t cpmh_network_launch_count(cpmh_network* net, int reset);
 CPMH_API void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset);
 CPMH_API void* cpmh_network_ctx(cpmh_network* net);
+/* the host layer's CPU light-plane fit (lcl/orientedboundingbox2d.cpp:80-100 + convexhull2d.cpp +
+ * pointplaneprojection.cpp), exposed for parity tests: out = origin[3], u[3], v[3].  No device needed. */
+CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
+                                  const float plane_normal[3], float out[9]);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */
 CPMH_API const char* cpmh_describe_processors(void);
 #ifdef __cplusplus

@@ -100,8 +100,12 @@ private:
 class CpmRuntime {
 public:
     static CpmRuntime& get();            // creates the context on first use (device 0 or CPM_DEVICE)
-    static void init(int device);        // explicit initialisation (one process per GPU)
+    static void init(int device, void* stream = nullptr);   // explicit initialisation (one process per GPU)
     static void shutdown();
+    // First photon id owned by this process when the photon set is sharded over GPUs: photon i of this
+    // process uses MWC64X stream photonShardOffset + i (and the matching host base offset), so that the
+    // shards of all GPUs together are the streams of one large single-GPU photon set.
+    uint64_t photonShardOffset = 0;
     cpm_ctx* ctx() { return ctx_; }
     void check(int rc) const {
         if (rc != CPM_OK) throw CpmError(rc, cpm_last_error(ctx_));
@@ -111,6 +115,36 @@ private:
     cpm_ctx* ctx_ = nullptr;
 };
 #define CPM_CHECK(call) ::inviwo::CpmRuntime::get().check(call)
+
+// ---- stage profiler: CUDA events on the context stream, the role of IVW_OPENCL_PROFILING ---------
+// Recording is asynchronous; totals are resolved (one event synchronise per pending pair) on query.
+class StageProfiler {
+public:
+    static StageProfiler& get();
+    bool enabled = false;
+    void begin(const char* stage);
+    void end();
+    void resolve();
+    void reset();
+    double totalMs(const std::string& stage);
+    int count(const std::string& stage);
+    double lastMs(const std::string& stage);
+    std::string stages();
+    void releaseEvents();
+private:
+    struct Pending { std::string stage; cpm_event* a; cpm_event* b; };
+    cpm_event* take();
+    std::vector<cpm_event*> pool_;
+    std::vector<Pending> pending_;
+    std::string open_;
+    cpm_event* openEv_ = nullptr;
+    struct Acc { double total = 0, last = 0; int n = 0; };
+    std::map<std::string, Acc> acc_;
+};
+struct ScopedStage {
+    explicit ScopedStage(const char* s) { StageProfiler::get().begin(s); }
+    ~ScopedStage() { StageProfiler::get().end(); }
+};
 
 // ---- Buffer<T>: RAM + device representation with lazy synchronisation ----------------------------
 enum class BufferUsage { Static, Dynamic };

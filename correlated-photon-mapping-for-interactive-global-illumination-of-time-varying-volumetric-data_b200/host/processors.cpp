@@ -48,16 +48,81 @@ CpmRuntime& CpmRuntime::get() {
     }
     return g_runtime;
 }
-void CpmRuntime::init(int device) {
+void CpmRuntime::init(int device, void* stream) {
     if (g_runtime.ctx_) return;
     cpm_ctx* c = nullptr;
-    int rc = cpm_ctx_create(device, nullptr, &c);
+    int rc = cpm_ctx_create(device, stream, &c);
     if (rc != CPM_OK) throw CpmError(rc, cpm_last_error(nullptr));
     g_runtime.ctx_ = c;
 }
 void CpmRuntime::shutdown() {
+    StageProfiler::get().releaseEvents();
     if (g_runtime.ctx_) cpm_ctx_destroy(g_runtime.ctx_);
     g_runtime.ctx_ = nullptr;
+}
+
+// ------------------------------------------------------------------------------ profiler --------
+static StageProfiler g_profiler;
+StageProfiler& StageProfiler::get() { return g_profiler; }
+cpm_event* StageProfiler::take() {
+    if (!pool_.empty()) {
+        cpm_event* e = pool_.back();
+        pool_.pop_back();
+        return e;
+    }
+    cpm_event* e = nullptr;
+    CPM_CHECK(cpm_event_create(CpmRuntime::get().ctx(), &e));
+    return e;
+}
+void StageProfiler::begin(const char* stage) {
+    if (!enabled || openEv_) return;   // stages do not nest: the outermost wins
+    open_ = stage;
+    openEv_ = take();
+    CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), openEv_));
+}
+void StageProfiler::end() {
+    if (!enabled || !openEv_) return;
+    cpm_event* b = take();
+    CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), b));
+    pending_.push_back({open_, openEv_, b});
+    openEv_ = nullptr;
+    if (pending_.size() >= 4096) resolve();
+}
+void StageProfiler::resolve() {
+    std::map<std::string, double> thisRound;
+    for (auto& p : pending_) {
+        float ms = 0.f;
+        CPM_CHECK(cpm_event_elapsed_ms(CpmRuntime::get().ctx(), p.a, p.b, &ms));
+        Acc& a = acc_[p.stage];
+        a.total += ms;
+        a.n += 1;
+        a.last = ms;
+        pool_.push_back(p.a);
+        pool_.push_back(p.b);
+    }
+    pending_.clear();
+}
+void StageProfiler::reset() {
+    resolve();
+    acc_.clear();
+}
+double StageProfiler::totalMs(const std::string& s) { resolve(); auto it = acc_.find(s); return it == acc_.end() ? 0.0 : it->second.total; }
+double StageProfiler::lastMs(const std::string& s) { resolve(); auto it = acc_.find(s); return it == acc_.end() ? 0.0 : it->second.last; }
+int StageProfiler::count(const std::string& s) { resolve(); auto it = acc_.find(s); return it == acc_.end() ? 0 : it->second.n; }
+std::string StageProfiler::stages() {
+    resolve();
+    std::string out;
+    for (auto& kv : acc_) out += (out.empty() ? "" : ",") + kv.first;
+    return out;
+}
+void StageProfiler::releaseEvents() {
+    cpm_ctx* c = g_runtime.ctx();
+    for (auto& p : pending_) { cpm_event_destroy(c, p.a); cpm_event_destroy(c, p.b); }
+    pending_.clear();
+    if (openEv_) cpm_event_destroy(c, openEv_);
+    openEv_ = nullptr;
+    for (auto* e : pool_) cpm_event_destroy(c, e);
+    pool_.clear();
 }
 
 // ------------------------------------------------------------------------------- buffers --------
@@ -170,6 +235,7 @@ const void* Volume::deviceRead() {
     ensureDevice();
     if (!devValid_ && devBytes_) {
         const void* p = ext_ ? ext_ : (const void*)ram_.data();
+        ScopedStage st("h2d");
         CPM_CHECK(cpm_mem_copy_h2d(CpmRuntime::get().ctx(), dev_, p, devBytes_));
         if (!ext_) CpmRuntime::get().sync();   // external (pinned) sources stay valid; stream order suffices
         BufferBase::h2dBytes() += devBytes_;
@@ -200,9 +266,11 @@ const cpm_volume* Volume::handle(int layout) {
         return lin_;
     }
     if (!tex_) {
+        ScopedStage st("texcopy");
         CPM_CHECK(cpm_volume_create(c, d, dims, fmt, scale, offset, CPM_VOLUME_TEXTURE, &tex_));
         texValid_ = true;
     } else if (!texValid_) {
+        ScopedStage st("texcopy");
         CPM_CHECK(cpm_volume_update(c, tex_, d));
         texValid_ = true;
     }
@@ -371,11 +439,12 @@ void LightSamples::setSize(size_t nSamples) {
 void MWC64XSeedGenerator::generateRandomSeeds(Buffer<uvec2>* buffer, unsigned int seed, bool, size_t) {
     auto* ram = buffer->getEditableRAMRepresentation();
     if (ram->empty()) return;
-    cpm_rng_host_base_offsets(seed, reinterpret_cast<uint32_t*>(ram->data()), ram->size());
     auto& rt = CpmRuntime::get();
+    cpm_rng_host_base_offsets_range(seed, rt.photonShardOffset, reinterpret_cast<uint32_t*>(ram->data()), ram->size());
     uint32_t* dev = static_cast<uint32_t*>(const_cast<void*>(buffer->deviceRead()));
     buffer->deviceWrite();
-    rt.check(cpm_rng_seed_streams(rt.ctx(), dev, ram->size(), 1099511627776ull, 0));
+    ScopedStage st("seed");
+    rt.check(cpm_rng_seed_streams(rt.ctx(), dev, ram->size(), 1099511627776ull, rt.photonShardOffset));
 }
 void MWC64XRandomNumberGenerator::generate(Buffer<float>& out) {
     if (out.getSize() != randomState_.getSize() || dirty_) {
@@ -776,29 +845,12 @@ void ProgressivePhotonTracerCL::resetPhotonImportance(size_t offset, size_t nPho
     rt.check(cpm_mem_fill_u32(rt.ctx(), keys + offset, 2147483647u, nPhotons));
 }
 
-namespace {
-struct StageTimer {   // wall-clock per stage with a stream sync, only when profiling is requested
-    bool on;
-    std::map<std::string, float>& out;
-    double t0 = 0;
-    static double now() {
-        struct timespec ts;
-        clock_gettime(CLOCK_MONOTONIC, &ts);
-        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-    }
-    void begin() { if (on) { CpmRuntime::get().sync(); t0 = now(); } }
-    void end(const char* name) { if (on) { CpmRuntime::get().sync(); out[name] += (float)(now() - t0); } }
-};
-}  // namespace
-
 void ProgressivePhotonTracerCL::process() {
     using R = PhotonData::InvalidationReason;
     auto lights = lightSamples_.getVectorData();
     auto volumeC = volumePort_.getData();
     if (!volumeC || lights.empty()) return;
     Volume* volume = const_cast<Volume*>(volumeC.get());
-    lastStageMs.clear();
-    StageTimer timer{profile, lastStageMs};
 
     size_t nPhotons = 0;
     for (auto& l : lights) nPhotons += l->getSize();
@@ -849,26 +901,26 @@ void ProgressivePhotonTracerCL::process() {
             photonRecomputationDetector_.setPercentage(static_cast<int>(maxIncrementalPhotonsToUpdate_.get()));
             photonRecomputationDetector_.setIteration(photonRecomputationDetector_.getIteration() + 1);
             // 1. importance of every stored path (one launch per light, as the reference)
-            timer.begin();
+            StageProfiler::get().begin("detector");
             int offset = 0;
             for (auto& l : lights) {
                 photonRecomputationDetector_.photonRecomputationImportance(photonData_.get(), offset, volume, grid, *l,
                                                                            photonRecomputationImportance_);
                 offset += (int)l->getSize();
             }
-            timer.end("detector");
+            StageProfiler::get().end();
             // 2. fused threshold + reduce + iota: exact, synchronous count (the reference reads its count early)
-            timer.begin();
+            StageProfiler::get().begin("count+iota");
             long long nInvalid = 0;
             const uint32_t* keys = static_cast<const uint32_t*>(photonRecomputationImportance_.deviceRead());
             rt.check(cpm_count_below(rt.ctx(), keys, N, 2147483647u, static_cast<uint32_t*>(indices.deviceWrite()), &nInvalid));
-            timer.end("count+iota");
+            StageProfiler::get().end();
             // 3. sort photon ids by importance key.  The keys are sorted on a COPY so that key[i] keeps belonging
             //    to photon i (the reference permutes them in place)
-            timer.begin();
+            StageProfiler::get().begin("sort");
             rt.check(cpm_mem_copy_d2d(rt.ctx(), sortedImportance_.deviceWrite(), keys, N * sizeof(uint32_t)));
             recomputationImportanceSorter_.enqueue(sortedImportance_, &indices, N, 0);
-            timer.end("sort");
+            StageProfiler::get().end();
             remainingPhotonsOffset_ = 0;
             if (remainingPhotonsToUpdate_ < 0 || nInvalid > 0) remainingPhotonsToUpdate_ = (int)nInvalid;
         }
@@ -884,18 +936,18 @@ void ProgressivePhotonTracerCL::process() {
         if (nPhotonsToCompute > 0) {
             if (spatialSorting_.get()) {
                 // keys-only sort of the selected ids: ascending id == raster order on the light plane (:467-473)
-                timer.begin();
+                StageProfiler::get().begin("indexsort");
                 recomputationIndexSorter_.enqueue(indices, nullptr, nPhotonsToCompute, 0);
-                timer.end("indexsort");
+                StageProfiler::get().end();
             }
-            timer.begin();
+            StageProfiler::get().begin("trace");
             int offset = 0;
             for (auto& l : lights) {
                 photonTracer_.tracePhotons(volume, transferFunction_.get(), aabb_, advancedMaterial_, stepSize, l.get(), &indices,
                                            (int)nPhotonsToCompute, offset, 0, maxInteractions, photonData_.get());
                 offset += (int)l->getSize();
             }
-            timer.end("trace");
+            StageProfiler::get().end();
             // reset the keys of the photons just re-traced.  Keys stay in photon order here, so the reset goes
             // through the id list (the reference resets the matching slice of its in-place sorted keys, :529)
             uint32_t* keysW = static_cast<uint32_t*>(const_cast<void*>(photonRecomputationImportance_.deviceRead()));
@@ -911,14 +963,14 @@ void ProgressivePhotonTracerCL::process() {
             enableProgressiveRefinement_.set(false);
         }
     } else {
-        timer.begin();
+        StageProfiler::get().begin("trace");
         int offset = 0;
         for (auto& l : lights) {
             photonTracer_.tracePhotons(volume, transferFunction_.get(), aabb_, advancedMaterial_, stepSize, l.get(), nullptr, 0, offset, 0,
                                        maxInteractions, photonData_.get());
             offset += (int)l->getSize();
         }
-        timer.end("trace");
+        StageProfiler::get().end();
         recomputedPhotonIndices_->nRecomputedPhotons = -1;
         remainingPhotonsToUpdate_ = 0;
         remainingPhotonsOffset_ = 0;
@@ -1022,12 +1074,14 @@ void PhotonToLightVolumeProcessorCL::process() {
         const uint32_t* idx = static_cast<const uint32_t*>(idxBuf->deviceRead());
         float* lv = static_cast<float*>(const_cast<void*>(lightVolume_->deviceRead()));
         lightVolume_->deviceWrite();
+        ScopedStage st("splat");
         rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, static_cast<const float*>(prevPhotons_.deviceRead()),
                                    idx, nRecomputed, N, I, radius, scale, -1.f));
         rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, photonsDev, idx, nRecomputed, N, I, radius, scale, 1.f));
         lastPath = "incremental";
     } else if (prevPhotons_.getSize() != photonData->photons_.getSize() || nRecomputed < 0 || nRecomputed >= maxRecomputationPhotons) {
         float* lv = static_cast<float*>(lightVolume_->deviceWrite());
+        ScopedStage st("splat");
         rt.check(cpm_mem_fill_u32(rt.ctx(), lv, 0u, od.x * od.y * od.z * (size_t)channels));
         const int n = referenceFullSplatBound ? N : N * I;
         rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, photonsDev, nullptr, n, N, I, radius, scale, 1.f));
@@ -1036,6 +1090,7 @@ void PhotonToLightVolumeProcessorCL::process() {
     if (idxData && nRecomputed != 0) {
         // keep a copy of the photons so that the next incremental update can subtract them (:488-497)
         if (prevPhotons_.getSize() != photonData->photons_.getSize()) prevPhotons_.setSize(photonData->photons_.getSize());
+        ScopedStage st("copyprev");
         rt.check(cpm_mem_copy_d2d(rt.ctx(), prevPhotons_.deviceWrite(), photonsDev, photonData->photons_.getSizeInBytes()));
     }
     outport_.setData(lightVolume_);
@@ -1071,7 +1126,9 @@ std::unique_ptr<MinMaxUniformGrid3D> VolumeMinMaxCLProcessor::compute(const Volu
     out->setWorldMatrix(volume->getWorldMatrix());
     out->setDimensions(outDim);
     auto& rt = CpmRuntime::get();
-    rt.check(cpm_volume_minmax(rt.ctx(), const_cast<Volume*>(volume)->handle(CPM_VOLUME_LINEAR), (int)r,
+    const cpm_volume* vh = const_cast<Volume*>(volume)->handle(CPM_VOLUME_LINEAR);
+    ScopedStage st("minmax");
+    rt.check(cpm_volume_minmax(rt.ctx(), vh, (int)r,
                                static_cast<uint16_t*>(out->data.deviceWrite()), nullptr));
     return out;
 }
@@ -1095,28 +1152,32 @@ DynamicVolumeDifferenceAnalysis::DynamicVolumeDifferenceAnalysis()
     addPort(outport_);
     addProperty(volumeRegionSize_);
 }
+std::shared_ptr<DynamicVolumeInfoUniformGrid3D> DynamicVolumeDifferenceAnalysis::difference(Volume* cur, Volume* nxt, size_t r) {
+    auto& rt = CpmRuntime::get();
+    const size3_t dim = cur->getDimensions();
+    const size3_t outDim((dim.x + r - 1) / r, (dim.y + r - 1) / r, (dim.z + r - 1) / r);
+    auto out = std::make_shared<DynamicVolumeInfoUniformGrid3D>(size3_t(r));
+    out->setModelMatrix(cur->getModelMatrix());
+    out->setWorldMatrix(cur->getWorldMatrix());
+    out->setDimensions(outDim);
+    dvec2 dataRange = cur->dataMap_.dataRange;
+    double typeRange = cur->getDataFormat()->maxValue;   // DataMapper(format).dataRange = (0, max)
+    double defaultToDataRange = typeRange / (dataRange.y - dataRange.x);
+    const cpm_volume* a = cur->handle(CPM_VOLUME_LINEAR);
+    const cpm_volume* b = nxt->handle(CPM_VOLUME_LINEAR);
+    ScopedStage st("voldiff");
+    rt.check(cpm_volume_diff_bricks(rt.ctx(), a, b, (int)r, defaultToDataRange, dataRange.x, dataRange.y,
+                                    static_cast<float*>(out->data.deviceWrite())));
+    return out;
+}
 void DynamicVolumeDifferenceAnalysis::process() {
     auto data = inport_.getData();
     if (!data) return;
     auto output = std::make_shared<UniformGrid3DVector>();
-    auto& rt = CpmRuntime::get();
     const size_t r = (size_t)volumeRegionSize_.get();
     for (size_t t = 0; t < data->size(); ++t) {
         size_t next = (t + 1) % data->size();
-        Volume* cur = (*data)[t].get();
-        Volume* nxt = (*data)[next].get();
-        const size3_t dim = cur->getDimensions();
-        const size3_t outDim((dim.x + r - 1) / r, (dim.y + r - 1) / r, (dim.z + r - 1) / r);
-        auto out = std::make_shared<DynamicVolumeInfoUniformGrid3D>(size3_t(r));
-        out->setModelMatrix(cur->getModelMatrix());
-        out->setWorldMatrix(cur->getWorldMatrix());
-        out->setDimensions(outDim);
-        dvec2 dataRange = cur->dataMap_.dataRange;
-        double typeRange = cur->getDataFormat()->maxValue;   // DataMapper(format).dataRange = (0, max)
-        double defaultToDataRange = typeRange / (dataRange.y - dataRange.x);
-        rt.check(cpm_volume_diff_bricks(rt.ctx(), cur->handle(CPM_VOLUME_LINEAR), nxt->handle(CPM_VOLUME_LINEAR), (int)r, defaultToDataRange,
-                                        dataRange.x, dataRange.y, static_cast<float*>(out->data.deviceWrite())));
-        output->emplace_back(out);
+        output->emplace_back(difference((*data)[t].get(), (*data)[next].get(), r));
     }
     outport_.setData(output);
 }
@@ -1270,6 +1331,7 @@ void MinMaxUniformGrid3DImportanceCLProcessor::process() {
     const uint16_t* mm = static_cast<const uint16_t*>(minMax->data.deviceRead());
     float* out = static_cast<float*>(importanceUniformGrid3D_->data.deviceWrite());
     auto prevMM = dynamic_cast<const MinMaxUniformGrid3D*>(prevMinMaxUniformGrid3D_.get());
+    ScopedStage st("classify");
     if (volumeDifferenceInfoInport_.isReady() && prevMM && prevMM != minMax) {
         auto diff = dynamic_cast<const DynamicVolumeInfoUniformGrid3D*>(volumeDifferenceInfoInport_.getData().get());
         if (!diff) {

@@ -296,10 +296,8 @@ public:
     void onTimerEvent();    // the reference's 100 ms Timer callback; call it to step progressive work
     PhotonTracerCL& tracer() { return photonTracer_; }
     int remainingPhotonsToUpdate() const { return remainingPhotonsToUpdate_; }
-    // stage timings of the last process() in ms (detector, count, sort, index sort, trace), like the
-    // reference's IVW_DETAILED_PROFILING log (:562-598); filled only when profile = true
-    bool profile = false;
-    std::map<std::string, float> lastStageMs;
+    // stage timings (detector, count+iota, sort, indexsort, trace), like the reference's
+    // IVW_DETAILED_PROFILING log (:562-598), are collected by StageProfiler when it is enabled
 private:
     void onClipChange();
     void progressiveRefinementChanged();
@@ -374,6 +372,8 @@ public:
     DataInport<VolumeSequence> inport_;
     DataOutport<UniformGrid3DVector> outport_;
     IntProperty volumeRegionSize_;
+    // one pair of the sequence loop (dynamicvolumedifferenceanalysis.cpp:66-101), on the device
+    static std::shared_ptr<DynamicVolumeInfoUniformGrid3D> difference(Volume* cur, Volume* next, size_t region);
 };
 
 // org.inviwo.MinMaxUniformGrid3DImportanceCLProcessor -- isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:43-524

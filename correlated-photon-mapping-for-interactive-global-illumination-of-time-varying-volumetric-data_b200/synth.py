@@ -118,3 +118,27 @@ CUBE_INDICES = np.array([
 def normalize(v):
     v = np.asarray(v, np.float64)
     return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+def volume_field_torch(dims, seed: int, t: float = 0.0, device="cpu", n_blobs: int = 12, noise_res: int = 9):
+    """volume_field() evaluated with torch on `device` (benchmark-sized volumes: a 512^3 step takes
+    seconds in numpy).  Same blobs, orbits and noise lattice; values agree with volume_field() to
+    fp32 rounding, which is all a benchmark input needs.  Returns a (nz, ny, nx) float32 tensor."""
+    import torch
+    nx, ny, nz = dims
+    r = uniform01(seed, n_blobs * 8 + noise_res ** 3)
+    b = r[: n_blobs * 8].reshape(n_blobs, 8)
+    noise = torch.tensor(r[n_blobs * 8:].reshape(noise_res, noise_res, noise_res), dtype=torch.float32, device=device)
+    ax = [(torch.arange(n, dtype=torch.float32, device=device) + 0.5) / n for n in (nx, ny, nz)]
+    cx, cy, cz, rad, a, orad, oph = (b[:, k] for k in range(7))
+    ang = 2 * np.pi * (t + oph)
+    centre = [0.15 + 0.7 * cx + 0.12 * orad * np.cos(ang), 0.15 + 0.7 * cy + 0.12 * orad * np.sin(ang), 0.15 + 0.7 * cz]
+    s = torch.tensor(0.04 + 0.08 * rad, dtype=torch.float32, device=device)[:, None]
+    g = [torch.exp(-0.5 * ((ax[k][None, :] - torch.tensor(centre[k], dtype=torch.float32, device=device)[:, None]) / s) ** 2)
+         for k in range(3)]
+    amp = torch.tensor(0.35 + 0.65 * a, dtype=torch.float32, device=device)
+    f = torch.einsum("kz,ky,kx->zyx", g[2] * amp[:, None], g[1], g[0])
+    m = [torch.tensor(_interp_matrix(n, noise_res), device=device) for n in (nx, ny, nz)]
+    nf = torch.einsum("zc,cyx->zyx", m[2], torch.einsum("yb,cbx->cyx", m[1], torch.einsum("xa,cba->cbx", m[0], noise)))
+    f = 0.93 * torch.clamp(f, max=1.0) + 0.07 * nf
+    return torch.clamp(f, 0.0, 1.0).contiguous()

@@ -63,12 +63,26 @@ CPM_API const char* cpm_version(void);
 /* number of kernel launches issued through this context since creation / last reset */
 CPM_API uint64_t cpm_ctx_launch_count(cpm_ctx* ctx, int reset);
 
+/* ---- stage timing ------------------------------------------------------------------- */
+/* CUDA events on the context stream: what IVW_OPENCL_PROFILING / cl::Event timestamps are in the
+ * reference (ppm/processor/progressivephotontracercl.cpp:562-598).  cpm_event_record is
+ * asynchronous; cpm_event_elapsed_ms waits for `end` and returns the device time between the two. */
+typedef struct cpm_event cpm_event;
+CPM_API int cpm_event_create(cpm_ctx* ctx, cpm_event** out);
+CPM_API int cpm_event_record(cpm_ctx* ctx, cpm_event* ev);
+CPM_API int cpm_event_elapsed_ms(cpm_ctx* ctx, cpm_event* begin, cpm_event* end, float* ms_host);
+CPM_API void cpm_event_destroy(cpm_ctx* ctx, cpm_event* ev);
+
 /* ---- (1) MWC64X per-photon RNG streams -------------------------------------------- */
 /* Fill the per-stream base offsets exactly as MWC64XSeedGenerator::generateRandomSeeds
  * does on the host (rng/mwc64xseedgenerator.cpp:56-64): srand(seed); state[i].x = rand().
  * Only .x is written by the reference; we also zero .y.  Host-side, synchronous.
  * glibc's rand() is reproduced bit-exactly (TYPE_3 additive feedback generator). */
 CPM_API int cpm_rng_host_base_offsets(uint32_t seed, uint32_t* state_host /* 2*n */, size_t n);
+/* The same sequence starting at its element `first`: the base offsets of photons
+ * [first, first + n) of a larger photon set, for a GPU that owns that photon range. */
+CPM_API int cpm_rng_host_base_offsets_range(uint32_t seed, uint64_t first, uint32_t* state_host /* 2*n */,
+                                            size_t n);
 
 /* MWC64X_GenerateRandomState (rng/cl/randstategen.cl:39-47): in place,
  * state[i] = SeedStreams(baseOffset = state[i].x, perStreamOffset = stream_gap) for stream

@@ -240,6 +240,7 @@ void orc_detect_invalid(const float* grid, const int grid_dims[3], const float c
                         const float* photons, int photon_offset, const float* light_samples, const float* isect,
                         int n_light_samples, int max_interactions, int total_photons, uint32_t* importances,
                         int equal_importance, int percentage, int iteration, int fix_exit) {
+#pragma omp parallel for schedule(dynamic, 1024)
     for (int threadId = 0; threadId < n_light_samples; ++threadId) {
         float recomputationImportance = 0.f;
         if (equal_importance) {

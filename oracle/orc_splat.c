@@ -36,12 +36,26 @@ static void splatPhoton(double* vol, int channels, const float tex2idx[16], cons
                 float xk = dist / radius;
                 float weight = xk <= 1.f ? 0.75f * (1.f - xk * xk) : 0.f; /* Epanechnikov */
                 float fr = pr * weight, fg = pg * weight, fb = pb * weight;
+                /* photons are splatted by several threads: atomic double adds (exact enough that the
+                 * order does not show at the tolerances the tests use) */
                 if (channels == 1) {
-                    if (fr != 0.f) vol[voxelIndex] += fr;
+                    if (fr != 0.f) {
+#pragma omp atomic
+                        vol[voxelIndex] += fr;
+                    }
                 } else {
-                    if (fr != 0.f) vol[voxelIndex * 4] += fr;
-                    if (fg != 0.f) vol[voxelIndex * 4 + 1] += fg;
-                    if (fb != 0.f) vol[voxelIndex * 4 + 2] += fb;
+                    if (fr != 0.f) {
+#pragma omp atomic
+                        vol[voxelIndex * 4] += fr;
+                    }
+                    if (fg != 0.f) {
+#pragma omp atomic
+                        vol[voxelIndex * 4 + 1] += fg;
+                    }
+                    if (fb != 0.f) {
+#pragma omp atomic
+                        vol[voxelIndex * 4 + 2] += fb;
+                    }
                 }
             }
 }
@@ -53,6 +67,7 @@ void orc_splat(double* vol, int channels, const float tex2idx[16], const float i
                const float* photons, const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
                float radius, float relative_irradiance_scale, float multiplier) {
     const float phase = CPM_INV_4PI_F; /* isotropicPhaseFunction() */
+#pragma omp parallel for schedule(dynamic, 1024)
     for (int g = 0; g < n; ++g) {
         if (!indices) {
             const float* ph = photons + 8 * (size_t)g;

@@ -60,13 +60,15 @@ def test_network_full_trace_matches_oracle(host, cpm, orc, synth, torch_cuda):
     assert net.evaluate() >= 4
     ph = net.read_photons(I)
     # the oracle with the same set-up (light plane fit done by the oracle's own CPU geometry)
-    L = scenes.directional_light(ns, d)
+    L = scenes.directional_light(ns, d, radiance=(1.0, 1.0, 1.0))   # the network's default light intensity
     tf = synth.rasterise_tf(width=1024)
     want, _, _ = oracle_trace(orc, vol, tf, L, max_interactions=I, step_size=1.0 / 64)
     stored = want[:, 0] != FLT_MAX
     assert stored.sum() > 1000
     # the host layer fits the light plane in its own float arithmetic: positions agree to fp32 noise,
     # and wherever the light samples are bit-identical the photons are too
+    same_pos = np.all(ph[:, :3].view(np.uint32) == want[:, :3].view(np.uint32), axis=1)
+    assert same_pos.mean() > 0.99, same_pos.mean()
     same = np.all(ph.view(np.uint32) == want.view(np.uint32), axis=1)
     assert same.mean() > 0.99, same.mean()
     assert net.last_splat_path == "full"
@@ -83,7 +85,8 @@ def test_network_correlated_retrace(host, cpm, orc, synth, torch_cuda):
     dims, ns, I = (64, 64, 64), 128, 2
     d = (0.2, 0.3, 0.9)
     vol = synth.volume_u8(dims, 8)
-    kw = dict(max_scattering_events=I, light_volume_option=2, with_importance_grid=True, reference_full_splat_bound=False)
+    kw = dict(max_scattering_events=I, light_volume_option=2, with_importance_grid=True, reference_full_splat_bound=False,
+              incremental_threshold=100.0)
     net = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], **kw)
     net.set_transfer_function(synth.WS_TF_POINTS)
     net.set_volume_host(vol)
