@@ -77,8 +77,10 @@ def main():
                         print(f"  trace I={I} {lname:8s}: {ms:.3f} ms  photons/s={n/ms*1e3:.3e}  tests={tests} "
                               f"({tests/n:.1f}/photon) tests/s={tests/ms*1e3:.3e} stored={stored}  runs={['%.3f'%x for x in all_]}")
                         V.destroy()
+        if "sort26" in what:
+            what = what + ["sort"]
         if "sort" in what:
-            for logn in (20, 24, 26, 28):
+            for logn in ((26,) if "sort26" in what else (20, 24, 26, 28)):
                 n = 1 << logn
                 keys = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
                 imp = torch.full((n,), 0x7FFFFFFF, dtype=torch.int32, device="cuda")
