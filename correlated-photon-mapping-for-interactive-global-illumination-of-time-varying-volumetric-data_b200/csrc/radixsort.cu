@@ -10,28 +10,33 @@
 // histograms and then moves each element exactly once per pass with a single-pass chained scan
 // (decoupled look-back): 4 + 4 x 2 x (4+4) = 68 B per pair, 36 B per key for keys only.
 //
-// Kernel structure per pass (one CTA = one tile of TILE elements, tiles taken in order from an
-// atomic ticket so that look-back never waits on a CTA that has not started):
+// Kernel structure per pass (one CTA = one tile of SORT_TILE = 8192 elements, tiles taken in order from
+// an atomic ticket so that look-back never waits on a CTA that has not started):
 //   1. warp-striped coalesced load of ITEMS keys (and values) per thread
-//   2. stable ranking inside each warp with MATCH.ANY on the digit + warp-private digit counters
-//      in shared memory (no atomics); items are ranked in load order, so the order of equal
-//      digits is the input order
-//   3. thread d owns digit d: sums the warp counters, publishes the tile's count for d
-//      (FLAG_AGGREGATE), walks back over predecessor tiles until it meets an inclusive prefix
-//      (FLAG_PREFIX), publishes its own inclusive prefix
-//   4. keys/values are permuted through shared memory into tile-sorted order and written out in
-//      runs of equal digit (coalesced stores)
+//   2. EARLY COUNTS: per-warp digit histograms with shared-memory atomics (order-free), summed per
+//      digit by thread d -> the tile's count for d is published (FLAG_AGGREGATE) before any ranking,
+//      and the first window of predecessor status words is already requested, so that the chained
+//      scan's L2 round trips overlap the ranking below
+//   3. stable ranking inside each warp: peers = lanes with the same digit, found with 8 ballots (one
+//      per digit bit; MATCH.ANY serialises over the distinct values of a warp and was 55 % of the
+//      round-1 kernel time); running per-(warp,digit) offsets in shared memory start at the final
+//      tile-local position (known from step 2), so every element goes straight to its slot in the
+//      tile-sorted staging buffer -- no rank registers
+//   4. decoupled look-back over windows of 4 predecessors (4 independent loads in flight per digit),
+//      publish FLAG_PREFIX
+//   5. coalesced write-out in runs of equal digit
 #include "common.cuh"
 
 namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 256;
+constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 constexpr int MAX_PASSES = 4;
+constexpr int LOOKBACK_WINDOW = 4;
 
 constexpr uint32_t FLAG_AGGREGATE = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
@@ -81,54 +86,143 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
+// one block per pass: digit histogram -> exclusive prefix (the global base of every digit), in place
+__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_warp[RADIX / 32];
+    uint32_t* h = hist + blockIdx.x * RADIX;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v = h[tid], incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w)
+        if (w < (int)warp) off += s_warp[w];
+    h[tid] = off + incl - v;
+}
+
+template <bool HAS_VALUES>
 struct SortSmem {
-    uint32_t warp_count[SORT_WARPS][RADIX];  // per-warp digit counters, later exclusive warp offsets
-    uint32_t gbase[RADIX];                   // global index of local position 0 of each digit run
+    uint32_t warp_count[SORT_WARPS][RADIX];  // per-warp digit counts, then running tile-local offsets
+    uint32_t gbase[RADIX];                   // global index of tile-local position 0 of each digit run
     uint32_t keys[SORT_TILE];
-    uint32_t vals[SORT_TILE];
-    uint32_t scan_tmp[SORT_WARPS];
+    uint32_t vals[HAS_VALUES ? SORT_TILE : 1];
+    uint32_t scan_tmp[RADIX / 32];
     uint32_t tile;
 };
 
+// lanes of the warp whose digit equals this lane's: one ballot per digit bit (full rate, fixed cost)
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+        bool bit = (d >> b) & 1u;
+        uint32_t m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
 template <bool HAS_VALUES>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
-                                                                const uint32_t* __restrict__ vals_in,
-                                                                uint32_t* __restrict__ keys_out,
-                                                                uint32_t* __restrict__ vals_out, size_t n, int shift,
-                                                                const uint32_t* __restrict__ hist,  // this pass
-                                                                volatile uint32_t* status,          // [tiles][RADIX]
-                                                                uint32_t* ticket) {
+__global__ void __launch_bounds__(SORT_THREADS, 2) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in,
+                                                                   uint32_t* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out, size_t n, int shift,
+                                                                   const uint32_t* __restrict__ digit_base,  // this pass
+                                                                   volatile uint32_t* status,                // [tiles][RADIX]
+                                                                   uint32_t* ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    SortSmem<HAS_VALUES>& S = *reinterpret_cast<SortSmem<HAS_VALUES>*>(smem_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+    {
+        uint32_t* wc0 = &S.warp_count[0][0];
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) S.warp_count[w][tid] = 0;
+        for (int i = 0; i < SORT_WARPS * RADIX / SORT_THREADS; ++i) wc0[i * SORT_THREADS + tid] = 0;
+    }
     __syncthreads();
     const uint32_t tile = S.tile;
     const size_t tile_base = (size_t)tile * SORT_TILE;
     const uint32_t n_valid = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
 
     // 1. load (warp-striped): warp w owns [w*32*ITEMS, (w+1)*32*ITEMS) of the tile
-    uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
-    uint32_t rank[SORT_ITEMS];
+    uint32_t key[SORT_ITEMS], val[HAS_VALUES ? SORT_ITEMS : 1];
     const uint32_t warp_base = warp * 32 * SORT_ITEMS;
+    if (n_valid == SORT_TILE) {
+        const uint32_t* kp = keys_in + tile_base + warp_base + lane;
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        uint32_t local = warp_base + j * 32 + lane;
-        bool ok = local < n_valid;
-        key[j] = ok ? keys_in[tile_base + local] : 0xffffffffu;
-        if (HAS_VALUES) val[j] = ok ? vals_in[tile_base + local] : 0u;
+        for (int j = 0; j < SORT_ITEMS; ++j) key[j] = kp[j * 32];
+        if (HAS_VALUES) {
+            const uint32_t* vp = vals_in + tile_base + warp_base + lane;
+#pragma unroll
+            for (int j = 0; j < SORT_ITEMS; ++j) val[j] = vp[j * 32];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; ++j) {
+            uint32_t local = warp_base + j * 32 + lane;
+            bool ok = local < n_valid;
+            key[j] = ok ? keys_in[tile_base + local] : 0xffffffffu;   // padding: last digit, after every real key
+            if (HAS_VALUES) val[j] = ok ? vals_in[tile_base + local] : 0u;
+        }
     }
 
-    // 2. stable in-warp ranking
+    // 2. early counts
     uint32_t* wc = S.warp_count[warp];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) atomicAdd(&wc[(key[j] >> shift) & (RADIX - 1)], 1u);
+    __syncthreads();
+
+    uint32_t total = 0, digit_start = 0, exclusive = 0;
+    uint32_t early[LOOKBACK_WINDOW];
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) total += S.warp_count[w][tid];
+        uint32_t real_total = total;
+        if (tid == RADIX - 1) real_total -= (SORT_TILE - n_valid);
+        status[(size_t)tile * RADIX + tid] = (tile == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) | real_total;
+        // request the first look-back window now; it is consumed after the ranking
+#pragma unroll
+        for (int i = 0; i < LOOKBACK_WINDOW; ++i)
+            early[i] = ((int64_t)tile - 1 - i >= 0) ? status[((size_t)tile - 1 - i) * RADIX + tid] : 0u;
+        // tile-local start of each digit run: exclusive scan of `total` over the 256 digits
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += v;
+        }
+        if (lane == 31) S.scan_tmp[warp] = incl;
+        digit_start = incl - total;
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; ++w)
+            if (w < (int)warp) digit_start += S.scan_tmp[w];
+        // per-warp running offsets start at the final tile-local position
+        uint32_t run = digit_start;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = S.warp_count[w][tid];
+            S.warp_count[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+
+    // 3. stable in-warp ranking, elements go straight to their tile-sorted slot
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; ++j) {
         uint32_t d = (key[j] >> shift) & (RADIX - 1);
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers = match_digit(d);
         int leader = __ffs(peers) - 1;
         uint32_t before = 0;
         if ((int)lane == leader) {
@@ -136,101 +230,54 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
             wc[d] = before + __popc(peers);
         }
         before = __shfl_sync(0xffffffffu, before, leader);
-        rank[j] = before + __popc(peers & lt_mask);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // 3. thread `tid` owns digit `tid`: warp-exclusive offsets, tile total
-    uint32_t total = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) {
-        uint32_t c = S.warp_count[w][tid];
-        S.warp_count[w][tid] = total;
-        total += c;
-    }
-    // padding of the last tile sits in digit 255, after every real key
-    uint32_t real_total = total;
-    if (tid == RADIX - 1) real_total -= (SORT_TILE - n_valid);
-
-    // publish + decoupled look-back (value and flag travel in one 32-bit word)
-    uint32_t exclusive = 0;
-    if (tile == 0) {
-        status[(size_t)tile * RADIX + tid] = FLAG_PREFIX | real_total;
-    } else {
-        status[(size_t)tile * RADIX + tid] = FLAG_AGGREGATE | real_total;
-        int64_t t = (int64_t)tile - 1;
-        while (true) {
-            uint32_t s = status[(size_t)t * RADIX + tid];
-            uint32_t f = s & FLAG_MASK;
-            if (f == FLAG_PREFIX) {
-                exclusive += s & VALUE_MASK;
-                break;
-            }
-            if (f == FLAG_AGGREGATE) {
-                exclusive += s & VALUE_MASK;
-                --t;
-            }
-            // else: not published yet, poll again
-        }
-        status[(size_t)tile * RADIX + tid] = FLAG_PREFIX | (exclusive + real_total);
-    }
-
-    // exclusive scan of the tile totals over the 256 digits (tile-local start of each digit run)
-    uint32_t incl = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
-    }
-    if (lane == 31) S.scan_tmp[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w)
-        if (w < (int)warp) woff += S.scan_tmp[w];
-    const uint32_t digit_start = woff + incl - total;
-
-    // global digit base = exclusive scan of the global histogram (256 values: recomputed per CTA)
-    uint32_t h = hist[tid];
-    uint32_t hincl = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, hincl, o);
-        if (lane >= (unsigned)o) hincl += v;
-    }
-    __syncthreads();  // scan_tmp reuse
-    if (lane == 31) S.scan_tmp[warp] = hincl;
-    __syncthreads();
-    uint32_t hoff = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w)
-        if (w < (int)warp) hoff += S.scan_tmp[w];
-    const uint32_t digit_base = hoff + hincl - h;
-
-    // local position p of digit d goes to global index gbase[d] + p
-    S.gbase[tid] = digit_base + exclusive - digit_start;
-    // fold the tile-local digit start into the warp offsets: local pos = warp_count[w][d] + rank
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) S.warp_count[w][tid] += digit_start;
-    __syncthreads();
-
-    // 4. permute through shared memory, then coalesced stores
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        uint32_t d = (key[j] >> shift) & (RADIX - 1);
-        uint32_t pos = wc[d] + rank[j];
+        uint32_t pos = before + __popc(peers & lt_mask);
         S.keys[pos] = key[j];
         if (HAS_VALUES) S.vals[pos] = val[j];
+        __syncwarp();
+    }
+
+    // 4. decoupled look-back, windows of LOOKBACK_WINDOW predecessors (value and flag share one word)
+    if (tid < RADIX) {
+        if (tile != 0) {
+            int64_t t = (int64_t)tile - 1;
+            uint32_t win[LOOKBACK_WINDOW];
+#pragma unroll
+            for (int i = 0; i < LOOKBACK_WINDOW; ++i) win[i] = early[i];
+            while (true) {
+                int used = 0;
+                bool done = false;
+#pragma unroll
+                for (int i = 0; i < LOOKBACK_WINDOW; ++i) {
+                    uint32_t f = win[i] & FLAG_MASK;
+                    if (f == 0u) break;                      // not published yet: poll again from here
+                    exclusive += win[i] & VALUE_MASK;
+                    ++used;
+                    if (f == FLAG_PREFIX) {                  // tile 0 always publishes a prefix
+                        done = true;
+                        break;
+                    }
+                }
+                if (done) break;
+                t -= used;
+#pragma unroll
+                for (int i = 0; i < LOOKBACK_WINDOW; ++i) win[i] = (t - i >= 0) ? status[(size_t)(t - i) * RADIX + tid] : 0u;
+            }
+            uint32_t real_total = total;
+            if (tid == RADIX - 1) real_total -= (SORT_TILE - n_valid);
+            status[(size_t)tile * RADIX + tid] = FLAG_PREFIX | (exclusive + real_total);
+        }
+        // tile-local position p of digit d goes to global index gbase[d] + p
+        S.gbase[tid] = digit_base[tid] + exclusive - digit_start;
     }
     __syncthreads();
+
+    // 5. coalesced stores in runs of equal digit
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; ++j) {
         uint32_t p = j * SORT_THREADS + tid;
         if (p < n_valid) {
             uint32_t k = S.keys[p];
-            uint32_t d = (k >> shift) & (RADIX - 1);
-            size_t g = (size_t)S.gbase[d] + p;
+            size_t g = (size_t)S.gbase[(k >> shift) & (RADIX - 1)] + p;
             keys_out[g] = k;
             if (HAS_VALUES) vals_out[g] = S.vals[p];
         }
@@ -305,19 +352,21 @@ int cpm_radix_sort_u32(cpm_ctx* ctx, uint32_t* keys, uint32_t* values, size_t n,
     unsigned hgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, std::max<size_t>(1, n / (512 * 4)));
     CPM_LAUNCH(ctx, histogram_kernel, hgrid, 512, 0, keys, n, passes, hist);
 
+    CPM_LAUNCH(ctx, hist_scan_kernel, passes, RADIX, 0, hist);
+
     static bool attr_set = false;
     if (!attr_set) {
-        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
-        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<true>)));
+        CPM_CUDA(ctx, cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<false>)));
         attr_set = true;
     }
     uint32_t *kin = keys, *kout = tmp_keys, *vin = values, *vout = tmp_values;
     for (int p = 0; p < passes; ++p) {
         if (values) {
-            CPM_LAUNCH(ctx, onesweep_kernel<true>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem), kin, vin, kout, vout, n,
+            CPM_LAUNCH(ctx, onesweep_kernel<true>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem<true>), kin, vin, kout, vout, n,
                        p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
         } else {
-            CPM_LAUNCH(ctx, onesweep_kernel<false>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem), kin, nullptr, kout, nullptr,
+            CPM_LAUNCH(ctx, onesweep_kernel<false>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem<false>), kin, nullptr, kout, nullptr,
                        n, p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
         }
         std::swap(kin, kout);

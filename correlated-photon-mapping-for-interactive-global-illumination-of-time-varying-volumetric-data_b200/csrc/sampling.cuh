@@ -72,27 +72,65 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int k, f
 
 __device__ __forceinline__ float lerpf(float p, float q, float a) { return fmaf(a, q - p, p); }
 
-// getNormalizedVoxel(volume, params, pos).x  -- trilinear, normalised coordinates.
+// getNormalizedVoxel(volume, params, pos).x  -- trilinear, normalised coordinates -- in two steps so that
+// the tracer can request the taps of its NEXT sample before it consumes the current one:
+// fetch_taps issues the loads (2 x tld4 or 8 x LDG) and keeps the blend weights, blend_taps does the
+// fp32 arithmetic of OpenCL 1.2 section 8.2 in the order the oracle follows.
+struct Taps {
+    float4 g0, g1;   // TEXTURE: tld4 results of layers k0, k1 (raw texel values); LINEAR: t000,t100,t010,t110 / t001,...
+    float a, b, c;
+};
+
+template <int FMT>
+__device__ __forceinline__ float4 gather_layer_raw(cudaTextureObject_t tex, int k, float cx, float cy) {
+    float4 r;
+    if (FMT == CPM_FMT_F32) {
+        asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "l"(tex), "r"(k), "f"(cx), "f"(cy));
+    } else {
+        unsigned a, b, c, d;
+        asm volatile("tld4.r.a2d.v4.u32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
+                     : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                     : "l"(tex), "r"(k), "f"(cx), "f"(cy));
+        r.x = __uint_as_float(a); r.y = __uint_as_float(b); r.z = __uint_as_float(c); r.w = __uint_as_float(d);
+    }
+    return r;
+}
+
+template <int FMT>
+__device__ __forceinline__ float raw_to_float(float raw) {
+    if (FMT == CPM_FMT_U8) return unorm8((float)__float_as_uint(raw));
+    if (FMT == CPM_FMT_U16) return unorm16((float)__float_as_uint(raw));
+    return raw;
+}
+
+template <int FMT>
+__device__ __forceinline__ float load_linear_raw(const void* base, size_t idx) {
+    if (FMT == CPM_FMT_U8) return __uint_as_float((unsigned)__ldg((const unsigned char*)base + idx));
+    if (FMT == CPM_FMT_U16) return __uint_as_float((unsigned)__ldg((const unsigned short*)base + idx));
+    return __ldg((const float*)base + idx);
+}
+
 template <int FMT, int LAYOUT>
-__device__ __forceinline__ float sample_volume(const VolumeView& V, float px, float py, float pz) {
+__device__ __forceinline__ Taps fetch_taps(const VolumeView& V, float px, float py, float pz) {
+    Taps T;
     float u = fmaf(px, V.fx, -0.5f);
     float v = fmaf(py, V.fy, -0.5f);
     float w = fmaf(pz, V.fz, -0.5f);
     float fu = floorf(u), fv = floorf(v), fw = floorf(w);
-    float a = u - fu, b = v - fv, c = w - fw;
+    T.a = u - fu; T.b = v - fv; T.c = w - fw;
     // NaN/inf safe conversion: clamp in float first (NaN -> -1)
     int i0 = (int)cpm_clamp(fu, -1.0f, V.fx - 1.0f);
     int j0 = (int)cpm_clamp(fv, -1.0f, V.fy - 1.0f);
     int k0 = (int)cpm_clamp(fw, -1.0f, V.fz - 1.0f);
     int k1 = min(k0 + 1, V.nz - 1);
     k0 = max(k0, 0);
-    float t000, t100, t010, t110, t001, t101, t011, t111;
     if (LAYOUT == CPM_VOLUME_TEXTURE) {
+        // (i0+1, j0+1) is the centre of the 2x2 footprint; PTX tld4 order: x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0)
         float cx = (float)(i0 + 1), cy = (float)(j0 + 1);
-        float4 g0 = gather_layer<FMT>(V.tex, k0, cx, cy);
-        float4 g1 = gather_layer<FMT>(V.tex, k1, cx, cy);
-        t000 = g0.w; t100 = g0.z; t010 = g0.x; t110 = g0.y;
-        t001 = g1.w; t101 = g1.z; t011 = g1.x; t111 = g1.y;
+        T.g0 = gather_layer_raw<FMT>(V.tex, k0, cx, cy);
+        T.g1 = gather_layer_raw<FMT>(V.tex, k1, cx, cy);
     } else {
         int i1 = min(i0 + 1, V.nx - 1);
         int j1 = min(j0 + 1, V.ny - 1);
@@ -101,16 +139,32 @@ __device__ __forceinline__ float sample_volume(const VolumeView& V, float px, fl
         size_t sy = (size_t)V.nx, sz = (size_t)V.nx * V.ny;
         size_t b00 = (size_t)k0 * sz + (size_t)j0 * sy, b10 = (size_t)k0 * sz + (size_t)j1 * sy;
         size_t b01 = (size_t)k1 * sz + (size_t)j0 * sy, b11 = (size_t)k1 * sz + (size_t)j1 * sy;
-        t000 = load_linear<FMT>(V.lin, b00 + i0); t100 = load_linear<FMT>(V.lin, b00 + i1);
-        t010 = load_linear<FMT>(V.lin, b10 + i0); t110 = load_linear<FMT>(V.lin, b10 + i1);
-        t001 = load_linear<FMT>(V.lin, b01 + i0); t101 = load_linear<FMT>(V.lin, b01 + i1);
-        t011 = load_linear<FMT>(V.lin, b11 + i0); t111 = load_linear<FMT>(V.lin, b11 + i1);
+        // same slots as the tld4 result: x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0)
+        T.g0.w = load_linear_raw<FMT>(V.lin, b00 + i0); T.g0.z = load_linear_raw<FMT>(V.lin, b00 + i1);
+        T.g0.x = load_linear_raw<FMT>(V.lin, b10 + i0); T.g0.y = load_linear_raw<FMT>(V.lin, b10 + i1);
+        T.g1.w = load_linear_raw<FMT>(V.lin, b01 + i0); T.g1.z = load_linear_raw<FMT>(V.lin, b01 + i1);
+        T.g1.x = load_linear_raw<FMT>(V.lin, b11 + i0); T.g1.y = load_linear_raw<FMT>(V.lin, b11 + i1);
     }
-    float x00 = lerpf(t000, t100, a), x10 = lerpf(t010, t110, a);
-    float x01 = lerpf(t001, t101, a), x11 = lerpf(t011, t111, a);
-    float y0 = lerpf(x00, x10, b), y1 = lerpf(x01, x11, b);
-    float val = lerpf(y0, y1, c);
+    return T;
+}
+
+template <int FMT>
+__device__ __forceinline__ float blend_taps(const VolumeView& V, const Taps& T) {
+    float t000 = raw_to_float<FMT>(T.g0.w), t100 = raw_to_float<FMT>(T.g0.z);
+    float t010 = raw_to_float<FMT>(T.g0.x), t110 = raw_to_float<FMT>(T.g0.y);
+    float t001 = raw_to_float<FMT>(T.g1.w), t101 = raw_to_float<FMT>(T.g1.z);
+    float t011 = raw_to_float<FMT>(T.g1.x), t111 = raw_to_float<FMT>(T.g1.y);
+    float x00 = lerpf(t000, t100, T.a), x10 = lerpf(t010, t110, T.a);
+    float x01 = lerpf(t001, t101, T.a), x11 = lerpf(t011, t111, T.a);
+    float y0 = lerpf(x00, x10, T.b), y1 = lerpf(x01, x11, T.b);
+    float val = lerpf(y0, y1, T.c);
     return (val + V.offset) * V.scale;
+}
+
+template <int FMT, int LAYOUT>
+__device__ __forceinline__ float sample_volume(const VolumeView& V, float px, float py, float pz) {
+    Taps T = fetch_taps<FMT, LAYOUT>(V, px, py, pz);
+    return blend_taps<FMT>(V, T);
 }
 
 // read_imagef(tf, smpNormClampEdgeLinear, (v, 0.5)).w on a width x 1 image: 1-D linear.

