@@ -308,11 +308,12 @@ def run_b200(a):
     cpm = importlib.import_module(PKG)
     host = importlib.import_module(PKG + ".host")
     synth = importlib.import_module(PKG + ".synth")
+    sharding = importlib.import_module(PKG + ".sharding")
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
     T, D, I = a.timesteps, a.dims, a.max_interactions
     n_photons = a.photons_side ** 2
-    host.runtime_init(local, stream.cuda_stream, rank * n_photons)
+    host.runtime_init(local, stream.cuda_stream, sharding.photon_shard(rank, world, n_photons)[0])
 
     # ---- the time series: generated on the device, staged in pinned host memory (the e2e source) ----
     pinned = []
@@ -344,12 +345,9 @@ def run_b200(a):
         torch.cuda.synchronize()
         wall = time.perf_counter() - w0
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
-        tr = torch.tensor([traced], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
-        return float(t[0]), float(t[1]), float(tr[0])
+        t = sharding.max_over_ranks([ms, wall * 1e3], device=dev)
+        tr = sharding.sum_over_ranks([traced], device=dev)
+        return t[0], t[1], tr[0]
 
     with torch.cuda.stream(stream):
         net = host.Network((D, D, D), cpm.CPM_FMT_F32, a.photons_side, [LIGHT_DIR], max_scattering_events=I,
@@ -360,12 +358,13 @@ def run_b200(a):
         lv_view = {}
 
         def allreduce_light_volume():
-            if world == 1:
-                return
+            """frame result = sum of the per-rank light volumes, out of place (the local one is updated
+            incrementally by the next frame); returns the tensor holding the result"""
             ptr, n = net.light_volume_device()
             if lv_view.get("ptr") != ptr:
                 lv_view["ptr"], lv_view["t"] = ptr, torch.as_tensor(DevTensorView(ptr, n), device=dev)
-            dist.all_reduce(lv_view["t"], op=dist.ReduceOp.SUM)
+                lv_view["sum"] = torch.empty_like(lv_view["t"]) if world > 1 else None
+            return sharding.allreduce_light_volume(lv_view["t"], lv_view["sum"])
 
         # ---------------- resident leg (value) ----------------
         net.set_sequence_host(pinned)          # uploads all T steps once, min-max + difference grids on the device
@@ -407,17 +406,24 @@ def run_b200(a):
             def step_e2e(t):
                 net.stream_timestep_host(pinned[t % T])
                 net.evaluate()
-                allreduce_light_volume()
-                net.read_light_volume(out_host)
+                if world > 1:
+                    out_host.copy_(allreduce_light_volume(), non_blocking=True)   # D2H of the summed volume
+                    stream.synchronize()
+                    d2h_extra[0] += out_host.numel() * 4
+                else:
+                    net.read_light_volume(out_host)
                 return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
 
+            d2h_extra = [0]
             first = 1 + a.warmup + a.steps
             for k in range(max(a.warmup, 2)):
                 step_e2e(first + k)
             first += max(a.warmup, 2)
             host.Network.transfer_bytes(reset=True)
+            d2h_extra[0] = 0
             ms_e, wall_e, traced_e = time_loop(net, a.steps, first, step_e2e)
             h2d, d2h = host.Network.transfer_bytes()
+            d2h += d2h_extra[0]
             e2e = {"value": traced_e / (wall_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                    "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": wall_e / a.steps,
                    "frames_per_sec": a.steps / (wall_e * 1e-3),

@@ -42,6 +42,7 @@ def lib():
         _lib.cpmh_network_destroy.argtypes = [C.c_void_p]
         _lib.cpmh_network_destroy.restype = None
         _lib.cpmh_runtime_init.argtypes = [C.c_int, C.c_void_p, C.c_uint64]
+        _lib.cpmh_runtime_set_photon_shard_offset.argtypes = [C.c_uint64]
         _lib.cpmh_network_stream_timestep_host.argtypes = [C.c_void_p, C.c_void_p]
         _lib.cpmh_network_sync.argtypes = [C.c_void_p]
         _lib.cpmh_network_light_volume_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -61,6 +62,13 @@ def lib():
 def runtime_init(device=0, stream=None, photon_shard_offset=0):
     """one context per process; stream = cudaStream_t handle (int) or None; see cpmh_runtime_init"""
     rc = lib().cpmh_runtime_init(int(device), C.c_void_p(stream or 0), C.c_uint64(photon_shard_offset))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+
+
+def set_photon_shard_offset(offset: int):
+    """first global photon id of this process (used by the next RNG seeding); see cpmh_runtime_init"""
+    rc = lib().cpmh_runtime_set_photon_shard_offset(C.c_uint64(offset))
     if rc < 0:
         raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
 

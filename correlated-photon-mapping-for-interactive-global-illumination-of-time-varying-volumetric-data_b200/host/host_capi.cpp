@@ -61,6 +61,13 @@ int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset) {
     });
 }
 
+int cpmh_runtime_set_photon_shard_offset(uint64_t photon_shard_offset) {
+    return guarded([&]() {
+        CpmRuntime::get().photonShardOffset = photon_shard_offset;
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
     return guarded([&]() {
         if (!cfg || !out) throw std::invalid_argument("null argument");

@@ -41,6 +41,7 @@ typedef struct cpmh_config {
  * stream (a cudaStream_t, NULL = own stream) and this process's photon shard: photon i of this process
  * is photon photon_shard_offset + i of the global photon set (MWC64X stream and host base offset). */
 CPMH_API int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset);
+CPMH_API int cpmh_runtime_set_photon_shard_offset(uint64_t photon_shard_offset);
 CPMH_API int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out);
 CPMH_API void cpmh_network_destroy(cpmh_network* net);
 CPMH_API const char* cpmh_last_error(void);

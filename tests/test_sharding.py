@@ -1,0 +1,115 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo processes for the exchange helpers,
+host-only checks of the per-shard RNG base offsets, and (GPU) shards == one large photon set."""
+import ctypes as C
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG_NAME
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = importlib.import_module(PKG_NAME + ".sharding")
+    local = torch.full((1000,), float(rank + 1))
+    keep = local.clone()
+    out = sh.allreduce_light_volume(local)
+    ok = bool(torch.equal(local, keep)) and bool((out == sum(range(1, world + 1))).all()) and out.data_ptr() != local.data_ptr()
+    # a second frame re-uses the caller's buffer and must not accumulate the previous global sum
+    out2 = sh.allreduce_light_volume(local, out)
+    ok = ok and out2.data_ptr() == out.data_ptr() and bool((out2 == sum(range(1, world + 1))).all())
+    mx = sh.max_over_ranks([float(rank), 5.0 - rank])
+    sm = sh.sum_over_ranks([float(rank + 1)])
+    first, count = sh.photon_shard(rank, world, 4096)
+    q.put((rank, ok, mx, sm, first, count))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_helpers():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, mx, sm, first, count in res:
+        assert ok
+        assert mx == [1.0, 5.0] and sm == [3.0]
+        assert (first, count) == (rank * 4096, 4096)
+
+
+def test_shard_ranges_cover_the_photon_set():
+    sh = importlib.import_module(PKG_NAME + ".sharding")
+    for total, world in ((10, 3), (4194304, 8), (7, 8), (1, 1)):
+        spans = [sh.strong_shard(r, world, total) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+            assert f0 + c0 == f1
+    with pytest.raises(ValueError):
+        sh.photon_shard(2, 2, 10)
+
+
+def test_host_base_offsets_of_a_shard_are_a_slice_of_the_whole(cpm):
+    """cpm_rng_host_base_offsets_range(first, n) == cpm_rng_host_base_offsets(first + n)[first:]"""
+    whole = cpm.capi.rng_host_base_offsets(0, 5000)
+    for first, n in ((0, 5000), (1234, 1000), (4999, 1)):
+        out = np.zeros((n, 2), np.uint32)
+        rc = cpm.lib().cpm_rng_host_base_offsets_range(C.c_uint32(0), C.c_uint64(first), out.ctypes.data_as(C.c_void_p),
+                                                       C.c_size_t(n))
+        assert rc == 0 and np.array_equal(out, whole[first:first + n])
+
+
+@pytest.mark.gpu
+def test_photon_shards_equal_one_large_photon_set(cpm, orc, synth, torch_cuda):
+    """Two ranks with one light each == one GPU with the same light twice (2N photons): the photon records of
+    shard r are bit-identical to photons [rN, (r+1)N) of the large set, and the per-shard light volumes
+    (each normalised by its own N) sum to twice the large set's (normalised by 2N)."""
+    host = importlib.import_module(PKG_NAME + ".host")
+    dims, ns, I = (48, 48, 48), 64, 2
+    n = ns * ns
+    d = (0.3, -0.5, 0.8)
+    vol = synth.volume_u8(dims, 8)
+
+    def run(lights, shard_offset):
+        host.set_photon_shard_offset(shard_offset)
+        net = host.Network(dims, cpm.CPM_FMT_U8, ns, lights, max_scattering_events=I, light_volume_option=2,
+                           reference_full_splat_bound=False)
+        net.set_transfer_function(synth.WS_TF_POINTS)
+        net.set_volume_host(vol)
+        net.evaluate()
+        ph, lv = net.read_photons(I).copy(), net.read_light_volume().astype(np.float64)
+        net.close()
+        return ph, lv
+
+    try:
+        big_ph, big_lv = run([d, d], 0)
+        big = big_ph.reshape(I, 2 * n, 8)
+        lv_sum = np.zeros_like(big_lv)
+        for r in range(2):
+            ph, lv = run([d], r * n)
+            assert np.array_equal(ph.reshape(I, n, 8).view(np.uint32), big[:, r * n:(r + 1) * n].view(np.uint32)), r
+            lv_sum += lv
+    finally:
+        host.set_photon_shard_offset(0)
+    rel = np.sqrt(((lv_sum - 2.0 * big_lv) ** 2).mean()) / np.sqrt(((2.0 * big_lv) ** 2).mean())
+    assert rel < 1e-5, rel
