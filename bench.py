@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="budget of the whole --impl reference run")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
     return ap.parse_args()
 
 
@@ -293,6 +295,45 @@ class DevTensorView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
 
+def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
+    """gathered frames/s: photon-map build (cell keys, onesweep sort, cell ranges, reorder) + view ray march of
+    the network's current photon records; CUDA events on the launch stream, median of `reps`"""
+    ctx = cpm.Context(dev.index, stream.cuda_stream)
+    D, I, n = a.dims, a.max_interactions, a.photons_side ** 2
+    ptr, nf = net.photons_device()
+    photons = torch.as_tensor(DevTensorView(ptr, nf), device=dev)
+    dvol = vol_host.to(dev, non_blocking=True)
+    V = ctx.volume_create(dvol, (D, D, D), cpm.CPM_FMT_F32, layout=cpm.CPM_VOLUME_TEXTURE)
+    synth = importlib.import_module(PKG + ".synth")
+    tf = torch.from_numpy(synth.rasterise_tf(width=1024)).to(dev)
+    radius = float(np.float32(np.sqrt(3.0) / D))                       # the tracer's 1-voxel photon radius
+    g = int(min(512, max(1, int(1.0 / (2.0 * radius)))))                # cell edge >= 2 r: at most 8 cells per gather
+    scale = float((1.0 / np.pi) / (4.0 / 3.0 * np.pi * radius ** 3 * n))
+    P = cpm.capi.make_gather_params(a.view, a.view, (1.7, 1.4, -1.3), (0.5, 0.5, 0.5), fov_deg=40.0, step=0.5 / D,
+                                    radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g))
+    img = torch.empty(a.view * a.view * 4, dtype=torch.float32, device=dev)
+    build_ms, march_ms = [], []
+    for it in range(reps + 1):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream)
+        sp, start, end, _ = ctx.build_photon_map(photons, n * I, (g, g, g), torch)
+        e[1].record(stream)
+        ctx.gather_raymarch(V, tf, P, sp, start, end, img)
+        e[2].record(stream)
+        e[2].synchronize()
+        if it:
+            build_ms.append(e[0].elapsed_time(e[1])); march_ms.append(e[1].elapsed_time(e[2]))
+    cover = float((img.view(-1, 4)[:, 3] > 0).float().mean().item())
+    lit = float((img.view(-1, 4)[:, :3].sum(dim=1) > 0).float().mean().item())
+    V.destroy()
+    ctx.close()
+    b, m = float(np.median(build_ms)), float(np.median(march_ms))
+    return {"frames_per_sec": 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m, "view": f"{a.view}x{a.view}",
+            "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
+            "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
+                    f"{n * I} photon records; march = step 0.5 voxel, Epanechnikov gather r = 1 voxel"}
+
+
 def run_b200(a):
     import ctypes as C
 
@@ -399,6 +440,11 @@ def run_b200(a):
 
         # ---------------- e2e leg: host volume in, light volume out, every step ----------------
         e2e = None
+        # ---------------- gathered frames: photon-map build + view ray march (north-star 5-7) ----------------
+        gather = None
+        if rank == 0 and not a.no_gather:
+            # the resident leg ended on time step warmup + steps: its photons and its volume
+            gather = gather_leg(a, cpm, torch, stream, net, pinned[(a.warmup + a.steps) % T], dev)
         if not a.no_e2e:
             lvd = net.light_volume_dims
             out_host = torch.empty(lvd[0] * lvd[1] * lvd[2], dtype=torch.float32, pin_memory=True)
@@ -477,7 +523,7 @@ def run_b200(a):
             "collision_tests_per_sec": float(tests_t[0]) / (ms * 1e-3),
             "wall_ms_per_step": wall_ms / a.steps,
             "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(stages.items())},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -327,3 +327,81 @@ Context.classify_importance = _classify_importance
 Context.hash_light_samples = _hash_light_samples
 Context.build_cell_ranges = _build_cell_ranges
 Context.splat_photons = _splat_photons
+
+
+# -- photon map for gathering --------------------------------------------------------------------------
+class GatherParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cam_origin", C.c_float * 3), ("cam_dir00", C.c_float * 3),
+                ("cam_du", C.c_float * 3), ("cam_dv", C.c_float * 3), ("aabb_min", C.c_float * 3),
+                ("aabb_max", C.c_float * 3), ("step", C.c_float), ("radius", C.c_float), ("scale", C.c_float),
+                ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3)]
+
+
+def make_gather_params(width, height, eye, look_at, up=(0, 1, 0), fov_deg=60.0, step=1.0 / 256, radius=1.0 / 64,
+                       scale=1.0, sigma_scale=150.0, grid_dims=(32, 32, 32), aabb_min=(0, 0, 0), aabb_max=(1, 1, 1),
+                       cls=None):
+    """pinhole camera in texture space -> the (dir00, du, dv) ray basis of cpm_gather_params"""
+    import numpy as np
+    eye, look_at, up = (np.asarray(v, np.float64) for v in (eye, look_at, up))
+    f = look_at - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, up)
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    h = np.tan(np.radians(fov_deg) / 2.0)
+    w = h * width / height
+    du = 2.0 * w * r / width
+    dv = -2.0 * h * u / height
+    dir00 = f - w * r + h * u
+    p = (cls or GatherParams)()
+    p.width, p.height = int(width), int(height)
+    for name, v in (("cam_origin", eye), ("cam_dir00", dir00), ("cam_du", du), ("cam_dv", dv), ("aabb_min", aabb_min),
+                    ("aabb_max", aabb_max)):
+        getattr(p, name)[:] = [float(np.float32(x)) for x in v]
+    p.step, p.radius, p.scale, p.sigma_scale = float(step), float(radius), float(scale), float(sigma_scale)
+    p.grid_dims[:] = [int(g) for g in grid_dims]
+    return p
+
+
+def _photon_cell_keys(self, photons, n_records, grid_dims, keys, ids=None):
+    self._check(lib().cpm_photon_cell_keys(self.h, _p(photons), C.c_size_t(n_records), _i3(grid_dims), _p(keys), _p(ids)))
+
+
+def _reorder_photons(self, photons, ids, n, out):
+    self._check(lib().cpm_reorder_photons(self.h, _p(photons), _p(ids), C.c_size_t(n), _p(out)))
+
+
+def _gather_raymarch(self, vol, tf_rgba, params, sorted_photons, cell_start, cell_end, image):
+    self._check(lib().cpm_gather_raymarch(self.h, vol.handle, _p(tf_rgba), int(tf_rgba.numel() // 4), C.byref(params),
+                                          _p(sorted_photons), _p(cell_start), _p(cell_end), _p(image)))
+
+
+def _gather_points(self, params, sorted_photons, cell_start, cell_end, points, n_points, out):
+    self._check(lib().cpm_gather_points(self.h, C.byref(params), _p(sorted_photons), _p(cell_start), _p(cell_end),
+                                        _p(points), int(n_points), _p(out)))
+
+
+def _build_photon_map(self, photons, n_records, grid_dims, torch):
+    """cell keys -> radix sort (keys, ids) -> cell ranges -> records in cell order.
+    Returns (sorted_photons, cell_start, cell_end, n_stored)."""
+    dev = photons.device
+    n_cells = int(grid_dims[0]) * int(grid_dims[1]) * int(grid_dims[2])
+    keys = torch.empty(n_records, dtype=torch.int32, device=dev)
+    ids = torch.empty_like(keys)
+    self.photon_cell_keys(photons, n_records, grid_dims, keys, ids)
+    tk, tv = torch.empty_like(keys), torch.empty_like(ids)
+    bits = max(1, int(n_cells).bit_length())     # keys <= n_cells
+    self.radix_sort(keys, ids, tk, tv, max_bits=bits)
+    start = torch.zeros(n_cells, dtype=torch.int32, device=dev)
+    end = torch.zeros(n_cells, dtype=torch.int32, device=dev)
+    self.build_cell_ranges(keys, n_records, n_cells, start, end)
+    out = torch.empty_like(photons)
+    self.reorder_photons(photons, ids, n_records, out)
+    return out, start, end, keys
+
+
+Context.photon_cell_keys = _photon_cell_keys
+Context.reorder_photons = _reorder_photons
+Context.gather_raymarch = _gather_raymarch
+Context.gather_points = _gather_points
+Context.build_photon_map = _build_photon_map

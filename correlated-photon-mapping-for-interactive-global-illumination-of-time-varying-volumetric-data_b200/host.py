@@ -46,6 +46,7 @@ def lib():
         _lib.cpmh_network_stream_timestep_host.argtypes = [C.c_void_p, C.c_void_p]
         _lib.cpmh_network_sync.argtypes = [C.c_void_p]
         _lib.cpmh_network_light_volume_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        _lib.cpmh_network_photons_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _lib.cpmh_network_count_collision_tests.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_read_collision_tests.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_read_collision_tests.restype = C.c_ulonglong
@@ -187,6 +188,12 @@ class Network:
         """(device pointer, number of floats) of the light volume"""
         p, n = C.c_void_p(), C.c_size_t()
         self._check(lib().cpmh_network_light_volume_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def photons_device(self):
+        """(device pointer, number of floats) of the photon records"""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(lib().cpmh_network_photons_device(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def count_collision_tests(self, on=True):

@@ -253,6 +253,16 @@ int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_fl
     });
 }
 
+int cpmh_network_photons_device(cpmh_network* net, void** ptr, size_t* n_floats) {
+    return guarded([&]() {
+        auto p = std::const_pointer_cast<PhotonData>(net->tracer.outport_.getData());
+        if (!p || !ptr) throw std::invalid_argument("no photons yet");
+        *ptr = const_cast<void*>(p->photons_.deviceRead());
+        if (n_floats) *n_floats = p->photons_.getSizeInBytes() / sizeof(float);
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_count_collision_tests(cpmh_network* net, int on) {
     return guarded([&]() {
         auto& rt = CpmRuntime::get();

@@ -63,6 +63,9 @@ CPMH_API int cpmh_network_sync(cpmh_network* net);
 /* device pointer of the light volume (float[dims] or float4[dims]) for zero-copy consumers, e.g. an
  * NCCL all-reduce across the GPUs that each splatted their photon shard */
 CPMH_API int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_floats);
+/* device pointer of the photon records (float8 x N x maxScatteringEvents) for zero-copy consumers (the
+ * photon-map gather) */
+CPMH_API int cpmh_network_photons_device(cpmh_network* net, void** ptr, size_t* n_floats);
 /* count delta-tracking collision tests of every trace from now on (device counter); read = sync */
 CPMH_API int cpmh_network_count_collision_tests(cpmh_network* net, int on);
 CPMH_API unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset);

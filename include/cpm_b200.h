@@ -281,6 +281,49 @@ CPM_API int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels,
                               int n, int photons_per_interaction, int n_interactions, float radius,
                               float relative_irradiance_scale, float multiplier);
 
+/* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
+/* Not launched anywhere in the reference; the estimator is the reference's
+ * (Epanechnikov kernel, ppm/cl/densityestimationkernel.cl:56-60; power * 1/(4 pi) * relativeIrradianceScale,
+ * ppm/cl/photonstolightvolume.cl:160-165), the per-point formulation is the one of its disabled
+ * photonsToLightVolumeKernel (ppm/cl/photonstolightvolume.cl:81-134).  Parity: the oracle's restatement.
+ *
+ * Photon map build: cpm_photon_cell_keys -> cpm_radix_sort_u32(keys, ids) -> cpm_build_cell_ranges ->
+ * cpm_reorder_photons; then cpm_gather_raymarch / cpm_gather_points. */
+
+/* keys[i] = cell of photon record i in a grid of grid_dims cells over texture space [0,1]^3
+ * (x + gx*(y + gy*z)); empty records (FLT_MAX sentinel) get n_cells.  ids (optional) = iota. */
+CPM_API int cpm_photon_cell_keys(cpm_ctx* ctx, const float* photons, size_t n_records, const int grid_dims[3],
+                                 uint32_t* keys, uint32_t* ids);
+/* out[j] = photons[ids[j]] (32 B records), j < n */
+CPM_API int cpm_reorder_photons(cpm_ctx* ctx, const float* photons, const uint32_t* ids, size_t n, float* out);
+
+typedef struct cpm_gather_params {
+    int32_t width, height;
+    float cam_origin[3];  /* texture space */
+    float cam_dir00[3];   /* ray through pixel (x, y) = normalize(dir00 + (x+0.5) du + (y+0.5) dv) */
+    float cam_du[3];
+    float cam_dv[3];
+    float aabb_min[3];    /* clip box, texture space */
+    float aabb_max[3];
+    float step;           /* ray-march step, texture units */
+    float radius;         /* gather radius, texture units */
+    float scale;          /* relative irradiance scale, as cpm_splat_photons */
+    float sigma_scale;    /* extinction per unit opacity and unit length: 150 matches the tracer
+                             (invTauMaxSampleBaseInterval = 1/(tauMax*150), ppm/cl/transmittance.cl:40,130) */
+    int32_t grid_dims[3];
+} cpm_gather_params;
+
+/* image[y*width + x] = (radiance rgb, 1 - transmittance): front-to-back emission-absorption ray march,
+ * the in-scattered radiance at every sample = TF colour * gathered irradiance (isotropic phase). */
+CPM_API int cpm_gather_raymarch(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgba, int tf_width,
+                                const cpm_gather_params* params, const float* sorted_photons,
+                                const uint32_t* cell_start, const uint32_t* cell_end, float* image /* float4[w*h] */);
+/* irradiance[3*i..] at points[3*i..] (only radius, scale and grid_dims of params are used): at a light-volume
+ * voxel centre this equals what cpm_splat_photons accumulates there. */
+CPM_API int cpm_gather_points(cpm_ctx* ctx, const cpm_gather_params* params, const float* sorted_photons,
+                              const uint32_t* cell_start, const uint32_t* cell_end, const float* points,
+                              int n_points, float* irradiance);
+
 /* ---- device memory (cl::Buffer, enqueueWrite/Read/Copy/FillBuffer) -------------------- */
 /* Lets host code above this ABI (host/: the Inviwo processor mirror) stay free of CUDA headers.
  * Copies and fills are asynchronous on the context stream; use cpm_ctx_sync before reading a

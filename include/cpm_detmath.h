@@ -113,6 +113,27 @@ CPM_HD float cpm_logf(float x) {
     return fmaf(fe, 0.693359375f, r);
 }
 
+/* exp(x) for x in [-87, 0] (the path uses it for the transmittance of one ray-march step).
+ * k = rint(x log2 e), r = x - k ln2 (two fma steps with the 16-bit-exact LN2_HI), degree-6 Taylor kernel
+ * on |r| <= 0.347 (next term r^7/5040 < 1.2e-7 relative), scaled by 2^k through the exponent field.
+ * x < -87 returns 0, x > 0 is clamped to 0 (returns 1). */
+CPM_HD float cpm_expf(float x) {
+    if (!(x < 0.0f)) return 1.0f;
+    if (x < -87.0f) return 0.0f;
+    float kf = rintf(x * 1.44269502162933349609f);
+    float r = fmaf(-kf, CPM_LN2_HI, x);
+    r = fmaf(-kf, CPM_LN2_LO, r);
+    float p = 1.3888889225e-3f;                 /* 1/720 */
+    p = fmaf(p, r, 8.3333337680e-3f);           /* 1/120 */
+    p = fmaf(p, r, 4.1666667908e-2f);           /* 1/24  */
+    p = fmaf(p, r, 1.6666667163e-1f);           /* 1/6   */
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    int k = (int)kf;                            /* -126 <= k <= 0 */
+    return p * cpm_u2f((uint32_t)(k + 127) << 23);
+}
+
 /* sin and cos for |x| <= ~16 (path uses [-pi, 2pi]).  Cody-Waite reduction with two fma
  * steps, Taylor kernels on [-pi/4, pi/4] (next omitted term < 2.3e-9 relative). */
 CPM_HD void cpm_sincosf(float x, float* sn, float* cs) {

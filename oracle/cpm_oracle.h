@@ -103,6 +103,20 @@ void orc_splat(double* vol, int channels, const float tex2idx[16], const float i
                const float* photons, const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
                float radius, float relative_irradiance_scale, float multiplier);
 
+/* --- photon-map gather (orc_gather.c): parity unpinned, own restatement ------------------------ */
+typedef struct orc_gather_params {
+    int32_t width, height;
+    float cam_origin[3], cam_dir00[3], cam_du[3], cam_dv[3];
+    float aabb_min[3], aabb_max[3];
+    float step, radius, scale, sigma_scale;
+    int32_t grid_dims[3];
+} orc_gather_params;
+void orc_photon_cell_keys(const float* photons, size_t n, const int grid_dims[3], uint32_t* keys);
+void orc_gather_points(const orc_gather_params* P, const float* photons, size_t n_records, const float* points,
+                       int n_points, float* irradiance);
+void orc_gather_raymarch(const orc_volume* vol, const float* tf_rgba, int tf_width, const orc_gather_params* P,
+                         const float* photons, size_t n_records, float* image);
+
 void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_t n);
 int orc_num_threads(void);
 

@@ -234,3 +234,34 @@ def splat(vol64, channels, tex2idx, idx2tex, out_dims, photons, indices, n, per_
     lib().orc_splat(_ptr(vol64), int(channels), _fN(tex2idx, 16), _fN(idx2tex, 16), _i3(out_dims), _ptr(photons),
                     _ptr(indices), int(n), int(per_interaction), int(n_interactions), C.c_float(radius), C.c_float(scale),
                     C.c_float(multiplier))
+
+
+# -- photon-map gather (parity unpinned: own restatement) ----------------------------------------------
+class GatherParams(C.Structure):
+    """layout shared by cpm_gather_params (include/cpm_b200.h) and orc_gather_params"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cam_origin", C.c_float * 3), ("cam_dir00", C.c_float * 3),
+                ("cam_du", C.c_float * 3), ("cam_dv", C.c_float * 3), ("aabb_min", C.c_float * 3),
+                ("aabb_max", C.c_float * 3), ("step", C.c_float), ("radius", C.c_float), ("scale", C.c_float),
+                ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3)]
+
+
+def photon_cell_keys(photons, grid_dims):
+    n = photons.shape[0]
+    keys = np.empty(n, np.uint32)
+    lib().orc_photon_cell_keys(_ptr(photons), C.c_size_t(n), _i3(grid_dims), _ptr(keys))
+    return keys
+
+
+def gather_points(params, photons, points):
+    pts = np.ascontiguousarray(points, np.float32)
+    out = np.empty_like(pts)
+    lib().orc_gather_points(C.byref(params), _ptr(photons), C.c_size_t(photons.shape[0]), _ptr(pts), int(pts.shape[0]),
+                            _ptr(out))
+    return out
+
+
+def gather_raymarch(vol, tf_rgba, params, photons):
+    img = np.empty((params.height, params.width, 4), np.float32)
+    lib().orc_gather_raymarch(C.byref(vol), _ptr(tf_rgba), int(tf_rgba.shape[0]), C.byref(params), _ptr(photons),
+                              C.c_size_t(photons.shape[0]), _ptr(img))
+    return img
