@@ -13,7 +13,7 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 ROOT = _HERE.parent
-LIB_PATH = _HERE / "libcpm_b200.so"
+LIB_PATH = Path(os.environ.get("CPM_B200_LIB", _HERE / "libcpm_b200.so"))   # override: tuning sweeps only
 HEADER = ROOT / "include" / "cpm_b200.h"
 
 CPM_FMT_U8, CPM_FMT_U16, CPM_FMT_F32 = 0, 1, 2

@@ -21,6 +21,12 @@ struct cpm_ctx {
     // pinned host word for synchronous scalar read-backs
     uint32_t* pinned = nullptr;
     void* comm = nullptr;  // ncclComm_t when multi-GPU is initialised
+    cudaStream_t xfer_stream = nullptr;  // transfer stream of cpm_mem_prefetch_h2d (lazy)
+    cudaEvent_t xfer_fence = nullptr;
+};
+
+struct cpm_event {
+    cudaEvent_t ev;
 };
 
 struct cpm_volume {

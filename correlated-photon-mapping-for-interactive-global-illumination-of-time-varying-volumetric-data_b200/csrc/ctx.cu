@@ -94,6 +94,11 @@ void cpm_ctx_destroy(cpm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->xfer_stream) {
+        cudaStreamSynchronize(ctx->xfer_stream);
+        cudaStreamDestroy(ctx->xfer_stream);
+    }
+    if (ctx->xfer_fence) cudaEventDestroy(ctx->xfer_fence);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -116,10 +121,6 @@ uint64_t cpm_ctx_launch_count(cpm_ctx* ctx, int reset) {
 }
 
 // ---- events ----------------------------------------------------------------------------
-struct cpm_event {
-    cudaEvent_t ev;
-};
-
 int cpm_event_create(cpm_ctx* ctx, cpm_event** out) {
     if (!ctx) return CPM_E_INVALID;
     CPM_REQUIRE(ctx, out, "null argument");

@@ -55,6 +55,35 @@ int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes
     return CPM_OK;
 }
 
+int cpm_mem_prefetch_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes, cpm_event** done) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, dst && src_host && done && bytes > 0, "null argument");
+    if (!ctx->xfer_stream) {
+        CPM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->xfer_stream, cudaStreamNonBlocking));
+        CPM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->xfer_fence, cudaEventDisableTiming));
+    }
+    // earlier readers / writers of dst on the context stream finish first
+    CPM_CUDA(ctx, cudaEventRecord(ctx->xfer_fence, ctx->stream));
+    CPM_CUDA(ctx, cudaStreamWaitEvent(ctx->xfer_stream, ctx->xfer_fence, 0));
+    CPM_CUDA(ctx, cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, ctx->xfer_stream));
+    cpm_event* e = new cpm_event();
+    cudaError_t rc = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+    if (rc != cudaSuccess) {
+        delete e;
+        return cpm_fail(ctx, CPM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(rc));
+    }
+    CPM_CUDA(ctx, cudaEventRecord(e->ev, ctx->xfer_stream));
+    *done = e;
+    return CPM_OK;
+}
+
+int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, ev != nullptr, "null argument");
+    CPM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
+    return CPM_OK;
+}
+
 int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return CPM_E_INVALID;
     if (bytes == 0) return CPM_OK;

@@ -31,12 +31,28 @@ namespace {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 512;
+constexpr int RADIX_THREADS_MIN = RADIX;
+// tuning knobs (tools/sort_variants.sh sweeps them; the defaults are the round-1 winners on B200)
+#ifndef CPM_SORT_THREADS
+#define CPM_SORT_THREADS 512
+#endif
+#ifndef CPM_SORT_ITEMS
+#define CPM_SORT_ITEMS 16
+#endif
+#ifndef CPM_SORT_MIN_BLOCKS
+#define CPM_SORT_MIN_BLOCKS 2
+#endif
+#ifndef CPM_SORT_LOOKBACK
+#define CPM_SORT_LOOKBACK 4
+#endif
+constexpr int SORT_THREADS = CPM_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
+constexpr int SORT_ITEMS = CPM_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 constexpr int MAX_PASSES = 4;
-constexpr int LOOKBACK_WINDOW = 4;
+constexpr int LOOKBACK_WINDOW = CPM_SORT_LOOKBACK;
+static_assert(SORT_THREADS >= RADIX_THREADS_MIN && SORT_THREADS % 32 == 0, "one thread per digit is needed");
+static_assert((SORT_WARPS * 256) % SORT_THREADS == 0, "counter clear loop");
 
 constexpr uint32_t FLAG_AGGREGATE = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
@@ -129,7 +145,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 }
 
 template <bool HAS_VALUES>
-__global__ void __launch_bounds__(SORT_THREADS, 2) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, CPM_SORT_MIN_BLOCKS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
                                                                    const uint32_t* __restrict__ vals_in,
                                                                    uint32_t* __restrict__ keys_out,
                                                                    uint32_t* __restrict__ vals_out, size_t n, int shift,

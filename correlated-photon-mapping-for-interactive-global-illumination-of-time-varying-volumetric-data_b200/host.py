@@ -45,6 +45,7 @@ def lib():
         _lib.cpmh_runtime_set_photon_shard_offset.argtypes = [C.c_uint64]
         _lib.cpmh_network_stream_timestep_host.argtypes = [C.c_void_p, C.c_void_p]
         _lib.cpmh_network_sync.argtypes = [C.c_void_p]
+        _lib.cpmh_network_prefetch_timestep_host.argtypes = [C.c_void_p, C.c_void_p]
         _lib.cpmh_network_light_volume_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _lib.cpmh_network_photons_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         _lib.cpmh_network_count_collision_tests.argtypes = [C.c_void_p, C.c_int]
@@ -180,6 +181,12 @@ class Network:
         ptr = array.data_ptr() if hasattr(array, "data_ptr") else array.ctypes.data
         self._stream_keep = array
         self._check(lib().cpmh_network_stream_timestep_host(self.h, C.c_void_p(ptr)))
+
+    def prefetch_timestep_host(self, array):
+        """announce the next stream_timestep_host buffer: its upload overlaps the current evaluation"""
+        ptr = array.data_ptr() if hasattr(array, "data_ptr") else array.ctypes.data
+        self._prefetch_keep = array
+        self._check(lib().cpmh_network_prefetch_timestep_host(self.h, C.c_void_p(ptr)))
 
     def sync(self):
         self._check(lib().cpmh_network_sync(self.h))

@@ -28,10 +28,10 @@ struct cpmh_network {
     std::vector<std::shared_ptr<UniformGrid3DBase>> seqMinMax, seqDiff;
     DataOutport<UniformGrid3DBase> minMaxSelector{"selectedMinMax"}, diffSelector{"selectedDiff"};
     bool useSequence = false;
-    // streaming time steps (cpmh_network_stream_timestep_host): two volumes / min-max grids in ping-pong
-    std::shared_ptr<Volume> streamVol[2];
-    std::shared_ptr<MinMaxUniformGrid3D> streamMinMax[2];
-    std::shared_ptr<DynamicVolumeInfoUniformGrid3D> streamDiff[2];
+    // streaming time steps (cpmh_network_stream_timestep_host): previous / current / incoming volumes rotate
+    std::shared_ptr<Volume> streamVol[3];
+    std::shared_ptr<MinMaxUniformGrid3D> streamMinMax[3];
+    std::shared_ptr<DynamicVolumeInfoUniformGrid3D> streamDiff[3];
     int streamSlot = -1;
     unsigned long long* collisionCounter = nullptr;
 };
@@ -205,7 +205,7 @@ int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
         auto& rt = CpmRuntime::get();
         DataFormatId fid = c.format == CPM_FMT_U8 ? DataFormatId::UInt8 : (c.format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
         const int prev = net->streamSlot;
-        const int cur = prev < 0 ? 0 : 1 - prev;
+        const int cur = prev < 0 ? 0 : (prev + 1) % 3;
         if (!net->streamVol[cur]) net->streamVol[cur] = std::make_shared<Volume>(size3_t(c.dims[0], c.dims[1], c.dims[2]), DataFormatBase::get(fid));
         Volume* v = net->streamVol[cur].get();
         v->setExternalRAMData(const_cast<void*>(voxels));
@@ -230,6 +230,18 @@ int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
         net->useSequence = true;
         net->streamSlot = cur;
         net->volumeSource.setData(net->streamVol[cur]);
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_prefetch_timestep_host(cpmh_network* net, const void* voxels) {
+    return guarded([&]() {
+        if (!voxels) throw std::invalid_argument("null voxel buffer");
+        const cpmh_config& c = net->cfg;
+        DataFormatId fid = c.format == CPM_FMT_U8 ? DataFormatId::UInt8 : (c.format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
+        const int nxt = net->streamSlot < 0 ? 0 : (net->streamSlot + 1) % 3;   // the slot the next stream call will use
+        if (!net->streamVol[nxt]) net->streamVol[nxt] = std::make_shared<Volume>(size3_t(c.dims[0], c.dims[1], c.dims[2]), DataFormatBase::get(fid));
+        net->streamVol[nxt]->prefetchExternalRAMData(const_cast<void*>(voxels));
         return (int)CPM_OK;
     });
 }

@@ -59,6 +59,10 @@ CPMH_API int cpmh_network_set_timestep(cpmh_network* net, int t);
  * streamed step on the device, and mark volume / grids changed.  The buffer must stay valid until the
  * next evaluate has been synchronised (cpmh_network_read_* or cpmh_network_sync). */
 CPMH_API int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels_host);
+/* Optional: announce the buffer of the NEXT cpmh_network_stream_timestep_host call.  Its upload starts at once
+ * on a transfer stream and overlaps the evaluation of the current step (three device volumes rotate: previous,
+ * current, incoming).  The buffer must be pinned and stay untouched until that step has been evaluated. */
+CPMH_API int cpmh_network_prefetch_timestep_host(cpmh_network* net, const void* voxels_host);
 CPMH_API int cpmh_network_sync(cpmh_network* net);
 /* device pointer of the light volume (float[dims] or float4[dims]) for zero-copy consumers, e.g. an
  * NCCL all-reduce across the GPUs that each splatted their photon shard */

@@ -248,6 +248,9 @@ public:
     const void* getRAMData();            // downloads when the device copy is newer
     // point the RAM representation at caller-owned (e.g. pinned) memory; marks the device copy stale
     void setExternalRAMData(void* ptr);
+    // start uploading caller-owned pinned memory on the transfer stream; a later setExternalRAMData(ptr) with
+    // the same pointer adopts the upload instead of copying again
+    void prefetchExternalRAMData(void* ptr);
     size_t getSizeInBytes() const { return dim_.x * dim_.y * dim_.z * format_->size; }
     // VolumeCL: linear device buffer (+ the cpm_volume handle the kernels take)
     const void* deviceRead();
@@ -266,6 +269,8 @@ private:
     cpm_volume* lin_ = nullptr;
     cpm_volume* tex_ = nullptr;
     bool texValid_ = false;
+    void* prefetched_ = nullptr;
+    cpm_event* prefetchDone_ = nullptr;
 };
 using VolumeSequence = std::vector<std::shared_ptr<Volume>>;
 

@@ -181,6 +181,7 @@ Volume::Volume(size3_t dim, const DataFormatBase* format) : dim_(dim), format_(f
 }
 Volume::~Volume() {
     cpm_ctx* c = g_runtime.ctx();
+    if (prefetchDone_) cpm_event_destroy(c, prefetchDone_);
     if (lin_) cpm_volume_destroy(c, lin_);
     if (tex_) cpm_volume_destroy(c, tex_);
     if (dev_ && c) cpm_mem_free(c, dev_);
@@ -215,6 +216,30 @@ const void* Volume::getRAMData() {
 void Volume::setExternalRAMData(void* ptr) {
     ext_ = ptr;
     ramValid_ = true;
+    texValid_ = false;
+    if (ptr && ptr == prefetched_ && prefetchDone_) {
+        // adopt the upload started by prefetchExternalRAMData: the context stream waits for it, nothing is copied
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_ctx_wait_event(rt.ctx(), prefetchDone_));
+        cpm_event_destroy(rt.ctx(), prefetchDone_);
+        prefetchDone_ = nullptr;
+        prefetched_ = nullptr;
+        devValid_ = true;
+        return;
+    }
+    devValid_ = false;
+}
+void Volume::prefetchExternalRAMData(void* ptr) {
+    ensureDevice();
+    auto& rt = CpmRuntime::get();
+    if (prefetchDone_) {
+        rt.check(cpm_ctx_wait_event(rt.ctx(), prefetchDone_));
+        cpm_event_destroy(rt.ctx(), prefetchDone_);
+        prefetchDone_ = nullptr;
+    }
+    rt.check(cpm_mem_prefetch_h2d(rt.ctx(), dev_, ptr, devBytes_, &prefetchDone_));
+    BufferBase::h2dBytes() += devBytes_;
+    prefetched_ = ptr;
     devValid_ = false;
     texValid_ = false;
 }

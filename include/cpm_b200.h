@@ -334,6 +334,12 @@ CPM_API int cpm_host_alloc(cpm_ctx* ctx, size_t bytes, void** out);
 CPM_API int cpm_host_free(cpm_ctx* ctx, void* ptr);
 CPM_API int cpm_mem_copy_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes);
 CPM_API int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes);
+/* Upload on the context's TRANSFER stream (created on first use), so that the copy of the next time step
+ * overlaps the kernels of the current one.  The transfer first waits for everything enqueued on the context
+ * stream so far (earlier readers of dst); *done receives a new event (cpm_event_destroy) that
+ * cpm_ctx_wait_event makes the context stream wait for before dst is consumed.  src_host must be pinned. */
+CPM_API int cpm_mem_prefetch_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes, cpm_event** done);
+CPM_API int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev);
 /* overlapping ranges are allowed when dst < src (the index-list slide-down of
  * ppm/processor/progressivephotontracercl.cpp:389-419) */
 CPM_API int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes);
