@@ -34,13 +34,13 @@ constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int RADIX_THREADS_MIN = RADIX;
 // tuning knobs (tools/sort_variants.sh sweeps them; the defaults are the round-1 winners on B200)
 #ifndef CPM_SORT_THREADS
-#define CPM_SORT_THREADS 512
+#define CPM_SORT_THREADS 256
 #endif
 #ifndef CPM_SORT_ITEMS
-#define CPM_SORT_ITEMS 16
+#define CPM_SORT_ITEMS 24
 #endif
 #ifndef CPM_SORT_MIN_BLOCKS
-#define CPM_SORT_MIN_BLOCKS 2
+#define CPM_SORT_MIN_BLOCKS 3
 #endif
 #ifndef CPM_SORT_LOOKBACK
 #define CPM_SORT_LOOKBACK 4
@@ -102,12 +102,15 @@ __global__ void __launch_bounds__(512) histogram_kernel(const uint32_t* __restri
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
 }
 
-// one block per pass: digit histogram -> exclusive prefix (the global base of every digit), in place
-__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* __restrict__ hist) {
+// one block per pass: digit histogram -> exclusive prefix (the global base of every digit), in place;
+// trivial[pass] = 1 when every key has the same digit in this pass (the pass is then the identity
+// permutation: the importance keys share their two top bytes, photon ids their top byte)
+__global__ void __launch_bounds__(RADIX) hist_scan_kernel(uint32_t* __restrict__ hist, uint32_t n, uint32_t* __restrict__ trivial) {
     __shared__ uint32_t s_warp[RADIX / 32];
     uint32_t* h = hist + blockIdx.x * RADIX;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v = h[tid], incl = v;
+    if (v == n) trivial[blockIdx.x] = 1u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -151,10 +154,26 @@ __global__ void __launch_bounds__(SORT_THREADS, CPM_SORT_MIN_BLOCKS) onesweep_ke
                                                                    uint32_t* __restrict__ vals_out, size_t n, int shift,
                                                                    const uint32_t* __restrict__ digit_base,  // this pass
                                                                    volatile uint32_t* status,                // [tiles][RADIX]
-                                                                   uint32_t* ticket) {
+                                                                   uint32_t* ticket, const uint32_t* __restrict__ trivial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem<HAS_VALUES>& S = *reinterpret_cast<SortSmem<HAS_VALUES>*>(smem_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (*trivial) {
+        // every key has the same digit: a stable pass leaves the order unchanged -- straight tile copy
+        // (the ping-pong parity of the passes is kept), no ranking, no chained scan
+        const size_t base = (size_t)blockIdx.x * SORT_TILE;
+        const uint32_t nv = (uint32_t)min((size_t)SORT_TILE, n - base);
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; ++j) {
+            uint32_t i = j * SORT_THREADS + tid;
+            if (i < nv) {
+                keys_out[base + i] = keys_in[base + i];
+                if (HAS_VALUES) vals_out[base + i] = vals_in[base + i];
+            }
+        }
+        return;
+    }
 
     if (tid == 0) S.tile = atomicAdd(ticket, 1u);
     {
@@ -368,7 +387,8 @@ int cpm_radix_sort_u32(cpm_ctx* ctx, uint32_t* keys, uint32_t* values, size_t n,
     unsigned hgrid = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 4, std::max<size_t>(1, n / (512 * 4)));
     CPM_LAUNCH(ctx, histogram_kernel, hgrid, 512, 0, keys, n, passes, hist);
 
-    CPM_LAUNCH(ctx, hist_scan_kernel, passes, RADIX, 0, hist);
+    uint32_t* trivial = tickets + 16;   // [MAX_PASSES], zeroed with the tickets
+    CPM_LAUNCH(ctx, hist_scan_kernel, passes, RADIX, 0, hist, (uint32_t)n, trivial);
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -380,10 +400,10 @@ int cpm_radix_sort_u32(cpm_ctx* ctx, uint32_t* keys, uint32_t* values, size_t n,
     for (int p = 0; p < passes; ++p) {
         if (values) {
             CPM_LAUNCH(ctx, onesweep_kernel<true>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem<true>), kin, vin, kout, vout, n,
-                       p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+                       p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p, trivial + p);
         } else {
             CPM_LAUNCH(ctx, onesweep_kernel<false>, (unsigned)tiles, SORT_THREADS, sizeof(SortSmem<false>), kin, nullptr, kout, nullptr,
-                       n, p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p);
+                       n, p * RADIX_BITS, hist + p * RADIX, status + (size_t)p * tiles * RADIX, tickets + p, trivial + p);
         }
         std::swap(kin, kout);
         std::swap(vin, vout);

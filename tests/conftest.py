@@ -44,7 +44,12 @@ def torch_cuda():
 
 @pytest.fixture(scope="session")
 def ctx(cpm, torch_cuda):
-    c = cpm.Context(0)
+    """One context for the session, on a stream that is also torch's current stream: tensor initialisation
+    (torch.zeros, .cuda() uploads) and the library's kernels are then ordered without explicit syncs."""
+    torch = torch_cuda
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    c = cpm.Context(0, stream.cuda_stream)
     yield c
     c.close()
 
