@@ -236,9 +236,6 @@ def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False):
     frames = steps + warmup + 1
     side = int(np.sqrt(max(rate * budget_s / frames, 64.0 * 64.0)))
     side = int(min(a.photons_side, max(64, side // 32 * 32)))
-    if side == a.photons_side and grow_steps:
-        # the whole photon set fits the budget: spend the rest of it on more frames (at most one period)
-        steps = int(min(max(steps, rate * budget_s / (side * side) - warmup - 1), a.timesteps, len(volumes) - warmup - 2))
     arm = CpuArm(a, volumes, side)
     arm.first_frame(0)
     for t in range(1, warmup + 1):
@@ -246,13 +243,18 @@ def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False):
         arm.frame(t)
     traced = tests = 0
     elapsed = 0.0
-    for t in range(warmup + 1, warmup + 1 + steps):
+    t, done = warmup + 1, 0
+    cap = min(a.timesteps, len(volumes) - warmup - 2) if grow_steps else steps
+    while done < steps or (grow_steps and elapsed < 0.6 * budget_s and done < cap):
         arm.prepare(t)
         t0 = time.perf_counter()
         n_inv, nt = arm.frame(t)
         elapsed += time.perf_counter() - t0
         traced += n_inv
         tests += nt
+        t += 1
+        done += 1
+    steps = done
     return {"value": traced / elapsed if elapsed > 0 else 0.0, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{side}x{side} = {side * side} photons of the {a.photons_side}^2 light-sample grid, {steps} correlated "
                       f"frames ({elapsed:.2f} s CPU) on the full {a.dims}^3 volumes; min-max / difference grids "

@@ -405,3 +405,31 @@ Context.reorder_photons = _reorder_photons
 Context.gather_raymarch = _gather_raymarch
 Context.gather_points = _gather_points
 Context.build_photon_map = _build_photon_map
+
+
+# -- view importance + importance-driven sample generator ------------------------------------------------
+def _view_importance(self, minmax, grid_dims, cell_size, tex2idx, idx2tex, entry, exit_, width, height, tf_min, tf_max, out):
+    self._check(lib().cpm_view_importance(self.h, _p(minmax), _i3(grid_dims), _f3(cell_size), _fN(tex2idx, 16),
+                                          _fN(idx2tex, 16), _p(entry), _p(exit_), int(width), int(height), C.c_float(tf_min),
+                                          C.c_float(tf_max), _p(out)))
+
+
+def _sample_importance2d(self, importance, width, height, floor_value, uniform_samples, n, scratch, out):
+    self._check(lib().cpm_sample_importance2d(self.h, _p(importance), int(width), int(height), C.c_float(floor_value),
+                                              _p(uniform_samples), int(n), _p(scratch), _p(out)))
+
+
+def sample_importance2d_scratch_floats(width, height):
+    lib().cpm_sample_importance2d_scratch_floats.restype = C.c_size_t
+    return int(lib().cpm_sample_importance2d_scratch_floats(int(width), int(height)))
+
+
+Context.view_importance = _view_importance
+Context.sample_importance2d = _sample_importance2d
+
+
+def _mix(self, x, y, a, n, fmt, out):
+    self._check(lib().cpm_mix(self.h, _p(x), _p(y), C.c_float(a), C.c_size_t(n), int(fmt), _p(out)))
+
+
+Context.mix = _mix

@@ -115,6 +115,48 @@ __global__ void scatter_fill_u32_kernel(uint32_t* p, const uint32_t* idx, size_t
 }
 }  // namespace
 
+namespace {
+// mixKernel (ugc/cl/buffermixer.cl:37-48): out = mix(x, y, a) = x + (y - x) * a; integer formats go through
+// float and back with OpenCL's default float->int conversion (round toward zero)
+template <typename T>
+__global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ x, const T* __restrict__ y, float a, size_t n,
+                                                  T* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx = (float)x[i], fy = (float)y[i];
+    float m = fx + (fy - fx) * a;
+    if (sizeof(T) == 4) {
+        out[i] = (T)m;
+    } else {
+        const float hi = sizeof(T) == 1 ? 255.0f : 65535.0f;
+        out[i] = (T)(int)cpm_clamp(truncf(m), 0.0f, hi);
+    }
+}
+}  // namespace
+
+int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out) {
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, x && y && out, "null pointer");
+    unsigned grid = cpm_div_up(n, 256);
+    switch (format) {
+        case CPM_FMT_U8:
+            CPM_LAUNCH(ctx, mix_kernel<unsigned char>, grid, 256, 0, (const unsigned char*)x, (const unsigned char*)y, a, n,
+                       (unsigned char*)out);
+            break;
+        case CPM_FMT_U16:
+            CPM_LAUNCH(ctx, mix_kernel<unsigned short>, grid, 256, 0, (const unsigned short*)x, (const unsigned short*)y, a, n,
+                       (unsigned short*)out);
+            break;
+        case CPM_FMT_F32:
+            CPM_LAUNCH(ctx, mix_kernel<float>, grid, 256, 0, (const float*)x, (const float*)y, a, n, (float*)out);
+            break;
+        default:
+            return cpm_fail(ctx, CPM_E_INVALID, "cpm_mix: unknown format");
+    }
+    return CPM_OK;
+}
+
 int cpm_mem_scatter_fill_u32(cpm_ctx* ctx, void* dst, const uint32_t* indices, size_t n, uint32_t value) {
     if (!ctx) return CPM_E_INVALID;
     if (n == 0) return CPM_OK;

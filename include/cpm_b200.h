@@ -127,6 +127,26 @@ CPM_API int cpm_light_mesh_intersect(cpm_ctx* ctx, const float* vertices /* floa
                                      const float* light_samples, int n,
                                      float* intersections /* float2[n] */);
 
+/* View (or light) importance image: uniformGridImportanceKernel
+ * (isc/cl/minmaxuniformgrid3dimportance.cl:336-378 with uniformGridImportance :86-133); host side
+ * MinMaxUniformGrid3DImportanceCL::computeImportance (isc/minmaxuniformgrid3dimportancecl.cpp:99-132).  Per
+ * pixel: length of the segment entry -> exit (texture coordinates, float4 per pixel) that lies in min-max
+ * bricks overlapping [tf_min, tf_max].  minmax = ushort2 per brick as written by cpm_volume_minmax. */
+CPM_API int cpm_view_importance(cpm_ctx* ctx, const uint16_t* minmax, const int grid_dims[3], const float cell_size[3],
+                                const float texture_to_index[16], const float index_to_texture[16],
+                                const float* entry /* float4[w*h] */, const float* exit /* float4[w*h] */, int width,
+                                int height, float tf_min, float tf_max, float* importance /* w*h */);
+/* Importance-driven 2-D sample generator behind the SampleGenerator2DCL interface
+ * (lcl/samplegenerator2dcl.h:53-88; the reference ships only the uniform implementation): warps uniform
+ * samples (u, v, w, pdf) through the inverse CDF of the piecewise-constant density
+ * max(importance, 0) + floor_value on a width x height grid; the output pdf slot is multiplied by the density
+ * (integral 1 over the unit square), which cpm_light_sample_directional divides the power by.
+ * cdf_scratch: cpm_sample_importance2d_scratch_floats(width, height) floats. */
+CPM_API size_t cpm_sample_importance2d_scratch_floats(int width, int height);
+CPM_API int cpm_sample_importance2d(cpm_ctx* ctx, const float* importance, int width, int height, float floor_value,
+                                    const float* uniform_samples /* float4[n] */, int n, float* cdf_scratch,
+                                    float* samples_out /* float4[n] */);
+
 /* ---- volumes ----------------------------------------------------------------------- */
 enum { CPM_FMT_U8 = 0, CPM_FMT_U16 = 1, CPM_FMT_F32 = 2 };
 enum {
@@ -350,6 +370,12 @@ CPM_API int cpm_mem_fill_u32(cpm_ctx* ctx, void* dst, uint32_t value, size_t cou
  * order and are addressed through the sorted id list.) */
 CPM_API int cpm_mem_scatter_fill_u32(cpm_ctx* ctx, void* dst, const uint32_t* indices, size_t n,
                                      uint32_t value);
+
+/* mixKernel (ugc/cl/buffermixer.cl:37-48), host side BufferMixerCL::mix (ugc/buffermixercl.cpp:47-85); also the
+ * voxel arithmetic of VolumeSequencePlayer's volume_mix.frag (ugc/processors/volumesequenceplayer.cpp:94-143):
+ * out[i] = x[i] + (y[i] - x[i]) * a over n scalars of format CPM_FMT_* (float2/3/4 buffers: n = elements *
+ * components); u8 / u16 are mixed in float and converted back with round-toward-zero. */
+CPM_API int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out);
 
 /* ---- self test ----------------------------------------------------------------------- */
 /* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,

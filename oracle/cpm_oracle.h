@@ -117,6 +117,13 @@ void orc_gather_points(const orc_gather_params* P, const float* photons, size_t 
 void orc_gather_raymarch(const orc_volume* vol, const float* tf_rgba, int tf_width, const orc_gather_params* P,
                          const float* photons, size_t n_records, float* image);
 
+/* --- view importance + importance-driven sample generator (orc_importance.c) ---------------------- */
+void orc_view_importance(const uint16_t* minmax, const int dims[3], const float cellDim[3], const float tex2idx[16],
+                         const float idx2tex[16], const float* entry, const float* exit, int width, int height,
+                         float tf_min, float tf_max, float* out);
+void orc_sample_importance2d(const float* importance, int w, int h, float floor_value, const float* uniform_samples,
+                             int n, float* out);
+
 void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_t n);
 int orc_num_threads(void);
 

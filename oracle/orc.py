@@ -265,3 +265,20 @@ def gather_raymarch(vol, tf_rgba, params, photons):
     lib().orc_gather_raymarch(C.byref(vol), _ptr(tf_rgba), int(tf_rgba.shape[0]), C.byref(params), _ptr(photons),
                               C.c_size_t(photons.shape[0]), _ptr(img))
     return img
+
+
+# -- view importance + importance-driven sample generator ------------------------------------------------
+def view_importance(minmax, grid_dims, cell_size, tex2idx, idx2tex, entry, exit_, tf_min, tf_max):
+    h, w = entry.shape[0], entry.shape[1]
+    out = np.empty((h, w), np.float32)
+    lib().orc_view_importance(_ptr(minmax), _i3(grid_dims), _f3(cell_size), _fN(tex2idx, 16), _fN(idx2tex, 16), _ptr(entry),
+                              _ptr(exit_), int(w), int(h), C.c_float(tf_min), C.c_float(tf_max), _ptr(out))
+    return out
+
+
+def sample_importance2d(importance, floor_value, uniform_samples):
+    h, w = importance.shape
+    out = np.empty_like(uniform_samples)
+    lib().orc_sample_importance2d(_ptr(importance), int(w), int(h), C.c_float(floor_value), _ptr(uniform_samples),
+                                  int(uniform_samples.shape[0]), _ptr(out))
+    return out

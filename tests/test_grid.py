@@ -162,3 +162,25 @@ def test_cuda_hash_and_cell_ranges(cpm, orc, ctx, torch_cuda, synth):
         ctx.sync()
         assert np.array_equal(s.cpu().numpy().view(np.uint32), ws)
         assert np.array_equal(e.cpu().numpy().view(np.uint32), we)
+
+
+@pytest.mark.gpu
+def test_cuda_mix_kernel(cpm, ctx, torch_cuda, synth):
+    """mixKernel (ugc/cl/buffermixer.cl:37-48): x + (y - x) * a; integer formats truncate toward zero"""
+    torch = torch_cuda
+    n = 100_003
+    for a in (0.0, 0.25, 1.0):
+        fx = synth.uniform01(1, n).astype(np.float32)
+        fy = synth.uniform01(2, n).astype(np.float32)
+        out = torch.zeros(n, dtype=torch.float32, device="cuda")
+        ctx.mix(torch.from_numpy(fx).cuda(), torch.from_numpy(fy).cuda(), a, n, cpm.CPM_FMT_F32, out)
+        ctx.sync()
+        want = (fx + (fy - fx) * np.float32(a)).astype(np.float32)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        bx = (synth.splitmix64(3, n) & np.uint64(255)).astype(np.uint8)
+        by = (synth.splitmix64(4, n) & np.uint64(255)).astype(np.uint8)
+        ob = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        ctx.mix(torch.from_numpy(bx).cuda(), torch.from_numpy(by).cuda(), a, n, cpm.CPM_FMT_U8, ob)
+        ctx.sync()
+        wb = np.trunc(bx.astype(np.float32) + (by.astype(np.float32) - bx.astype(np.float32)) * np.float32(a)).astype(np.uint8)
+        assert np.array_equal(ob.cpu().numpy(), wb)
