@@ -115,6 +115,8 @@ __global__ void scatter_fill_u32_kernel(uint32_t* p, const uint32_t* idx, size_t
 }
 }  // namespace
 
+}  // extern "C"
+
 namespace {
 // mixKernel (ugc/cl/buffermixer.cl:37-48): out = mix(x, y, a) = x + (y - x) * a; integer formats go through
 // float and back with OpenCL's default float->int conversion (round toward zero)
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ x, const
     }
 }
 }  // namespace
+
+extern "C" {
 
 int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out) {
     if (!ctx) return CPM_E_INVALID;
