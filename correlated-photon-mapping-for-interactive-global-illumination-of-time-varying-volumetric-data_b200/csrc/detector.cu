@@ -50,27 +50,32 @@ __device__ float uniform_grid_importance(const GridArgs& G, float3_ x1, float3_ 
         dt[k] = ((a1[k] > a2[k]) ? (a1[k] - minx) : (maxx - a1[k])) * inv_abs;
         deltatx[k] = G.cell[k] * inv_abs;
     }
+    // The walk keeps one linear cell index and, per axis, the number of cells left to the end cell.
+    // "selected axis already in its end cell" (uniformgrid.cl:147-197) is rem == 0: a cell only ever moves
+    // toward its end cell (di = sign(x2 - x1), end cell on that side after clamping), and an axis with
+    // di == 0 starts in its end cell.
+    int rem0 = abs(cell_end[0] - cell[0]), rem1 = abs(cell_end[1] - cell[1]), rem2 = abs(cell_end[2] - cell[2]);
+    const int sy = G.dims[0], sz = G.dims[0] * G.dims[1];
+    const int s0 = di[0], s1 = di[1] * sy, s2 = di[2] * sz;
+    int idx = cell[0] + cell[1] * sy + cell[2] * sz;
+    float d0 = dt[0], d1 = dt[1], d2 = dt[2];
     bool go = true;
     float importance = 0.0f, dt1 = 0.0f;
-    const int sy = G.dims[0], sz = G.dims[0] * G.dims[1];
     while (go) {
-        float val = __ldg(G.grid + cell[0] + cell[1] * sy + cell[2] * sz);
+        float val = __ldg(G.grid + idx);
         float dt0 = dt1;
-        bool ax = (dt[0] <= dt[1] && dt[0] <= dt[2]);
-        bool ay = !ax && (dt[0] > dt[1] && dt[1] <= dt[2]);
-        // select the axis without dynamic register indexing
-        float dsel = ax ? dt[0] : (ay ? dt[1] : dt[2]);
-        int csel = ax ? cell[0] : (ay ? cell[1] : cell[2]);
-        int esel = ax ? cell_end[0] : (ay ? cell_end[1] : cell_end[2]);
-        dt1 = dsel;
-        if (csel == esel) {
+        bool ax = (d0 <= d1 && d0 <= d2);
+        bool ay = !ax && (d0 > d1 && d1 <= d2);
+        dt1 = ax ? d0 : (ay ? d1 : d2);
+        int rsel = ax ? rem0 : (ay ? rem1 : rem2);
+        if (rsel == 0) {
             go = false;
         } else if (ax) {
-            dt[0] += deltatx[0]; cell[0] += di[0];
+            d0 += deltatx[0]; idx += s0; --rem0;
         } else if (ay) {
-            dt[1] += deltatx[1]; cell[1] += di[1];
+            d1 += deltatx[1]; idx += s1; --rem1;
         } else {
-            dt[2] += deltatx[2]; cell[2] += di[2];
+            d2 += deltatx[2]; idx += s2; --rem2;
         }
         importance += val * (cpm_fmin(1.0f, dt1) - dt0);
     }
