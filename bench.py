@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--max-interactions", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="budget of the whole --impl reference run")
+    ap.add_argument("--bound-log2", type=int, default=0,
+                    help="tracer opacity-bound cells: 0 = default (8^3 voxels), n = 2^n voxels per axis, -1 = off")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
@@ -395,7 +397,7 @@ def run_b200(a):
     with torch.cuda.stream(stream):
         net = host.Network((D, D, D), cpm.CPM_FMT_F32, a.photons_side, [LIGHT_DIR], max_scattering_events=I,
                            light_volume_option=2, with_importance_grid=True, volume_layout=cpm.CPM_VOLUME_TEXTURE,
-                           reference_full_splat_bound=False, device=local)
+                           reference_full_splat_bound=False, device=local, opacity_bound_cell_log2=a.bound_log2)
         net.set_transfer_function(synth.WS_TF_POINTS)
         net.count_collision_tests(True)
         lv_view = {}
@@ -432,7 +434,7 @@ def run_b200(a):
         ms, wall_ms, traced = time_loop(net, a.steps, 1 + a.warmup, step_resident)
         clk = clocks.stop() if rank == 0 else None
         launches = net.launch_count()
-        tests = net.read_collision_tests(reset=True)
+        tests, fetched = net.read_collision_stats(reset=True)
         stages = {s: (host.profile_total_ms(s), host.profile_count(s)) for s in host.profile_stages()}
         host.profile_enable(False)
         tests_t = torch.tensor([float(tests)], dtype=torch.float64, device=dev)
@@ -525,6 +527,7 @@ def run_b200(a):
                        "parallelism": f"photon shards x{world}, NCCL all-reduce of the light volume" if world > 1 else "1 GPU"},
             "frames_per_sec": a.steps / (ms * 1e-3), "retrace_fraction": traced / (a.steps * n_photons * world),
             "collision_tests_per_sec": float(tests_t[0]) / (ms * 1e-3),
+            "tests_fetching_voxels": fetched / tests if tests else None,
             "wall_ms_per_step": wall_ms / a.steps,
             "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(stages.items())},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "gpu_launches": int(launches), "clocks": clk}

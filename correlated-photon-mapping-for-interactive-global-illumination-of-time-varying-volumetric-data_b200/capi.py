@@ -18,7 +18,7 @@ HEADER = ROOT / "include" / "cpm_b200.h"
 
 CPM_FMT_U8, CPM_FMT_U16, CPM_FMT_F32 = 0, 1, 2
 CPM_VOLUME_LINEAR, CPM_VOLUME_TEXTURE = 0, 1
-CPM_TRACE_PROGRESSIVE, CPM_TRACE_NO_SINGLE_SCATTERING = 1, 2
+CPM_TRACE_PROGRESSIVE, CPM_TRACE_NO_SINGLE_SCATTERING, CPM_TRACE_STATS = 1, 2, 4
 CPM_PHASE_ISOTROPIC, CPM_PHASE_HENYEY_GREENSTEIN = 0, 1
 FLT_MAX = 3.4028234663852886e38
 
@@ -41,6 +41,9 @@ class TraceParams(C.Structure):
         ("total_photons", C.c_int32),
         ("n_light_samples", C.c_int32),
         ("flags", C.c_uint32),
+        ("opacity_bound", C.c_void_p),
+        ("bound_cell_log2", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -174,6 +177,17 @@ class Context:
                                             int(layout), C.byref(h)))
         return Volume(self, h, data, tuple(dims), fmt, layout)
 
+    # -- opacity-bound grid of the tracer -----------------------------------------------
+    def volume_value_range(self, vol: Volume, cell_log2, out):
+        """out: float tensor of 2 * prod(bound_grid_dims(vol.dims, cell_log2)); returns the grid dims"""
+        od = (C.c_int * 3)()
+        self._check(lib().cpm_volume_value_range(self.h, vol.handle, int(cell_log2), _p(out), od))
+        return tuple(od)
+
+    def opacity_bound(self, value_range, n_cells, tf_rgba, out, scale=1.0, offset=0.0):
+        self._check(lib().cpm_opacity_bound(self.h, _p(value_range), C.c_size_t(n_cells), C.c_float(scale),
+                                            C.c_float(offset), _p(tf_rgba), int(tf_rgba.numel() // 4), _p(out)))
+
     # -- tracer ------------------------------------------------------------------------
     def trace_photons(self, vol: Volume, tf_rgba, params: TraceParams, light_samples, intersections, photons,
                       rng_state, recompute_index=None, n_recompute=0, collision_tests=None):
@@ -194,7 +208,7 @@ def rng_host_base_offsets(seed: int, n: int):
 
 def make_trace_params(n_light_samples, total_photons=None, photon_offset=0, max_interactions=1, step_size=1.0 / 256,
                       aabb_min=(0, 0, 0), aabb_max=(1, 1, 1), phase=CPM_PHASE_ISOTROPIC, material=(0, 0, 0, 0),
-                      flags=0) -> TraceParams:
+                      flags=0, opacity_bound=None, bound_cell_log2=3) -> TraceParams:
     p = TraceParams()
     p.aabb_min[:] = [float(x) for x in aabb_min]
     p.aabb_max[:] = [float(x) for x in aabb_max]
@@ -206,7 +220,18 @@ def make_trace_params(n_light_samples, total_photons=None, photon_offset=0, max_
     p.total_photons = n_light_samples if total_photons is None else total_photons
     p.n_light_samples = n_light_samples
     p.flags = flags
+    p.opacity_bound = opacity_bound.data_ptr() if opacity_bound is not None else None
+    p.bound_cell_log2 = bound_cell_log2
     return p
+
+
+def bound_grid_dims(dims, cell_log2):
+    """dims of the opacity-bound grid of the tracer: (dims >> cell_log2) + 1"""
+    od = (C.c_int * 3)()
+    rc = lib().cpm_bound_grid_dims((C.c_int * 3)(*[int(x) for x in dims]), int(cell_log2), od)
+    if rc != 0:
+        raise CpmError(rc, "cpm_bound_grid_dims")
+    return tuple(od)
 
 
 def _selftest_math(self, fn, x, y, out):

@@ -1,0 +1,265 @@
+// bound.cu -- per-cell opacity bound for the delta-tracking tracer ("L2-resident bricks", north-star 3).
+//
+// Not in the reference: woodcockTracking (ppm/cl/transmittance.cl:126-144) fetches the volume and the
+// transfer function for EVERY collision test.  The accept/reject decision of a test is `u2 >= opacity`; if an
+// upper bound m >= opacity is known for the cell the sample falls in, `u2 >= m` already decides "reject"
+// and the 8 voxel taps + 2 TF taps are never fetched.  The random stream, the sample positions and every
+// stored photon stay exactly those of the reference loop -- the bound only removes memory traffic.
+//
+//  cpm_volume_value_range   (lo, hi) of the normalised voxel values that a trilinear footprint can touch, per
+//                           cell.  Cell c = floor((u + 1) / cell) per axis, u = p * dim - 0.5 the continuous
+//                           voxel coordinate of the sample; its footprints have lower tap i0 in
+//                           [c*cell - 1, c*cell + cell - 2].  The grid covers one voxel more on either side,
+//                           voxels [c*cell - 2, c*cell + cell] clamped to the volume, so that the tracer may
+//                           compute c with its own, differently rounded arithmetic (errors << 1 voxel).
+//                           One HBM pass over the linear buffer, overlap rows served by L2.
+//  cpm_opacity_bound        bound[c] >= alpha(TF((v + offset) * scale)) for every v in [lo, hi], widened by
+//                           the worst-case rounding of the fp32 blend (sampling.cuh blend_taps /
+//                           sample_tf_alpha); +inf ("always fetch") where a NaN/inf voxel or NaN alpha makes
+//                           the arithmetic non-monotone.
+#include "sampling.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t okey(float f) {  // monotone float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float oval(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+template <int FMT>
+struct VoxT;
+template <>
+struct VoxT<CPM_FMT_U8> {
+    typedef unsigned char T;
+    static constexpr int PER16 = 16;
+    __device__ static float norm(T v) { return unorm8((float)v); }
+};
+template <>
+struct VoxT<CPM_FMT_U16> {
+    typedef unsigned short T;
+    static constexpr int PER16 = 8;
+    __device__ static float norm(T v) { return unorm16((float)v); }
+};
+template <>
+struct VoxT<CPM_FMT_F32> {
+    typedef float T;
+    static constexpr int PER16 = 4;
+    __device__ static float norm(T v) { return v; }
+};
+
+// one CTA per (cy, cz): all cells along x of that row.  smem: ncx min keys, ncx max keys, ncx bad flags.
+template <int FMT>
+__global__ void __launch_bounds__(256) range_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int s, int ncx,
+                                                    float2* __restrict__ out, int vec_ok) {
+    typedef typename VoxT<FMT>::T T;
+    constexpr int K = VoxT<FMT>::PER16;
+    extern __shared__ uint32_t s_r[];
+    uint32_t *s_min = s_r, *s_max = s_r + ncx, *s_bad = s_r + 2 * ncx;
+    const int cy = blockIdx.x, cz = blockIdx.y, cell = 1 << s;
+    for (int i = threadIdx.x; i < ncx; i += blockDim.x) {
+        s_min[i] = 0xffffffffu;
+        s_max[i] = 0u;
+        s_bad[i] = 0u;
+    }
+    __syncthreads();
+    const int y0 = max(cy * cell - 2, 0), y1 = min(cy * cell + cell, ny - 1);
+    const int z0 = max(cz * cell - 2, 0), z1 = min(cz * cell + cell, nz - 1);
+    const int ry = y1 - y0 + 1, rz = z1 - z0 + 1;
+    const int rows = ry * rz;
+    const T* base = (const T*)vol;
+    if (vec_ok) {
+        const int chunks = nx / K;
+        const int items = rows * chunks;
+        for (int w = threadIdx.x; w < items; w += blockDim.x) {
+            int r = w / chunks, c = w - r * chunks;
+            int y = y0 + r % ry, z = z0 + r / ry;
+            const T* row = base + ((size_t)z * ny + y) * nx;
+            uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + c);
+            const T* e = reinterpret_cast<const T*>(&raw);
+            const int x = c * K;
+            float v[K];
+            bool isbad[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                v[k] = VoxT<FMT>::norm(e[k]);
+                isbad[k] = !(fabsf(v[k]) <= CPM_FLT_MAX_);
+            }
+            // voxel x is in cell q iff q*cell - 2 <= x <= q*cell + cell: the chunk touches a contiguous cell range
+            const int qmin = max(((x + cell - 1) >> s) - 1, 0), qmax = min((x + K + 1) >> s, ncx - 1);
+            for (int q = qmin; q <= qmax; ++q) {
+                const int lo = q * cell - 2 - x, hi = q * cell + cell - x;   // relative to the chunk
+                float mn = CPM_FLT_MAX_, mx = -CPM_FLT_MAX_;
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (k >= lo && k <= hi) {
+                        mn = fminf(mn, v[k]);
+                        mx = fmaxf(mx, v[k]);
+                        bad = bad || isbad[k];
+                    }
+                }
+                atomicMin(&s_min[q], okey(mn));
+                atomicMax(&s_max[q], okey(mx));
+                if (bad) s_bad[q] = 1u;
+            }
+        }
+    } else {
+        const int items = rows * nx;
+        for (int w = threadIdx.x; w < items; w += blockDim.x) {
+            int r = w / nx, x = w - r * nx;
+            int y = y0 + r % ry, z = z0 + r / ry;
+            float v = VoxT<FMT>::norm(base[((size_t)z * ny + y) * nx + x]);
+            bool isbad = !(fabsf(v) <= CPM_FLT_MAX_);
+            const int qmin = max(((x + cell - 1) >> s) - 1, 0), qmax = min((x + 2) >> s, ncx - 1);
+            for (int q = qmin; q <= qmax; ++q) {
+                atomicMin(&s_min[q], okey(v));
+                atomicMax(&s_max[q], okey(v));
+                if (isbad) s_bad[q] = 1u;
+            }
+        }
+    }
+    __syncthreads();
+    const int ncy = gridDim.x;
+    for (int i = threadIdx.x; i < ncx; i += blockDim.x) {
+        float2 o = make_float2(oval(s_min[i]), oval(s_max[i]));
+        if (s_bad[i]) o.x = o.y = __uint_as_float(0x7fc00000u);
+        out[((size_t)cz * ncy + cy) * ncx + i] = o;
+    }
+}
+
+// alpha column + per-32-texel summaries (max with NaN -> +inf, max |.|)
+__global__ void __launch_bounds__(256) tf_summary_kernel(const float4* __restrict__ tf, int w, float* __restrict__ alpha,
+                                                         float* __restrict__ bmax, float* __restrict__ babs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float a = i < w ? tf[i].w : -CPM_FLT_MAX_;
+    if (i < w) alpha[i] = a;
+    float m = (a != a) ? __uint_as_float(0x7f800000u) : a;
+    float ab = (i < w) ? fabsf(m) : 0.0f;
+    for (int off = 16; off; off >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        ab = fmaxf(ab, __shfl_xor_sync(0xffffffffu, ab, off));
+    }
+    if ((threadIdx.x & 31) == 0 && i < w) {
+        bmax[i >> 5] = m;
+        babs[i >> 5] = ab;
+    }
+}
+
+__device__ __forceinline__ int tf_index(float v, float fw) {  // i0 of sample_tf_alpha before the max(.,0)
+    return (int)cpm_clamp(floorf(fmaf(v, fw, -0.5f)), -1.0f, fw - 1.0f);
+}
+
+__global__ void __launch_bounds__(256) bound_kernel(const float2* __restrict__ range, size_t n, float scale, float offset,
+                                                    const float* __restrict__ alpha, const float* __restrict__ bmax,
+                                                    const float* __restrict__ babs, int w, float* __restrict__ out) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const float INF = __uint_as_float(0x7f800000u);
+    float2 r = range[id];
+    float res = INF;
+    if (fabsf(r.x) <= CPM_FLT_MAX_ && fabsf(r.y) <= CPM_FLT_MAX_) {
+        // three nested fp32 lerps of values in [lo, hi] stay within a few ulp of max(|lo|, |hi|) of the interval
+        float slack = fmaf(fmaxf(fabsf(r.x), fabsf(r.y)), 0x1p-18f, 1e-37f);
+        float lo = (r.x - slack + offset) * scale, hi = (r.y + slack + offset) * scale;  // blend_taps: (val + offset) * scale
+        if (lo > hi) {
+            float t = lo;
+            lo = hi;
+            hi = t;
+        }
+        if (fabsf(lo) <= CPM_FLT_MAX_ && fabsf(hi) <= CPM_FLT_MAX_) {
+            const float fw = (float)w;
+            int ia = max(tf_index(lo, fw), 0), ib = min(tf_index(hi, fw) + 1, w - 1);
+            float m = -INF, ab = 0.0f;
+            int i = ia;
+#define ACC(v)                                  \
+    {                                           \
+        float v_ = (v);                         \
+        m = (v_ != v_) ? INF : fmaxf(m, v_);    \
+        ab = fmaxf(ab, fabsf(v_));              \
+    }
+            while (i <= ib && (i & 31)) {
+                ACC(alpha[i]);
+                ++i;
+            }
+            while (i + 31 <= ib) {
+                m = fmaxf(m, bmax[i >> 5]);
+                ab = fmaxf(ab, babs[i >> 5]);
+                i += 32;
+            }
+            while (i <= ib) {
+                ACC(alpha[i]);
+                ++i;
+            }
+#undef ACC
+            // sample_tf_alpha's lerp: within a few ulp of the larger magnitude of its two texels
+            res = m + fmaf(ab, 0x1p-18f, 1e-37f);
+            if (!(res == res)) res = INF;
+        }
+    }
+    out[id] = res;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpm_bound_grid_dims(const int dims[3], int cell_log2, int out_dims[3]) {
+    if (!dims || !out_dims || cell_log2 < 0 || cell_log2 > 8) return CPM_E_INVALID;
+    for (int k = 0; k < 3; ++k) out_dims[k] = (dims[k] >> cell_log2) + 1;
+    return CPM_OK;
+}
+
+int cpm_volume_value_range(cpm_ctx* ctx, const cpm_volume* vol, int cell_log2, float* range, int out_dims[3]) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, vol && range, "null argument");
+    CPM_REQUIRE(ctx, cell_log2 >= 0 && cell_log2 <= 8, "cell_log2 must be in 0..8");
+    CPM_REQUIRE(ctx, vol->linear != nullptr, "needs the LINEAR layout (reads the caller's buffer)");
+    const int nx = vol->dims[0], ny = vol->dims[1], nz = vol->dims[2];
+    int od[3];
+    cpm_bound_grid_dims(vol->dims, cell_log2, od);
+    if (out_dims) {
+        out_dims[0] = od[0];
+        out_dims[1] = od[1];
+        out_dims[2] = od[2];
+    }
+    CPM_REQUIRE(ctx, od[2] <= 65535, "too many cell layers");
+    size_t smem = (size_t)3 * od[0] * sizeof(uint32_t);
+    CPM_REQUIRE(ctx, smem <= 48 * 1024, "volume too wide for the cell size");
+    dim3 grid(od[1], od[2]);
+#define RG(F)                                                                                             \
+    {                                                                                                     \
+        int vec_ok = ((uintptr_t)vol->linear % 16 == 0) && (nx % VoxT<F>::PER16 == 0);                    \
+        CPM_LAUNCH(ctx, range_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, cell_log2, od[0],      \
+                   (float2*)range, vec_ok);                                                               \
+    }
+    switch (vol->format) {
+        case CPM_FMT_U8: RG(CPM_FMT_U8) break;
+        case CPM_FMT_U16: RG(CPM_FMT_U16) break;
+        default: RG(CPM_FMT_F32)
+    }
+#undef RG
+    return CPM_OK;
+}
+
+int cpm_opacity_bound(cpm_ctx* ctx, const float* range, size_t n_cells, float format_scale, float format_offset,
+                      const float* tf_rgba, int tf_width, float* bound) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, range && tf_rgba && bound, "null argument");
+    CPM_REQUIRE(ctx, tf_width >= 1 && tf_width <= 32768, "tf_width out of range");
+    if (n_cells == 0) return CPM_OK;
+    const int nb = (tf_width + 31) / 32;
+    void* scr = nullptr;
+    int rc = cpm_scratch(ctx, ((size_t)tf_width + 2 * (size_t)nb) * sizeof(float), &scr);
+    if (rc != CPM_OK) return rc;
+    float* alpha = (float*)scr;
+    float* bmax = alpha + tf_width;
+    float* babs = bmax + nb;
+    CPM_LAUNCH(ctx, tf_summary_kernel, cpm_div_up(tf_width, 256), 256, 0, (const float4*)tf_rgba, tf_width, alpha, bmax,
+               babs);
+    CPM_LAUNCH(ctx, bound_kernel, cpm_div_up(n_cells, 256), 256, 0, (const float2*)range, n_cells, format_scale,
+               format_offset, alpha, bmax, babs, tf_width, bound);
+    return CPM_OK;
+}
+
+}  // extern "C"

@@ -33,6 +33,12 @@ struct TraceArgs {
     float4* photons;
     uint2* rng;
     unsigned long long* tests;
+    const float* bound;  // per-cell opacity bound (cpm_opacity_bound) or null
+    // cell of a sample p, per axis: floor(p * bfc + bhc) = floor((p * dim + 0.5) / cell), clamped to [0, bmax]
+    float bfc[3], bhc, bmax[3];
+    unsigned bbias;  // (1 + bnx + bnxy) * 0x4B400000 mod 2^32: removes the float-bit biases of the three cell coordinates
+    int bnx, bnxy;
+    int scan;  // cheap tests a lane scans before the warp reconverges for the candidate fetches
 };
 
 __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x, float y, float z, float pr, float pg,
@@ -42,6 +48,9 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 }
 
 #define CPM_FLT_MAX 3.402823466e+38f
+#ifndef CPM_SCAN
+#define CPM_SCAN 8  // cheap tests a lane scans before the warp reconverges for the candidate fetches
+#endif
 
 // woodcockTracking (ppm/cl/transmittance.cl:126-144).  The step length of test k+1 depends only on the
 // random stream, not on the outcome of test k, so the taps of sample k+1 are requested BEFORE sample k is
@@ -82,14 +91,107 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
     return t;
 }
 
+// Opacity bound of the cell that holds the trilinear footprint of the sample at parameter t of the ray
+// w(t) = wo + t * wd, the ray in CELL coordinates (set up once per walk).  The cell is floor(w) per axis; bound.cu
+// pads every cell by one voxel, which absorbs the rounding difference between this arithmetic and
+// fetch_taps' i0 = floor(p * dim - 0.5).  No conversion instructions: clamp (fmaxf maps NaN to 0), then the
+// 1.5 * 2^23 addition rounded down leaves floor(w) + 0x4B400000 in the bits; the three biases leave the index
+// with one wrapping subtraction.
+struct CellRay {
+    float ox, oy, oz, dx, dy, dz;
+};
+__device__ __forceinline__ CellRay cell_ray(const TraceArgs& A, float3_ o, float3_ d) {
+    return {fmaf(o.x, A.bfc[0], A.bhc), fmaf(o.y, A.bfc[1], A.bhc), fmaf(o.z, A.bfc[2], A.bhc),
+            d.x * A.bfc[0], d.y * A.bfc[1], d.z * A.bfc[2]};
+}
+__device__ __forceinline__ unsigned cell_bits(float w, float wmax) {
+    return __float_as_uint(__fadd_rd(fminf(fmaxf(w, 0.0f), wmax), 12582912.0f));
+}
+__device__ __forceinline__ float bound_at(const TraceArgs& A, const CellRay& R, float t) {
+    unsigned bx = cell_bits(fmaf(t, R.dx, R.ox), A.bmax[0]);
+    unsigned by = cell_bits(fmaf(t, R.dy, R.oy), A.bmax[1]);
+    unsigned bz = cell_bits(fmaf(t, R.dz, R.oz), A.bmax[2]);
+    return __ldg(A.bound + (bx + by * (unsigned)A.bnx + bz * (unsigned)A.bnxy - A.bbias));
+}
+
+// log(u) for u = k * 2^-32, k a 32-bit integer (the values cpm_rng_01 returns): cpm_logf without its
+// subnormal / inf / NaN exits, which such arguments never take; the zero case becomes a select.
+__device__ __forceinline__ float log_unit(float x) {
+    uint32_t ix = __float_as_uint(x);
+    uint32_t jx = ix + (0x3f800000u - 0x3f3504f3u);
+    float fe = __uint_as_float((jx >> 23) + (0x4B400000u - 127u)) - 12582912.0f;
+    float f = __uint_as_float((jx & 0x007fffffu) + 0x3f3504f3u) - 1.0f;
+    float z = f * f;
+    float p = 7.0376836292E-2f;
+    p = fmaf(p, f, -1.1514610310E-1f);
+    p = fmaf(p, f, 1.1676998740E-1f);
+    p = fmaf(p, f, -1.2420140846E-1f);
+    p = fmaf(p, f, 1.4249322787E-1f);
+    p = fmaf(p, f, -1.6668057665E-1f);
+    p = fmaf(p, f, 2.0000714765E-1f);
+    p = fmaf(p, f, -2.4999993993E-1f);
+    p = fmaf(p, f, 3.3333331174E-1f);
+    float y = (f * z) * p;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(-0.5f, z, y);
+    float r = fmaf(fe, 0.693359375f, f + y);
+    return ix == 0u ? __uint_as_float(0xff800000u) : r;
+}
+
+// The same walk with the per-cell opacity bound (bound.cu).  A test continues the walk iff
+// `u2 >= opacity && t <= tEnd`; with m >= opacity known for the cell, `u2 >= m` decides "continue" without the
+// voxel and transfer-function fetches, and `!(t <= tEnd)` ends the walk whatever the opacity is.  Only the
+// remaining CANDIDATE tests are evaluated in full.  Draws, positions and results are those of the plain loop.
+//
+// Scheduling: every lane scans through cheap tests (two draws, one log, one L1/L2-resident bound lookup)
+// until it holds a candidate, leaves the volume, or has done A.scan tests; the warp then reconverges and all
+// lanes holding a candidate fetch their taps together, so the expensive path runs warp-coherently instead of
+// once per lane and iteration.
 template <int FMT, int LAYOUT>
+__device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const float* s_alpha, int tfw, float ftfw,
+                                                  float3_ o, float3_ d, float tStart, float tEnd, cpm_rng& rng,
+                                                  unsigned& tests, unsigned& fetched) {
+    const VolumeView& V = A.vol;
+    const float inv = 1.0f / 150.0f;
+    const CellRay R = cell_ray(A, o, d);
+    float t = tStart;
+    while (true) {
+        bool cand = false, done = false;
+        float u2 = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < A.scan; ++k) {
+            t = fmaf(-log_unit(cpm_rng_01(rng)), inv, t);
+            u2 = cpm_rng_01(rng);
+            ++tests;
+            if (!(t <= tEnd)) {
+                done = true;
+                break;
+            }
+            float m = bound_at(A, R, t);
+            if (!(u2 >= m)) {
+                cand = true;
+                break;
+            }
+        }
+        if (cand) {
+            ++fetched;
+            float v = sample_volume<FMT, LAYOUT>(V, fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+            float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
+            done = !(u2 >= opacity);
+        }
+        if (done) break;
+    }
+    return t;
+}
+
+template <int FMT, int LAYOUT, bool BOUNDED>
 __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
     extern __shared__ float s_alpha[];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
     __syncthreads();
 
     const cpm_trace_params& P = A.p;
-    unsigned tests = 0;
+    unsigned tests = 0, fetched = 0;
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int tid = -1;
     if (gid < A.n_work) {
@@ -118,7 +220,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
 
         if (P.flags & CPM_TRACE_NO_SINGLE_SCATTERING) {
             // photontracer.cl:143-157: the walk is executed even when the ray misses
-            float t = woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT>(A, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
+                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             if (scatter) {
                 o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
                 tStart = 0.0f;
@@ -134,7 +237,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
             }
         }
         while (scatter) {
-            float t = woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT>(A, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
+                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             scatter = t <= tEnd;
             if (scatter) {
                 o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
@@ -176,16 +280,25 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
         unsigned long long v = tests;
         for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(A.tests, v);
+        if (P.flags & CPM_TRACE_STATS) {
+            unsigned long long f = BOUNDED ? fetched : tests;
+            for (int off = 16; off; off >>= 1) f += __shfl_xor_sync(0xffffffffu, f, off);
+            if ((threadIdx.x & 31) == 0 && f) atomicAdd(A.tests + 1, f);
+        }
     }
 }
 
-template <int FMT, int LAYOUT>
-int launch(cpm_ctx* ctx, const TraceArgs& a) {
+template <int FMT, int LAYOUT, bool BOUNDED>
+int launch2(cpm_ctx* ctx, const TraceArgs& a) {
     size_t smem = (size_t)a.tf_width * sizeof(float);
     if (smem > 48 * 1024)
-        CPM_CUDA(ctx, cudaFuncSetAttribute(trace_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT>), cpm_div_up(a.n_work, 128), 128, smem, a);
+        CPM_CUDA(ctx, cudaFuncSetAttribute(trace_kernel<FMT, LAYOUT, BOUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT, BOUNDED>), cpm_div_up(a.n_work, 128), 128, smem, a);
     return CPM_OK;
+}
+template <int FMT, int LAYOUT>
+int launch(cpm_ctx* ctx, const TraceArgs& a) {
+    return a.bound ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
 }
 
 }  // namespace
@@ -214,6 +327,28 @@ extern "C" int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const floa
     a.photons = (float4*)photons;
     a.rng = (uint2*)rng_state;
     a.tests = collision_tests;
+    a.bound = params->opacity_bound;
+    a.bnx = a.bnxy = 0;
+    a.bbias = 0;
+    static const int scan_env = getenv("CPM_TRACE_SCAN") ? atoi(getenv("CPM_TRACE_SCAN")) : 0;   // tuning sweeps only
+    a.scan = scan_env > 0 ? scan_env : CPM_SCAN;
+    if (a.bound) {
+        CPM_REQUIRE(ctx, params->bound_cell_log2 >= 0 && params->bound_cell_log2 <= 8, "bound_cell_log2 must be in 0..8");
+        const int sh = params->bound_cell_log2;
+        const float cell = (float)(1 << sh);
+        int gd[3];
+        for (int k = 0; k < 3; ++k) {
+            gd[k] = (vol->dims[k] >> sh) + 1;
+            a.bfc[k] = (float)vol->dims[k] / cell;   // exact: cell is a power of two
+            a.bmax[k] = (float)(gd[k] - 1);
+        }
+        a.bhc = 0.5f / cell;
+        a.bnx = gd[0];
+        a.bnxy = gd[0] * gd[1];
+        CPM_REQUIRE(ctx, (double)gd[0] * gd[1] * gd[2] < 2147483648.0, "bound grid too large");
+        // indices are formed from raw float bits (cell + 0x4B400000 per axis) with wrapping 32-bit arithmetic
+        a.bbias = 0x4B400000u * (1u + (uint32_t)a.bnx + (uint32_t)a.bnxy);
+    }
     if (a.n_work == 0) return CPM_OK;
 #define CPM_DISPATCH(F)                                                                  \
     return vol->layout == CPM_VOLUME_TEXTURE ? launch<F, CPM_VOLUME_TEXTURE>(ctx, a)      \

@@ -19,7 +19,7 @@ class HostConfig(C.Structure):
         ("max_scattering_events", C.c_int32), ("light_volume_option", C.c_int32), ("light_volume_channels", C.c_int32),
         ("with_importance_grid", C.c_int32), ("volume_layout", C.c_int32), ("photon_radius_voxels", C.c_float),
         ("max_incremental_percent", C.c_float), ("clip", C.c_int32 * 6), ("reference_full_splat_bound", C.c_int32),
-        ("incremental_threshold_percent", C.c_float),
+        ("incremental_threshold_percent", C.c_float), ("opacity_bound_cell_log2", C.c_int32),
     ]
 
 
@@ -51,6 +51,7 @@ def lib():
         _lib.cpmh_network_count_collision_tests.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_read_collision_tests.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_read_collision_tests.restype = C.c_ulonglong
+        _lib.cpmh_network_read_collision_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
         _lib.cpmh_profile_enable.argtypes = [C.c_int]
         _lib.cpmh_profile_enable.restype = None
         _lib.cpmh_profile_reset.restype = None
@@ -115,7 +116,7 @@ class Network:
     def __init__(self, dims, fmt, samples_per_side, light_directions, max_scattering_events=1, light_volume_option=2,
                  light_volume_channels=1, with_importance_grid=False, volume_layout=1, photon_radius_voxels=1.0,
                  max_incremental_percent=100.0, clip=None, device=0, light_intensity=None,
-                 reference_full_splat_bound=True, incremental_threshold=0.0):
+                 reference_full_splat_bound=True, incremental_threshold=0.0, opacity_bound_cell_log2=0):
         cfg = HostConfig()
         cfg.device = device
         cfg.dims[:] = [int(d) for d in dims]
@@ -137,6 +138,7 @@ class Network:
             cfg.clip[:] = [int(c) for c in clip]
         cfg.reference_full_splat_bound = int(reference_full_splat_bound)
         cfg.incremental_threshold_percent = incremental_threshold
+        cfg.opacity_bound_cell_log2 = opacity_bound_cell_log2   # 0 default (8^3 cells), < 0 off
         self.h = C.c_void_p()
         self._keep = []
         self._check(lib().cpmh_network_create(C.byref(cfg), C.byref(self.h)))
@@ -208,6 +210,12 @@ class Network:
 
     def read_collision_tests(self, reset=False):
         return int(lib().cpmh_network_read_collision_tests(self.h, int(reset)))
+
+    def read_collision_stats(self, reset=False):
+        """(collision tests, tests that fetched voxels); the rest were decided by the opacity bound"""
+        out = (C.c_ulonglong * 2)()
+        self._check(lib().cpmh_network_read_collision_stats(self.h, out, int(reset)))
+        return int(out[0]), int(out[1])
 
     def evaluate(self) -> int:
         return self._check(lib().cpmh_network_evaluate(self.h))

@@ -100,6 +100,8 @@ int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
         n->tracer.radius_.set(cfg->photon_radius_voxels > 0 ? cfg->photon_radius_voxels : 1.f);
         if (cfg->max_incremental_percent > 0) n->tracer.maxIncrementalPhotonsToUpdate_.set(cfg->max_incremental_percent);
         n->tracer.tracer().volumeLayout = cfg->volume_layout;
+        n->tracer.tracer().useOpacityBound = cfg->opacity_bound_cell_log2 >= 0;
+        if (cfg->opacity_bound_cell_log2 > 0) n->tracer.tracer().boundCellLog2 = cfg->opacity_bound_cell_log2;
         n->toLightVolume.volumeInport_.connectTo(&n->volumeSource);
         n->toLightVolume.photons_.connectTo(&n->tracer.outport_);
         n->toLightVolume.recomputedPhotonIndicesPort_.connectTo(&n->tracer.recomputedIndicesPort_);
@@ -164,6 +166,7 @@ int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels,
             v->setExternalRAMData(const_cast<void*>(voxels[t]));
             v->deviceRead();   // keep the whole series resident in HBM ...
             v->handle(net->tracer.tracer().volumeLayout);   // ... in the layout the tracer samples (no allocation inside a frame)
+            if (net->tracer.tracer().useOpacityBound) v->valueRange(net->tracer.tracer().boundCellLog2, nullptr);   // per-step, like the min-max grids
             seq->push_back(v);
         }
         CpmRuntime::get().sync();
@@ -280,8 +283,8 @@ int cpmh_network_count_collision_tests(cpmh_network* net, int on) {
         auto& rt = CpmRuntime::get();
         if (on && !net->collisionCounter) {
             void* p = nullptr;
-            rt.check(cpm_mem_alloc(rt.ctx(), sizeof(unsigned long long), &p));
-            rt.check(cpm_mem_fill_u32(rt.ctx(), p, 0u, 2));
+            rt.check(cpm_mem_alloc(rt.ctx(), 2 * sizeof(unsigned long long), &p));   // [0] tests, [1] tests that fetched voxels
+            rt.check(cpm_mem_fill_u32(rt.ctx(), p, 0u, 4));
             net->collisionCounter = static_cast<unsigned long long*>(p);
         }
         net->tracer.tracer().collisionCounter = on ? net->collisionCounter : nullptr;
@@ -289,17 +292,21 @@ int cpmh_network_count_collision_tests(cpmh_network* net, int on) {
     });
 }
 
-unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset) {
-    unsigned long long v = 0;
-    guarded([&]() {
+int cpmh_network_read_collision_stats(cpmh_network* net, unsigned long long out[2], int reset) {
+    out[0] = out[1] = 0;
+    return guarded([&]() {
         if (!net->collisionCounter) return (int)CPM_OK;
         auto& rt = CpmRuntime::get();
-        rt.check(cpm_mem_copy_d2h(rt.ctx(), &v, net->collisionCounter, sizeof(v)));
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, net->collisionCounter, 2 * sizeof(unsigned long long)));
         rt.sync();
-        if (reset) rt.check(cpm_mem_fill_u32(rt.ctx(), net->collisionCounter, 0u, 2));
+        if (reset) rt.check(cpm_mem_fill_u32(rt.ctx(), net->collisionCounter, 0u, 4));
         return (int)CPM_OK;
     });
-    return v;
+}
+unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset) {
+    unsigned long long v[2];
+    cpmh_network_read_collision_stats(net, v, reset);
+    return v[0];
 }
 
 int cpmh_network_evaluate(cpmh_network* net) {

@@ -35,6 +35,9 @@ typedef struct cpmh_config {
     int32_t clip[6];             /* clipX.min,max, clipY.., clipZ..; all zero = no clipping */
     int32_t reference_full_splat_bound;
     float incremental_threshold_percent; /* `incrementalRecomputationThreshold`; 0 = the reference's default 50 */
+    int32_t opacity_bound_cell_log2; /* tracer's per-cell opacity bound (cpm_opacity_bound): 0 = default (8^3-voxel
+                                        cells), n > 0 = 2^n voxels per axis, < 0 = off (fetch for every test, as
+                                        the reference does); photons are identical in every setting */
 } cpmh_config;
 
 /* One context per process.  Optional: call before the first network is created to choose the CUDA
@@ -73,6 +76,8 @@ CPMH_API int cpmh_network_photons_device(cpmh_network* net, void** ptr, size_t* 
 /* count delta-tracking collision tests of every trace from now on (device counter); read = sync */
 CPMH_API int cpmh_network_count_collision_tests(cpmh_network* net, int on);
 CPMH_API unsigned long long cpmh_network_read_collision_tests(cpmh_network* net, int reset);
+/* out[0] = collision tests, out[1] = the ones that fetched voxels (the rest were decided by the opacity bound) */
+CPMH_API int cpmh_network_read_collision_stats(cpmh_network* net, unsigned long long out[2], int reset);
 /* evaluate every invalid processor in network order; returns the number of processors that ran */
 CPMH_API int cpmh_network_evaluate(cpmh_network* net);
 /* progressive work left (budgeted re-trace batches): call evaluate again while > 0 */

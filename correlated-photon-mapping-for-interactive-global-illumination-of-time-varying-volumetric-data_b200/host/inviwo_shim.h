@@ -138,6 +138,7 @@ private:
     std::vector<Pending> pending_;
     std::string open_;
     cpm_event* openEv_ = nullptr;
+    int depth_ = 0;
     struct Acc { double total = 0, last = 0; int n = 0; };
     std::map<std::string, Acc> acc_;
 };
@@ -256,8 +257,19 @@ public:
     const void* deviceRead();
     void* deviceWrite();
     const cpm_volume* handle(int layout);   // CPM_VOLUME_LINEAR or CPM_VOLUME_TEXTURE; refreshed after uploads
+    // (min, max) voxel value per cell of the tracer's opacity-bound grid (cpm_volume_value_range): a derived
+    // device representation like the texture copy, recomputed after the voxels changed
+    const float* valueRange(int cellLog2, size_t* nCells);
+    void formatScaleOffset(float& scale, float& offset) const;
+    uint64_t dataVersion() const { return version_; }   // changes whenever the voxels may have changed
 private:
     void ensureDevice();
+    void touch();
+    void* range_ = nullptr;
+    size_t rangeCells_ = 0;
+    int rangeLog2_ = -1;
+    bool rangeValid_ = false;
+    uint64_t version_ = 0;
     size3_t dim_;
     const DataFormatBase* format_;
     mat4 model_, world_;
@@ -304,8 +316,10 @@ public:
     // the RGBA float32 layer (piecewise linear between points, constant outside), device side
     const float* deviceData();
     const std::vector<vec4>& ramData();
+    uint64_t version() { if (dirty_) rasterise(); return version_; }   // changes with the rasterised texels
 private:
     void rasterise();
+    uint64_t version_ = 0;
     std::vector<TFPrimitive> points_;
     Buffer<vec4> data_;
     bool dirty_ = true;

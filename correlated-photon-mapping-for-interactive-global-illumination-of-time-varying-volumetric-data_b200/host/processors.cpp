@@ -1,5 +1,6 @@
 // processors.cpp -- implementation of the Inviwo shim, the kernel-launcher classes and the
 // drop-in processors.  Every device operation is one call into the C ABI (include/cpm_b200.h).
+#include <atomic>
 #include "processors.h"
 
 #include <cstdio>
@@ -75,13 +76,15 @@ cpm_event* StageProfiler::take() {
     return e;
 }
 void StageProfiler::begin(const char* stage) {
-    if (!enabled || openEv_) return;   // stages do not nest: the outermost wins
+    if (!enabled) return;
+    if (depth_++ > 0) return;   // stages do not nest: the outermost wins
     open_ = stage;
     openEv_ = take();
     CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), openEv_));
 }
 void StageProfiler::end() {
-    if (!enabled || !openEv_) return;
+    if (!enabled || depth_ == 0) return;
+    if (--depth_ > 0 || !openEv_) return;
     cpm_event* b = take();
     CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), b));
     pending_.push_back({open_, openEv_, b});
@@ -104,6 +107,9 @@ void StageProfiler::resolve() {
 }
 void StageProfiler::reset() {
     resolve();
+    if (openEv_) pool_.push_back(openEv_);   // a stage left open by an exception
+    openEv_ = nullptr;
+    depth_ = 0;
     acc_.clear();
 }
 double StageProfiler::totalMs(const std::string& s) { resolve(); auto it = acc_.find(s); return it == acc_.end() ? 0.0 : it->second.total; }
@@ -178,12 +184,14 @@ Volume::Volume(size3_t dim, const DataFormatBase* format) : dim_(dim), format_(f
     dataMap_.dataRange = {0.0, format->maxValue};
     dataMap_.valueRange = dataMap_.dataRange;
     ram_.assign(getSizeInBytes(), 0);
+    touch();
 }
 Volume::~Volume() {
     cpm_ctx* c = g_runtime.ctx();
     if (prefetchDone_) cpm_event_destroy(c, prefetchDone_);
     if (lin_) cpm_volume_destroy(c, lin_);
     if (tex_) cpm_volume_destroy(c, tex_);
+    if (range_ && c) cpm_mem_free(c, range_);
     if (dev_ && c) cpm_mem_free(c, dev_);
 }
 void Volume::setDimensions(size3_t d) {
@@ -200,7 +208,7 @@ void Volume::setDimensions(size3_t d) {
 void* Volume::getEditableRAMData() {
     getRAMData();
     devValid_ = false;
-    texValid_ = false;
+    texValid_ = false; touch();
     return ext_ ? ext_ : (void*)ram_.data();
 }
 const void* Volume::getRAMData() {
@@ -216,7 +224,7 @@ const void* Volume::getRAMData() {
 void Volume::setExternalRAMData(void* ptr) {
     ext_ = ptr;
     ramValid_ = true;
-    texValid_ = false;
+    texValid_ = false; touch();
     if (ptr && ptr == prefetched_ && prefetchDone_) {
         // adopt the upload started by prefetchExternalRAMData: the context stream waits for it, nothing is copied
         auto& rt = CpmRuntime::get();
@@ -241,7 +249,7 @@ void Volume::prefetchExternalRAMData(void* ptr) {
     BufferBase::h2dBytes() += devBytes_;
     prefetched_ = ptr;
     devValid_ = false;
-    texValid_ = false;
+    texValid_ = false; touch();
 }
 void Volume::ensureDevice() {
     size_t bytes = getSizeInBytes();
@@ -264,7 +272,7 @@ const void* Volume::deviceRead() {
         CPM_CHECK(cpm_mem_copy_h2d(CpmRuntime::get().ctx(), dev_, p, devBytes_));
         if (!ext_) CpmRuntime::get().sync();   // external (pinned) sources stay valid; stream order suffices
         BufferBase::h2dBytes() += devBytes_;
-        texValid_ = false;
+        texValid_ = false; touch();
     }
     devValid_ = true;
     return dev_;
@@ -273,7 +281,7 @@ void* Volume::deviceWrite() {
     ensureDevice();
     devValid_ = true;
     ramValid_ = false;
-    texValid_ = false;
+    texValid_ = false; touch();
     return dev_;
 }
 const cpm_volume* Volume::handle(int layout) {
@@ -282,10 +290,8 @@ const cpm_volume* Volume::handle(int layout) {
     const int dims[3] = {(int)dim_.x, (int)dim_.y, (int)dim_.z};
     int fmt = format_->id == DataFormatId::UInt8 ? CPM_FMT_U8 : (format_->id == DataFormatId::UInt16 ? CPM_FMT_U16 : CPM_FMT_F32);
     if (format_->id == DataFormatId::Vec4Float32) throw CpmError(CPM_E_UNSUPPORTED, "vec4 volumes cannot be sampled");
-    // "Scaling for 12-bit data": normalised = (v/typeMax) * typeMax/(dataRange.y - dataRange.x) - dataRange.x/(range)
-    double range = dataMap_.dataRange.y - dataMap_.dataRange.x;
-    float scale = (float)(format_->maxValue / range);
-    float offset = (float)(-dataMap_.dataRange.x / format_->maxValue);
+    float scale, offset;
+    formatScaleOffset(scale, offset);
     if (layout == CPM_VOLUME_LINEAR) {
         if (!lin_) CPM_CHECK(cpm_volume_create(c, d, dims, fmt, scale, offset, CPM_VOLUME_LINEAR, &lin_));
         return lin_;
@@ -300,6 +306,41 @@ const cpm_volume* Volume::handle(int layout) {
         texValid_ = true;
     }
     return tex_;
+}
+
+void Volume::formatScaleOffset(float& scale, float& offset) const {
+    // "Scaling for 12-bit data": normalised = (v/typeMax) * typeMax/(dataRange.y - dataRange.x) - dataRange.x/(range)
+    double range = dataMap_.dataRange.y - dataMap_.dataRange.x;
+    scale = (float)(format_->maxValue / range);
+    offset = (float)(-dataMap_.dataRange.x / format_->maxValue);
+}
+static std::atomic<uint64_t> g_dataVersion{0};
+void Volume::touch() {
+    rangeValid_ = false;
+    version_ = ++g_dataVersion;
+}
+const float* Volume::valueRange(int cellLog2, size_t* nCells) {
+    const cpm_volume* vh = handle(CPM_VOLUME_LINEAR);   // uploads when the device copy is stale
+    cpm_ctx* c = CpmRuntime::get().ctx();
+    const int dims[3] = {(int)dim_.x, (int)dim_.y, (int)dim_.z};
+    int gd[3];
+    CPM_CHECK(cpm_bound_grid_dims(dims, cellLog2, gd));
+    const size_t n = (size_t)gd[0] * gd[1] * gd[2];
+    if (n != rangeCells_ || cellLog2 != rangeLog2_) {
+        if (range_) cpm_mem_free(c, range_);
+        range_ = nullptr;
+        CPM_CHECK(cpm_mem_alloc(c, n * 2 * sizeof(float), &range_));
+        rangeCells_ = n;
+        rangeLog2_ = cellLog2;
+        rangeValid_ = false;
+    }
+    if (!rangeValid_) {
+        ScopedStage st("range");
+        CPM_CHECK(cpm_volume_value_range(c, vh, cellLog2, static_cast<float*>(range_), nullptr));
+        rangeValid_ = true;
+    }
+    if (nCells) *nCells = n;
+    return static_cast<const float*>(range_);
 }
 
 mat4 StructuredCoordinateTransformer::getTextureToIndexMatrix() const {
@@ -347,6 +388,7 @@ void TransferFunction::rasterise() {
         (*ram)[i] = c;
     }
     dirty_ = false;
+    version_ = ++g_dataVersion;
 }
 const float* TransferFunction::deviceData() {
     if (dirty_) rasterise();
@@ -634,6 +676,7 @@ void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, co
     // the reference overwrites instead of appending its -D flags (ppm/photontracercl.cpp:202-207);
     // here the two switches are independent
     p.flags = (progressive_ ? CPM_TRACE_PROGRESSIVE : 0) | (onlyMultipleScattering_ ? CPM_TRACE_NO_SINGLE_SCATTERING : 0);
+    if (collisionCounter) p.flags |= CPM_TRACE_STATS;   // the counter buffer holds two counters
     auto& rt = CpmRuntime::get();
     const cpm_volume* vh = const_cast<Volume*>(volume)->handle(volumeLayout);
     uint32_t* rng = static_cast<uint32_t*>(const_cast<void*>(randomState_.deviceRead()));
@@ -644,7 +687,25 @@ void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, co
     // a re-trace rewrites part of the buffer: the rest must be valid on the device first
     float* photons = recomputeIdx ? static_cast<float*>(const_cast<void*>(photonOutData->photons_.deviceRead())) : nullptr;
     photons = static_cast<float*>(photonOutData->photons_.deviceWrite());
-    rt.check(cpm_trace_photons(rt.ctx(), vh, tf.deviceData(), (int)tf.getTextureSize(), &p, ls, ip, idx, nInvalidPhotons, photons,
+    const float* tfData = tf.deviceData();
+    if (useOpacityBound) {
+        // per-cell opacity bound of (this volume, this transfer function): refreshed when either changed
+        size_t nCells = 0;
+        const float* range = const_cast<Volume*>(volume)->valueRange(boundCellLog2, &nCells);
+        if (opacityBound_.getSize() != nCells || boundVolumeVersion_ != volume->dataVersion() || boundTfVersion_ != tf.version()) {
+            ScopedStage st("bound");
+            float scale, offset;
+            volume->formatScaleOffset(scale, offset);
+            opacityBound_.setSize(nCells);
+            rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tfData, (int)tf.getTextureSize(),
+                                       static_cast<float*>(opacityBound_.deviceWrite())));
+            boundVolumeVersion_ = volume->dataVersion();
+            boundTfVersion_ = tf.version();
+        }
+        p.opacity_bound = static_cast<const float*>(opacityBound_.deviceRead());
+        p.bound_cell_log2 = boundCellLog2;
+    }
+    rt.check(cpm_trace_photons(rt.ctx(), vh, tfData, (int)tf.getTextureSize(), &p, ls, ip, idx, nInvalidPhotons, photons,
                                rng, collisionCounter));
 }
 

@@ -197,7 +197,12 @@ public:
     bool isProgressive() const { return progressive_; }
     bool isValid() const { return true; }
     unsigned long long* collisionCounter = nullptr;   // optional device counter (benchmarks)
+    // per-cell opacity bound (cpm_opacity_bound): collision tests it decides skip the voxel fetch, results unchanged
+    bool useOpacityBound = true;
+    int boundCellLog2 = 3;
 private:
+    Buffer<float> opacityBound_;
+    uint64_t boundVolumeVersion_ = 0, boundTfVersion_ = 0;
     Buffer<uvec2> randomState_;
     bool onlyMultipleScattering_ = false, progressive_ = false;
 };

@@ -169,8 +169,10 @@ CPM_API void cpm_volume_destroy(cpm_ctx* ctx, cpm_volume* vol);
 
 /* ---- (3) photon tracer -------------------------------------------------------------- */
 enum {
-    CPM_TRACE_PROGRESSIVE = 1,         /* -D PROGRESSIVE_PHOTON_MAPPING: save RNG state */
-    CPM_TRACE_NO_SINGLE_SCATTERING = 2 /* -D NO_SINGLE_SCATTERING */
+    CPM_TRACE_PROGRESSIVE = 1,          /* -D PROGRESSIVE_PHOTON_MAPPING: save RNG state */
+    CPM_TRACE_NO_SINGLE_SCATTERING = 2, /* -D NO_SINGLE_SCATTERING */
+    CPM_TRACE_STATS = 4                 /* collision_tests points to TWO counters: [0] collision tests,
+                                           [1] tests that fetched voxels (== [0] without an opacity bound) */
 };
 enum { CPM_PHASE_ISOTROPIC = 0, CPM_PHASE_HENYEY_GREENSTEIN = 1 };
 
@@ -186,6 +188,12 @@ typedef struct cpm_trace_params {
     int32_t total_photons; /* photonData->getNumberOfPhotons(): stride between interactions */
     int32_t n_light_samples;
     uint32_t flags;        /* CPM_TRACE_* */
+    /* Optional per-cell opacity bound written by cpm_opacity_bound for THIS volume and THIS transfer function
+     * (NULL = test every sample like the reference).  Results are identical either way; with a bound, tests whose
+     * second random number is >= the bound of their cell are decided without fetching voxels. */
+    const float* opacity_bound;
+    int32_t bound_cell_log2; /* the cell_log2 the bound grid was built with */
+    int32_t reserved_;
 } cpm_trace_params;
 
 /* photonTracerKernel (ppm/cl/photontracer.cl:69-216) incl. woodcockTracking
@@ -207,6 +215,25 @@ CPM_API int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const float* 
                               const float* light_samples, const float* intersections,
                               const uint32_t* recompute_index, int n_recompute, float* photons,
                               uint32_t* rng_state, unsigned long long* collision_tests);
+
+/* ---- (3b) opacity-bound grid for the tracer ("L2-resident bricks") ------------------------ */
+/* Not in the reference, which fetches 8 voxels + the transfer function for every collision test
+ * (ppm/cl/transmittance.cl:134-140).  A test rejects when u2 >= opacity; with an upper bound of the opacity over
+ * the cell the sample falls in, u2 >= bound decides the same without the fetch.  Random stream, positions and
+ * photons are unchanged (tests compare the bounded tracer bit for bit with the unbounded one and the oracle).
+ *
+ * Cells have 2^cell_log2 voxels per axis; grid dims = (dims >> cell_log2) + 1 (cpm_bound_grid_dims).  Cell c
+ * holds the trilinear footprints whose lower tap i0 has (i0 + 1) >> cell_log2 == c.
+ * cpm_volume_value_range: range[c] = float2 (min, max) of the normalised voxel values (v/255, v/65535, v) those
+ * footprints touch; NaN pair when a voxel is NaN/inf.  Needs a LINEAR volume.  One pass per volume / time step. */
+CPM_API int cpm_bound_grid_dims(const int dims[3], int cell_log2, int out_dims[3]);
+CPM_API int cpm_volume_value_range(cpm_ctx* ctx, const cpm_volume* vol, int cell_log2, float* range /* float2 per cell */,
+                                   int out_dims[3]);
+/* bound[c] >= alpha of tf_rgba at every value (v + format_offset) * format_scale, v in range[c], including the
+ * rounding of the fp32 trilinear / TF blends; +inf (always fetch) where NaN/inf makes that impossible.  Re-run
+ * when the volume (range) or the transfer function changes. */
+CPM_API int cpm_opacity_bound(cpm_ctx* ctx, const float* range, size_t n_cells, float format_scale, float format_offset,
+                              const float* tf_rgba, int tf_width, float* bound);
 
 /* ---- (5) selection: threshold / count / iota / radix sort --------------------------- */
 /* thresholdKernel (ppm/cl/threshold.cl:33-40): out[i] = data[i] < threshold. */
