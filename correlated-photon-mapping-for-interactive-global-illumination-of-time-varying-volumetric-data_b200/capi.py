@@ -256,6 +256,13 @@ def _reduce_sum_i32(self, data):
     return r.value
 
 
+def _select_below(self, data, threshold, ids_out, n=None):
+    r = C.c_longlong(0)
+    n = data.numel() if n is None else n
+    self._check(lib().cpm_select_below(self.h, _p(data), C.c_size_t(n), C.c_uint32(threshold), _p(ids_out), C.byref(r)))
+    return r.value
+
+
 def _count_below(self, data, threshold, iota_out=None, n=None):
     r = C.c_longlong(0)
     n = data.numel() if n is None else n
@@ -273,6 +280,7 @@ Context.threshold = _threshold
 Context.iota = _iota
 Context.reduce_sum_i32 = _reduce_sum_i32
 Context.count_below = _count_below
+Context.select_below = _select_below
 Context.radix_sort = _radix_sort
 
 

@@ -355,6 +355,66 @@ __global__ void __launch_bounds__(256) reduce_kernel(const uint32_t* __restrict_
     }
 }
 
+// ---- stable selection: ids of the elements below a threshold, ascending ---------------------------------
+// One pass: a tile (8 warps x 512 consecutive elements) ranks its hits with ballots (16 coalesced loads per
+// lane, order = element order), one thread chains the tile totals through a decoupled look-back over status
+// words (2 flag bits + 30 value bits), then every warp writes its ids to a contiguous range.
+constexpr int SEL_ROUNDS = 16, SEL_WARPS = 8, SEL_TILE = SEL_ROUNDS * 32 * SEL_WARPS;
+constexpr uint32_t SEL_AGG = 1u << 30, SEL_INC = 2u << 30, SEL_VAL = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const uint32_t* __restrict__ data, size_t n, uint32_t threshold,
+                                                                uint32_t* __restrict__ out, volatile uint32_t* status,
+                                                                uint32_t* ticket, unsigned long long* __restrict__ result,
+                                                                unsigned n_tiles) {
+    __shared__ uint32_t s_tile, s_base, s_warp[SEL_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t base = (size_t)tile * SEL_TILE + (size_t)warp * (SEL_ROUNDS * 32);
+    uint32_t masks[SEL_ROUNDS];
+    uint32_t wtotal = 0;
+#pragma unroll
+    for (int r = 0; r < SEL_ROUNDS; ++r) {
+        size_t i = base + r * 32 + lane;
+        bool hit = i < n && data[i] < threshold;
+        masks[r] = __ballot_sync(0xffffffffu, hit);
+        wtotal += __popc(masks[r]);
+    }
+    if (lane == 0) s_warp[warp] = wtotal;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < SEL_WARPS; ++w) total += s_warp[w];
+        uint32_t excl = 0;
+        if (tile > 0) {
+            status[tile] = SEL_AGG | total;
+            __threadfence();
+            for (int p = (int)tile - 1; p >= 0; --p) {
+                uint32_t st;
+                while (((st = status[p]) & (SEL_AGG | SEL_INC)) == 0) {
+                }
+                excl += st & SEL_VAL;
+                if (st & SEL_INC) break;
+            }
+        }
+        status[tile] = SEL_INC | (excl + total);
+        __threadfence();
+        s_base = excl;
+        if (tile == n_tiles - 1) *result = (unsigned long long)(excl + total);
+    }
+    __syncthreads();
+    uint32_t wbase = s_base;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SEL_ROUNDS; ++r) {
+        uint32_t m = masks[r];
+        if ((m >> lane) & 1u) out[wbase + __popc(m & lt)] = (uint32_t)(base + r * 32 + lane);
+        wbase += __popc(m);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -451,6 +511,31 @@ static int reduce_common(cpm_ctx* ctx, bool count_below, const uint32_t* data, u
     CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
     CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *result_host = (long long)*pinned;
+    return CPM_OK;
+}
+
+int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out,
+                     long long* count_host) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, count_host != nullptr, "result pointer is NULL");
+    *count_host = 0;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, data && ids_out, "null buffer");
+    if (n >= (1ull << 30)) return cpm_fail(ctx, CPM_E_UNSUPPORTED, "cpm_select_below: n must be < 2^30");
+    const size_t tiles = (n + SEL_TILE - 1) / SEL_TILE;
+    void* scratch;
+    int rc = cpm_scratch(ctx, 4096 + tiles * sizeof(uint32_t), &scratch);
+    if (rc != CPM_OK) return rc;
+    unsigned long long* acc = (unsigned long long*)((char*)scratch + 2048);
+    uint32_t* ticket = (uint32_t*)((char*)scratch + 2048 + 8);
+    uint32_t* status = (uint32_t*)((char*)scratch + 4096);
+    CPM_CUDA(ctx, cudaMemsetAsync((char*)scratch + 2048, 0, 2048 + tiles * sizeof(uint32_t), ctx->stream));
+    CPM_LAUNCH(ctx, select_kernel, (unsigned)tiles, SEL_WARPS * 32, 0, data, n, threshold, ids_out, status, ticket, acc,
+               (unsigned)tiles);
+    unsigned long long* pinned = (unsigned long long*)ctx->pinned;
+    CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
+    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *count_host = (long long)*pinned;
     return CPM_OK;
 }
 

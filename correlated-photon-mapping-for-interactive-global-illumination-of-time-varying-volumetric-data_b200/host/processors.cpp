@@ -995,18 +995,28 @@ void ProgressivePhotonTracerCL::process() {
                 offset += (int)l->getSize();
             }
             StageProfiler::get().end();
-            // 2. fused threshold + reduce + iota: exact, synchronous count (the reference reads its count early)
-            StageProfiler::get().begin("count+iota");
+            // 2. exact, synchronous count of the invalid photons (the reference reads its count early) together
+            //    with their ids in ascending order
+            StageProfiler::get().begin("select");
             long long nInvalid = 0;
             const uint32_t* keys = static_cast<const uint32_t*>(photonRecomputationImportance_.deviceRead());
-            rt.check(cpm_count_below(rt.ctx(), keys, N, 2147483647u, static_cast<uint32_t*>(indices.deviceWrite()), &nInvalid));
+            rt.check(cpm_select_below(rt.ctx(), keys, N, 2147483647u, static_cast<uint32_t*>(indices.deviceWrite()), &nInvalid));
             StageProfiler::get().end();
-            // 3. sort photon ids by importance key.  The keys are sorted on a COPY so that key[i] keeps belonging
-            //    to photon i (the reference permutes them in place)
-            StageProfiler::get().begin("sort");
-            rt.check(cpm_mem_copy_d2d(rt.ctx(), sortedImportance_.deviceWrite(), keys, N * sizeof(uint32_t)));
-            recomputationImportanceSorter_.enqueue(sortedImportance_, &indices, N, 0);
-            StageProfiler::get().end();
+            const long long budget = static_cast<long long>((maxIncrementalPhotonsToUpdate_.get() / 100.f) * (float)N);
+            selectionIsSorted_ = spatialSorting_.get() && nInvalid <= budget;
+            if (!selectionIsSorted_) {
+                // 3. the budget cuts the list (or the importance order is wanted): sort all photon ids by importance key.
+                //    The keys are sorted on a COPY so that key[i] keeps belonging to photon i (the reference permutes
+                //    them in place)
+                StageProfiler::get().begin("sort");
+                rt.check(cpm_iota_u32(rt.ctx(), static_cast<uint32_t*>(indices.deviceWrite()), N));
+                rt.check(cpm_mem_copy_d2d(rt.ctx(), sortedImportance_.deviceWrite(), keys, N * sizeof(uint32_t)));
+                recomputationImportanceSorter_.enqueue(sortedImportance_, &indices, N, 0);
+                StageProfiler::get().end();
+            }
+            // else: every invalid photon fits the budget and the ids are wanted in ascending order -- sorting by
+            // importance, cutting at nInvalid and re-sorting by id (:361-363, 467-473) yields exactly the list
+            // cpm_select_below just wrote
             remainingPhotonsOffset_ = 0;
             if (remainingPhotonsToUpdate_ < 0 || nInvalid > 0) remainingPhotonsToUpdate_ = (int)nInvalid;
         }
@@ -1020,7 +1030,7 @@ void ProgressivePhotonTracerCL::process() {
         }
         recomputedPhotonIndices_->nRecomputedPhotons = static_cast<int>(nPhotonsToCompute);
         if (nPhotonsToCompute > 0) {
-            if (spatialSorting_.get()) {
+            if (spatialSorting_.get() && !selectionIsSorted_) {
                 // keys-only sort of the selected ids: ascending id == raster order on the light plane (:467-473)
                 StageProfiler::get().begin("indexsort");
                 recomputationIndexSorter_.enqueue(indices, nullptr, nPhotonsToCompute, 0);

@@ -321,6 +321,7 @@ private:
     Radixsort recomputationIndexSorter_{false};
     int remainingPhotonsToUpdate_ = -1;
     int remainingPhotonsOffset_ = 0;
+    bool selectionIsSorted_ = false;   // the id list came from cpm_select_below: ascending, complete
 };
 
 // org.inviwo.PhotonToLightVolumeProcessorCL -- ppm/processor/photontolightvolumeprocessorcl.cpp:45-509

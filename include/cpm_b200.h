@@ -252,6 +252,14 @@ CPM_API int cpm_reduce_sum_i32(cpm_ctx* ctx, const int32_t* data, size_t n, long
 CPM_API int cpm_count_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold,
                             uint32_t* iota_out, long long* count_host);
 
+/* Stable selection: ids_out[0 .. count) = the indices i < n with data[i] < threshold, ascending; entries from
+ * count on are left untouched.  This is what threshold + count + sort-by-importance + keys-only id sort
+ * (ppm/processor/progressivephotontracercl.cpp:318-473) produce when the update budget covers every invalid
+ * photon and `spatialSorting` is on: all invalid ids, ascending -- one 4 B/photon pass instead of two radix
+ * sorts.  SYNCHRONOUS (returns the count). */
+CPM_API int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out,
+                             long long* count_host);
+
 /* clogs::Radixsort::enqueue (rsc/ext/clogs/radixsort.h:227-262, src/radixsort.cpp:169-259) for
  * TYPE_UINT keys with TYPE_UINT values (values == NULL: keys only, as recomputationIndexSorter_).
  * Ascending, stable, in place; max_bits = 0 means all 32 bits; tmp_* are the ping-pong buffers

@@ -158,3 +158,32 @@ def test_cuda_threshold_count_iota(orc, synth, ctx, torch_cuda):
         assert ctx.count_below(d, 2147483647) == want
     neg = torch.tensor([-5, 3, -1], dtype=torch.int32, device="cuda")
     assert ctx.reduce_sum_i32(neg) == -3
+
+
+@pytest.mark.gpu
+def test_cuda_select_below_equals_sort_select_sort(orc, synth, ctx, torch_cuda):
+    """cpm_select_below == threshold/count + sort ids by importance + cut at the count + keys-only id sort
+    (ppm/processor/progressivephotontracercl.cpp:318-473 with a budget that covers every invalid photon)"""
+    torch = torch_cuda
+    for n, seed in ((1, 1), (31, 2), (4096, 3), (4097, 4), (1_234_567, 5), (1 << 22, 6)):
+        keys = importance_like_keys(synth, n, seed)
+        # reference pipeline on the oracle
+        cnt = orc.count_below(keys, 2147483647)
+        sk, ids = keys.copy(), np.arange(n, dtype=np.uint32)
+        orc.radix_sort(sk, ids)
+        sel = np.ascontiguousarray(ids[:cnt])
+        if cnt:
+            orc.radix_sort(sel, None)
+        d = _dev(torch, keys)
+        out = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        got = ctx.select_below(d, 2147483647, out)
+        ctx.sync()
+        assert got == cnt
+        h = _host(out)
+        assert np.array_equal(h[:cnt], sel)
+        assert (h[cnt:] == 0xFFFFFFFF).all()          # entries past the count are untouched
+    # all / none selected
+    d = _dev(torch, np.zeros(5000, np.uint32))
+    out = torch.zeros(5000, dtype=torch.int32, device="cuda")
+    assert ctx.select_below(d, 1, out) == 5000 and np.array_equal(_host(out), np.arange(5000, dtype=np.uint32))
+    assert ctx.select_below(d, 0, out) == 0
