@@ -26,6 +26,7 @@ struct SplatArgs {
     Mat4s tex2idx, idx2tex;
     int dim[3];
     const float4* photons;
+    const float4* old_photons;  // cpm_splat_photons_update: records to remove (same ids), or null
     const uint32_t* indices;
     int n;
     int per_interaction;
@@ -33,6 +34,10 @@ struct SplatArgs {
     float radius, scale, multiplier;
 };
 
+// One photon record into the (2 r s + 2)^3 voxels around it.  The weight 0.75 (1 - (d/r)^2) for d <= r is
+// evaluated from the squared distance (no square root, no division) and the voxel centre is built per loop level
+// (3 fma per voxel instead of a full matrix product): a few ulp from the reference's operation order, far
+// inside the order-dependence of the float adds themselves (tests: relative RMSE <= 1e-5 vs a double sum).
 template <int CH>
 __device__ __forceinline__ void splat_one(const SplatArgs& A, float4 p0, float pr, float pg, float pb) {
     if (p0.x == CPM_FLT_MAX_ || p0.y == CPM_FLT_MAX_ || p0.z == CPM_FLT_MAX_) return;
@@ -44,25 +49,34 @@ __device__ __forceinline__ void splat_one(const SplatArgs& A, float4 p0, float p
     int ex = (int)cpm_clamp(truncf(hi.x + 1.f), -2147483520.f, (float)A.dim[0]),
         ey = (int)cpm_clamp(truncf(hi.y + 1.f), -2147483520.f, (float)A.dim[1]),
         ez = (int)cpm_clamp(truncf(hi.z + 1.f), -2147483520.f, (float)A.dim[2]);
-    for (int z = sz; z < ez; ++z)
-        for (int y = sy; y < ey; ++y)
+    const float* M = A.idx2tex.m;
+    const float r2 = r * r, k = 0.75f / r2;
+    // voxel centre minus photon position, split by loop level
+    const float bx = M[12] - p0.x, by = M[13] - p0.y, bz = M[14] - p0.z;
+    for (int z = sz; z < ez; ++z) {
+        const float fz = (float)z;
+        const float zx = fmaf(M[8], fz, bx), zy = fmaf(M[9], fz, by), zz = fmaf(M[10], fz, bz);
+        for (int y = sy; y < ey; ++y) {
+            const float fy = (float)y;
+            const float yx = fmaf(M[4], fy, zx), yy = fmaf(M[5], fy, zy), yz = fmaf(M[6], fy, zz);
+            float* row = A.vol + ((size_t)y + (size_t)z * A.dim[1]) * A.dim[0] * CH;
             for (int x = sx; x < ex; ++x) {
-                size_t vi = (size_t)x + (size_t)y * A.dim[0] + (size_t)z * A.dim[0] * A.dim[1];
-                float3_ c = xform(A.idx2tex, (float)x, (float)y, (float)z);
-                float dx = c.x - p0.x, dy = c.y - p0.y, dz = c.z - p0.z;
-                float dist = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-                float xk = dist / r;
-                float w = xk <= 1.0f ? 0.75f * (1.0f - xk * xk) : 0.0f;
+                const float fx = (float)x;
+                float dx = fmaf(M[0], fx, yx), dy = fmaf(M[1], fx, yy), dz = fmaf(M[2], fx, yz);
+                float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float w = d2 <= r2 ? fmaf(-k, d2, 0.75f) : 0.0f;
                 float fr = pr * w;
                 if (CH == 1) {
-                    if (fr != 0.0f) atomicAdd(A.vol + vi, fr);
+                    if (fr != 0.0f) atomicAdd(row + x, fr);
                 } else {
                     float fg = pg * w, fb = pb * w;
-                    if (fr != 0.0f) atomicAdd(A.vol + 4 * vi, fr);
-                    if (fg != 0.0f) atomicAdd(A.vol + 4 * vi + 1, fg);
-                    if (fb != 0.0f) atomicAdd(A.vol + 4 * vi + 2, fb);
+                    if (fr != 0.0f) atomicAdd(row + 4 * x, fr);
+                    if (fg != 0.0f) atomicAdd(row + 4 * x + 1, fg);
+                    if (fb != 0.0f) atomicAdd(row + 4 * x + 2, fb);
                 }
             }
+        }
+    }
 }
 
 template <int CH>
@@ -78,6 +92,13 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
         for (int k = 0; k < A.n_interactions; ++k) {
             size_t pid = (size_t)k * A.per_interaction + id;
             float4 p0 = A.photons[2 * pid], p1 = A.photons[2 * pid + 1];
+            if (A.old_photons) {
+                // incremental update: -old +new in one pass; a record the re-trace reproduced bit for bit
+                // contributes nothing and is skipped (the two passes would cancel up to rounding)
+                float4 q0 = A.old_photons[2 * pid], q1 = A.old_photons[2 * pid + 1];
+                if (q0.x == p0.x && q0.y == p0.y && q0.z == p0.z && q0.w == p0.w && q1.x == p1.x && q1.y == p1.y) continue;
+                splat_one<CH>(A, q0, -(q0.w * s * A.multiplier), -(q1.x * s * A.multiplier), -(q1.y * s * A.multiplier));
+            }
             splat_one<CH>(A, p0, p0.w * s * A.multiplier, p1.x * s * A.multiplier, p1.y * s * A.multiplier);
         }
     }
@@ -85,11 +106,10 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
 
 }  // namespace
 
-extern "C" int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
-                                 const float index_to_texture[16], const int out_dims[3], const float* photons,
-                                 const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
-                                 float radius, float relative_irradiance_scale, float multiplier) {
-    if (!ctx) return CPM_E_INVALID;
+static int splat_common(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
+                        const float index_to_texture[16], const int out_dims[3], const float* photons,
+                        const float* old_photons, const uint32_t* indices, int n, int photons_per_interaction,
+                        int n_interactions, float radius, float relative_irradiance_scale, float multiplier) {
     CPM_REQUIRE(ctx, n >= 0, "negative n");
     if (n == 0) return CPM_OK;
     CPM_REQUIRE(ctx, light_volume && texture_to_index && index_to_texture && out_dims && photons, "null argument");
@@ -103,6 +123,7 @@ extern "C" int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels
     }
     for (int k = 0; k < 3; ++k) a.dim[k] = out_dims[k];
     a.photons = (const float4*)photons;
+    a.old_photons = (const float4*)old_photons;
     a.indices = indices;
     a.n = n;
     a.per_interaction = photons_per_interaction;
@@ -115,4 +136,24 @@ extern "C" int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels
     else
         CPM_LAUNCH(ctx, splat_kernel<4>, cpm_div_up(n, 128), 128, 0, a);
     return CPM_OK;
+}
+
+extern "C" int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
+                                 const float index_to_texture[16], const int out_dims[3], const float* photons,
+                                 const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
+                                 float radius, float relative_irradiance_scale, float multiplier) {
+    if (!ctx) return CPM_E_INVALID;
+    return splat_common(ctx, light_volume, channels, texture_to_index, index_to_texture, out_dims, photons, nullptr, indices, n,
+                        photons_per_interaction, n_interactions, radius, relative_irradiance_scale, multiplier);
+}
+
+extern "C" int cpm_splat_photons_update(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
+                                        const float index_to_texture[16], const int out_dims[3], const float* old_photons,
+                                        const float* new_photons, const uint32_t* indices, int n,
+                                        int photons_per_interaction, int n_interactions, float radius,
+                                        float relative_irradiance_scale) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, old_photons && indices, "null argument");
+    return splat_common(ctx, light_volume, channels, texture_to_index, index_to_texture, out_dims, new_photons, old_photons,
+                        indices, n, photons_per_interaction, n_interactions, radius, relative_irradiance_scale, 1.0f);
 }

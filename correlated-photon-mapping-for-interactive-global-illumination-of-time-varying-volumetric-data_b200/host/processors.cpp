@@ -1171,9 +1171,9 @@ void PhotonToLightVolumeProcessorCL::process() {
         float* lv = static_cast<float*>(const_cast<void*>(lightVolume_->deviceRead()));
         lightVolume_->deviceWrite();
         ScopedStage st("splat");
-        rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, static_cast<const float*>(prevPhotons_.deviceRead()),
-                                   idx, nRecomputed, N, I, radius, scale, -1.f));
-        rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, photonsDev, idx, nRecomputed, N, I, radius, scale, 1.f));
+        rt.check(cpm_splat_photons_update(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim,
+                                          static_cast<const float*>(prevPhotons_.deviceRead()), photonsDev, idx, nRecomputed, N, I,
+                                          radius, scale));
         lastPath = "incremental";
     } else if (prevPhotons_.getSize() != photonData->photons_.getSize() || nRecomputed < 0 || nRecomputed >= maxRecomputationPhotons) {
         float* lv = static_cast<float*>(lightVolume_->deviceWrite());

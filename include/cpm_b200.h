@@ -336,6 +336,16 @@ CPM_API int cpm_splat_photons(cpm_ctx* ctx, float* light_volume, int channels,
                               int n, int photons_per_interaction, int n_interactions, float radius,
                               float relative_irradiance_scale, float multiplier);
 
+/* The incremental update of photonsToLightVolume (ppm/processor/photontolightvolumeprocessorcl.cpp:262-274: one
+ * splatSelected pass with multiplier -1 over the previous records, one with +1 over the new ones) as ONE pass:
+ * per listed id and interaction, remove old_photons' contribution and add new_photons'; records the re-trace
+ * reproduced bit for bit are skipped (their two contributions cancel). */
+CPM_API int cpm_splat_photons_update(cpm_ctx* ctx, float* light_volume, int channels,
+                                     const float texture_to_index[16], const float index_to_texture[16],
+                                     const int out_dims[3], const float* old_photons, const float* new_photons,
+                                     const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
+                                     float radius, float relative_irradiance_scale);
+
 /* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
 /* Not launched anywhere in the reference; the estimator is the reference's
  * (Epanechnikov kernel, ppm/cl/densityestimationkernel.cl:56-60; power * 1/(4 pi) * relativeIrradianceScale,

@@ -140,3 +140,43 @@ def test_cuda_splat_matches_double_oracle(cpm, orc, ctx, torch_cuda, synth, chan
     ctx.sync()
     g3 = lv.cpu().numpy().astype(np.float64)
     assert np.sqrt(((g3 - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels", [1, 4])
+def test_cuda_splat_update_equals_remove_then_add(cpm, orc, ctx, torch_cuda, synth, channels):
+    """cpm_splat_photons_update == splatSelected(-1, old records) + splatSelected(+1, new records)
+    (ppm/processor/photontolightvolumeprocessorcl.cpp:262-274); unchanged records are skipped"""
+    torch = torch_cuda
+    c = make_case(orc, synth, cpm, I=2, n_side=96)
+    n = c["L"]["n"]
+    od = (32, 32, 32)
+    nvox = od[0] * od[1] * od[2]
+    t2i, i2t = cpm.capi.texture_to_index_matrix(od), cpm.capi.index_to_texture_matrix(od)
+    radius, scale = 1.3 / 32, 0.37
+    old = c["photons"]
+    new = old.copy()
+    ph = new.reshape(2, n, 8)
+    moved = np.arange(0, n, 3)
+    stored = ph[0, moved, 0] != np.float32(3.4028234663852886e38)
+    ph[0, moved[stored], 0:3] = np.clip(ph[0, moved[stored], 0:3] + np.float32(0.03), 0, 1)    # a third of the photons move
+    ph[0, moved[stored], 3:6] *= np.float32(1.5)
+    idx = np.arange(0, n, 2, dtype=np.uint32)                                               # half are listed
+    want = np.zeros(nvox * channels, np.float64)
+    orc.splat(want, channels, t2i, i2t, od, old, None, n, n, 2, radius, scale)
+    base = want.copy()
+    orc.splat(want, channels, t2i, i2t, od, old, idx, idx.size, n, 2, radius, scale, -1.0)
+    orc.splat(want, channels, t2i, i2t, od, new, idx, idx.size, n, 2, radius, scale, 1.0)
+    lv = torch.from_numpy(base.astype(np.float32)).cuda()
+    ctx.splat_photons_update(lv, channels, t2i, i2t, od, torch.from_numpy(old).cuda(), torch.from_numpy(new).cuda(),
+                             torch.from_numpy(idx.view(np.int32)).cuda(), idx.size, n, 2, radius, scale)
+    ctx.sync()
+    got = lv.cpu().numpy().astype(np.float64)
+    assert np.abs(want - base).max() > 0
+    assert np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
+    # no listed record changed: the light volume is untouched bit for bit
+    lv2 = torch.from_numpy(base.astype(np.float32)).cuda()
+    ctx.splat_photons_update(lv2, channels, t2i, i2t, od, torch.from_numpy(old).cuda(), torch.from_numpy(old).cuda(),
+                             torch.from_numpy(idx.view(np.int32)).cuda(), idx.size, n, 2, radius, scale)
+    ctx.sync()
+    assert np.array_equal(lv2.cpu().numpy(), base.astype(np.float32))
