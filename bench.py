@@ -313,14 +313,28 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
     radius = float(np.float32(np.sqrt(3.0) / D))                       # the tracer's 1-voxel photon radius
     g = int(min(512, max(1, int(1.0 / (2.0 * radius)))))                # cell edge >= 2 r: at most 8 cells per gather
     scale = float((1.0 / np.pi) / (4.0 / 3.0 * np.pi * radius ** 3 * n))
+    # per-cell opacity bound of (this volume, this TF), as the tracer keeps it: the value-range grid is per-step data
+    # like the min-max grid (untimed), the TF classification of its cells belongs to the frame (timed with the build)
+    bs = 3 if a.bound_log2 <= 0 else a.bound_log2
+    bound = None
+    if a.bound_log2 >= 0:
+        Vl = ctx.volume_create(dvol, (D, D, D), cpm.CPM_FMT_F32)
+        gd = cpm.capi.bound_grid_dims((D, D, D), bs)
+        ncell = gd[0] * gd[1] * gd[2]
+        vrange = torch.empty(2 * ncell, dtype=torch.float32, device=dev)
+        ctx.volume_value_range(Vl, bs, vrange)
+        bound = torch.empty(ncell, dtype=torch.float32, device=dev)
     P = cpm.capi.make_gather_params(a.view, a.view, (1.7, 1.4, -1.3), (0.5, 0.5, 0.5), fov_deg=40.0, step=0.5 / D,
-                                    radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g))
+                                    radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g),
+                                    opacity_bound=bound, bound_cell_log2=bs)
     img = torch.empty(a.view * a.view * 4, dtype=torch.float32, device=dev)
     build_ms, march_ms = [], []
     for it in range(reps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record(stream)
         sp, start, end, _ = ctx.build_photon_map(photons, n * I, (g, g, g), torch)
+        if bound is not None:
+            ctx.opacity_bound(vrange, ncell, tf, bound)
         e[1].record(stream)
         ctx.gather_raymarch(V, tf, P, sp, start, end, img)
         e[2].record(stream)
@@ -335,7 +349,8 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
     return {"frames_per_sec": 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m, "view": f"{a.view}x{a.view}",
             "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
             "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
-                    f"{n * I} photon records; march = step 0.5 voxel, Epanechnikov gather r = 1 voxel"}
+                    f"{n * I} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
+                    "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 8 samples gathered per photon pass"}
 
 
 def run_b200(a):

@@ -376,12 +376,13 @@ class GatherParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cam_origin", C.c_float * 3), ("cam_dir00", C.c_float * 3),
                 ("cam_du", C.c_float * 3), ("cam_dv", C.c_float * 3), ("aabb_min", C.c_float * 3),
                 ("aabb_max", C.c_float * 3), ("step", C.c_float), ("radius", C.c_float), ("scale", C.c_float),
-                ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3)]
+                ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3), ("opacity_bound", C.c_void_p),
+                ("bound_cell_log2", C.c_int32), ("reserved_", C.c_int32)]
 
 
 def make_gather_params(width, height, eye, look_at, up=(0, 1, 0), fov_deg=60.0, step=1.0 / 256, radius=1.0 / 64,
                        scale=1.0, sigma_scale=150.0, grid_dims=(32, 32, 32), aabb_min=(0, 0, 0), aabb_max=(1, 1, 1),
-                       cls=None):
+                       cls=None, opacity_bound=None, bound_cell_log2=3):
     """pinhole camera in texture space -> the (dir00, du, dv) ray basis of cpm_gather_params"""
     import numpy as np
     eye, look_at, up = (np.asarray(v, np.float64) for v in (eye, look_at, up))
@@ -402,6 +403,9 @@ def make_gather_params(width, height, eye, look_at, up=(0, 1, 0), fov_deg=60.0, 
         getattr(p, name)[:] = [float(np.float32(x)) for x in v]
     p.step, p.radius, p.scale, p.sigma_scale = float(step), float(radius), float(scale), float(sigma_scale)
     p.grid_dims[:] = [int(g) for g in grid_dims]
+    if opacity_bound is not None:
+        p.opacity_bound = opacity_bound.data_ptr()
+        p.bound_cell_log2 = bound_cell_log2
     return p
 
 

@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(256) bound_kernel(const float2* __restrict__ r
             // sample_tf_alpha's lerp: within a few ulp of the larger magnitude of its two texels
             res = m + fmaf(ab, 0x1p-18f, 1e-37f);
             if (!(res == res)) res = INF;
+            // every texel the cell can reach is exactly zero: the opacity is exactly zero (lerp(0, 0, a) = 0), which
+            // the ray marchers use to skip the cell altogether
+            if (ab == 0.0f) res = 0.0f;
         }
     }
     out[id] = res;

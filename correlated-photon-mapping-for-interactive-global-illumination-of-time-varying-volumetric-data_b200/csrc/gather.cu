@@ -15,6 +15,8 @@
 //        order, so a cell's photons are one contiguous 32 B-strided run)  -> cpm_gather_raymarch.
 #include <string.h>
 
+#include <algorithm>
+
 #include "sampling.cuh"
 
 namespace {
@@ -57,6 +59,7 @@ struct GatherArgs {
     const uint32_t* cell_start;
     const uint32_t* cell_end;
     float4* image;
+    BoundGrid bound;   // optional per-cell opacity bound of (volume, tf): zero cells are skipped
 };
 
 // read_imagef(tf, smpNormClampEdgeLinear, (v, 0.5)) on a width x 1 image: all four channels
@@ -69,6 +72,16 @@ __device__ __forceinline__ float4 sample_tf_rgba(const float4* __restrict__ tf, 
     i0 = max(i0, 0);
     float4 p = tf[i0], q = tf[i1];
     return make_float4(lerpf(p.x, q.x, a), lerpf(p.y, q.y, a), lerpf(p.z, q.z, a), lerpf(p.w, q.w, a));
+}
+
+__device__ __forceinline__ float sample_tf_alpha4(const float4* __restrict__ tf, int width, float fwidth, float v) {
+    float u = fmaf(v, fwidth, -0.5f);
+    float fu = floorf(u);
+    float a = u - fu;
+    int i0 = (int)cpm_clamp(fu, -1.0f, fwidth - 1.0f);
+    int i1 = min(i0 + 1, width - 1);
+    i0 = max(i0, 0);
+    return lerpf(tf[i0].w, tf[i1].w, a);
 }
 
 // irradiance estimate at x: sum over photons within `radius` of power * Epanechnikov weight
@@ -100,50 +113,164 @@ __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float
             }
 }
 
+// View-ray-march gather.  Same samples t_k = t0 + (k + 1/2) step, same estimator and compositing as the
+// per-sample formulation (oracle/orc_gather.c), organised for the machine:
+//  * warps take 8 x 4 pixel tiles from a global counter (rays differ in cost by orders of magnitude: a static
+//    tile assignment leaves two thirds of the warp slots idle behind the few expensive tiles);
+//  * samples in cells whose opacity bound is exactly zero are never fetched: the march jumps to the cell's exit
+//    (the bound grid pads cells by one voxel, i.e. two samples, which covers the rounding of the exit point);
+//  * the remaining samples are taken GATHER_S at a time: their taps are requested together, and if any of them is
+//    visible the photons of the cells around the whole segment are read ONCE -- per photon the distance to
+//    the ray (|q|^2 - (q.d)^2) rejects most candidates, and the survivors update the batch's estimates through
+//    d_k^2 = d_perp^2 + (t_k - q.d)^2 -- instead of once per sample through 8 cells.
+constexpr int GATHER_S = 8;
+
 template <int FMT, int LAYOUT>
-__global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A) {
+__global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
     extern __shared__ float4 s_tf[];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_tf[i] = A.tf[i];
     __syncthreads();
     const cpm_gather_params& P = A.p;
-    // a warp covers an 8 x 4 pixel tile: neighbouring rays walk neighbouring cells
-    const int tiles_x = (P.width + 7) / 8;
-    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int tiles_x = (P.width + 7) / 8, tiles_y = (P.height + 3) / 4;
+    const unsigned n_tiles = (unsigned)tiles_x * (unsigned)tiles_y;
     const int lane = threadIdx.x & 31;
-    const int px = (warp_global % tiles_x) * 8 + (lane & 7);
-    const int py = (warp_global / tiles_x) * 4 + (lane >> 3);
-    if (px >= P.width || py >= P.height) return;
-    float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-    float dx = fmaf(fy, P.cam_dv[0], fmaf(fx, P.cam_du[0], P.cam_dir00[0]));
-    float dy = fmaf(fy, P.cam_dv[1], fmaf(fx, P.cam_du[1], P.cam_dir00[1]));
-    float dz = fmaf(fy, P.cam_dv[2], fmaf(fx, P.cam_du[2], P.cam_dir00[2]));
-    float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-    float3_ d = {dx * inv, dy * inv, dz * inv};
-    float3_ o = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2]};
-    float t0 = 0.0f, t1 = CPM_FLT_MAX_;
-    float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
-    if (ray_box(P.aabb_min, P.aabb_max, o, d, t0, t1)) {
-        const float ftfw = (float)A.tf_width;
-        const float s = CPM_INV_4PI_F * P.scale;
-        int k = 0;
-        for (float t = fmaf(0.5f, P.step, t0); t < t1; ++k, t = fmaf((float)k + 0.5f, P.step, t0)) {
-            float x = fmaf(t, d.x, o.x), y = fmaf(t, d.y, o.y), z = fmaf(t, d.z, o.z);
-            float v = sample_volume<FMT, LAYOUT>(A.vol, x, y, z);
-            float4 c = sample_tf_rgba(s_tf, A.tf_width, ftfw, v);
-            if (c.w > 0.0f) {
-                float er = 0.f, eg = 0.f, eb = 0.f;
-                gather_point(A, x, y, z, er, eg, eb);
-                float Ts = cpm_expf(-(c.w * P.sigma_scale) * P.step);
-                float wgt = T * (1.0f - Ts);
-                lr = fmaf(wgt * c.x, er * s, lr);
-                lg = fmaf(wgt * c.y, eg * s, lg);
-                lb = fmaf(wgt * c.z, eb * s, lb);
-                T *= Ts;
-                if (T < 1e-4f) break;
+    const float ftfw = (float)A.tf_width;
+    const float s = CPM_INV_4PI_F * P.scale;
+    const float r = P.radius, r2 = r * r, kw = 0.75f / r2;
+    const int gx = P.grid_dims[0], gy = P.grid_dims[1], gz = P.grid_dims[2];
+    const float inv_step = 1.0f / P.step;
+    while (true) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int px = (int)(tile % tiles_x) * 8 + (lane & 7);
+        const int py = (int)(tile / tiles_x) * 4 + (lane >> 3);
+        if (px >= P.width || py >= P.height) continue;
+        float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+        float dx = fmaf(fy, P.cam_dv[0], fmaf(fx, P.cam_du[0], P.cam_dir00[0]));
+        float dy = fmaf(fy, P.cam_dv[1], fmaf(fx, P.cam_du[1], P.cam_dir00[1]));
+        float dz = fmaf(fy, P.cam_dv[2], fmaf(fx, P.cam_du[2], P.cam_dir00[2]));
+        float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        float3_ d = {dx * inv, dy * inv, dz * inv};
+        float3_ o = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2]};
+        float t0 = 0.0f, t1 = CPM_FLT_MAX_;
+        float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
+        if (ray_box(P.aabb_min, P.aabb_max, o, d, t0, t1)) {
+            CellRay R = {0, 0, 0, 0, 0, 0};
+            float ix = 0.f, iy = 0.f, iz = 0.f;
+            if (A.bound.g) {
+                R = cell_ray(A.bound, o, d);
+                ix = 1.0f / R.dx; iy = 1.0f / R.dy; iz = 1.0f / R.dz;
+            }
+            int k = 0;
+            bool live = true;
+            while (live) {
+                float t = fmaf((float)k + 0.5f, P.step, t0);
+                if (A.bound.g) {
+                    // leave all-transparent cells in one jump each; the lane does all its jumps here, so that the
+                    // warp's next trip through the batch code finds every live lane at a visible sample
+                    while (t < t1) {
+                        float wx = fminf(fmaxf(fmaf(t, R.dx, R.ox), 0.0f), A.bound.mx[0]);
+                        float wy = fminf(fmaxf(fmaf(t, R.dy, R.oy), 0.0f), A.bound.mx[1]);
+                        float wz = fminf(fmaxf(fmaf(t, R.dz, R.oz), 0.0f), A.bound.mx[2]);
+                        float cx = floorf(wx), cy = floorf(wy), cz = floorf(wz);
+                        int ci = (int)cx + (int)cy * A.bound.nx + (int)cz * A.bound.nxy;
+                        if (__ldg(A.bound.g + ci) != 0.0f) break;
+                        float ex = ((R.dx > 0.0f ? cx + 1.0f : cx) - R.ox) * ix;
+                        float ey = ((R.dy > 0.0f ? cy + 1.0f : cy) - R.oy) * iy;
+                        float ez = ((R.dz > 0.0f ? cz + 1.0f : cz) - R.oz) * iz;
+                        float te = fminf(fminf(R.dx != 0.0f ? ex : CPM_FLT_MAX_, R.dy != 0.0f ? ey : CPM_FLT_MAX_),
+                                         R.dz != 0.0f ? ez : CPM_FLT_MAX_);
+                        // first sample at or past the exit; at least one step forward
+                        float kf = ceilf(fmaf(te - t0, inv_step, -0.5f));
+                        int kn = (kf < 1.0e9f) ? (int)kf : 1000000000;
+                        k = max(k + 1, kn);
+                        t = fmaf((float)k + 0.5f, P.step, t0);
+                    }
+                }
+                if (!(t < t1)) break;
+                // ---- a batch of GATHER_S samples: request all taps, then classify
+                float v[GATHER_S];
+                bool any = false;
+                int nb = 0;   // samples of the batch that lie before t1
+#pragma unroll
+                for (int h = 0; h < GATHER_S; h += 4) {   // four samples' taps in flight at a time
+                    Taps tp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float tj = fmaf((float)(k + h + j) + 0.5f, P.step, t0);
+                        tp[j] = fetch_taps<FMT, LAYOUT>(A.vol, fmaf(tj, d.x, o.x), fmaf(tj, d.y, o.y), fmaf(tj, d.z, o.z));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float tj = fmaf((float)(k + h + j) + 0.5f, P.step, t0);
+                        v[h + j] = blend_taps<FMT>(A.vol, tp[j]);
+                        if (tj < t1) {
+                            nb = h + j + 1;
+                            any = any || sample_tf_alpha4(s_tf, A.tf_width, ftfw, v[h + j]) > 0.0f;
+                        }
+                    }
+                }
+                if (any) {
+                    float er[GATHER_S], eg[GATHER_S], eb[GATHER_S];
+#pragma unroll
+                    for (int j = 0; j < GATHER_S; ++j) er[j] = eg[j] = eb[j] = 0.0f;
+                    // cells touched by the segment [x_first, x_last] grown by r
+                    const float ta = fmaf((float)k + 0.5f, P.step, t0), tb = fmaf((float)(k + nb - 1) + 0.5f, P.step, t0);
+                    const float ax = fmaf(ta, d.x, o.x), ay = fmaf(ta, d.y, o.y), az = fmaf(ta, d.z, o.z);
+                    const float bx = fmaf(tb, d.x, o.x), by = fmaf(tb, d.y, o.y), bz = fmaf(tb, d.z, o.z);
+                    const int x0 = cell_coord(fminf(ax, bx) - r, (float)gx, gx), x1 = cell_coord(fmaxf(ax, bx) + r, (float)gx, gx);
+                    const int y0 = cell_coord(fminf(ay, by) - r, (float)gy, gy), y1 = cell_coord(fmaxf(ay, by) + r, (float)gy, gy);
+                    const int z0 = cell_coord(fminf(az, bz) - r, (float)gz, gz), z1 = cell_coord(fmaxf(az, bz) + r, (float)gz, gz);
+                    const float tlen = tb - ta;
+                    for (int cz = z0; cz <= z1; ++cz)
+                        for (int cy = y0; cy <= y1; ++cy) {
+                            // cells x0..x1 of a row are contiguous in the cell-sorted record array
+                            uint32_t c0 = (uint32_t)x0 + (uint32_t)gx * ((uint32_t)cy + (uint32_t)gy * (uint32_t)cz);
+                            uint32_t b = __ldg(A.cell_start + c0), e = __ldg(A.cell_end + c0 + (uint32_t)(x1 - x0));
+                            for (uint32_t i = b; i < e; ++i) {
+                                float4 p0 = __ldg(A.photons + 2 * (size_t)i);
+                                float qx = p0.x - ax, qy = p0.y - ay, qz = p0.z - az;
+                                float tc = fmaf(qz, d.z, fmaf(qy, d.y, qx * d.x));       // parameter of the closest approach
+                                float q2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+                                float dp2 = fmaf(-tc, tc, q2);                              // squared distance to the ray
+                                if (dp2 <= r2 && tc >= -r && tc <= tlen + r) {
+                                    float4 p1 = __ldg(A.photons + 2 * (size_t)i + 1);
+#pragma unroll
+                                    for (int j = 0; j < GATHER_S; ++j) {
+                                        float dt = fmaf((float)j, P.step, -tc);
+                                        float d2 = fmaf(dt, dt, fmaxf(dp2, 0.0f));
+                                        float w = d2 <= r2 ? fmaf(-kw, d2, 0.75f) : 0.0f;
+                                        er[j] = fmaf(p0.w, w, er[j]);
+                                        eg[j] = fmaf(p1.x, w, eg[j]);
+                                        eb[j] = fmaf(p1.y, w, eb[j]);
+                                    }
+                                }
+                            }
+                        }
+                    // ---- composite front to back
+#pragma unroll
+                    for (int j = 0; j < GATHER_S; ++j) {
+                        if (j < nb && live) {
+                            float4 c = sample_tf_rgba(s_tf, A.tf_width, ftfw, v[j]);
+                            if (c.w > 0.0f) {
+                                float Ts = cpm_expf(-(c.w * P.sigma_scale) * P.step);
+                                float wgt = T * (1.0f - Ts);
+                                lr = fmaf(wgt * c.x, er[j] * s, lr);
+                                lg = fmaf(wgt * c.y, eg[j] * s, lg);
+                                lb = fmaf(wgt * c.z, eb[j] * s, lb);
+                                T *= Ts;
+                                if (T < 1e-4f) live = false;
+                            }
+                        }
+                    }
+                }
+                k += GATHER_S;
             }
         }
+        A.image[(size_t)py * P.width + px] = make_float4(lr, lg, lb, 1.0f - T);
     }
-    A.image[(size_t)py * P.width + px] = make_float4(lr, lg, lb, 1.0f - T);
 }
 
 // irradiance at arbitrary points (the per-voxel formulation of the reference's disabled
@@ -176,6 +303,7 @@ static int fill_gather_args(cpm_ctx* ctx, GatherArgs& a, const cpm_volume* vol, 
     a.cell_start = cell_start;
     a.cell_end = cell_end;
     a.image = nullptr;
+    memset(&a.bound, 0, sizeof(a.bound));
     return CPM_OK;
 }
 
@@ -184,8 +312,17 @@ static int launch_gather(cpm_ctx* ctx, const GatherArgs& a) {
     size_t smem = (size_t)a.tf_width * sizeof(float4);
     if (smem > 48 * 1024)
         CPM_CUDA(ctx, cudaFuncSetAttribute(gather_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent warps: tiles are handed out through a counter in the context scratch
+    void* scratch;
+    int rc = cpm_scratch(ctx, 4096, &scratch);
+    if (rc != CPM_OK) return rc;
+    unsigned* counter = (unsigned*)((char*)scratch + 3072);
+    CPM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
     int tiles = ((a.p.width + 7) / 8) * ((a.p.height + 3) / 4);
-    CPM_LAUNCH(ctx, (gather_kernel<FMT, LAYOUT>), cpm_div_up(tiles, 4), 128, smem, a);
+    int per_sm = 0;
+    CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<FMT, LAYOUT>, 128, smem));
+    unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), (long long)cpm_div_up(tiles, 4));
+    CPM_LAUNCH(ctx, (gather_kernel<FMT, LAYOUT>), grid, 128, smem, a, counter);
     return CPM_OK;
 }
 
@@ -223,6 +360,8 @@ int cpm_gather_raymarch(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgb
     if (rc != CPM_OK) return rc;
     CPM_REQUIRE(ctx, params->width > 0 && params->height > 0 && params->step > 0.0f, "bad image size / step");
     a.image = (float4*)image;
+    CPM_REQUIRE(ctx, make_bound_grid(a.bound, params->opacity_bound, vol->dims, params->bound_cell_log2),
+                "bound_cell_log2 must be in 0..8 and the bound grid smaller than 2^31 cells");
 #define CPM_DISPATCH(F)                                                                       \
     return vol->layout == CPM_VOLUME_TEXTURE ? launch_gather<F, CPM_VOLUME_TEXTURE>(ctx, a)  \
                                              : launch_gather<F, CPM_VOLUME_LINEAR>(ctx, a);

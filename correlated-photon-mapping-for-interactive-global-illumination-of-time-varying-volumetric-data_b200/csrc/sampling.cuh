@@ -7,7 +7,13 @@
 // CLK_ADDRESS_CLAMP_TO_EDGE | CLK_FILTER_LINEAR.  The operation order here is the contract
 // that oracle/cpm_oracle.c follows op for op; do not reorder without changing both.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
+
+struct float3_ {
+    float x, y, z;
+};
 
 struct VolumeView {
     const void* lin;
@@ -167,6 +173,57 @@ __device__ __forceinline__ float sample_volume(const VolumeView& V, float px, fl
     return blend_taps<FMT>(V, T);
 }
 
+// ---- per-cell opacity bound grid (bound.cu) ----------------------------------------------------------------
+// Cell of a sample p, per axis: floor(p * fc + hc) = floor((p * dim + 0.5) / cell), clamped to [0, mx].
+struct BoundGrid {
+    const float* g;   // null: no grid
+    float fc[3], hc, mx[3];
+    unsigned bias;    // (1 + nx + nxy) * 0x4B400000 mod 2^32: removes the float-bit biases of the three cell coordinates
+    int nx, nxy;
+};
+static inline bool make_bound_grid(BoundGrid& B, const float* g, const int dims[3], int cell_log2) {
+    memset(&B, 0, sizeof(B));
+    if (!g) return true;
+    if (cell_log2 < 0 || cell_log2 > 8) return false;
+    const float cell = (float)(1 << cell_log2);
+    int gd[3];
+    for (int k = 0; k < 3; ++k) {
+        gd[k] = (dims[k] >> cell_log2) + 1;
+        B.fc[k] = (float)dims[k] / cell;   // exact: cell is a power of two
+        B.mx[k] = (float)(gd[k] - 1);
+    }
+    if ((double)gd[0] * gd[1] * gd[2] >= 2147483648.0) return false;
+    B.g = g;
+    B.hc = 0.5f / cell;
+    B.nx = gd[0];
+    B.nxy = gd[0] * gd[1];
+    // indices are formed from raw float bits (cell + 0x4B400000 per axis) with wrapping 32-bit arithmetic
+    B.bias = 0x4B400000u * (1u + (uint32_t)B.nx + (uint32_t)B.nxy);
+    return true;
+}
+// Opacity bound of the cell that holds the trilinear footprint of the sample at parameter t of the ray
+// w(t) = wo + t * wd, the ray in CELL coordinates (set up once per walk).  The cell is floor(w) per axis; bound.cu
+// pads every cell by one voxel, which absorbs the rounding difference between this arithmetic and
+// fetch_taps' i0 = floor(p * dim - 0.5).  No conversion instructions: clamp (fmaxf maps NaN to 0), then the
+// 1.5 * 2^23 addition rounded down leaves floor(w) + 0x4B400000 in the bits; the three biases leave the index
+// with one wrapping subtraction.
+struct CellRay {
+    float ox, oy, oz, dx, dy, dz;
+};
+__device__ __forceinline__ CellRay cell_ray(const BoundGrid& A, float3_ o, float3_ d) {
+    return {fmaf(o.x, A.fc[0], A.hc), fmaf(o.y, A.fc[1], A.hc), fmaf(o.z, A.fc[2], A.hc),
+            d.x * A.fc[0], d.y * A.fc[1], d.z * A.fc[2]};
+}
+__device__ __forceinline__ unsigned cell_bits(float w, float wmax) {
+    return __float_as_uint(__fadd_rd(fminf(fmaxf(w, 0.0f), wmax), 12582912.0f));
+}
+__device__ __forceinline__ float bound_at(const BoundGrid& A, const CellRay& R, float t) {
+    unsigned bx = cell_bits(fmaf(t, R.dx, R.ox), A.mx[0]);
+    unsigned by = cell_bits(fmaf(t, R.dy, R.oy), A.mx[1]);
+    unsigned bz = cell_bits(fmaf(t, R.dz, R.oz), A.mx[2]);
+    return __ldg(A.g + (bx + by * (unsigned)A.nx + bz * (unsigned)A.nxy - A.bias));
+}
+
 // read_imagef(tf, smpNormClampEdgeLinear, (v, 0.5)).w on a width x 1 image: 1-D linear.
 __device__ __forceinline__ float sample_tf_alpha(const float* __restrict__ alpha, int width, float fwidth, float v) {
     float u = fmaf(v, fwidth, -0.5f);
@@ -179,10 +236,6 @@ __device__ __forceinline__ float sample_tf_alpha(const float* __restrict__ alpha
 }
 
 #define CPM_FLT_MAX_ 3.402823466e+38f
-
-struct float3_ {
-    float x, y, z;
-};
 
 // decodeDirection / encodeDirection (Inviwo transformations.cl; host twin
 // ppm/photondata.cpp:100-117): theta = acos(clamp(z)), phi = atan2(y, x).

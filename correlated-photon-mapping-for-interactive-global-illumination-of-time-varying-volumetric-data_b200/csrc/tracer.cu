@@ -33,11 +33,7 @@ struct TraceArgs {
     float4* photons;
     uint2* rng;
     unsigned long long* tests;
-    const float* bound;  // per-cell opacity bound (cpm_opacity_bound) or null
-    // cell of a sample p, per axis: floor(p * bfc + bhc) = floor((p * dim + 0.5) / cell), clamped to [0, bmax]
-    float bfc[3], bhc, bmax[3];
-    unsigned bbias;  // (1 + bnx + bnxy) * 0x4B400000 mod 2^32: removes the float-bit biases of the three cell coordinates
-    int bnx, bnxy;
+    BoundGrid bound;  // per-cell opacity bound (cpm_opacity_bound); bound.g == null: off
     int scan;  // cheap tests a lane scans before the warp reconverges for the candidate fetches
 };
 
@@ -91,29 +87,6 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
     return t;
 }
 
-// Opacity bound of the cell that holds the trilinear footprint of the sample at parameter t of the ray
-// w(t) = wo + t * wd, the ray in CELL coordinates (set up once per walk).  The cell is floor(w) per axis; bound.cu
-// pads every cell by one voxel, which absorbs the rounding difference between this arithmetic and
-// fetch_taps' i0 = floor(p * dim - 0.5).  No conversion instructions: clamp (fmaxf maps NaN to 0), then the
-// 1.5 * 2^23 addition rounded down leaves floor(w) + 0x4B400000 in the bits; the three biases leave the index
-// with one wrapping subtraction.
-struct CellRay {
-    float ox, oy, oz, dx, dy, dz;
-};
-__device__ __forceinline__ CellRay cell_ray(const TraceArgs& A, float3_ o, float3_ d) {
-    return {fmaf(o.x, A.bfc[0], A.bhc), fmaf(o.y, A.bfc[1], A.bhc), fmaf(o.z, A.bfc[2], A.bhc),
-            d.x * A.bfc[0], d.y * A.bfc[1], d.z * A.bfc[2]};
-}
-__device__ __forceinline__ unsigned cell_bits(float w, float wmax) {
-    return __float_as_uint(__fadd_rd(fminf(fmaxf(w, 0.0f), wmax), 12582912.0f));
-}
-__device__ __forceinline__ float bound_at(const TraceArgs& A, const CellRay& R, float t) {
-    unsigned bx = cell_bits(fmaf(t, R.dx, R.ox), A.bmax[0]);
-    unsigned by = cell_bits(fmaf(t, R.dy, R.oy), A.bmax[1]);
-    unsigned bz = cell_bits(fmaf(t, R.dz, R.oz), A.bmax[2]);
-    return __ldg(A.bound + (bx + by * (unsigned)A.bnx + bz * (unsigned)A.bnxy - A.bbias));
-}
-
 // log(u) for u = k * 2^-32, k a 32-bit integer (the values cpm_rng_01 returns): cpm_logf without its
 // subnormal / inf / NaN exits, which such arguments never take; the zero case becomes a select.
 __device__ __forceinline__ float log_unit(float x) {
@@ -153,7 +126,7 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
                                                   unsigned& tests, unsigned& fetched) {
     const VolumeView& V = A.vol;
     const float inv = 1.0f / 150.0f;
-    const CellRay R = cell_ray(A, o, d);
+    const CellRay R = cell_ray(A.bound, o, d);
     float t = tStart;
     while (true) {
         bool cand = false, done = false;
@@ -167,7 +140,7 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
                 done = true;
                 break;
             }
-            float m = bound_at(A, R, t);
+            float m = bound_at(A.bound, R, t);
             if (!(u2 >= m)) {
                 cand = true;
                 break;
@@ -298,7 +271,7 @@ int launch2(cpm_ctx* ctx, const TraceArgs& a) {
 }
 template <int FMT, int LAYOUT>
 int launch(cpm_ctx* ctx, const TraceArgs& a) {
-    return a.bound ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
+    return a.bound.g ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
 }
 
 }  // namespace
@@ -327,28 +300,10 @@ extern "C" int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const floa
     a.photons = (float4*)photons;
     a.rng = (uint2*)rng_state;
     a.tests = collision_tests;
-    a.bound = params->opacity_bound;
-    a.bnx = a.bnxy = 0;
-    a.bbias = 0;
     static const int scan_env = getenv("CPM_TRACE_SCAN") ? atoi(getenv("CPM_TRACE_SCAN")) : 0;   // tuning sweeps only
     a.scan = scan_env > 0 ? scan_env : CPM_SCAN;
-    if (a.bound) {
-        CPM_REQUIRE(ctx, params->bound_cell_log2 >= 0 && params->bound_cell_log2 <= 8, "bound_cell_log2 must be in 0..8");
-        const int sh = params->bound_cell_log2;
-        const float cell = (float)(1 << sh);
-        int gd[3];
-        for (int k = 0; k < 3; ++k) {
-            gd[k] = (vol->dims[k] >> sh) + 1;
-            a.bfc[k] = (float)vol->dims[k] / cell;   // exact: cell is a power of two
-            a.bmax[k] = (float)(gd[k] - 1);
-        }
-        a.bhc = 0.5f / cell;
-        a.bnx = gd[0];
-        a.bnxy = gd[0] * gd[1];
-        CPM_REQUIRE(ctx, (double)gd[0] * gd[1] * gd[2] < 2147483648.0, "bound grid too large");
-        // indices are formed from raw float bits (cell + 0x4B400000 per axis) with wrapping 32-bit arithmetic
-        a.bbias = 0x4B400000u * (1u + (uint32_t)a.bnx + (uint32_t)a.bnxy);
-    }
+    CPM_REQUIRE(ctx, make_bound_grid(a.bound, params->opacity_bound, vol->dims, params->bound_cell_log2),
+                "bound_cell_log2 must be in 0..8 and the bound grid smaller than 2^31 cells");
     if (a.n_work == 0) return CPM_OK;
 #define CPM_DISPATCH(F)                                                                  \
     return vol->layout == CPM_VOLUME_TEXTURE ? launch<F, CPM_VOLUME_TEXTURE>(ctx, a)      \

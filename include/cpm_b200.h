@@ -376,6 +376,11 @@ typedef struct cpm_gather_params {
     float sigma_scale;    /* extinction per unit opacity and unit length: 150 matches the tracer
                              (invTauMaxSampleBaseInterval = 1/(tauMax*150), ppm/cl/transmittance.cl:40,130) */
     int32_t grid_dims[3];
+    /* optional (NULL = off): the per-cell opacity bound of cpm_opacity_bound for the SAME volume and transfer
+     * function; cells whose bound is exactly zero are stepped over without fetching voxels (identical image) */
+    const float* opacity_bound;
+    int32_t bound_cell_log2;
+    int32_t reserved_;
 } cpm_gather_params;
 
 /* image[y*width + x] = (radiance rgb, 1 - transmittance): front-to-back emission-absorption ray march,
