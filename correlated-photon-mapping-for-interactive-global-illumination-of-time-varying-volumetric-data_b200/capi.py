@@ -188,6 +188,10 @@ class Context:
         self._check(lib().cpm_opacity_bound(self.h, _p(value_range), C.c_size_t(n_cells), C.c_float(scale),
                                             C.c_float(offset), _p(tf_rgba), int(tf_rgba.numel() // 4), _p(out)))
 
+    def opacity_bound_clearance(self, bound, grid_dims, max_radius=8):
+        self._check(lib().cpm_opacity_bound_clearance(self.h, _p(bound), (C.c_int * 3)(*[int(x) for x in grid_dims]),
+                                                      int(max_radius)))
+
     # -- tracer ------------------------------------------------------------------------
     def trace_photons(self, vol: Volume, tf_rgba, params: TraceParams, light_samples, intersections, photons,
                       rng_state, recompute_index=None, n_recompute=0, collision_tests=None):

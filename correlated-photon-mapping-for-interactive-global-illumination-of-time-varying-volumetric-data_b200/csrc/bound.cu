@@ -203,9 +203,62 @@ __global__ void __launch_bounds__(256) bound_kernel(const float2* __restrict__ r
     out[id] = res;
 }
 
+// ---- clearance of transparent cells ---------------------------------------------------------------------
+// For a cell whose bound is exactly zero: R = radius, in cells, of the largest cube around it that holds only such
+// cells (outside the grid counts as transparent: lookups clamp to the border cells).  A cube is the intersection of
+// three slabs, so R comes from three 1-D passes: out[c] = max r <= cap with min(in[c - r .. c + r]) >= r.
+template <bool FROM_BOUND, bool TO_BOUND>
+__global__ void __launch_bounds__(256) clearance_kernel(const signed char* __restrict__ in, signed char* __restrict__ out,
+                                                        float* __restrict__ bound, int nx, int ny, int nz, int axis, int cap) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)nx * ny * nz;
+    if (id >= n) return;
+    const int x = (int)(id % nx), y = (int)((id / nx) % ny), z = (int)(id / ((size_t)nx * ny));
+    const int pos = axis == 0 ? x : (axis == 1 ? y : z), len = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    const size_t stride = axis == 0 ? 1 : (axis == 1 ? (size_t)nx : (size_t)nx * ny);
+    auto value = [&](size_t i) -> int { return FROM_BOUND ? (bound[i] == 0.0f ? cap : -1) : (int)in[i]; };
+    int m = value(id), r = -1;
+    if (m >= 0) {
+        r = 0;
+        while (r < cap) {
+            const int rr = r + 1;
+            int a = pos - rr >= 0 ? value(id - (size_t)rr * stride) : cap;
+            int b = pos + rr < len ? value(id + (size_t)rr * stride) : cap;
+            m = min(m, min(a, b));
+            if (m < rr) break;
+            r = rr;
+        }
+    }
+    if (TO_BOUND) {
+        if (r >= 1) bound[id] = -(float)r;
+    } else {
+        out[id] = (signed char)r;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int cpm_opacity_bound_clearance(cpm_ctx* ctx, float* bound, const int grid_dims[3], int max_radius) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, bound && grid_dims, "null argument");
+    CPM_REQUIRE(ctx, grid_dims[0] > 0 && grid_dims[1] > 0 && grid_dims[2] > 0, "grid dims must be positive");
+    CPM_REQUIRE(ctx, max_radius >= 1 && max_radius <= 100, "max_radius must be in 1..100");
+    const size_t n = (size_t)grid_dims[0] * grid_dims[1] * grid_dims[2];
+    void* scr = nullptr;
+    int rc = cpm_scratch(ctx, 2 * n, &scr);
+    if (rc != CPM_OK) return rc;
+    signed char *a = (signed char*)scr, *b = a + n;
+    const unsigned grid = cpm_div_up(n, 256);
+    CPM_LAUNCH(ctx, (clearance_kernel<true, false>), grid, 256, 0, nullptr, a, bound, grid_dims[0], grid_dims[1], grid_dims[2], 0,
+               max_radius);
+    CPM_LAUNCH(ctx, (clearance_kernel<false, false>), grid, 256, 0, a, b, bound, grid_dims[0], grid_dims[1], grid_dims[2], 1,
+               max_radius);
+    CPM_LAUNCH(ctx, (clearance_kernel<false, true>), grid, 256, 0, b, nullptr, bound, grid_dims[0], grid_dims[1], grid_dims[2], 2,
+               max_radius);
+    return CPM_OK;
+}
 
 int cpm_bound_grid_dims(const int dims[3], int cell_log2, int out_dims[3]) {
     if (!dims || !out_dims || cell_log2 < 0 || cell_log2 > 8) return CPM_E_INVALID;

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigne
                         float wz = fminf(fmaxf(fmaf(t, R.dz, R.oz), 0.0f), A.bound.mx[2]);
                         float cx = floorf(wx), cy = floorf(wy), cz = floorf(wz);
                         int ci = (int)cx + (int)cy * A.bound.nx + (int)cz * A.bound.nxy;
-                        if (__ldg(A.bound.g + ci) != 0.0f) break;
+                        if (__ldg(A.bound.g + ci) > 0.0f) break;   // <= 0: transparent (negative: with clearance)
                         float ex = ((R.dx > 0.0f ? cx + 1.0f : cx) - R.ox) * ix;
                         float ey = ((R.dy > 0.0f ? cy + 1.0f : cy) - R.oy) * iy;
                         float ez = ((R.dz > 0.0f ? cz + 1.0f : cz) - R.oz) * iz;

@@ -140,6 +140,9 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
                 done = true;
                 break;
             }
+            // (a bound <= 0 -- transparent cell, negative when cpm_opacity_bound_clearance annotated it -- never
+            // makes a candidate.  Using the clearance to skip look-ups was measured: lanes leave their transparent
+            // stretches at different tests, the warp splits, and the walk gets slower, not faster.)
             float m = bound_at(A.bound, R, t);
             if (!(u2 >= m)) {
                 cand = true;

@@ -697,8 +697,9 @@ void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, co
             float scale, offset;
             volume->formatScaleOffset(scale, offset);
             opacityBound_.setSize(nCells);
-            rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tfData, (int)tf.getTextureSize(),
-                                       static_cast<float*>(opacityBound_.deviceWrite())));
+            float* bound = static_cast<float*>(opacityBound_.deviceWrite());
+            rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tfData, (int)tf.getTextureSize(), bound));
+
             boundVolumeVersion_ = volume->dataVersion();
             boundTfVersion_ = tf.version();
         }

@@ -235,6 +235,14 @@ CPM_API int cpm_volume_value_range(cpm_ctx* ctx, const cpm_volume* vol, int cell
 CPM_API int cpm_opacity_bound(cpm_ctx* ctx, const float* range, size_t n_cells, float format_scale, float format_offset,
                               const float* tf_rgba, int tf_width, float* bound);
 
+/* Clearance of transparent cells, in place: a cell whose bound is exactly 0 (every transfer-function texel it can
+ * reach is 0) and whose surrounding cube of radius R >= 1 cells (R <= max_radius) holds only such cells gets the
+ * value -R: the next R cell widths of any ray through the cell are transparent.  Optional annotation for ray
+ * marchers that want to leave transparent regions in one jump (tracer and gather treat every bound <= 0 as
+ * transparent; the tracer does not use R -- measured slower, see csrc/tracer.cu).  Cells with a positive bound
+ * are untouched.  grid_dims = cpm_bound_grid_dims. */
+CPM_API int cpm_opacity_bound_clearance(cpm_ctx* ctx, float* bound, const int grid_dims[3], int max_radius);
+
 /* ---- (5) selection: threshold / count / iota / radix sort --------------------------- */
 /* thresholdKernel (ppm/cl/threshold.cl:33-40): out[i] = data[i] < threshold. */
 CPM_API int cpm_threshold_u32(cpm_ctx* ctx, const uint32_t* data, uint32_t threshold, size_t n,

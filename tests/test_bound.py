@@ -131,12 +131,14 @@ def test_cuda_opacity_bound_dominates_sampler(cpm, orc, ctx, torch_cuda, synth, 
                 assert worst > 0.5   # the bound stays useful for the smallest cells
 
 
-def _bounded_trace(cpm, ctx, torch, vol, tf, L, layout, s, **kw):
+def _bounded_trace(cpm, ctx, torch, vol, tf, L, layout, s, clearance=True, **kw):
     """cuda_trace with an opacity bound built on the device for this volume / TF"""
     rng, gd = gpu_range(cpm, ctx, torch, vol, s)
     n_cells = gd[0] * gd[1] * gd[2]
     bound = torch.zeros(n_cells, dtype=torch.float32, device="cuda")
     ctx.opacity_bound(rng, n_cells, torch.from_numpy(tf).cuda(), bound)
+    if clearance:
+        ctx.opacity_bound_clearance(bound, gd, 6)
     return cuda_trace(cpm, ctx, torch, vol, tf, L, layout, opacity_bound=bound, bound_cell_log2=s, **kw)
 
 
@@ -210,3 +212,50 @@ def test_cuda_bounded_tracer_dense_and_empty_media(cpm, orc, ctx, torch_cuda, sy
         got, got_rng, gt, fetched = _bounded_trace(cpm, ctx, torch_cuda, volf, tf, L, lay, 2, max_interactions=2)
         assert gt == wt
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cuda_clearance_matches_brute_force(cpm, ctx, torch_cuda, synth):
+    """-R for transparent cells whose cube of radius R (cells; outside the grid counts as transparent) is all
+    transparent, R capped; cells with a positive bound untouched"""
+    torch = torch_cuda
+    gd = (19, 14, 11)
+    u = synth.uniform01(77, gd[0] * gd[1] * gd[2]).reshape(gd[2], gd[1], gd[0])
+    zz, yy, xx = np.meshgrid(np.arange(gd[2]), np.arange(gd[1]), np.arange(gd[0]), indexing="ij")
+    solid = (u < 0.004) | (((xx - 9) ** 2 + (yy - 7) ** 2 + (zz - 5) ** 2) < 5)
+    b0 = np.where(solid, 0.25 + u, 0.0).astype(np.float32)
+    for cap in (1, 3, 8):
+        d = torch.from_numpy(b0.copy()).cuda()
+        ctx.opacity_bound_clearance(d, gd, cap)
+        ctx.sync()
+        got = d.cpu().numpy()
+        want = b0.copy()
+        pad = np.pad(~solid, cap, constant_values=True)
+        for z in range(gd[2]):
+            for y in range(gd[1]):
+                for x in range(gd[0]):
+                    if solid[z, y, x]:
+                        continue
+                    r = 0
+                    while r < cap and pad[z + cap - r - 1:z + cap + r + 2, y + cap - r - 1:y + cap + r + 2,
+                                          x + cap - r - 1:x + cap + r + 2].all():
+                        r += 1
+                    want[z, y, x] = -float(r) if r >= 1 else 0.0
+        assert np.array_equal(got, want), cap
+
+
+@pytest.mark.gpu
+def test_cuda_bounded_tracer_with_and_without_clearance(cpm, orc, ctx, torch_cuda, synth):
+    """sparse medium (most of the volume transparent): clearance on/off, every cell size -- same photons as the oracle"""
+    vol = scenes.make_volume((64, 56, 48), "f32", 13).copy()
+    vol[vol < 0.35] = 0.0          # large exactly-transparent regions under the workspace TF
+    tf = synth.rasterise_tf(width=1024)
+    L = scenes.directional_light(80, (0.35, 0.2, 0.9))
+    want, want_rng, wt = oracle_trace(orc, vol, tf, L, max_interactions=3)
+    for s in (1, 2, 3):
+        for clearance in (False, True):
+            got, got_rng, gt, fetched = _bounded_trace(cpm, ctx, torch_cuda, vol, tf, L, cpm.CPM_VOLUME_TEXTURE, s,
+                                                       clearance=clearance, max_interactions=3)
+            assert gt == wt
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (s, clearance)
+            assert np.array_equal(got_rng, want_rng)
