@@ -45,6 +45,62 @@ def allreduce_light_volume(local: torch.Tensor, out: torch.Tensor | None = None,
     return out
 
 
+class LightVolumeExchange:
+    """The same sum, pipelined: submit() snapshots the rank's light volume and starts the all-reduce on a side
+    stream, so that the NEXT frame's detector / re-trace / splat run while NVLink moves this frame's volume;
+    result() makes the caller's stream wait for the most recent sum.  Two result buffers alternate, so a result
+    stays valid while the following frame is being exchanged.  On CPU tensors (gloo tests) and in a single process
+    it degrades to the synchronous allreduce_light_volume."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.bufs = [None, None]
+        self.turn = 0
+        self.pending = None     # (work, buffer) of the most recent submit
+        self.side = None
+        self.copied = None
+
+    def submit(self, local: torch.Tensor) -> None:
+        if not is_distributed():
+            self.pending = (None, local)
+            return
+        i = self.turn
+        self.turn ^= 1
+        b = self.bufs[i]
+        if b is None or b.shape != local.shape or b.dtype != local.dtype or b.device != local.device:
+            b = self.bufs[i] = torch.empty_like(local)
+        if local.device.type != "cuda":
+            b.copy_(local)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
+            self.pending = (None, b)
+            return
+        cur = torch.cuda.current_stream(local.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=local.device)
+            self.copied = torch.cuda.Event()
+        if self.pending is not None and self.pending[0] is not None:
+            with torch.cuda.stream(self.side):
+                self.pending[0].wait()          # collectives stay ordered on the side stream
+        self.side.wait_stream(cur)              # this frame's splat has to be complete
+        with torch.cuda.stream(self.side):
+            b.copy_(local, non_blocking=True)
+            self.copied.record(self.side)
+            work = dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        cur.wait_event(self.copied)             # the next frame may touch `local` once the snapshot is taken
+        b.record_stream(self.side)
+        self.pending = (work, b)
+
+    def result(self) -> torch.Tensor:
+        """the most recently submitted sum; the current stream is made to wait for it"""
+        if self.pending is None:
+            raise RuntimeError("LightVolumeExchange.result() before submit()")
+        work, b = self.pending
+        if work is not None:
+            work.wait()                          # current stream waits for the collective
+            self.pending = (None, b)
+        return b
+
+
 def max_over_ranks(values, device="cpu"):
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
     if is_distributed():

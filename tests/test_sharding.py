@@ -33,6 +33,14 @@ def _worker(rank, world, port, q):
     # a second frame re-uses the caller's buffer and must not accumulate the previous global sum
     out2 = sh.allreduce_light_volume(local, out)
     ok = ok and out2.data_ptr() == out.data_ptr() and bool((out2 == sum(range(1, world + 1))).all())
+    # the pipelined exchange: results alternate between two buffers and never accumulate
+    ex = sh.LightVolumeExchange()
+    ex.submit(local)
+    r1 = ex.result()
+    ex.submit(local * 2)
+    r2 = ex.result()
+    ok = ok and bool((r1 == sum(range(1, world + 1))).all()) and bool((r2 == 2 * sum(range(1, world + 1))).all())
+    ok = ok and r1.data_ptr() != r2.data_ptr() and bool(torch.equal(local, keep))
     mx = sh.max_over_ranks([float(rank), 5.0 - rank])
     sm = sh.sum_over_ranks([float(rank + 1)])
     first, count = sh.photon_shard(rank, world, 4096)
