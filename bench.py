@@ -341,12 +341,27 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
         e[2].synchronize()
         if it:
             build_ms.append(e[0].elapsed_time(e[1])); march_ms.append(e[1].elapsed_time(e[2]))
+    # final image from the light volume (the LightingRaycaster step of the workspace network), same camera
+    lptr, lnf = net.light_volume_device()
+    lvol = torch.as_tensor(DevTensorView(lptr, lnf), device=dev)
+    lvd = net.light_volume_dims
+    img2 = torch.empty_like(img)
+    cast_ms = []
+    for it in range(reps + 1):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record(stream)
+        ctx.raycast_light_volume(V, tf, P, lvol, lvd, 1, img2)
+        e[1].record(stream)
+        e[1].synchronize()
+        if it:
+            cast_ms.append(e[0].elapsed_time(e[1]))
     cover = float((img.view(-1, 4)[:, 3] > 0).float().mean().item())
     lit = float((img.view(-1, 4)[:, :3].sum(dim=1) > 0).float().mean().item())
     V.destroy()
     ctx.close()
     b, m = float(np.median(build_ms)), float(np.median(march_ms))
-    return {"frames_per_sec": 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m, "view": f"{a.view}x{a.view}",
+    return {"frames_per_sec": 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m,
+            "light_volume_raycast_ms": float(np.median(cast_ms)), "view": f"{a.view}x{a.view}",
             "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
             "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
                     f"{n * I} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
@@ -568,6 +583,7 @@ def run_b200(a):
             "tests_fetching_voxels": fetched / tests if tests else None,
             "wall_ms_per_step": wall_ms / a.steps,
             "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(stages.items())},
+            "view_frames_per_sec": (1e3 / (ms / a.steps + gather["light_volume_raycast_ms"])) if gather else None,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line), flush=True)
     if world > 1:

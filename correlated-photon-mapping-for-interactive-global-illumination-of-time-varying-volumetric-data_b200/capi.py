@@ -421,6 +421,11 @@ def _reorder_photons(self, photons, ids, n, out):
     self._check(lib().cpm_reorder_photons(self.h, _p(photons), _p(ids), C.c_size_t(n), _p(out)))
 
 
+def _raycast_light_volume(self, vol, tf_rgba, params, light_volume, lv_dims, channels, image):
+    self._check(lib().cpm_raycast_light_volume(self.h, vol.handle, _p(tf_rgba), int(tf_rgba.numel() // 4), C.byref(params),
+                                               _p(light_volume), _i3(lv_dims), int(channels), _p(image)))
+
+
 def _gather_raymarch(self, vol, tf_rgba, params, sorted_photons, cell_start, cell_end, image):
     self._check(lib().cpm_gather_raymarch(self.h, vol.handle, _p(tf_rgba), int(tf_rgba.numel() // 4), C.byref(params),
                                           _p(sorted_photons), _p(cell_start), _p(cell_end), _p(image)))
@@ -453,6 +458,7 @@ def _build_photon_map(self, photons, n_records, grid_dims, torch):
 Context.photon_cell_keys = _photon_cell_keys
 Context.reorder_photons = _reorder_photons
 Context.gather_raymarch = _gather_raymarch
+Context.raycast_light_volume = _raycast_light_volume
 Context.gather_points = _gather_points
 Context.build_photon_map = _build_photon_map
 

@@ -17,7 +17,7 @@
 
 #include <algorithm>
 
-#include "sampling.cuh"
+#include "raymarch.cuh"
 
 namespace {
 
@@ -61,28 +61,6 @@ struct GatherArgs {
     float4* image;
     BoundGrid bound;   // optional per-cell opacity bound of (volume, tf): zero cells are skipped
 };
-
-// read_imagef(tf, smpNormClampEdgeLinear, (v, 0.5)) on a width x 1 image: all four channels
-__device__ __forceinline__ float4 sample_tf_rgba(const float4* __restrict__ tf, int width, float fwidth, float v) {
-    float u = fmaf(v, fwidth, -0.5f);
-    float fu = floorf(u);
-    float a = u - fu;
-    int i0 = (int)cpm_clamp(fu, -1.0f, fwidth - 1.0f);
-    int i1 = min(i0 + 1, width - 1);
-    i0 = max(i0, 0);
-    float4 p = tf[i0], q = tf[i1];
-    return make_float4(lerpf(p.x, q.x, a), lerpf(p.y, q.y, a), lerpf(p.z, q.z, a), lerpf(p.w, q.w, a));
-}
-
-__device__ __forceinline__ float sample_tf_alpha4(const float4* __restrict__ tf, int width, float fwidth, float v) {
-    float u = fmaf(v, fwidth, -0.5f);
-    float fu = floorf(u);
-    float a = u - fu;
-    int i0 = (int)cpm_clamp(fu, -1.0f, fwidth - 1.0f);
-    int i1 = min(i0 + 1, width - 1);
-    i0 = max(i0, 0);
-    return lerpf(tf[i0].w, tf[i1].w, a);
-}
 
 // irradiance estimate at x: sum over photons within `radius` of power * Epanechnikov weight
 __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float y, float z, float& er, float& eg, float& eb) {
@@ -167,28 +145,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigne
             bool live = true;
             while (live) {
                 float t = fmaf((float)k + 0.5f, P.step, t0);
-                if (A.bound.g) {
-                    // leave all-transparent cells in one jump each; the lane does all its jumps here, so that the
-                    // warp's next trip through the batch code finds every live lane at a visible sample
-                    while (t < t1) {
-                        float wx = fminf(fmaxf(fmaf(t, R.dx, R.ox), 0.0f), A.bound.mx[0]);
-                        float wy = fminf(fmaxf(fmaf(t, R.dy, R.oy), 0.0f), A.bound.mx[1]);
-                        float wz = fminf(fmaxf(fmaf(t, R.dz, R.oz), 0.0f), A.bound.mx[2]);
-                        float cx = floorf(wx), cy = floorf(wy), cz = floorf(wz);
-                        int ci = (int)cx + (int)cy * A.bound.nx + (int)cz * A.bound.nxy;
-                        if (__ldg(A.bound.g + ci) > 0.0f) break;   // <= 0: transparent (negative: with clearance)
-                        float ex = ((R.dx > 0.0f ? cx + 1.0f : cx) - R.ox) * ix;
-                        float ey = ((R.dy > 0.0f ? cy + 1.0f : cy) - R.oy) * iy;
-                        float ez = ((R.dz > 0.0f ? cz + 1.0f : cz) - R.oz) * iz;
-                        float te = fminf(fminf(R.dx != 0.0f ? ex : CPM_FLT_MAX_, R.dy != 0.0f ? ey : CPM_FLT_MAX_),
-                                         R.dz != 0.0f ? ez : CPM_FLT_MAX_);
-                        // first sample at or past the exit; at least one step forward
-                        float kf = ceilf(fmaf(te - t0, inv_step, -0.5f));
-                        int kn = (kf < 1.0e9f) ? (int)kf : 1000000000;
-                        k = max(k + 1, kn);
-                        t = fmaf((float)k + 0.5f, P.step, t0);
-                    }
-                }
+                if (A.bound.g) k = skip_transparent(A.bound, R, ix, iy, iz, t0, t1, P.step, inv_step, k, t);
                 if (!(t < t1)) break;
                 // ---- a batch of GATHER_S samples: request all taps, then classify
                 float v[GATHER_S];

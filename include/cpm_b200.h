@@ -402,6 +402,17 @@ CPM_API int cpm_gather_points(cpm_ctx* ctx, const cpm_gather_params* params, con
                               const uint32_t* cell_start, const uint32_t* cell_end, const float* points,
                               int n_points, float* irradiance);
 
+/* Final image from the light volume: image[y*width + x] = (radiance rgb, 1 - transmittance) of a front-to-back
+ * emission-absorption ray march of volume x transfer function x light volume -- what the workspace network
+ * does with Inviwo's LightingRaycaster after PhotonToLightVolumeProcessorCL (ws:1178-1271; an Inviwo core OpenGL
+ * processor outside the reference tree: parity unpinned, checker = the oracle's restatement).  Camera, clip box,
+ * step, sigma_scale and the optional opacity bound are taken from params exactly as cpm_gather_raymarch takes
+ * them (radius / scale / grid_dims are unused); light_volume is float[lv_dims] (channels = 1: scalar irradiance
+ * applied to the three colour channels) or float4[lv_dims] (channels = 4), sampled trilinearly. */
+CPM_API int cpm_raycast_light_volume(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgba, int tf_width,
+                                     const cpm_gather_params* params, const float* light_volume, const int lv_dims[3],
+                                     int channels, float* image /* float4[w*h] */);
+
 /* ---- device memory (cl::Buffer, enqueueWrite/Read/Copy/FillBuffer) -------------------- */
 /* Lets host code above this ABI (host/: the Inviwo processor mirror) stay free of CUDA headers.
  * Copies and fills are asynchronous on the context stream; use cpm_ctx_sync before reading a

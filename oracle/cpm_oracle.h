@@ -117,6 +117,10 @@ void orc_gather_points(const orc_gather_params* P, const float* photons, size_t 
 void orc_gather_raymarch(const orc_volume* vol, const float* tf_rgba, int tf_width, const orc_gather_params* P,
                          const float* photons, size_t n_records, float* image);
 
+/* final image from the light volume (the LightingRaycaster step of the workspace network): parity unpinned */
+void orc_raycast_light_volume(const orc_volume* vol, const float* tf_rgba, int tf_width, const orc_gather_params* P,
+                              const float* light_volume, const int lv_dims[3], int channels, float* image);
+
 /* --- view importance + importance-driven sample generator (orc_importance.c) ---------------------- */
 void orc_view_importance(const uint16_t* minmax, const int dims[3], const float cellDim[3], const float tex2idx[16],
                          const float idx2tex[16], const float* entry, const float* exit, int width, int height,

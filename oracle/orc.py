@@ -267,6 +267,13 @@ def gather_raymarch(vol, tf_rgba, params, photons):
     return img
 
 
+def raycast_light_volume(vol, tf_rgba, params, light_volume, lv_dims, channels=1):
+    img = np.empty((params.height, params.width, 4), np.float32)
+    lib().orc_raycast_light_volume(C.byref(vol), _ptr(tf_rgba), int(tf_rgba.shape[0]), C.byref(params), _ptr(light_volume),
+                                   _i3(lv_dims), int(channels), _ptr(img))
+    return img
+
+
 # -- view importance + importance-driven sample generator ------------------------------------------------
 def view_importance(minmax, grid_dims, cell_size, tex2idx, idx2tex, entry, exit_, tf_min, tf_max):
     h, w = entry.shape[0], entry.shape[1]

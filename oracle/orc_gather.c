@@ -145,3 +145,65 @@ void orc_gather_raymarch(const orc_volume* vol, const float* tf_rgba, int tf_wid
         }
     free_bins(&b);
 }
+
+/* ---- final image from the light volume ------------------------------------------------------------------
+ * The role Inviwo's LightingRaycaster plays after PhotonToLightVolumeProcessorCL in the workspace network
+ * (ws:1178-1271; an Inviwo core processor, not part of the reference tree: PARITY UNPINNED).  Same camera,
+ * samples and emission-absorption compositing as orc_gather_raymarch; the in-scattered radiance of a sample is
+ * TF colour x light volume (trilinear, normalised coordinates, clamp-to-edge) instead of a photon gather. */
+static float sample_lv(const float* lv, const int d[3], int nch, int ch, float px, float py, float pz) {
+    float fx = (float)d[0], fy = (float)d[1], fz = (float)d[2];
+    float u = fmaf(px, fx, -0.5f), v = fmaf(py, fy, -0.5f), w = fmaf(pz, fz, -0.5f);
+    float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+    float a = u - fu, b = v - fv, c = w - fw;
+    int i0 = (int)cpm_clamp(fu, -1.0f, fx - 1.0f), j0 = (int)cpm_clamp(fv, -1.0f, fy - 1.0f), k0 = (int)cpm_clamp(fw, -1.0f, fz - 1.0f);
+    int i1 = i0 + 1 < d[0] - 1 ? i0 + 1 : d[0] - 1, j1 = j0 + 1 < d[1] - 1 ? j0 + 1 : d[1] - 1, k1 = k0 + 1 < d[2] - 1 ? k0 + 1 : d[2] - 1;
+    if (i0 < 0) i0 = 0;
+    if (j0 < 0) j0 = 0;
+    if (k0 < 0) k0 = 0;
+#define LV(i, j, k) lv[((size_t)(i) + (size_t)d[0] * ((size_t)(j) + (size_t)d[1] * (size_t)(k))) * nch + ch]
+    float x00 = lerpf_(LV(i0, j0, k0), LV(i1, j0, k0), a), x10 = lerpf_(LV(i0, j1, k0), LV(i1, j1, k0), a);
+    float x01 = lerpf_(LV(i0, j0, k1), LV(i1, j0, k1), a), x11 = lerpf_(LV(i0, j1, k1), LV(i1, j1, k1), a);
+#undef LV
+    float y0 = lerpf_(x00, x10, b), y1 = lerpf_(x01, x11, b);
+    return lerpf_(y0, y1, c);
+}
+
+void orc_raycast_light_volume(const orc_volume* vol, const float* tf_rgba, int tf_width, const orc_gather_params* P,
+                              const float* light_volume, const int lv_dims[3], int channels, float* image) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int py = 0; py < P->height; ++py)
+        for (int px = 0; px < P->width; ++px) {
+            float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+            float dx = fmaf(fy, P->cam_dv[0], fmaf(fx, P->cam_du[0], P->cam_dir00[0]));
+            float dy = fmaf(fy, P->cam_dv[1], fmaf(fx, P->cam_du[1], P->cam_dir00[1]));
+            float dz = fmaf(fy, P->cam_dv[2], fmaf(fx, P->cam_du[2], P->cam_dir00[2]));
+            float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+            v3 d = v3_make(dx * inv, dy * inv, dz * inv);
+            v3 o = v3_make(P->cam_origin[0], P->cam_origin[1], P->cam_origin[2]);
+            float t0 = 0.0f, t1 = FLT_MAX;
+            float L[3] = {0.f, 0.f, 0.f}, T = 1.0f;
+            if (rayBoxIntersection(P->aabb_min, P->aabb_max, o, d, &t0, &t1)) {
+                int k = 0;
+                for (float t = fmaf(0.5f, P->step, t0); t < t1; ++k, t = fmaf((float)k + 0.5f, P->step, t0)) {
+                    v3 x = v3_madd(o, t, d);
+                    float v = orc_sample_volume(vol, x.x, x.y, x.z);
+                    float c[4];
+                    sample_tf_rgba(tf_rgba, tf_width, v, c);
+                    if (c[3] > 0.0f) {
+                        float e[3];
+                        e[0] = sample_lv(light_volume, lv_dims, channels, 0, x.x, x.y, x.z);
+                        e[1] = channels == 4 ? sample_lv(light_volume, lv_dims, channels, 1, x.x, x.y, x.z) : e[0];
+                        e[2] = channels == 4 ? sample_lv(light_volume, lv_dims, channels, 2, x.x, x.y, x.z) : e[0];
+                        float Ts = cpm_expf(-(c[3] * P->sigma_scale) * P->step);
+                        float wgt = T * (1.0f - Ts);
+                        for (int ch = 0; ch < 3; ++ch) L[ch] = fmaf(wgt * c[ch], e[ch], L[ch]);
+                        T *= Ts;
+                        if (T < 1e-4f) break;
+                    }
+                }
+            }
+            float* out = image + 4 * ((size_t)py * P->width + px);
+            out[0] = L[0]; out[1] = L[1]; out[2] = L[2]; out[3] = 1.0f - T;
+        }
+}
