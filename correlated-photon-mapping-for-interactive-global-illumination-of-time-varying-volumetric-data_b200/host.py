@@ -52,6 +52,12 @@ def lib():
         _lib.cpmh_network_read_collision_tests.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_read_collision_tests.restype = C.c_ulonglong
         _lib.cpmh_network_read_collision_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
+        _lib.cpmh_u3d_write.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), C.c_void_p]
+        _lib.cpmh_u3d_read_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib.cpmh_u3d_read_data.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
+        _lib.cpmh_network_export_sequence_grids.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         _lib.cpmh_profile_enable.argtypes = [C.c_int]
         _lib.cpmh_profile_enable.restype = None
         _lib.cpmh_profile_reset.restype = None
@@ -271,3 +277,52 @@ class Network:
         a, b = C.c_uint64(), C.c_uint64()
         lib().cpmh_transfer_bytes(C.byref(a), C.byref(b), int(reset))
         return a.value, b.value
+
+
+# ---- ".u3d" uniform-grid sequences (host only) -------------------------------------------------------------------
+U3D_FLOAT32, U3D_VEC2UINT16 = 0, 1
+
+
+def u3d_write(path, grids, cell=(8, 8, 8), model=None, world=None):
+    """grids: float32 array (t, z, y, x) or uint16 array (t, z, y, x, 2) -> path (.u3d header) + path's .raw"""
+    import numpy as np
+    g = np.ascontiguousarray(grids)
+    if g.dtype == np.float32 and g.ndim == 4:
+        fmt = U3D_FLOAT32
+    elif g.dtype == np.uint16 and g.ndim == 5 and g.shape[4] == 2:
+        fmt = U3D_VEC2UINT16
+    else:
+        raise ValueError("grids must be float32 (t,z,y,x) or uint16 (t,z,y,x,2)")
+    dims4 = (C.c_int * 4)(g.shape[3], g.shape[2], g.shape[1], g.shape[0])
+    ident = np.eye(4, dtype=np.float32)
+    m = np.ascontiguousarray(ident if model is None else np.asarray(model, np.float32)).reshape(-1)
+    w = np.ascontiguousarray(ident if world is None else np.asarray(world, np.float32)).reshape(-1)
+    rc = lib().cpmh_u3d_write(str(path).encode(), fmt, dims4, (C.c_int * 3)(*[int(c) for c in cell]),
+                              m.ctypes.data_as(C.POINTER(C.c_float)), w.ctypes.data_as(C.POINTER(C.c_float)),
+                              g.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+
+
+def u3d_read(path):
+    """-> (grids, cell, model, world); grids shaped like u3d_write's input, matrices column-major (4,4)"""
+    import numpy as np
+    fmt, dims4, cell = C.c_int(0), (C.c_int * 4)(), (C.c_int * 3)()
+    m, w = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    rc = lib().cpmh_u3d_read_info(str(path).encode(), C.byref(fmt), dims4, cell, m.ctypes.data_as(C.POINTER(C.c_float)),
+                                  w.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+    shape = (dims4[3], dims4[2], dims4[1], dims4[0])
+    out = np.empty(shape, np.float32) if fmt.value == U3D_FLOAT32 else np.empty(shape + (2,), np.uint16)
+    rc = lib().cpmh_u3d_read_data(str(path).encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+    return out, tuple(cell), m.reshape(4, 4), w.reshape(4, 4)
+
+
+def _export_sequence_grids(self, which, path):
+    self._check(lib().cpmh_network_export_sequence_grids(self.h, int(which), str(path).encode()))
+
+
+Network.export_sequence_grids = _export_sequence_grids

@@ -1,6 +1,7 @@
 // host_capi.cpp -- headless driver of the drop-in processor network (see host_capi.h).
 #include "host_capi.h"
 
+#include <cstring>
 #include <sstream>
 
 #include "processors.h"
@@ -398,6 +399,81 @@ void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset) {
     if (reset) BufferBase::h2dBytes() = BufferBase::d2hBytes() = 0;
 }
 void* cpmh_network_ctx(cpmh_network*) { return CpmRuntime::get().ctx(); }
+
+int cpmh_u3d_write(const char* path, int format, const int dims4[4], const int cell[3], const float model[16],
+                   const float world[16], const void* data) {
+    return guarded([&]() {
+        if (!path || !dims4 || !cell || !data) throw std::invalid_argument("null argument");
+        if (format != 0 && format != 1) throw std::invalid_argument("format must be 0 (FLOAT32) or 1 (Vec2UINT16)");
+        UniformGrid3DVector v;
+        const size3_t dim(dims4[0], dims4[1], dims4[2]), cd(cell[0], cell[1], cell[2]);
+        const size_t elem = 4, bytes = (size_t)dims4[0] * dims4[1] * dims4[2] * elem;
+        for (int t = 0; t < dims4[3]; ++t) {
+            std::shared_ptr<UniformGrid3DBase> g;
+            if (format == 0) g = std::make_shared<UniformGrid3D<float>>(dim, cd);
+            else g = std::make_shared<UniformGrid3D<u16vec2>>(dim, cd);
+            mat4 m, w;
+            for (int k = 0; k < 16; ++k) {
+                if (model) m[k / 4][k % 4] = model[k];
+                if (world) w[k / 4][k % 4] = world[k];
+            }
+            g->setModelMatrix(m);
+            g->setWorldMatrix(w);
+            std::memcpy(g->getData(), static_cast<const char*>(data) + (size_t)t * bytes, bytes);
+            v.push_back(g);
+        }
+        UniformGrid3DWriter().writeData(&v, path);
+        return (int)CPM_OK;
+    });
+}
+static thread_local std::shared_ptr<UniformGrid3DVector> g_u3d;
+static thread_local std::string g_u3dPath;
+static std::shared_ptr<UniformGrid3DVector> u3dLoad(const char* path) {
+    if (!g_u3d || g_u3dPath != path) {
+        g_u3d = UniformGrid3DReader().readData(path);
+        g_u3dPath = path;
+    }
+    return g_u3d;
+}
+int cpmh_u3d_read_info(const char* path, int* format, int dims4[4], int cell[3], float model[16], float world[16]) {
+    return guarded([&]() {
+        if (!path) throw std::invalid_argument("null argument");
+        g_u3d.reset();
+        auto v = u3dLoad(path);
+        UniformGrid3DBase* g = v->front().get();
+        if (format) *format = std::string(g->getFormatString()) == "FLOAT32" ? 0 : 1;
+        size3_t d = g->getDimensions(), c = g->getCellDimension();
+        if (dims4) { dims4[0] = (int)d.x; dims4[1] = (int)d.y; dims4[2] = (int)d.z; dims4[3] = (int)v->size(); }
+        if (cell) { cell[0] = (int)c.x; cell[1] = (int)c.y; cell[2] = (int)c.z; }
+        mat4 m = g->getModelMatrix(), w = g->getWorldMatrix();
+        for (int k = 0; k < 16; ++k) {
+            if (model) model[k] = m[k / 4][k % 4];
+            if (world) world[k] = w[k / 4][k % 4];
+        }
+        return (int)CPM_OK;
+    });
+}
+int cpmh_u3d_read_data(const char* path, void* out, size_t bytes) {
+    return guarded([&]() {
+        if (!path || !out) throw std::invalid_argument("null argument");
+        auto v = u3dLoad(path);
+        size_t each = v->front()->getSizeInBytes();
+        if (bytes != each * v->size()) throw std::invalid_argument("output buffer size does not match the file");
+        for (size_t t = 0; t < v->size(); ++t) std::memcpy(static_cast<char*>(out) + t * each, (*v)[t]->getData(), each);
+        g_u3d.reset();
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_export_sequence_grids(cpmh_network* net, int which, const char* path) {
+    return guarded([&]() {
+        if (!net || !path) throw std::invalid_argument("null argument");
+        const auto& v = which == 0 ? net->seqMinMax : net->seqDiff;
+        if (v.empty()) throw std::invalid_argument("no resident sequence (cpmh_network_set_sequence_host first)");
+        UniformGrid3DVector copy(v.begin(), v.end());
+        UniformGrid3DWriter().writeData(&copy, path);
+        return (int)CPM_OK;
+    });
+}
 
 int cpmh_fit_light_plane(const float* points, int n, const float P[3], const float N[3], float out[9]) {
     return guarded([&]() {

@@ -106,6 +106,17 @@ CPMH_API void cpmh_transfer_bytes(uint64_t* h2d, uint64_t* d2h, int reset);
 CPMH_API void* cpmh_network_ctx(cpmh_network* net);
 /* the host layer's CPU light-plane fit (lcl/orientedboundingbox2d.cpp:80-100 + convexhull2d.cpp +
  * pointplaneprojection.cpp), exposed for parity tests: out = origin[3], u[3], v[3].  No device needed. */
+/* ".u3d" uniform-grid sequences (ugc/uniformgrid3dreader.cpp:59-183, ugc/uniformgrid3dwriter.cpp:47-102): text
+ * header + raw file.  format: 0 = FLOAT32 (importance / difference grids), 1 = Vec2UINT16 (min-max grids).
+ * Host-only (no device needed).  dims4 = (x, y, z, number of grids); matrices are column-major 4x4. */
+CPMH_API int cpmh_u3d_write(const char* path, int format, const int dims4[4], const int cell[3], const float model[16],
+                            const float world[16], const void* data);
+CPMH_API int cpmh_u3d_read_info(const char* path, int* format, int dims4[4], int cell[3], float model[16], float world[16]);
+CPMH_API int cpmh_u3d_read_data(const char* path, void* out, size_t bytes);
+/* UniformGrid3DExport (ugc/processors/uniformgrid3dexport.cpp) for the grids of the resident sequence:
+ * which = 0 the per-step min-max grids, 1 the step-to-step difference grids */
+CPMH_API int cpmh_network_export_sequence_grids(cpmh_network* net, int which, const char* path);
+
 CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
                                   const float plane_normal[3], float out[9]);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */

@@ -1,6 +1,9 @@
 // processors.cpp -- implementation of the Inviwo shim, the kernel-launcher classes and the
 // drop-in processors.  Every device operation is one call into the C ABI (include/cpm_b200.h).
 #include <atomic>
+#include <cctype>
+#include <sstream>
+#include <fstream>
 #include "processors.h"
 
 #include <cstdio>
@@ -1078,6 +1081,140 @@ void ProgressivePhotonTracerCL::process() {
     invalidationFlag_ = R(0);
     outport_.setData(photonData_);
     if (enableProgressiveRefinement_.get() && remainingPhotonsToUpdate_ > 0) invalidate(InvalidationLevel::InvalidOutput);
+}
+
+// ---- .u3d reader / writer ---------------------------------------------------------------------------
+namespace {
+std::string trimmed(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::string lowered(std::string s) {
+    for (auto& c : s) c = (char)std::tolower((unsigned char)c);
+    return s;
+}
+std::string parentDir(const std::string& path) {
+    size_t k = path.find_last_of('/');
+    return k == std::string::npos ? std::string() : path.substr(0, k + 1);
+}
+void readMatrix(std::istream& ss, mat4& m) {
+    // written row by row (the writer transposes glm's column-major matrix first), read back and transposed again
+    mat4 t;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) ss >> t[i][j];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) m[i][j] = t[j][i];
+}
+}  // namespace
+
+std::shared_ptr<UniformGrid3DVector> UniformGrid3DReader::readData(const std::string& filePath) {
+    std::ifstream f(filePath);
+    if (!f.good()) throw std::invalid_argument("Error: Unable to open file: " + filePath);
+    std::string rawFile, formatFlag;
+    mat4 modelMatrix, worldMatrix;
+    size3_t cellDimensions(0);
+    size_t resolution[4] = {0, 0, 0, 0};
+    // the header is line oriented except for the matrices, whose four rows follow the key on four lines
+    std::string textLine;
+    while (std::getline(f, textLine)) {
+        textLine = trimmed(textLine);
+        if (textLine.empty() || textLine[0] == '#' || textLine[0] == '/') continue;
+        std::string noComment = textLine.substr(0, textLine.find('#'));
+        size_t colon = noComment.find(':');
+        if (colon == std::string::npos || noComment.find(':', colon + 1) != std::string::npos) continue;
+        std::string key = lowered(trimmed(noComment.substr(0, colon))), value = trimmed(noComment.substr(colon + 1));
+        if (key == "modelmatrix" || key == "worldmatrix") {
+            // the reference parses only the key's own line (one row) and leaves the rest of the matrix at identity
+            // rows (uniformgrid3dreader.cpp:100-113); its writer, however, emits four lines.  Read all four so that
+            // a written file round-trips.
+            for (int r = 1; r < 4; ++r) {
+                std::streampos pos = f.tellg();
+                std::string more;
+                if (!std::getline(f, more)) break;
+                if (more.find(':') != std::string::npos) {   // next key already: a one-line matrix
+                    f.seekg(pos);
+                    break;
+                }
+                value += " " + trimmed(more);
+            }
+        }
+        std::stringstream ss(value);
+        if (key == "objectfilename" || key == "rawfile") {
+            rawFile = parentDir(filePath) + value;
+        } else if (key == "resolution" || key == "dimensions") {
+            ss >> resolution[0] >> resolution[1] >> resolution[2] >> resolution[3];
+        } else if (key == "format") {
+            ss >> formatFlag;
+        } else if (key == "modelmatrix") {
+            readMatrix(ss, modelMatrix);
+        } else if (key == "worldmatrix") {
+            readMatrix(ss, worldMatrix);
+        } else if (key == "celldimensions") {
+            ss >> cellDimensions.x >> cellDimensions.y >> cellDimensions.z;
+        }
+    }
+    if (resolution[0] == 0 && resolution[1] == 0 && resolution[2] == 0 && resolution[3] == 0)
+        throw std::invalid_argument("Error: Unable to find \"Resolution\" tag in file: " + filePath);
+    if (formatFlag.empty()) throw std::invalid_argument("Error: Unable to find \"Format\" tag in file: " + filePath);
+    std::shared_ptr<UniformGrid3DBase> data;
+    const size3_t dim(resolution[0], resolution[1], resolution[2]);
+    if (formatFlag == "FLOAT32")
+        data = std::make_shared<UniformGrid3D<float>>(dim, cellDimensions);
+    else if (formatFlag == "Vec2UINT16")
+        data = std::make_shared<UniformGrid3D<u16vec2>>(dim, cellDimensions);
+    else
+        throw std::invalid_argument("Error: Unsupported data fromat \"Format\" tag in file: " + filePath + " (" + formatFlag +
+                                    "; this build reads FLOAT32 and Vec2UINT16 grids)");
+    data->setModelMatrix(modelMatrix);
+    data->setWorldMatrix(worldMatrix);
+    auto dataVector = std::make_shared<UniformGrid3DVector>();
+    std::ifstream fin(rawFile, std::ios::in | std::ios::binary);
+    if (!fin.good()) throw std::invalid_argument("Error: Unable to read from  file: " + rawFile);
+    const size_t bytes = data->getSizeInBytes();
+    for (size_t t = 0; t < resolution[3]; ++t) {
+        dataVector->push_back(t == 0 ? data : data->cloneEmpty());
+        fin.read(static_cast<char*>(dataVector->back()->getData()), (std::streamsize)bytes);
+        if ((size_t)fin.gcount() != bytes) throw std::invalid_argument("Error: raw file too short: " + rawFile);
+    }
+    return dataVector;
+}
+
+void UniformGrid3DWriter::writeData(const UniformGrid3DVector* vectorData, const std::string& filePath) const {
+    if (!vectorData || vectorData->size() < 1) throw std::invalid_argument("Error: Cannot write empty vector");
+    std::string rawPath = filePath;
+    size_t dot = rawPath.find_last_of('.');
+    if (dot != std::string::npos && rawPath.find('/', dot) == std::string::npos) rawPath.erase(dot);
+    rawPath += ".raw";
+    if (!overwrite_) {
+        if (std::ifstream(filePath).good() || std::ifstream(rawPath).good())
+            throw std::invalid_argument("Error: file exists and overwrite is off: " + filePath);
+    }
+    size_t slash = rawPath.find_last_of('/');
+    const std::string rawName = slash == std::string::npos ? rawPath : rawPath.substr(slash + 1);
+    UniformGrid3DBase* data = vectorData->front().get();
+    std::stringstream ss;
+    const size3_t dim = data->getDimensions(), cell = data->getCellDimension();
+    ss << "RawFile: " << rawName << std::endl;
+    ss << "Resolution: " << dim.x << " " << dim.y << " " << dim.z << " " << vectorData->size() << std::endl;
+    ss << "Format: " << data->getFormatString() << std::endl;
+    const mat4 mats[2] = {data->getModelMatrix(), data->getWorldMatrix()};
+    const char* names[2] = {"ModelMatrix", "WorldMatrix"};
+    for (int k = 0; k < 2; ++k) {
+        ss << names[k] << ":";
+        for (int i = 0; i < 4; ++i) {   // row i of the matrix = element [j][i] of the column-major storage
+            for (int j = 0; j < 4; ++j) ss << " " << mats[k][j][i];
+            ss << std::endl;
+        }
+    }
+    ss << "CellDimensions: " << cell.x << " " << cell.y << " " << cell.z << std::endl;
+    std::ofstream f(filePath);
+    if (!f.good()) throw std::invalid_argument("Could not write to file: " + filePath);
+    f << ss.str();
+    f.close();
+    std::ofstream fout(rawPath, std::ios::out | std::ios::binary);
+    if (!fout.good()) throw std::invalid_argument("Could not write to raw file: " + rawPath);
+    for (auto& element : *vectorData)
+        fout.write(static_cast<const char*>(element->getData()), (std::streamsize)element->getSizeInBytes());
 }
 
 // ---- PhotonToLightVolumeProcessorCL -----------------------------------------------------------------

@@ -113,10 +113,19 @@ public:
     void setModelMatrix(const mat4& m) { model_ = m; }
     mat4 getWorldMatrix() const { return world_; }
     void setWorldMatrix(const mat4& m) { world_ = m; }
+    // what the .u3d reader / writer need (ugc/uniformgrid3d.h:84-98): raw element storage, its format name
+    // ("FLOAT32", "Vec2UINT16") and an empty grid of the same type
+    virtual void* getData() = 0;
+    virtual const char* getFormatString() const = 0;
+    virtual std::shared_ptr<UniformGrid3DBase> cloneEmpty() const = 0;
 private:
     size3_t cellDimension_;
     mat4 model_, world_;
 };
+struct u16vec2 { uint16_t x = 0, y = 0; };
+template <typename T> struct GridFormatName;
+template <> struct GridFormatName<float> { static const char* get() { return "FLOAT32"; } };
+template <> struct GridFormatName<u16vec2> { static const char* get() { return "Vec2UINT16"; } };
 template <typename T>
 class UniformGrid3D : public UniformGrid3DBase {
 public:
@@ -128,15 +137,37 @@ public:
         data.setSize(dim.x * dim.y * dim.z);
     }
     size_t getSizeInBytes() const override { return data.getSizeInBytes(); }
+    void* getData() override { return data.getEditableRAMRepresentation()->data(); }
+    const char* getFormatString() const override { return GridFormatName<T>::get(); }
+    std::shared_ptr<UniformGrid3DBase> cloneEmpty() const override {
+        auto g = std::make_shared<UniformGrid3D<T>>(dimensions_, getCellDimension());
+        g->setModelMatrix(getModelMatrix());
+        g->setWorldMatrix(getWorldMatrix());
+        return g;
+    }
     mutable Buffer<T> data;   // id = x + y*dx + z*dx*dy
 private:
     size3_t dimensions_;
 };
-struct u16vec2 { uint16_t x = 0, y = 0; };
 using MinMaxUniformGrid3D = UniformGrid3D<u16vec2>;                 // ugc/minmaxuniformgrid3d.h:42
 using ImportanceUniformGrid3D = UniformGrid3D<float>;              // isc/importanceuniformgrid3d.h:46
 using DynamicVolumeInfoUniformGrid3D = UniformGrid3D<float>;       // ugc/processors/dynamicvolumedifferenceanalysis.h:60-61
 using UniformGrid3DVector = std::vector<std::shared_ptr<UniformGrid3DBase>>;
+
+// ".u3d" uniform-grid sequences on disk: a text header (RawFile, Resolution x y z t, Format, ModelMatrix,
+// WorldMatrix, CellDimensions) next to a raw file holding the t grids back to back.
+// ugc/uniformgrid3dreader.cpp:59-183, ugc/uniformgrid3dwriter.cpp:47-102.
+class UniformGrid3DReader {
+public:
+    std::shared_ptr<UniformGrid3DVector> readData(const std::string& filePath);
+};
+class UniformGrid3DWriter {
+public:
+    void writeData(const UniformGrid3DVector* data, const std::string& filePath) const;
+    void setOverwrite(bool v) { overwrite_ = v; }
+private:
+    bool overwrite_ = true;
+};
 
 // ===================================================================== kernel launchers ======
 // rng/mwc64xseedgenerator.h:60
