@@ -69,39 +69,41 @@ __global__ void __launch_bounds__(256) range_kernel(const void* __restrict__ vol
     const int rows = ry * rz;
     const T* base = (const T*)vol;
     if (vec_ok) {
+        // one warp per row, lanes stride over its 16-byte chunks: no per-item index divisions
         const int chunks = nx / K;
-        const int items = rows * chunks;
-        for (int w = threadIdx.x; w < items; w += blockDim.x) {
-            int r = w / chunks, c = w - r * chunks;
-            int y = y0 + r % ry, z = z0 + r / ry;
-            const T* row = base + ((size_t)z * ny + y) * nx;
-            uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + c);
-            const T* e = reinterpret_cast<const T*>(&raw);
-            const int x = c * K;
-            float v[K];
-            bool isbad[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                v[k] = VoxT<FMT>::norm(e[k]);
-                isbad[k] = !(fabsf(v[k]) <= CPM_FLT_MAX_);
-            }
-            // voxel x is in cell q iff q*cell - 2 <= x <= q*cell + cell: the chunk touches a contiguous cell range
-            const int qmin = max(((x + cell - 1) >> s) - 1, 0), qmax = min((x + K + 1) >> s, ncx - 1);
-            for (int q = qmin; q <= qmax; ++q) {
-                const int lo = q * cell - 2 - x, hi = q * cell + cell - x;   // relative to the chunk
-                float mn = CPM_FLT_MAX_, mx = -CPM_FLT_MAX_;
-                bool bad = false;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+        for (int r = warp; r < rows; r += n_warps) {
+            const int zr = r / ry;
+            const int y = y0 + (r - zr * ry), z = z0 + zr;
+            const uint4* row = reinterpret_cast<const uint4*>(base + ((size_t)z * ny + y) * nx);
+            for (int c = lane; c < chunks; c += 32) {
+                uint4 raw = __ldg(row + c);
+                const T* e = reinterpret_cast<const T*>(&raw);
+                const int x = c * K;
+                float v[K];
+                bool anybad = false;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    if (k >= lo && k <= hi) {
-                        mn = fminf(mn, v[k]);
-                        mx = fmaxf(mx, v[k]);
-                        bad = bad || isbad[k];
-                    }
+                    v[k] = VoxT<FMT>::norm(e[k]);
+                    anybad = anybad || !(fabsf(v[k]) <= CPM_FLT_MAX_);
                 }
-                atomicMin(&s_min[q], okey(mn));
-                atomicMax(&s_max[q], okey(mx));
-                if (bad) s_bad[q] = 1u;
+                // voxel x is in cell q iff q*cell - 2 <= x <= q*cell + cell: the chunk touches a contiguous cell range
+                const int qmin = max(((x + cell - 1) >> s) - 1, 0), qmax = min((x + K + 1) >> s, ncx - 1);
+                for (int q = qmin; q <= qmax; ++q) {
+                    const int lo = q * cell - 2 - x, hi = q * cell + cell - x;   // relative to the chunk
+                    float mn = CPM_FLT_MAX_, mx = -CPM_FLT_MAX_;
+                    bool bad = false;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const bool in = k >= lo && k <= hi;
+                        mn = in ? fminf(mn, v[k]) : mn;
+                        mx = in ? fmaxf(mx, v[k]) : mx;
+                        if (anybad) bad = bad || (in && !(fabsf(v[k]) <= CPM_FLT_MAX_));
+                    }
+                    atomicMin(&s_min[q], okey(mn));
+                    atomicMax(&s_max[q], okey(mx));
+                    if (bad) s_bad[q] = 1u;
+                }
             }
         }
     } else {

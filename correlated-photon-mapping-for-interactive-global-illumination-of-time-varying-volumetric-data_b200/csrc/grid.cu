@@ -288,17 +288,22 @@ __global__ void __launch_bounds__(128) hash_kernel(const float4* __restrict__ ls
     bucket[out_offset + g] = hz * (uint32_t)nbx * (uint32_t)nby + hy * (uint32_t)nbx + hx;
 }
 
-// boundary i (0..n): between key[i-1] (virtual -1) and key[i] (virtual n_cells).  Every cell c with
-// prev < c <= next starts at i; every cell with prev <= c < next ends at i.
+// One thread per cell boundary c in [0, n_cells]: lb = lower_bound(keys, c) is where cell c starts and where cell
+// c - 1 ends.  A binary search per cell (22 L2-resident probes for 4 Mi keys) costs the same for dense and for empty
+// stretches of the grid; walking the key array instead leaves one thread to fill every cell of a long empty run
+// (measured: 0.87 ms of a 1.2 ms photon-map build for the run behind the last occupied cell).
 __global__ void __launch_bounds__(256) cell_range_kernel(const uint32_t* __restrict__ keys, size_t n, uint32_t n_cells,
                                                          uint32_t* __restrict__ start, uint32_t* __restrict__ end) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    long long prev = (i == 0) ? -1 : (long long)min(keys[i - 1], n_cells);
-    long long next = (i == n) ? (long long)n_cells : (long long)min(keys[i], n_cells);
-    if (prev == next) return;
-    for (long long c = prev + 1; c <= next && c < (long long)n_cells; ++c) start[c] = (uint32_t)i;
-    for (long long c = max(prev, 0ll); c < next; ++c) end[c] = (uint32_t)i;
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    size_t lo = 0, hi = n;   // first index with keys[index] >= c
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) < (uint32_t)c) lo = mid + 1;
+        else hi = mid;
+    }
+    if (c < n_cells) start[c] = (uint32_t)lo;
+    if (c > 0) end[c - 1] = (uint32_t)lo;
 }
 
 }  // namespace
@@ -405,7 +410,7 @@ int cpm_build_cell_ranges(cpm_ctx* ctx, const uint32_t* sorted_keys, size_t n, u
     if (!ctx) return CPM_E_INVALID;
     if (n_cells == 0) return CPM_OK;
     CPM_REQUIRE(ctx, cell_start && cell_end && (sorted_keys || n == 0), "null argument");
-    CPM_LAUNCH(ctx, cell_range_kernel, cpm_div_up(n + 1, 256), 256, 0, sorted_keys, n, n_cells, cell_start, cell_end);
+    CPM_LAUNCH(ctx, cell_range_kernel, cpm_div_up((size_t)n_cells + 1, 256), 256, 0, sorted_keys, n, n_cells, cell_start, cell_end);
     return CPM_OK;
 }
 

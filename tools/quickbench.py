@@ -77,6 +77,27 @@ def main():
                         print(f"  trace I={I} {lname:8s}: {ms:.3f} ms  photons/s={n/ms*1e3:.3e}  tests={tests} "
                               f"({tests/n:.1f}/photon) tests/s={tests/ms*1e3:.3e} stored={stored}  runs={['%.3f'%x for x in all_]}")
                         V.destroy()
+        if "grids" in what:
+            # per-volume grid builders on the C3 / C4 / C5 volumes: min-max bricks, value range of the bound cells
+            for dims, fmt in (((256, 256, 256), "u8"), ((512, 512, 512), "f32"), ((1024, 1024, 1024), "u8")):
+                n = dims[0] * dims[1] * dims[2]
+                if fmt == "u8":
+                    dvol = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+                else:
+                    dvol = torch.rand(n, dtype=torch.float32, device="cuda")
+                V = ctx.volume_create(dvol, dims, cpm.CPM_FMT_U8 if fmt == "u8" else cpm.CPM_FMT_F32)
+                nb = [-(-x // 8) for x in dims]
+                mm = torch.empty(nb[0] * nb[1] * nb[2] * 2, dtype=torch.int16, device="cuda")
+                ms, _ = timed(lambda: ctx.volume_minmax(V, 8, mm), stream)
+                bytes_ = n * (1 if fmt == "u8" else 4)
+                print(f"  [{dims[0]}^3 {fmt}] volume_minmax: {ms:.3f} ms = {bytes_/ms/1e6:.0f} GB/s")
+                for s_ in (2, 3, 4):
+                    gd = cpm.capi.bound_grid_dims(dims, s_)
+                    rg = torch.empty(2 * gd[0] * gd[1] * gd[2], dtype=torch.float32, device="cuda")
+                    ms, _ = timed(lambda: ctx.volume_value_range(V, s_, rg), stream)
+                    print(f"  [{dims[0]}^3 {fmt}] volume_value_range cell {1 << s_}: {ms:.3f} ms = {bytes_/ms/1e6:.0f} GB/s")
+                V.destroy()
+                del dvol
         if "sort26" in what:
             what = what + ["sort"]
         if "sort" in what:
