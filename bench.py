@@ -365,7 +365,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
             "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
             "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
                     f"{n * I} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
-                    "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 8 samples gathered per photon pass"}
+                    "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 12 samples gathered per photon pass"}
 
 
 def run_b200(a):

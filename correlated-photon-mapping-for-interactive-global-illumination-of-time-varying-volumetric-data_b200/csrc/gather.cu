@@ -101,7 +101,7 @@ __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float
 //    visible the photons of the cells around the whole segment are read ONCE -- per photon the distance to
 //    the ray (|q|^2 - (q.d)^2) rejects most candidates, and the survivors update the batch's estimates through
 //    d_k^2 = d_perp^2 + (t_k - q.d)^2 -- instead of once per sample through 8 cells.
-constexpr int GATHER_S = 8;
+constexpr int GATHER_S = 12;
 
 template <int FMT, int LAYOUT>
 __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
