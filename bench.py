@@ -299,9 +299,12 @@ class DevTensorView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
 
-def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
+def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, world=1, reps=5):
     """gathered frames/s: photon-map build (cell keys, onesweep sort, cell ranges, reorder) + view ray march of
-    the network's current photon records; CUDA events on the launch stream, median of `reps`"""
+    the network's current photon records; CUDA events on the launch stream, median of `reps`.
+    world > 1 (SURVEY 8e option A): the ranks' photon records are all-gathered over NCCL, every rank builds the
+    replicated map and marches its own strips of the image, the strips are all-gathered into the whole image;
+    per-repetition times are the max over ranks."""
     ctx = cpm.Context(dev.index, stream.cuda_stream)
     D, I, n = a.dims, a.max_interactions, a.photons_side ** 2
     ptr, nf = net.photons_device()
@@ -312,7 +315,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
     tf = torch.from_numpy(synth.rasterise_tf(width=1024)).to(dev)
     radius = float(np.float32(np.sqrt(3.0) / D))                       # the tracer's 1-voxel photon radius
     g = int(min(512, max(1, int(1.0 / (2.0 * radius)))))                # cell edge >= 2 r: at most 8 cells per gather
-    scale = float((1.0 / np.pi) / (4.0 / 3.0 * np.pi * radius ** 3 * n))
+    scale = float((1.0 / np.pi) / (4.0 / 3.0 * np.pi * radius ** 3 * n * world))
     # per-cell opacity bound of (this volume, this TF), as the tracer keeps it: the value-range grid is per-step data
     # like the min-max grid (untimed), the TF classification of its cells belongs to the frame (timed with the build)
     bs = 3 if a.bound_log2 <= 0 else a.bound_log2
@@ -327,20 +330,32 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
     P = cpm.capi.make_gather_params(a.view, a.view, (1.7, 1.4, -1.3), (0.5, 0.5, 0.5), fov_deg=40.0, step=0.5 / D,
                                     radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g),
                                     opacity_bound=bound, bound_cell_log2=bs)
-    img = torch.empty(a.view * a.view * 4, dtype=torch.float32, device=dev)
-    build_ms, march_ms = [], []
+    first, stride, rows = sharding.image_strips(rank, world, a.view)
+    if world > 1:
+        P.height, P.strip_first, P.strip_stride = rows, first, stride
+    img = torch.empty(rows * a.view * 4, dtype=torch.float32, device=dev)
+    allp = None
+    xchg_ms, build_ms, march_ms, total_ms = [], [], [], []
     for it in range(reps + 1):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if world > 1:
+            torch.distributed.barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record(stream)
-        sp, start, end, _ = ctx.build_photon_map(photons, n * I, (g, g, g), torch)
+        allp = sharding.allgather_photons(photons, allp)
+        e[1].record(stream)
+        sp, start, end, _ = ctx.build_photon_map(allp, n * I * world, (g, g, g), torch)
         if bound is not None:
             ctx.opacity_bound(vrange, ncell, tf, bound)
-        e[1].record(stream)
-        ctx.gather_raymarch(V, tf, P, sp, start, end, img)
         e[2].record(stream)
-        e[2].synchronize()
+        ctx.gather_raymarch(V, tf, P, sp, start, end, img)
+        e[3].record(stream)
+        full = sharding.allgather_image(img, a.view, a.view)
+        e[4].record(stream)
+        e[4].synchronize()
         if it:
-            build_ms.append(e[0].elapsed_time(e[1])); march_ms.append(e[1].elapsed_time(e[2]))
+            t = [e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]), e[0].elapsed_time(e[4])]
+            t = sharding.max_over_ranks(t, device=dev)
+            xchg_ms.append(t[0]); build_ms.append(t[1]); march_ms.append(t[2]); total_ms.append(t[3])
     # final image from the light volume (the LightingRaycaster step of the workspace network), same camera
     lptr, lnf = net.light_volume_device()
     lvol = torch.as_tensor(DevTensorView(lptr, lnf), device=dev)
@@ -355,17 +370,23 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, reps=5):
         e[1].synchronize()
         if it:
             cast_ms.append(e[0].elapsed_time(e[1]))
-    cover = float((img.view(-1, 4)[:, 3] > 0).float().mean().item())
-    lit = float((img.view(-1, 4)[:, :3].sum(dim=1) > 0).float().mean().item())
+    full = full.reshape(-1, 4)
+    cover = float((full[:, 3] > 0).float().mean().item())
+    lit = float((full[:, :3].sum(dim=1) > 0).float().mean().item())
     V.destroy()
     ctx.close()
-    b, m = float(np.median(build_ms)), float(np.median(march_ms))
-    return {"frames_per_sec": 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m,
-            "light_volume_raycast_ms": float(np.median(cast_ms)), "view": f"{a.view}x{a.view}",
-            "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
-            "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
-                    f"{n * I} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
-                    "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 12 samples gathered per photon pass"}
+    b, m, x, tot = (float(np.median(v)) for v in (build_ms, march_ms, xchg_ms, total_ms))
+    out = {"frames_per_sec": 1e3 / tot if world > 1 else 1e3 / (b + m), "photon_map_build_ms": b, "raymarch_ms": m,
+           "light_volume_raycast_ms": float(np.median(cast_ms)), "view": f"{a.view}x{a.view}",
+           "grid": f"{g}^3 cells", "pixels_hitting_volume": cover, "pixels_lit": lit,
+           "note": "not part of `value`: build = cell keys + onesweep (keys, ids) + cell ranges + reorder of "
+                   f"{n * I * world} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
+                   "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 12 samples gathered per photon pass"}
+    if world > 1:
+        out.update({"photon_allgather_ms": x, "frame_ms": tot, "photons_in_map": n * I * world,
+                    "tiling": f"strips of 4 rows dealt round robin over {world} ranks, NCCL all-gather of photon records "
+                              f"({32 * n * I * world} B) and of the image strips; times are max over ranks"})
+    return out
 
 
 def run_b200(a):
@@ -492,9 +513,9 @@ def run_b200(a):
         e2e = None
         # ---------------- gathered frames: photon-map build + view ray march (north-star 5-7) ----------------
         gather = None
-        if rank == 0 and not a.no_gather:
+        if not a.no_gather:
             # the resident leg ended on time step warmup + steps: its photons and its volume
-            gather = gather_leg(a, cpm, torch, stream, net, pinned[(a.warmup + a.steps) % T], dev)
+            gather = gather_leg(a, cpm, torch, stream, net, pinned[(a.warmup + a.steps) % T], dev, sharding, rank, world)
         if not a.no_e2e:
             lvd = net.light_volume_dims
             out_host = torch.empty(lvd[0] * lvd[1] * lvd[2], dtype=torch.float32, pin_memory=True)

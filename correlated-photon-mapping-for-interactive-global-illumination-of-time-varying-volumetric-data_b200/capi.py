@@ -381,7 +381,8 @@ class GatherParams(C.Structure):
                 ("cam_du", C.c_float * 3), ("cam_dv", C.c_float * 3), ("aabb_min", C.c_float * 3),
                 ("aabb_max", C.c_float * 3), ("step", C.c_float), ("radius", C.c_float), ("scale", C.c_float),
                 ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3), ("opacity_bound", C.c_void_p),
-                ("bound_cell_log2", C.c_int32), ("reserved_", C.c_int32)]
+                ("bound_cell_log2", C.c_int32), ("strip_first", C.c_int32), ("strip_stride", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 def make_gather_params(width, height, eye, look_at, up=(0, 1, 0), fov_deg=60.0, step=1.0 / 256, radius=1.0 / 64,

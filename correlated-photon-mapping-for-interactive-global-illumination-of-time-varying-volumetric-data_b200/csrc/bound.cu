@@ -130,6 +130,166 @@ __global__ void __launch_bounds__(256) range_kernel(const void* __restrict__ vol
     }
 }
 
+// ---- cells of 8 voxels (the default), 16-byte aligned rows: streaming version --------------------------------
+// Same CTA mapping (one CTA per (cy, cz), 11 x 11 rows of the padded cell row), but a thread owns one 16-byte chunk
+// COLUMN and walks down the rows: the cells a chunk feeds are then fixed per thread, min / max stay in registers
+// (packed bytes / halves for the integer formats, order keys for f32 so that NaN and inf show up in the extremes),
+// four independent loads are in flight per thread, and shared memory sees a handful of atomics per thread instead
+// of several per chunk.  Voxel v feeds cell q iff 8q - 2 <= v <= 8q + 8.
+template <int FMT>
+struct ChunkAcc;
+
+template <>
+struct ChunkAcc<CPM_FMT_F32> {   // 4 voxels: x = 8m + 4j .. + 3, j = column parity
+    uint32_t mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = 0xffffffffu, mx[k] = 0u;
+    }
+    __device__ void add(const uint4& r) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t key = w[k] ^ (uint32_t)(((int32_t)w[k] >> 31) | 0x80000000);   // okey()
+            mn[k] = min(mn[k], key);
+            mx[k] = max(mx[k], key);
+        }
+    }
+    // order keys: +inf / +NaN are >= key(+inf), -inf / -NaN are <= key(-inf)
+    __device__ static bool bad(uint32_t kmin, uint32_t kmax) { return kmax >= 0xff800000u || kmin <= 0x007fffffu; }
+    __device__ void flush(int c, int ncx, uint32_t* s_min, uint32_t* s_max, uint32_t* s_bad) const {
+        const int m = c >> 1, j = c & 1;
+        uint32_t a = min(min(mn[0], mn[1]), min(mn[2], mn[3])), b = max(max(mx[0], mx[1]), max(mx[2], mx[3]));
+        put(m, ncx, a, b, s_min, s_max, s_bad);
+        if (j == 0) {
+            if (m >= 1) put(m - 1, ncx, mn[0], mx[0], s_min, s_max, s_bad);                     // voxel 8m = 8(m-1) + 8
+        } else {
+            put(m + 1, ncx, min(mn[2], mn[3]), max(mx[2], mx[3]), s_min, s_max, s_bad);         // voxels 8m+6, 8m+7
+        }
+    }
+    __device__ static void put(int q, int ncx, uint32_t a, uint32_t b, uint32_t* s_min, uint32_t* s_max, uint32_t* s_bad) {
+        if (q >= ncx || a > b) return;
+        if (bad(a, b)) s_bad[q] = 1u;
+        // the generic path reduces with fminf / fmaxf, which skip NaN: keep the extremes over the non-NaN values
+        // comparable by clamping NaN keys to the infinities (the cell is flagged bad either way)
+        atomicMin(&s_min[q], max(a, 0x007fffffu));
+        atomicMax(&s_max[q], min(b, 0xff800000u));
+    }
+};
+
+template <>
+struct ChunkAcc<CPM_FMT_U16> {   // 8 voxels: x = 8m .. 8m + 7
+    uint32_t mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = 0xffffffffu, mx[k] = 0u;
+    }
+    __device__ void add(const uint4& r) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mn[k] = __vminu2(mn[k], w[k]);
+            mx[k] = __vmaxu2(mx[k], w[k]);
+        }
+    }
+    __device__ static uint32_t lo2(uint32_t v) { return min(v & 0xffffu, v >> 16); }
+    __device__ static uint32_t hi2(uint32_t v) { return max(v & 0xffffu, v >> 16); }
+    __device__ static void put(int q, int ncx, uint32_t a, uint32_t b, uint32_t* s_min, uint32_t* s_max) {
+        if (q < 0 || q >= ncx) return;
+        atomicMin(&s_min[q], okey(unorm16((float)a)));
+        atomicMax(&s_max[q], okey(unorm16((float)b)));
+    }
+    __device__ void flush(int c, int ncx, uint32_t* s_min, uint32_t* s_max, uint32_t*) const {
+        uint32_t a = lo2(__vminu2(__vminu2(mn[0], mn[1]), __vminu2(mn[2], mn[3])));
+        uint32_t b = hi2(__vmaxu2(__vmaxu2(mx[0], mx[1]), __vmaxu2(mx[2], mx[3])));
+        put(c, ncx, a, b, s_min, s_max);
+        put(c - 1, ncx, mn[0] & 0xffffu, mx[0] & 0xffffu, s_min, s_max);     // voxel 8m
+        put(c + 1, ncx, lo2(mn[3]), hi2(mx[3]), s_min, s_max);               // voxels 8m+6, 8m+7
+    }
+};
+
+template <>
+struct ChunkAcc<CPM_FMT_U8> {    // 16 voxels: x = 16m .. 16m + 15 = cells 2m (bytes 0-7) and 2m + 1 (bytes 8-15)
+    uint32_t mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = 0xffffffffu, mx[k] = 0u;
+    }
+    __device__ void add(const uint4& r) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mn[k] = __vminu4(mn[k], w[k]);
+            mx[k] = __vmaxu4(mx[k], w[k]);
+        }
+    }
+    __device__ static uint32_t lo4(uint32_t v) { v = __vminu4(v, v >> 16); return min(v & 0xffu, (v >> 8) & 0xffu); }
+    __device__ static uint32_t hi4(uint32_t v) { v = __vmaxu4(v, v >> 16); return max(v & 0xffu, (v >> 8) & 0xffu); }
+    __device__ static void put(int q, int ncx, uint32_t a, uint32_t b, uint32_t* s_min, uint32_t* s_max) {
+        if (q < 0 || q >= ncx) return;
+        atomicMin(&s_min[q], okey(unorm8((float)a)));
+        atomicMax(&s_max[q], okey(unorm8((float)b)));
+    }
+    __device__ void flush(int c, int ncx, uint32_t* s_min, uint32_t* s_max, uint32_t*) const {
+        const int q = 2 * c;
+        const uint32_t b8n = mn[2] & 0xffu, b8x = mx[2] & 0xffu;                       // byte 8 = voxel 8q + 8
+        const uint32_t p67n = min((mn[1] >> 16) & 0xffu, mn[1] >> 24), p67x = max((mx[1] >> 16) & 0xffu, mx[1] >> 24);
+        put(q, ncx, min(lo4(__vminu4(mn[0], mn[1])), b8n), max(hi4(__vmaxu4(mx[0], mx[1])), b8x), s_min, s_max);
+        put(q + 1, ncx, min(lo4(__vminu4(mn[2], mn[3])), p67n), max(hi4(__vmaxu4(mx[2], mx[3])), p67x), s_min, s_max);
+        put(q - 1, ncx, mn[0] & 0xffu, mx[0] & 0xffu, s_min, s_max);                   // byte 0 = voxel 8(q-1) + 8
+        put(q + 2, ncx, min((mn[3] >> 16) & 0xffu, mn[3] >> 24), max((mx[3] >> 16) & 0xffu, mx[3] >> 24), s_min, s_max);
+    }
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) range8_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int ncx,
+                                                     float2* __restrict__ out) {
+    constexpr int K = VoxT<FMT>::PER16;
+    extern __shared__ uint32_t s_r[];
+    uint32_t *s_min = s_r, *s_max = s_r + ncx, *s_bad = s_r + 2 * ncx;
+    __shared__ unsigned long long s_row[121];
+    const int cy = blockIdx.x, cz = blockIdx.y;
+    for (int i = threadIdx.x; i < ncx; i += blockDim.x) {
+        s_min[i] = 0xffffffffu;
+        s_max[i] = 0u;
+        s_bad[i] = 0u;
+    }
+    const int y0 = max(cy * 8 - 2, 0), y1 = min(cy * 8 + 8, ny - 1);
+    const int z0 = max(cz * 8 - 2, 0), z1 = min(cz * 8 + 8, nz - 1);
+    const int ry = y1 - y0 + 1, rz = z1 - z0 + 1;
+    const int rows = ry * rz;
+    const int chunks = nx / K;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        const int zr = i / ry;
+        s_row[i] = ((unsigned long long)(z0 + zr) * ny + (y0 + i - zr * ry)) * chunks;
+    }
+    __syncthreads();
+    const uint4* V = reinterpret_cast<const uint4*>(vol);
+    const int cols = min(chunks, (int)blockDim.x), groups = blockDim.x / cols;
+    const int col = threadIdx.x % cols, rg = threadIdx.x / cols;
+    if (rg < groups) {
+        for (int c = col; c < chunks; c += cols) {
+            ChunkAcc<FMT> acc;
+            acc.init();
+            int r = rg;
+            for (; r + 3 * groups < rows; r += 4 * groups) {
+                uint4 a0 = __ldg(V + s_row[r] + c), a1 = __ldg(V + s_row[r + groups] + c);
+                uint4 a2 = __ldg(V + s_row[r + 2 * groups] + c), a3 = __ldg(V + s_row[r + 3 * groups] + c);
+                acc.add(a0); acc.add(a1); acc.add(a2); acc.add(a3);
+            }
+            for (; r < rows; r += groups) acc.add(__ldg(V + s_row[r] + c));
+            acc.flush(c, ncx, s_min, s_max, s_bad);
+        }
+    }
+    __syncthreads();
+    const int ncy = gridDim.x;
+    for (int i = threadIdx.x; i < ncx; i += blockDim.x) {
+        float2 o = make_float2(oval(s_min[i]), oval(s_max[i]));
+        if (s_bad[i]) o.x = o.y = __uint_as_float(0x7fc00000u);
+        out[((size_t)cz * ncy + cy) * ncx + i] = o;
+    }
+}
+
 // alpha column + per-32-texel summaries (max with NaN -> +inf, max |.|)
 __global__ void __launch_bounds__(256) tf_summary_kernel(const float4* __restrict__ tf, int w, float* __restrict__ alpha,
                                                          float* __restrict__ bmax, float* __restrict__ babs) {
@@ -285,11 +445,17 @@ int cpm_volume_value_range(cpm_ctx* ctx, const cpm_volume* vol, int cell_log2, f
     size_t smem = (size_t)3 * od[0] * sizeof(uint32_t);
     CPM_REQUIRE(ctx, smem <= 48 * 1024, "volume too wide for the cell size");
     dim3 grid(od[1], od[2]);
+    static const int generic_env = getenv("CPM_GRID_GENERIC") ? atoi(getenv("CPM_GRID_GENERIC")) : 0;   // A/B timing only
 #define RG(F)                                                                                             \
     {                                                                                                     \
         int vec_ok = ((uintptr_t)vol->linear % 16 == 0) && (nx % VoxT<F>::PER16 == 0);                    \
-        CPM_LAUNCH(ctx, range_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, cell_log2, od[0],      \
-                   (float2*)range, vec_ok);                                                               \
+        if (vec_ok && cell_log2 == 3 && !generic_env) {                                                   \
+            CPM_LAUNCH(ctx, range8_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, od[0],            \
+                       (float2*)range);                                                                   \
+        } else {                                                                                          \
+            CPM_LAUNCH(ctx, range_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, cell_log2, od[0],  \
+                       (float2*)range, vec_ok);                                                           \
+        }                                                                                                 \
     }
     switch (vol->format) {
         case CPM_FMT_U8: RG(CPM_FMT_U8) break;

@@ -125,12 +125,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigne
         const int px = (int)(tile % tiles_x) * 8 + (lane & 7);
         const int py = (int)(tile / tiles_x) * 4 + (lane >> 3);
         if (px >= P.width || py >= P.height) continue;
-        float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-        float dx = fmaf(fy, P.cam_dv[0], fmaf(fx, P.cam_du[0], P.cam_dir00[0]));
-        float dy = fmaf(fy, P.cam_dv[1], fmaf(fx, P.cam_du[1], P.cam_dir00[1]));
-        float dz = fmaf(fy, P.cam_dv[2], fmaf(fx, P.cam_du[2], P.cam_dir00[2]));
-        float inv = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-        float3_ d = {dx * inv, dy * inv, dz * inv};
+        float3_ d = camera_ray(P, px, camera_row(P, py));
         float3_ o = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2]};
         float t0 = 0.0f, t1 = CPM_FLT_MAX_;
         float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
@@ -316,6 +311,7 @@ int cpm_gather_raymarch(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgb
     int rc = fill_gather_args(ctx, a, vol, tf_rgba, tf_width, params, sorted_photons, cell_start, cell_end);
     if (rc != CPM_OK) return rc;
     CPM_REQUIRE(ctx, params->width > 0 && params->height > 0 && params->step > 0.0f, "bad image size / step");
+    CPM_REQUIRE(ctx, params->strip_first >= 0 && params->strip_stride >= 0, "negative strip_first / strip_stride");
     a.image = (float4*)image;
     CPM_REQUIRE(ctx, make_bound_grid(a.bound, params->opacity_bound, vol->dims, params->bound_cell_log2),
                 "bound_cell_log2 must be in 0..8 and the bound grid smaller than 2^31 cells");

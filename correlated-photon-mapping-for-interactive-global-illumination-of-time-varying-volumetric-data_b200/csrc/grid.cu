@@ -169,6 +169,179 @@ __global__ void __launch_bounds__(256) diff_kernel(const void* __restrict__ va, 
         out[((size_t)bz * nby + by) * nbx + i] = (float)((s_sum[i] / r3 - rmin) / (rmax - rmin));
 }
 
+// ---- bricks of 8 voxels (the default region), 16-byte aligned rows: streaming versions ---------------------------
+// Same CTA mapping, but a thread owns one 16-byte chunk COLUMN and walks down the brick row's 64 voxel rows: the
+// brick(s) a chunk feeds are fixed per thread, partial results stay in registers (packed bytes / halves for the
+// integer formats: min / max commute with the monotone normalisation), four rows are in flight per thread and
+// shared memory sees one or two atomics per thread instead of several per chunk.
+template <int FMT>
+struct MinMaxAcc;
+template <>
+struct MinMaxAcc<CPM_FMT_F32> {
+    float mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = CPM_FLT_MAX_, mx[k] = -CPM_FLT_MAX_;
+    }
+    __device__ void add(const uint4& r) {
+        const float w[4] = {__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = fminf(mn[k], w[k]), mx[k] = fmaxf(mx[k], w[k]);   // NaN voxels are skipped
+    }
+    template <class PUT>
+    __device__ void flush(int c, PUT put) const {
+        put(c >> 1, fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3])), fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+    }
+};
+template <>
+struct MinMaxAcc<CPM_FMT_U16> {
+    uint32_t mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = 0xffffffffu, mx[k] = 0u;
+    }
+    __device__ void add(const uint4& r) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = __vminu2(mn[k], w[k]), mx[k] = __vmaxu2(mx[k], w[k]);
+    }
+    template <class PUT>
+    __device__ void flush(int c, PUT put) const {
+        uint32_t a = __vminu2(__vminu2(mn[0], mn[1]), __vminu2(mn[2], mn[3]));
+        uint32_t b = __vmaxu2(__vmaxu2(mx[0], mx[1]), __vmaxu2(mx[2], mx[3]));
+        put(c, unorm16((float)min(a & 0xffffu, a >> 16)), unorm16((float)max(b & 0xffffu, b >> 16)));
+    }
+};
+template <>
+struct MinMaxAcc<CPM_FMT_U8> {
+    uint32_t mn[4], mx[4];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = 0xffffffffu, mx[k] = 0u;
+    }
+    __device__ void add(const uint4& r) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mn[k] = __vminu4(mn[k], w[k]), mx[k] = __vmaxu4(mx[k], w[k]);
+    }
+    __device__ static uint32_t lo4(uint32_t v) { v = __vminu4(v, v >> 16); return min(v & 0xffu, (v >> 8) & 0xffu); }
+    __device__ static uint32_t hi4(uint32_t v) { v = __vmaxu4(v, v >> 16); return max(v & 0xffu, (v >> 8) & 0xffu); }
+    template <class PUT>
+    __device__ void flush(int c, PUT put) const {
+        put(2 * c, unorm8((float)lo4(__vminu4(mn[0], mn[1]))), unorm8((float)hi4(__vmaxu4(mx[0], mx[1]))));
+        put(2 * c + 1, unorm8((float)lo4(__vminu4(mn[2], mn[3]))), unorm8((float)hi4(__vmaxu4(mx[2], mx[3]))));
+    }
+};
+
+// row r of the brick row (by, bz) -> index of its first 16-byte chunk
+__device__ __forceinline__ void brick_row_offsets(unsigned long long* s_row, int rows, int ry, int y0, int z0, int ny,
+                                                  int chunks) {
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        const int zr = i / ry;
+        s_row[i] = ((unsigned long long)(z0 + zr) * ny + (y0 + i - zr * ry)) * chunks;
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) minmax8_kernel(const void* __restrict__ vol, int nx, int ny, int nz, int nbx,
+                                                      float scale, float offset, ushort2* __restrict__ out) {
+    constexpr int K = Vox<FMT>::PER16;
+    extern __shared__ uint32_t s_mm[];  // [0,nbx) min keys, [nbx,2nbx) max keys
+    __shared__ unsigned long long s_row[64];
+    const int by = blockIdx.x, bz = blockIdx.y;
+    for (int i = threadIdx.x; i < nbx; i += blockDim.x) {
+        s_mm[i] = 0xffffffffu;
+        s_mm[nbx + i] = 0u;
+    }
+    const int y0 = by * 8, z0 = bz * 8;
+    const int ry = min(8, ny - y0), rz = min(8, nz - z0);
+    const int rows = ry * rz, chunks = nx / K;
+    brick_row_offsets(s_row, rows, ry, y0, z0, ny, chunks);
+    __syncthreads();
+    const uint4* V = reinterpret_cast<const uint4*>(vol);
+    const int cols = min(chunks, (int)blockDim.x), groups = blockDim.x / cols;
+    const int col = threadIdx.x % cols, rg = threadIdx.x / cols;
+    auto put = [&](int b, float lo, float hi) {
+        if (b >= nbx || lo > hi) return;
+        // the normalisation (v + offset) * scale is monotone (either way) and so is its rounding
+        const float a = (lo + offset) * scale, c = (hi + offset) * scale;
+        atomicMin(&s_mm[b], order_key(fminf(a, c)));
+        atomicMax(&s_mm[nbx + b], order_key(fmaxf(a, c)));
+    };
+    if (rg < groups) {
+        for (int c = col; c < chunks; c += cols) {
+            MinMaxAcc<FMT> acc;
+            acc.init();
+            int r = rg;
+            for (; r + 3 * groups < rows; r += 4 * groups) {
+                uint4 a0 = __ldg(V + s_row[r] + c), a1 = __ldg(V + s_row[r + groups] + c);
+                uint4 a2 = __ldg(V + s_row[r + 2 * groups] + c), a3 = __ldg(V + s_row[r + 3 * groups] + c);
+                acc.add(a0); acc.add(a1); acc.add(a2); acc.add(a3);
+            }
+            for (; r < rows; r += groups) acc.add(__ldg(V + s_row[r] + c));
+            acc.flush(c, put);
+        }
+    }
+    __syncthreads();
+    const int nby = gridDim.x;
+    for (int i = threadIdx.x; i < nbx; i += blockDim.x) {
+        float mn = fminf(CPM_FLT_MAX_, order_val(s_mm[i]));
+        float mx = fmaxf(0.0f, order_val(s_mm[nbx + i]));
+        out[((size_t)bz * nby + by) * nbx + i] = make_ushort2(to_u16(mn), to_u16(mx));
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) diff8_kernel(const void* __restrict__ va, const void* __restrict__ vb, int nx,
+                                                    int ny, int nz, int nbx, double scaling, double rmin, double rmax,
+                                                    float* __restrict__ out) {
+    typedef typename Vox<FMT>::T T;
+    constexpr int K = Vox<FMT>::PER16;
+    constexpr int NB = K > 8 ? K / 8 : 1;      // bricks per chunk
+    extern __shared__ double s_sum[];
+    __shared__ unsigned long long s_row[64];
+    const int by = blockIdx.x, bz = blockIdx.y;
+    for (int i = threadIdx.x; i < nbx; i += blockDim.x) s_sum[i] = 0.0;
+    const int y0 = by * 8, z0 = bz * 8;
+    const int ry = min(8, ny - y0), rz = min(8, nz - z0);
+    const int rows = ry * rz, chunks = nx / K;
+    brick_row_offsets(s_row, rows, ry, y0, z0, ny, chunks);
+    __syncthreads();
+    const uint4 *A = reinterpret_cast<const uint4*>(va), *B = reinterpret_cast<const uint4*>(vb);
+    const int cols = min(chunks, (int)blockDim.x), groups = blockDim.x / cols;
+    const int col = threadIdx.x % cols, rg = threadIdx.x / cols;
+    if (rg < groups) {
+        for (int c = col; c < chunks; c += cols) {
+            double acc[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+            auto add = [&](const uint4& ra, const uint4& rb) {
+                const T* ea = reinterpret_cast<const T*>(&ra);
+                const T* eb = reinterpret_cast<const T*>(&rb);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[NB > 1 ? k / 8 : 0] += fabs(scaling * ((double)eb[k] - (double)ea[k]));
+            };
+            int r = rg;
+            for (; r + 3 * groups < rows; r += 4 * groups) {
+                const unsigned long long o0 = s_row[r] + c, o1 = s_row[r + groups] + c, o2 = s_row[r + 2 * groups] + c,
+                                         o3 = s_row[r + 3 * groups] + c;
+                uint4 a0 = __ldg(A + o0), b0 = __ldg(B + o0), a1 = __ldg(A + o1), b1 = __ldg(B + o1);
+                uint4 a2 = __ldg(A + o2), b2 = __ldg(B + o2), a3 = __ldg(A + o3), b3 = __ldg(B + o3);
+                add(a0, b0); add(a1, b1); add(a2, b2); add(a3, b3);
+            }
+            for (; r < rows; r += groups) add(__ldg(A + s_row[r] + c), __ldg(B + s_row[r] + c));
+            const int first = (c * K) / 8;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                if (first + b < nbx) atomicAdd(&s_sum[first + b], acc[b]);
+        }
+    }
+    __syncthreads();
+    const int nby = gridDim.x;
+    for (int i = threadIdx.x; i < nbx; i += blockDim.x)
+        out[((size_t)bz * nby + by) * nbx + i] = (float)((s_sum[i] / 512.0 - rmin) / (rmax - rmin));
+}
+
 // ---- importance classification ----------------------------------------------------------------
 __device__ __forceinline__ float4 mix4(float4 a, float4 b, float t) {
     return make_float4(fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z), fmaf(b.w - a.w, t, a.w));
@@ -306,6 +479,11 @@ __global__ void __launch_bounds__(256) cell_range_kernel(const uint32_t* __restr
     if (c > 0) end[c - 1] = (uint32_t)lo;
 }
 
+static bool grid_generic() {   // CPM_GRID_GENERIC=1: the generic kernels also for region 8 (A/B timing only)
+    static const int v = getenv("CPM_GRID_GENERIC") ? atoi(getenv("CPM_GRID_GENERIC")) : 0;
+    return v != 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -328,8 +506,13 @@ int cpm_volume_minmax(cpm_ctx* ctx, const cpm_volume* vol, int region, uint16_t*
 #define MM(F)                                                                                              \
     {                                                                                                      \
         int vec_ok = ((uintptr_t)vol->linear % 16 == 0) && (nx % Vox<F>::PER16 == 0);                      \
-        CPM_LAUNCH(ctx, minmax_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, region, nbx, vol->scale, \
-                   vol->offset, (ushort2*)out, vec_ok);                                                    \
+        if (vec_ok && region == 8 && !grid_generic()) {                                                    \
+            CPM_LAUNCH(ctx, minmax8_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, nbx, vol->scale,  \
+                       vol->offset, (ushort2*)out);                                                        \
+        } else {                                                                                           \
+            CPM_LAUNCH(ctx, minmax_kernel<F>, grid, 256, smem, vol->linear, nx, ny, nz, region, nbx, vol->scale, \
+                       vol->offset, (ushort2*)out, vec_ok);                                                \
+        }                                                                                                  \
     }
     switch (vol->format) {
         case CPM_FMT_U8: MM(CPM_FMT_U8) break;
@@ -356,8 +539,13 @@ int cpm_volume_diff_bricks(cpm_ctx* ctx, const cpm_volume* a, const cpm_volume* 
 #define DF(F)                                                                                                      \
     {                                                                                                              \
         int vec_ok = ((uintptr_t)a->linear % 16 == 0) && ((uintptr_t)b->linear % 16 == 0) && (nx % Vox<F>::PER16 == 0); \
-        CPM_LAUNCH(ctx, diff_kernel<F>, grid, 256, smem, a->linear, b->linear, nx, ny, nz, region, nbx, data_scaling, \
-                   range_min, range_max, out, vec_ok);                                                             \
+        if (vec_ok && region == 8 && !grid_generic()) {                                                            \
+            CPM_LAUNCH(ctx, diff8_kernel<F>, grid, 256, smem, a->linear, b->linear, nx, ny, nz, nbx, data_scaling, \
+                       range_min, range_max, out);                                                                 \
+        } else {                                                                                                   \
+            CPM_LAUNCH(ctx, diff_kernel<F>, grid, 256, smem, a->linear, b->linear, nx, ny, nz, region, nbx, data_scaling, \
+                       range_min, range_max, out, vec_ok);                                                         \
+        }                                                                                                          \
     }
     switch (a->format) {
         case CPM_FMT_U8: DF(CPM_FMT_U8) break;

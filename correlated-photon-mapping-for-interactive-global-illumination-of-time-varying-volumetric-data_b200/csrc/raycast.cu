@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs A, unsig
         const int px = (int)(tile % tiles_x) * 8 + (lane & 7);
         const int py = (int)(tile / tiles_x) * 4 + (lane >> 3);
         if (px >= P.width || py >= P.height) continue;
-        float3_ d = camera_ray(P, px, py);
+        float3_ d = camera_ray(P, px, camera_row(P, py));
         float3_ o = {P.cam_origin[0], P.cam_origin[1], P.cam_origin[2]};
         float t0 = 0.0f, t1 = CPM_FLT_MAX_;
         float lr = 0.f, lg = 0.f, lb = 0.f, T = 1.0f;
@@ -145,6 +145,7 @@ extern "C" int cpm_raycast_light_volume(cpm_ctx* ctx, const cpm_volume* vol, con
     CPM_REQUIRE(ctx, channels == 1 || channels == 4, "channels must be 1 or 4");
     CPM_REQUIRE(ctx, lv_dims[0] > 0 && lv_dims[1] > 0 && lv_dims[2] > 0, "light volume dims must be positive");
     CPM_REQUIRE(ctx, params->width > 0 && params->height > 0 && params->step > 0.0f, "bad image size / step");
+    CPM_REQUIRE(ctx, params->strip_first >= 0 && params->strip_stride >= 0, "negative strip_first / strip_stride");
     RaycastArgs a;
     a.p = *params;
     a.vol = make_view(vol);

@@ -51,6 +51,12 @@ __device__ __forceinline__ int skip_transparent(const BoundGrid& B, const CellRa
     return k;
 }
 
+// camera row of local image row py when the call renders strips of 4 rows (cpm_gather_params::strip_first/stride)
+__device__ __forceinline__ int camera_row(const cpm_gather_params& P, int py) {
+    const int stride = P.strip_stride > 1 ? P.strip_stride : 1;
+    return 4 * (P.strip_first + (py >> 2) * stride) + (py & 3);
+}
+
 // camera ray of pixel (px, py): normalize(dir00 + (px + 1/2) du + (py + 1/2) dv)
 __device__ __forceinline__ float3_ camera_ray(const cpm_gather_params& P, int px, int py) {
     float fx = (float)px + 0.5f, fy = (float)py + 0.5f;

@@ -101,6 +101,55 @@ class LightVolumeExchange:
         return b
 
 
+# ---- option A of SURVEY 8e: replicated photon map, image tiles per GPU --------------------------------------------
+def allgather_photons(local: torch.Tensor, out: torch.Tensor | None = None, group=None) -> torch.Tensor:
+    """Every rank's photon records (float32, 8 per record, any number of interactions) concatenated in rank order:
+    the replicated photon set the map for gathering is built from (cell keys treat records independently, so the
+    interaction-major order inside a rank's slice does not matter).  All ranks must hold the same number of
+    records (weak scaling).  Single process: returns `local`."""
+    if not is_distributed():
+        return local
+    world = dist.get_world_size(group)
+    n = local.numel()
+    if out is None or out.numel() != n * world or out.dtype != local.dtype or out.device != local.device:
+        out = torch.empty(n * world, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.reshape(-1), group=group)
+    return out
+
+
+STRIP_ROWS = 4      # tile height of the view ray marchers (cpm_gather_params::strip_first / strip_stride)
+
+
+def image_strips(rank: int, world: int, height: int):
+    """(strip_first, strip_stride, local_rows) of `rank`: strips of 4 image rows are dealt round robin, which
+    balances rays that miss the volume against rays that cross it.  Every rank renders the same number of strips
+    (ceil(strips / world)); strips past the image are camera rows outside it and are cropped by assemble_image."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    strips = (height + STRIP_ROWS - 1) // STRIP_ROWS
+    per_rank = (strips + world - 1) // world
+    return rank, world, per_rank * STRIP_ROWS
+
+
+def assemble_image(parts: torch.Tensor, world: int, width: int, height: int) -> torch.Tensor:
+    """parts: [world, local_rows, width, 4] as image_strips dealt them -> [height, width, 4]"""
+    local_rows = parts.shape[1]
+    s = local_rows // STRIP_ROWS
+    full = parts.reshape(world, s, STRIP_ROWS, width, 4).permute(1, 0, 2, 3, 4).reshape(s * world * STRIP_ROWS, width, 4)
+    return full[:height]
+
+
+def allgather_image(local: torch.Tensor, width: int, height: int, group=None) -> torch.Tensor:
+    """local: this rank's [local_rows, width, 4] strips -> the whole [height, width, 4] image on every rank"""
+    if not is_distributed():
+        return assemble_image(local.reshape(1, -1, width, 4), 1, width, height)
+    world = dist.get_world_size(group)
+    flat = local.reshape(-1).contiguous()
+    parts = torch.empty(world * flat.numel(), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(parts, flat, group=group)
+    return assemble_image(parts.reshape(world, -1, width, 4), world, width, height)
+
+
 def max_over_ranks(values, device="cpu"):
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
     if is_distributed():

@@ -388,6 +388,14 @@ typedef struct cpm_gather_params {
      * function; cells whose bound is exactly zero are stepped over without fetching voxels (identical image) */
     const float* opacity_bound;
     int32_t bound_cell_log2;
+    /* Image tiling across GPUs (SURVEY 8e option A: every GPU gathers its own image tiles against the replicated
+     * photon map).  The image buffer of a call holds `height` rows made of strips of 4 rows (the kernels' tile
+     * height); local strip s is strip `strip_first + s * strip_stride` of the camera's image, i.e. local row py is
+     * camera row 4 * (strip_first + (py >> 2) * strip_stride) + (py & 3).  strip_stride <= 1 with strip_first = 0
+     * is the whole image.  Interleaved strips balance the very different ray costs between ranks; pixels are
+     * bit-identical to the same pixels of a whole-image call. */
+    int32_t strip_first;
+    int32_t strip_stride;
     int32_t reserved_;
 } cpm_gather_params;
 

@@ -61,10 +61,12 @@ def test_bound_grid_dims(cpm):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt,dims", [("u8", (48, 40, 36)), ("u8", (37, 21, 19)), ("u16", (40, 24, 17)),
-                                      ("f32", (36, 31, 20)), ("f32", (64, 16, 8))])
+                                      ("f32", (36, 31, 20)), ("f32", (64, 16, 8)), ("u8", (4112, 9, 8)),
+                                      ("u16", (2056, 9, 8)), ("f32", (1028, 9, 11))])
 def test_cuda_value_range_exact(cpm, ctx, torch_cuda, fmt, dims):
+    """(the rows of the three wide volumes have more 16-byte chunks than the streaming kernel has threads)"""
     vol = scenes.make_volume(dims, fmt, 31)
-    for s in (0, 1, 3, 6):
+    for s in ((0, 1, 3, 6) if dims[0] < 1000 else (3,)):
         got, gd = gpu_range(cpm, ctx, torch_cuda, vol, s)
         got = got.cpu().numpy().reshape(gd[2], gd[1], gd[0], 2)
         lo, hi = np_value_range(vol, s)
@@ -73,17 +75,22 @@ def test_cuda_value_range_exact(cpm, ctx, torch_cuda, fmt, dims):
 
 
 @pytest.mark.gpu
-def test_cuda_value_range_flags_nonfinite(cpm, ctx, torch_cuda):
+@pytest.mark.parametrize("s", [2, 3])
+def test_cuda_value_range_flags_nonfinite(cpm, ctx, torch_cuda, s):
+    """(s = 3: the streaming kernel for cells of 8 voxels, which finds NaN / inf through the order keys)"""
     vol = scenes.make_volume((32, 16, 16), "f32", 2).copy()
     vol[5, 7, 9] = np.nan      # voxel (x=9, y=7, z=5)
     vol[12, 3, 31] = np.inf
-    got, gd = gpu_range(cpm, ctx, torch_cuda, vol, 2)
+    vol[8, 14, 16] = -np.inf
+    vol[2, 2, 6] = -np.nan
+    got, gd = gpu_range(cpm, ctx, torch_cuda, vol, s)
     got = got.cpu().numpy().reshape(gd[2], gd[1], gd[0], 2)
     bad = np.isnan(got[..., 0])
-    # voxel x belongs to the cells q with q*cell - 2 <= x <= q*cell + cell (cell = 4)
+    # voxel x belongs to the cells q with q*cell - 2 <= x <= q*cell + cell
+    cell = 1 << s
     want = np.zeros_like(bad)
-    for (x, y, z) in ((9, 7, 5), (31, 3, 12)):
-        qs = [[q for q in range(gd[k]) if q * 4 - 2 <= c <= q * 4 + 4] for k, c in enumerate((x, y, z))]
+    for (x, y, z) in ((9, 7, 5), (31, 3, 12), (16, 14, 8), (6, 2, 2)):
+        qs = [[q for q in range(gd[k]) if q * cell - 2 <= c <= q * cell + cell] for k, c in enumerate((x, y, z))]
         for qz in qs[2]:
             for qy in qs[1]:
                 for qx in qs[0]:

@@ -203,3 +203,48 @@ def test_cuda_gather_raymarch_matches_oracle(cpm, orc, synth, ctx, torch_cuda, l
     if Vl is not V:
         Vl.destroy()
     V.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_cuda_image_strips_reassemble_to_the_whole_image(cpm, orc, synth, ctx, torch_cuda, world):
+    """SURVEY 8e option A: every GPU marches its own strips of the image against the replicated photon map.  The
+    strips of `world` ranks (rendered here one after the other) reassemble to the whole-image call bit for bit, for
+    the photon gather and for the light-volume ray caster; height 62 leaves a partial last strip."""
+    torch = torch_cuda
+    sh = __import__("importlib").import_module(cpm.__name__ + ".sharding")
+    dims = (48, 48, 48)
+    vol, tf, ph, n = _photons(orc, synth, dims=dims)
+    g = (24, 24, 24)
+    W, H = 96, 62
+    kw = dict(fov_deg=35.0, step=0.5 / 48, radius=1.5 / 48, scale=50.0, sigma_scale=150.0, grid_dims=g)
+    dph = _dev(torch, ph.reshape(-1))
+    sp, start, end, _ = ctx.build_photon_map(dph, ph.shape[0], g, torch)
+    V = ctx.volume_create(_dev(torch, vol), dims, cpm.CPM_FMT_U8, layout=cpm.CPM_VOLUME_TEXTURE)
+    dtf = _dev(torch, tf.reshape(-1))
+    lv = (24, 24, 24)
+    dlv = torch.rand(lv[0] * lv[1] * lv[2], dtype=torch.float32, device="cuda")
+
+    def render(P, rows):
+        a = torch.zeros(rows * W * 4, dtype=torch.float32, device="cuda")
+        b = torch.zeros_like(a)
+        ctx.gather_raymarch(V, dtf, P, sp, start, end, a)
+        ctx.raycast_light_volume(V, dtf, P, dlv, lv, 1, b)
+        ctx.sync()
+        return a.view(rows, W, 4), b.view(rows, W, 4)
+
+    whole = render(cpm.capi.make_gather_params(W, H, (1.6, 1.3, -1.2), (0.5, 0.5, 0.5), **kw), H)
+    assert whole[0][..., :3].max() > 0
+    parts = ([], [])
+    for r in range(world):
+        first, stride, rows = sh.image_strips(r, world, H)
+        # the camera basis is the whole image's: only the strip mapping and the local height change
+        P = cpm.capi.make_gather_params(W, H, (1.6, 1.3, -1.2), (0.5, 0.5, 0.5), **kw)
+        P.height, P.strip_first, P.strip_stride = rows, first, stride
+        a, b = render(P, rows)
+        parts[0].append(a)
+        parts[1].append(b)
+    for k in range(2):
+        full = sh.assemble_image(torch.stack(parts[k]), world, W, H)
+        assert torch.equal(full, whole[k])
+    V.destroy()

@@ -65,7 +65,8 @@ def test_oracle_classify_incremental_is_sum_of_max_colour(orc, synth):
 # ------------------------------------------------------------------------------- GPU ---------
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["u8", "u16", "f32"])
-@pytest.mark.parametrize("dims,region", [((64, 48, 40), 8), ((50, 33, 17), 8), ((64, 64, 64), 5), ((32, 32, 32), 1)])
+@pytest.mark.parametrize("dims,region", [((64, 48, 40), 8), ((50, 33, 17), 8), ((48, 33, 17), 8), ((528, 9, 8), 8),
+                                         ((64, 64, 64), 5), ((32, 32, 32), 1)])
 def test_cuda_minmax_bit_exact(cpm, orc, ctx, torch_cuda, fmt, dims, region):
     torch = torch_cuda
     vol = scenes.make_volume(dims, fmt, 9)
@@ -81,9 +82,11 @@ def test_cuda_minmax_bit_exact(cpm, orc, ctx, torch_cuda, fmt, dims, region):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["u8", "f32"])
-def test_cuda_diff_bricks(cpm, orc, ctx, torch_cuda, synth, fmt):
+@pytest.mark.parametrize("dims", [(72, 40, 36), (80, 37, 19), (1040, 8, 9)])
+def test_cuda_diff_bricks(cpm, orc, ctx, torch_cuda, synth, fmt, dims):
+    """(72: the generic kernel for u8, 16-byte chunks do not tile the rows; 80 / 1040: the streaming kernels, ragged
+    y / z, more chunk columns than threads)"""
     torch = torch_cuda
-    dims = (72, 40, 36)
     if fmt == "u8":
         a, b = synth.volume_u8(dims, 1), synth.volume_u8(dims, 2)
         rng = (1.0, 0.0, 255.0)

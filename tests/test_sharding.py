@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
     r2 = ex.result()
     ok = ok and bool((r1 == sum(range(1, world + 1))).all()) and bool((r2 == 2 * sum(range(1, world + 1))).all())
     ok = ok and r1.data_ptr() != r2.data_ptr() and bool(torch.equal(local, keep))
+    # option A: photon records of all ranks in rank order; image strips dealt round robin and reassembled
+    rec = torch.arange(48, dtype=torch.float32) + 100 * rank
+    allp = sh.allgather_photons(rec)
+    ok = ok and bool(torch.equal(allp, torch.cat([torch.arange(48, dtype=torch.float32) + 100 * r for r in range(world)])))
+    W, H = 5, 22                                    # 6 strips (the last one partial) over `world` ranks
+    first, stride, rows = sh.image_strips(rank, world, H)
+    cam_row = torch.tensor([4 * (first + (py >> 2) * stride) + (py & 3) for py in range(rows)], dtype=torch.float32)
+    mine = cam_row[:, None, None].expand(rows, W, 4).contiguous()
+    img = sh.allgather_image(mine, W, H)
+    ok = ok and img.shape == (H, W, 4) and bool(torch.equal(img[:, 0, 0], torch.arange(H, dtype=torch.float32)))
     mx = sh.max_over_ranks([float(rank), 5.0 - rank])
     sm = sh.sum_over_ranks([float(rank + 1)])
     first, count = sh.photon_shard(rank, world, 4096)
@@ -64,6 +74,22 @@ def test_gloo_world2_exchange_helpers():
         assert ok
         assert mx == [1.0, 5.0] and sm == [3.0]
         assert (first, count) == (rank * 4096, 4096)
+
+
+def test_image_strips_single_process_assembly():
+    sh = importlib.import_module(PKG_NAME + ".sharding")
+    for world in (1, 2, 3, 8):
+        W, H = 3, 37
+        parts = []
+        for r in range(world):
+            first, stride, rows = sh.image_strips(r, world, H)
+            assert rows % sh.STRIP_ROWS == 0
+            cam = torch.tensor([4 * (first + (py >> 2) * stride) + (py & 3) for py in range(rows)], dtype=torch.float32)
+            parts.append(cam[:, None, None].expand(rows, W, 4))
+        img = sh.assemble_image(torch.stack(parts), world, W, H)
+        assert torch.equal(img[:, 1, 2], torch.arange(H, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        sh.image_strips(2, 2, 16)
 
 
 def test_shard_ranges_cover_the_photon_set():

@@ -96,8 +96,14 @@ def main():
                     rg = torch.empty(2 * gd[0] * gd[1] * gd[2], dtype=torch.float32, device="cuda")
                     ms, _ = timed(lambda: ctx.volume_value_range(V, s_, rg), stream)
                     print(f"  [{dims[0]}^3 {fmt}] volume_value_range cell {1 << s_}: {ms:.3f} ms = {bytes_/ms/1e6:.0f} GB/s")
+                dvol2 = dvol.flip(0).contiguous()
+                V2 = ctx.volume_create(dvol2, dims, cpm.CPM_FMT_U8 if fmt == "u8" else cpm.CPM_FMT_F32)
+                df = torch.empty(nb[0] * nb[1] * nb[2], dtype=torch.float32, device="cuda")
+                ms, _ = timed(lambda: ctx.volume_diff_bricks(V, V2, 8, 1.0, 0.0, 1.0, df), stream)
+                print(f"  [{dims[0]}^3 {fmt}] volume_diff_bricks: {ms:.3f} ms = {2*bytes_/ms/1e6:.0f} GB/s")
+                V2.destroy()
                 V.destroy()
-                del dvol
+                del dvol, dvol2
         if "sort26" in what:
             what = what + ["sort"]
         if "sort" in what:
