@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--gather-interleaved", action="store_true", help="photon map as 32-byte records instead of planar halves (A/B)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
     return ap.parse_args()
 
@@ -330,6 +331,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
     P = cpm.capi.make_gather_params(a.view, a.view, (1.7, 1.4, -1.3), (0.5, 0.5, 0.5), fov_deg=40.0, step=0.5 / D,
                                     radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g),
                                     opacity_bound=bound, bound_cell_log2=bs)
+    P.planar_records = 0 if a.gather_interleaved else n * I * world
     first, stride, rows = sharding.image_strips(rank, world, a.view)
     if world > 1:
         P.height, P.strip_first, P.strip_stride = rows, first, stride
@@ -343,7 +345,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
         e[0].record(stream)
         allp = sharding.allgather_photons(photons, allp)
         e[1].record(stream)
-        sp, start, end, _ = ctx.build_photon_map(allp, n * I * world, (g, g, g), torch)
+        sp, start, end, _ = ctx.build_photon_map(allp, n * I * world, (g, g, g), torch, planar=not a.gather_interleaved)
         if bound is not None:
             ctx.opacity_bound(vrange, ncell, tf, bound)
         e[2].record(stream)

@@ -382,7 +382,7 @@ class GatherParams(C.Structure):
                 ("aabb_max", C.c_float * 3), ("step", C.c_float), ("radius", C.c_float), ("scale", C.c_float),
                 ("sigma_scale", C.c_float), ("grid_dims", C.c_int32 * 3), ("opacity_bound", C.c_void_p),
                 ("bound_cell_log2", C.c_int32), ("strip_first", C.c_int32), ("strip_stride", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("planar_records", C.c_int32)]
 
 
 def make_gather_params(width, height, eye, look_at, up=(0, 1, 0), fov_deg=60.0, step=1.0 / 256, radius=1.0 / 64,
@@ -418,8 +418,9 @@ def _photon_cell_keys(self, photons, n_records, grid_dims, keys, ids=None):
     self._check(lib().cpm_photon_cell_keys(self.h, _p(photons), C.c_size_t(n_records), _i3(grid_dims), _p(keys), _p(ids)))
 
 
-def _reorder_photons(self, photons, ids, n, out):
-    self._check(lib().cpm_reorder_photons(self.h, _p(photons), _p(ids), C.c_size_t(n), _p(out)))
+def _reorder_photons(self, photons, ids, n, out, planar=False):
+    f = lib().cpm_reorder_photons_planar if planar else lib().cpm_reorder_photons
+    self._check(f(self.h, _p(photons), _p(ids), C.c_size_t(n), _p(out)))
 
 
 def _raycast_light_volume(self, vol, tf_rgba, params, light_volume, lv_dims, channels, image):
@@ -437,9 +438,9 @@ def _gather_points(self, params, sorted_photons, cell_start, cell_end, points, n
                                         _p(points), int(n_points), _p(out)))
 
 
-def _build_photon_map(self, photons, n_records, grid_dims, torch):
-    """cell keys -> radix sort (keys, ids) -> cell ranges -> records in cell order.
-    Returns (sorted_photons, cell_start, cell_end, n_stored)."""
+def _build_photon_map(self, photons, n_records, grid_dims, torch, planar=False):
+    """cell keys -> radix sort (keys, ids) -> cell ranges -> records in cell order (planar: first halves, then second
+    halves -- set cpm_gather_params.planar_records = n_records).  Returns (sorted_photons, cell_start, cell_end, keys)."""
     dev = photons.device
     n_cells = int(grid_dims[0]) * int(grid_dims[1]) * int(grid_dims[2])
     keys = torch.empty(n_records, dtype=torch.int32, device=dev)
@@ -452,7 +453,7 @@ def _build_photon_map(self, photons, n_records, grid_dims, torch):
     end = torch.zeros(n_cells, dtype=torch.int32, device=dev)
     self.build_cell_ranges(keys, n_records, n_cells, start, end)
     out = torch.empty_like(photons)
-    self.reorder_photons(photons, ids, n_records, out)
+    self.reorder_photons(photons, ids, n_records, out, planar=planar)
     return out, start, end, keys
 
 

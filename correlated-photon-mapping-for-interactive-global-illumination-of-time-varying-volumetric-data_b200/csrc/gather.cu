@@ -49,13 +49,24 @@ __global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__
     if (i >= n) return;
     out[g] = photons[2 * (size_t)ids[i] + (g & 1)];
 }
+// the same records, planar: out[j] = first half of record ids[j], out[n + j] = second half (the gather tests every
+// candidate against its first half only: packed halves put two candidates in a sector and halve the cache footprint
+// of a map that outgrows L2)
+__global__ void __launch_bounds__(256) reorder_planar_kernel(const float4* __restrict__ photons, const uint32_t* __restrict__ ids,
+                                                             size_t n, float4* __restrict__ out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= 2 * n) return;
+    const size_t j = g >> 1, h = g & 1;
+    out[h * n + j] = photons[2 * (size_t)ids[j] + h];
+}
 
 struct GatherArgs {
     cpm_gather_params p;
     VolumeView vol;
     const float4* tf;
     int tf_width;
-    const float4* photons;   // cell-sorted records
+    const float4* photons;   // cell-sorted records: (pos, power.r) of record i at [ps * i], (power.g, power.b, ..) ps * i + p1
+    size_t ps, p1;           // interleaved 32-byte records: 2, 1; planar: 1, number of records
     const uint32_t* cell_start;
     const uint32_t* cell_end;
     float4* image;
@@ -76,13 +87,13 @@ __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float
                 uint32_t c = (uint32_t)cx + (uint32_t)gx * ((uint32_t)cy + (uint32_t)gy * (uint32_t)cz);
                 uint32_t b = __ldg(A.cell_start + c), e = __ldg(A.cell_end + c);
                 for (uint32_t j = b; j < e; ++j) {
-                    float4 p0 = __ldg(A.photons + 2 * (size_t)j);
+                    float4 p0 = __ldg(A.photons + A.ps * (size_t)j);
                     float dx = p0.x - x, dy = p0.y - y, dz = p0.z - z;
                     float dist = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
                     float xk = dist / r;
                     if (xk <= 1.0f) {
                         float w = 0.75f * (1.0f - xk * xk);
-                        float4 p1 = __ldg(A.photons + 2 * (size_t)j + 1);
+                        float4 p1 = __ldg(A.photons + A.ps * (size_t)j + A.p1);
                         er = fmaf(p0.w, w, er);
                         eg = fmaf(p1.x, w, eg);
                         eb = fmaf(p1.y, w, eb);
@@ -104,7 +115,7 @@ __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float
 constexpr int GATHER_S = 12;
 
 template <int FMT, int LAYOUT>
-__global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
+__global__ void __launch_bounds__(128, 4) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
     extern __shared__ float4 s_tf[];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_tf[i] = A.tf[i];
     __syncthreads();
@@ -176,31 +187,56 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs A, unsigne
                     const int y0 = cell_coord(fminf(ay, by) - r, (float)gy, gy), y1 = cell_coord(fmaxf(ay, by) + r, (float)gy, gy);
                     const int z0 = cell_coord(fminf(az, bz) - r, (float)gz, gz), z1 = cell_coord(fmaxf(az, bz) + r, (float)gz, gz);
                     const float tlen = tb - ta;
-                    for (int cz = z0; cz <= z1; ++cz)
-                        for (int cy = y0; cy <= y1; ++cy) {
-                            // cells x0..x1 of a row are contiguous in the cell-sorted record array
-                            uint32_t c0 = (uint32_t)x0 + (uint32_t)gx * ((uint32_t)cy + (uint32_t)gy * (uint32_t)cz);
-                            uint32_t b = __ldg(A.cell_start + c0), e = __ldg(A.cell_end + c0 + (uint32_t)(x1 - x0));
-                            for (uint32_t i = b; i < e; ++i) {
-                                float4 p0 = __ldg(A.photons + 2 * (size_t)i);
-                                float qx = p0.x - ax, qy = p0.y - ay, qz = p0.z - az;
-                                float tc = fmaf(qz, d.z, fmaf(qy, d.y, qx * d.x));       // parameter of the closest approach
-                                float q2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
-                                float dp2 = fmaf(-tc, tc, q2);                              // squared distance to the ray
-                                if (dp2 <= r2 && tc >= -r && tc <= tlen + r) {
-                                    float4 p1 = __ldg(A.photons + 2 * (size_t)i + 1);
+                    // one photon against the batch: the distance to the ray rejects most, survivors update all estimates
+                    auto visit = [&](const float4& p0, const float4& p1) {
+                        float qx = p0.x - ax, qy = p0.y - ay, qz = p0.z - az;
+                        float tc = fmaf(qz, d.z, fmaf(qy, d.y, qx * d.x));       // parameter of the closest approach
+                        float q2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+                        float dp2 = fmaf(-tc, tc, q2);                              // squared distance to the ray
+                        if (dp2 <= r2 && tc >= -r && tc <= tlen + r) {
 #pragma unroll
-                                    for (int j = 0; j < GATHER_S; ++j) {
-                                        float dt = fmaf((float)j, P.step, -tc);
-                                        float d2 = fmaf(dt, dt, fmaxf(dp2, 0.0f));
-                                        float w = d2 <= r2 ? fmaf(-kw, d2, 0.75f) : 0.0f;
-                                        er[j] = fmaf(p0.w, w, er[j]);
-                                        eg[j] = fmaf(p1.x, w, eg[j]);
-                                        eb[j] = fmaf(p1.y, w, eb[j]);
-                                    }
-                                }
+                            for (int j = 0; j < GATHER_S; ++j) {
+                                float dt = fmaf((float)j, P.step, -tc);
+                                float d2 = fmaf(dt, dt, fmaxf(dp2, 0.0f));
+                                float w = d2 <= r2 ? fmaf(-kw, d2, 0.75f) : 0.0f;
+                                er[j] = fmaf(p0.w, w, er[j]);
+                                eg[j] = fmaf(p1.x, w, eg[j]);
+                                eb[j] = fmaf(p1.y, w, eb[j]);
                             }
                         }
+                    };
+                    // Cells x0..x1 of a row (cy, cz) are contiguous in the cell-sorted record array: one run per row.
+                    // The loads are dependent (range -> records) and the lanes of a warp walk different runs, so the
+                    // latency is hidden inside the lane: the next row's range is requested while this row's records
+                    // are tested, and two whole records are requested per iteration -- both halves, so that a
+                    // survivor never makes its warp wait for a dependent second load (for 32-byte records the
+                    // second half is the same sector).  Same visiting order as a plain loop.
+                    const int nyr = y1 - y0 + 1, nruns = nyr * (z1 - z0 + 1);
+                    const uint32_t xspan = (uint32_t)(x1 - x0);
+                    int ry = 0, rz = 0;   // row cursor of the next range request
+                    auto next_range = [&](uint32_t& b_, uint32_t& e_) {
+                        const uint32_t c0 = (uint32_t)x0 + (uint32_t)gx * ((uint32_t)(y0 + ry) + (uint32_t)gy * (uint32_t)(z0 + rz));
+                        b_ = __ldg(A.cell_start + c0);
+                        e_ = __ldg(A.cell_end + c0 + xspan);
+                        if (++ry == nyr) ry = 0, ++rz;
+                    };
+                    uint32_t nb_, ne_;
+                    next_range(nb_, ne_);
+                    for (int rr = 0; rr < nruns; ++rr) {
+                        const uint32_t b = nb_, e = ne_;
+                        if (rr + 1 < nruns) next_range(nb_, ne_);
+                        uint32_t i = b;
+                        for (; i + 2 <= e; i += 2) {
+                            const float4* rec = A.photons + A.ps * (size_t)i;
+                            const float4 a0 = __ldg(rec), a1 = __ldg(rec + A.p1), c0 = __ldg(rec + A.ps), c1 = __ldg(rec + A.ps + A.p1);
+                            visit(a0, a1);
+                            visit(c0, c1);
+                        }
+                        if (i < e) {
+                            const float4* rec = A.photons + A.ps * (size_t)i;
+                            visit(__ldg(rec), __ldg(rec + A.p1));
+                        }
+                    }
                     // ---- composite front to back
 #pragma unroll
                     for (int j = 0; j < GATHER_S; ++j) {
@@ -252,6 +288,9 @@ static int fill_gather_args(cpm_ctx* ctx, GatherArgs& a, const cpm_volume* vol, 
     a.tf = (const float4*)tf_rgba;
     a.tf_width = tf_width;
     a.photons = (const float4*)sorted_photons;
+    CPM_REQUIRE(ctx, params->planar_records >= 0, "negative planar_records");
+    a.ps = params->planar_records > 0 ? 1 : 2;
+    a.p1 = params->planar_records > 0 ? (size_t)params->planar_records : 1;
     a.cell_start = cell_start;
     a.cell_end = cell_end;
     a.image = nullptr;
@@ -298,6 +337,16 @@ int cpm_reorder_photons(cpm_ctx* ctx, const float* photons, const uint32_t* ids,
     CPM_REQUIRE(ctx, photons && ids && out, "null argument");
     CPM_REQUIRE(ctx, photons != out, "in-place reorder is not supported");
     CPM_LAUNCH(ctx, reorder_kernel, cpm_div_up(2 * n, 256), 256, 0, (const float4*)photons, ids, n, (float4*)out);
+    return CPM_OK;
+}
+
+int cpm_reorder_photons_planar(cpm_ctx* ctx, const float* photons, const uint32_t* ids, size_t n, float* out) {
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, photons && ids && out, "null argument");
+    CPM_REQUIRE(ctx, photons != out, "in-place reorder is not supported");
+    CPM_REQUIRE(ctx, n <= 2147483647u, "too many records for cpm_gather_params::planar_records");
+    CPM_LAUNCH(ctx, reorder_planar_kernel, cpm_div_up(2 * n, 256), 256, 0, (const float4*)photons, ids, n, (float4*)out);
     return CPM_OK;
 }
 

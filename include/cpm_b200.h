@@ -369,6 +369,10 @@ CPM_API int cpm_photon_cell_keys(cpm_ctx* ctx, const float* photons, size_t n_re
                                  uint32_t* keys, uint32_t* ids);
 /* out[j] = photons[ids[j]] (32 B records), j < n */
 CPM_API int cpm_reorder_photons(cpm_ctx* ctx, const float* photons, const uint32_t* ids, size_t n, float* out);
+/* the same records, planar: out[4*j..] = floats 0-3 of photons[ids[j]] (position, power.r), out[4*(n+j)..] = floats
+ * 4-7 (power.g, power.b, theta, phi).  The gather kernels test candidates against the first half only; pass
+ * cpm_gather_params::planar_records = n. */
+CPM_API int cpm_reorder_photons_planar(cpm_ctx* ctx, const float* photons, const uint32_t* ids, size_t n, float* out);
 
 typedef struct cpm_gather_params {
     int32_t width, height;
@@ -396,7 +400,9 @@ typedef struct cpm_gather_params {
      * bit-identical to the same pixels of a whole-image call. */
     int32_t strip_first;
     int32_t strip_stride;
-    int32_t reserved_;
+    /* layout of sorted_photons: 0 = 32-byte records as cpm_reorder_photons writes them; n > 0 = the n records as
+     * cpm_reorder_photons_planar writes them (n first halves, then n second halves) */
+    int32_t planar_records;
 } cpm_gather_params;
 
 /* image[y*width + x] = (radiance rgb, 1 - transmittance): front-to-back emission-absorption ray march,

@@ -247,4 +247,21 @@ def test_cuda_image_strips_reassemble_to_the_whole_image(cpm, orc, synth, ctx, t
     for k in range(2):
         full = sh.assemble_image(torch.stack(parts[k]), world, W, H)
         assert torch.equal(full, whole[k])
+    # the planar record layout (first halves, then second halves) is the same map: same image, same point estimates
+    spp, start2, end2, _ = ctx.build_photon_map(dph, ph.shape[0], g, torch, planar=True)
+    assert torch.equal(start, start2) and torch.equal(end, end2)
+    nrec = ph.shape[0]
+    assert torch.equal(spp.view(2, nrec, 4), sp.view(nrec, 2, 4).permute(1, 0, 2).contiguous())
+    Pp = cpm.capi.make_gather_params(W, H, (1.6, 1.3, -1.2), (0.5, 0.5, 0.5), **kw)
+    Pp.planar_records = nrec
+    a = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    ctx.gather_raymarch(V, dtf, Pp, spp, start, end, a)
+    pts = _dev(torch, synth.uniform01(6, 3 * 500).astype(np.float32))
+    e1, e2 = torch.zeros(1500, dtype=torch.float32, device="cuda"), torch.zeros(1500, dtype=torch.float32, device="cuda")
+    ctx.gather_points(Pp, spp, start, end, pts, 500, e1)
+    Pp.planar_records = 0
+    ctx.gather_points(Pp, sp, start, end, pts, 500, e2)
+    ctx.sync()
+    assert torch.equal(a.view(H, W, 4), whole[0])
+    assert torch.equal(e1, e2) and e1.max().item() > 0
     V.destroy()

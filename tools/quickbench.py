@@ -77,9 +77,12 @@ def main():
                         print(f"  trace I={I} {lname:8s}: {ms:.3f} ms  photons/s={n/ms*1e3:.3e}  tests={tests} "
                               f"({tests/n:.1f}/photon) tests/s={tests/ms*1e3:.3e} stored={stored}  runs={['%.3f'%x for x in all_]}")
                         V.destroy()
-        if "grids" in what:
+        if "grids" in what or "grids512" in what:
             # per-volume grid builders on the C3 / C4 / C5 volumes: min-max bricks, value range of the bound cells
-            for dims, fmt in (((256, 256, 256), "u8"), ((512, 512, 512), "f32"), ((1024, 1024, 1024), "u8")):
+            cases = (((256, 256, 256), "u8"), ((512, 512, 512), "f32"), ((1024, 1024, 1024), "u8"))
+            if "grids512" in what:
+                cases = cases[1:2]
+            for dims, fmt in cases:
                 n = dims[0] * dims[1] * dims[2]
                 if fmt == "u8":
                     dvol = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
