@@ -65,6 +65,11 @@ def lib():
         _lib.cpmh_profile_total_ms.restype = C.c_double
         _lib.cpmh_profile_count.argtypes = [C.c_char_p]
         _lib.cpmh_profile_stages.restype = C.c_char_p
+        _lib.cpmh_workspace_describe.restype = C.c_char_p
+        _lib.cpmh_workspace_describe.argtypes = [C.c_char_p]
+        _lib.cpmh_config_from_workspace.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.POINTER(HostConfig)]
+        _lib.cpmh_network_load_workspace.argtypes = [C.c_void_p, C.c_char_p]
+        _lib.cpmh_network_get_property.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
     return _lib
 
 
@@ -105,6 +110,37 @@ def profile_stages():
 
 class HostError(RuntimeError):
     pass
+
+
+def workspace_describe(path) -> dict:
+    """{"processors": [(class id, name, [stored property paths])], "connections": [(out, in)]} of an .inv file"""
+    t = lib().cpmh_workspace_describe(str(path).encode())
+    if t is None:
+        raise HostError(f"cpm host error: {lib().cpmh_last_error().decode()}")
+    out = {"processors": [], "connections": []}
+    for line in t.decode().splitlines():
+        f = line.split("|")
+        if f[0] == "processor":
+            out["processors"].append((f[1], f[2], [p for p in f[3].split(",") if p]))
+        elif f[0] == "connection":
+            out["connections"].append((f[1], f[2]))
+    return out
+
+
+def workspace_config(path, basis=None) -> HostConfig:
+    """HostConfig with the fields an .inv workspace determines (see cpmh_config_from_workspace)"""
+    cfg = HostConfig()
+    cfg.n_lights, cfg.samples_per_side, cfg.max_scattering_events = 1, 256, 1
+    cfg.light_volume_option, cfg.light_volume_channels = 0, 1
+    cfg.photon_radius_voxels, cfg.max_incremental_percent = 1.0, 100.0
+    cfg.light_directions[0][:] = [0.0, 0.0, 1.0]
+    for i in range(8):
+        cfg.light_intensity[i][:] = [1.0, 1.0, 1.0]
+    b = None if basis is None else (C.c_float * 3)(*[float(x) for x in basis])
+    rc = lib().cpmh_config_from_workspace(str(path).encode(), b, C.byref(cfg))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+    return cfg
 
 
 def describe_processors() -> dict:
@@ -149,6 +185,39 @@ class Network:
         self._keep = []
         self._check(lib().cpmh_network_create(C.byref(cfg), C.byref(self.h)))
         self.cfg = cfg
+
+    @classmethod
+    def from_workspace(cls, path, dims, fmt, basis=None, volume_layout=1, device=0, samples_per_side=None,
+                       opacity_bound_cell_log2=0, reference_full_splat_bound=True):
+        """The network an ".inv" workspace describes (host/workspace.h): topology parameters through
+        cpmh_config_from_workspace, then every stored property through cpmh_network_load_workspace.  The volume
+        itself is the caller's (dims, fmt); `samples_per_side` overrides the workspace's nSamples."""
+        cfg = workspace_config(path, basis)
+        n = cfg.n_lights
+        net = cls(dims, fmt, samples_per_side or cfg.samples_per_side, [tuple(cfg.light_directions[i]) for i in range(n)],
+                  max_scattering_events=cfg.max_scattering_events, light_volume_option=cfg.light_volume_option,
+                  light_volume_channels=cfg.light_volume_channels, with_importance_grid=bool(cfg.with_importance_grid),
+                  volume_layout=volume_layout, photon_radius_voxels=cfg.photon_radius_voxels,
+                  max_incremental_percent=cfg.max_incremental_percent, clip=list(cfg.clip), device=device,
+                  light_intensity=[tuple(cfg.light_intensity[i]) for i in range(n)],
+                  reference_full_splat_bound=reference_full_splat_bound,
+                  incremental_threshold=cfg.incremental_threshold_percent, opacity_bound_cell_log2=opacity_bound_cell_log2)
+        net.properties_applied = net.load_workspace(path)
+        if samples_per_side:
+            net.set_samples_per_side(samples_per_side)
+        return net
+
+    def load_workspace(self, path) -> int:
+        """apply every stored property of the workspace's processors to this network; returns how many"""
+        return self._check(lib().cpmh_network_load_workspace(self.h, str(path).encode()))
+
+    def get_property(self, class_id, prop, k=0) -> float:
+        v = C.c_double()
+        self._check(lib().cpmh_network_get_property(self.h, class_id.encode(), int(k), prop.encode(), C.byref(v)))
+        return v.value
+
+    def set_samples_per_side(self, n):
+        self._check(lib().cpmh_network_set_samples_per_side(self.h, int(n)))
 
     def _check(self, rc):
         if rc < 0:

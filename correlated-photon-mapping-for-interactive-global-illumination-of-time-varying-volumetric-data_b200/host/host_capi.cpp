@@ -1,10 +1,13 @@
 // host_capi.cpp -- headless driver of the drop-in processor network (see host_capi.h).
 #include "host_capi.h"
 
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
 #include "processors.h"
+#include "workspace.h"
 
 using namespace inviwo;
 
@@ -472,6 +475,146 @@ int cpmh_network_export_sequence_grids(cpmh_network* net, int which, const char*
         UniformGrid3DVector copy(v.begin(), v.end());
         UniformGrid3DWriter().writeData(&copy, path);
         return (int)CPM_OK;
+    });
+}
+
+static std::vector<std::pair<std::string, std::vector<Processor*>>> network_processors(cpmh_network* n) {
+    std::vector<Processor*> samplers;
+    for (auto& s : n->lightSamplers) samplers.push_back(s.get());
+    return {{"org.inviwo.UniformSampleGenerator2DCL", {&n->sampleGen}},
+            {"org.inviwo.DirectionalLightSamplerCL", samplers},
+            {"org.inviwo.VolumeMinMaxCLProcessor", {&n->minMax}},
+            {"org.inviwo.MinMaxUniformGrid3DImportanceCLProcessor", {&n->importance}},
+            {"org.inviwo.ProgressivePhotonTracerCL", {&n->tracer}},
+            {"org.inviwo.PhotonToLightVolumeProcessorCL", {&n->toLightVolume}}};
+}
+
+const char* cpmh_workspace_describe(const char* path) {
+    static thread_local std::string text;
+    int rc = guarded([&]() {
+        if (!path) throw std::invalid_argument("null argument");
+        text = Workspace::load(path).describe();
+        return (int)CPM_OK;
+    });
+    return rc == CPM_OK ? text.c_str() : nullptr;
+}
+
+int cpmh_config_from_workspace(const char* path, const float basis[3], cpmh_config* cfg) {
+    return guarded([&]() {
+        if (!path || !cfg) throw std::invalid_argument("null argument");
+        Workspace w = Workspace::load(path);
+        double s = 0, v[4];
+        int nv = 0;
+        std::string sel;
+        auto gens = w.ofType("org.inviwo.UniformSampleGenerator2DCL");
+        if (!gens.empty() && readVec(gens[0]->property("nSamples"), v, nv) && nv >= 2) {
+            if (v[0] != v[1]) throw std::invalid_argument("workspace: nSamples is not square; the headless network takes one side length");
+            cfg->samples_per_side = (int)v[0];
+        }
+        auto samplers = w.ofType("org.inviwo.DirectionalLightSamplerCL");
+        if (samplers.size() > 8) throw std::invalid_argument("workspace: more than 8 light samplers");
+        if (!samplers.empty()) cfg->n_lights = (int)samplers.size();
+        auto sources = w.ofType("org.inviwo.Directionallightsource");
+        for (size_t l = 0; l < sources.size() && l < 8; ++l) {
+            const XmlNode* pos = sources[l]->property("lightPosition");
+            double p[3] = {0, 0, 1};
+            bool have = false;
+            if (const XmlNode* ws = pos ? pos->child("positionWorldSpace") : nullptr) {
+                p[0] = std::atof(ws->attrOr("x", "0").c_str());
+                p[1] = std::atof(ws->attrOr("y", "0").c_str());
+                p[2] = std::atof(ws->attrOr("z", "0").c_str());
+                have = true;
+            } else if (readVec(sources[l]->property("lightPosition.position"), v, nv) && nv >= 3) {
+                p[0] = v[0]; p[1] = v[1]; p[2] = v[2];
+                have = true;
+            }
+            if (have) {
+                // world -> texture space for a direction: divide by the volume's world extents, renormalise
+                double d[3], len = 0;
+                for (int k = 0; k < 3; ++k) {
+                    d[k] = -p[k] / (basis ? (double)basis[k] : 1.0);
+                    len += d[k] * d[k];
+                }
+                len = std::sqrt(len);
+                if (!(len > 0)) throw std::invalid_argument("workspace: light source at the origin has no direction");
+                for (int k = 0; k < 3; ++k) cfg->light_directions[l][k] = (float)(d[k] / len);
+            }
+            double power = 1.0, diffuse[3] = {1, 1, 1};
+            readScalar(sources[l]->property("lighting.lightPower"), power);
+            if (readVec(sources[l]->property("lighting.lightDiffuse"), v, nv) && nv >= 3)
+                for (int k = 0; k < 3; ++k) diffuse[k] = v[k];
+            for (int k = 0; k < 3; ++k) cfg->light_intensity[l][k] = (float)(power * diffuse[k]);
+        }
+        auto tracers = w.ofType("org.inviwo.ProgressivePhotonTracerCL");
+        if (!tracers.empty()) {
+            const WorkspaceProcessor* t = tracers[0];
+            if (readScalar(t->property("maxScatteringEvents"), s)) cfg->max_scattering_events = (int)s;
+            if (readScalar(t->property("radius"), s)) cfg->photon_radius_voxels = (float)s;
+            if (readScalar(t->property("maxIncrementalPhotonsToUpdate"), s)) cfg->max_incremental_percent = (float)s;
+            const char* clips[3] = {"clipX", "clipY", "clipZ"};
+            for (int k = 0; k < 3; ++k)
+                if (readVec(t->property(clips[k]), v, nv) && nv >= 2) {
+                    cfg->clip[2 * k] = (int)v[0];
+                    cfg->clip[2 * k + 1] = (int)v[1];
+                }
+            cfg->with_importance_grid = w.connected("org.inviwo.MinMaxUniformGrid3DImportanceCLProcessor",
+                                                    "org.inviwo.ProgressivePhotonTracerCL", "recomputationImportance") ? 1 : 0;
+        }
+        auto lvs = w.ofType("org.inviwo.PhotonToLightVolumeProcessorCL");
+        if (!lvs.empty()) {
+            if (readSelected(lvs[0]->property("volumeSizeOption"), sel))
+                cfg->light_volume_option = sel == "1" ? 1 : (sel == "1/2" ? 2 : (sel == "1/4" ? 4 : 0));
+            if (readSelected(lvs[0]->property("volumeDataType"), sel)) cfg->light_volume_channels = sel == "4xfloat32" ? 4 : 1;
+            if (readScalar(lvs[0]->property("incrementalRecomputationThreshold"), s)) cfg->incremental_threshold_percent = (float)s;
+        }
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_load_workspace(cpmh_network* net, const char* path) {
+    return guarded([&]() {
+        if (!net || !path) throw std::invalid_argument("null argument");
+        Workspace w = Workspace::load(path);
+        int applied = 0;
+        for (auto& entry : network_processors(net)) {
+            auto found = w.ofType(entry.first);
+            if (found.size() > entry.second.size())
+                throw std::invalid_argument("workspace has " + std::to_string(found.size()) + " x " + entry.first +
+                                            ", the network " + std::to_string(entry.second.size()));
+            for (size_t k = 0; k < found.size(); ++k) applied += applyWorkspaceProperties(*entry.second[k], *found[k]);
+        }
+        return applied;
+    });
+}
+
+int cpmh_network_set_samples_per_side(cpmh_network* net, int n) {
+    return guarded([&]() {
+        if (!net) throw std::invalid_argument("null argument");
+        if (n < net->sampleGen.nSamples_.getMinValue().x || n > net->sampleGen.nSamples_.getMaxValue().x)
+            throw std::invalid_argument("nSamples out of range");
+        net->sampleGen.nSamples_.set(ivec2{n, n});
+        net->cfg.samples_per_side = n;
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_get_property(cpmh_network* net, const char* class_id, int k, const char* property, double* out) {
+    return guarded([&]() {
+        if (!net || !class_id || !property || !out) throw std::invalid_argument("null argument");
+        for (auto& entry : network_processors(net)) {
+            if (entry.first != class_id) continue;
+            if (k < 0 || k >= (int)entry.second.size()) throw std::invalid_argument("no such processor instance");
+            Property* p = entry.second[k]->getPropertyByIdentifier(property);
+            if (!p) throw std::invalid_argument(std::string("no property ") + property);
+            if (auto* f = dynamic_cast<FloatProperty*>(p)) *out = f->get();
+            else if (auto* i = dynamic_cast<IntProperty*>(p)) *out = i->get();
+            else if (auto* b = dynamic_cast<BoolProperty*>(p)) *out = b->get() ? 1.0 : 0.0;
+            else if (auto* o = dynamic_cast<OptionProperty<int>*>(p)) *out = o->get();
+            else if (auto* t = dynamic_cast<TransferFunctionProperty*>(p)) *out = (double)t->get().size();
+            else throw std::invalid_argument(std::string("property ") + property + " is not scalar");
+            return (int)CPM_OK;
+        }
+        throw std::invalid_argument(std::string("no processor of class ") + class_id);
     });
 }
 

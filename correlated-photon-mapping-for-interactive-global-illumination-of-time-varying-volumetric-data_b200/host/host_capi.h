@@ -117,6 +117,32 @@ CPMH_API int cpmh_u3d_read_data(const char* path, void* out, size_t bytes);
  * which = 0 the per-step min-max grids, 1 the step-to-step difference grids */
 CPMH_API int cpmh_network_export_sequence_grids(cpmh_network* net, int which, const char* path);
 
+/* ".inv" workspaces (host only, no device needed for the first two).  The reference ships
+ * workspaces/CorrelatedPhotonMappingSingleVolume.inv; the drop-in processors keep the reference's class and property
+ * identifiers, so the file configures them headless.
+ *   cpmh_workspace_describe      "processor|<class id>|<name>|<stored property paths>" and
+ *                                "connection|<name>.<outport>|<name>.<inport>" lines
+ *   cpmh_config_from_workspace   fills what the workspace determines -- samples_per_side (UniformSampleGenerator2DCL
+ *                                nSamples), n_lights (DirectionalLightSamplerCL processors), light directions and
+ *                                intensities (k-th org.inviwo.Directionallightsource: direction = -normalize(position
+ *                                in world space), converted to texture space with the volume's world extents `basis`,
+ *                                NULL = unit cube; intensity = lightPower * lightDiffuse -- Inviwo base-module
+ *                                behaviour, outside the reference tree: parity unpinned), max_scattering_events,
+ *                                photon_radius_voxels, max_incremental_percent, clip, light_volume_option / channels,
+ *                                incremental_threshold_percent, with_importance_grid (is the tracer's
+ *                                recomputationImportance port connected) -- and leaves device, dims, format, layout.
+ *   cpmh_network_load_workspace  applies every stored property (transfer functions, weights, options, clip ranges,
+ *                                material, camera ...) to the network's processors of the same class id, k-th
+ *                                occurrence to k-th instance; returns the number of properties applied (>= 0). */
+CPMH_API const char* cpmh_workspace_describe(const char* path);
+CPMH_API int cpmh_config_from_workspace(const char* path, const float basis[3], cpmh_config* cfg);
+CPMH_API int cpmh_network_load_workspace(cpmh_network* net, const char* path);
+/* value of a scalar / bool / option property of the network's processors, for checks: processor = class id
+ * ("org.inviwo.ProgressivePhotonTracerCL"), occurrence k, property identifier; options report their selected value */
+/* UniformSampleGenerator2DCL nSamples = (n, n): e.g. a smaller photon count than the workspace stores */
+CPMH_API int cpmh_network_set_samples_per_side(cpmh_network* net, int n);
+CPMH_API int cpmh_network_get_property(cpmh_network* net, const char* class_id, int k, const char* property, double* out);
+
 CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
                                   const float plane_normal[3], float out[9]);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */
