@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
-    ap.add_argument("--gather-interleaved", action="store_true", help="photon map as 32-byte records instead of planar halves (A/B)")
+    ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
     return ap.parse_args()
 
@@ -331,7 +331,36 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
     P = cpm.capi.make_gather_params(a.view, a.view, (1.7, 1.4, -1.3), (0.5, 0.5, 0.5), fov_deg=40.0, step=0.5 / D,
                                     radius=radius, scale=scale, sigma_scale=150.0, grid_dims=(g, g, g),
                                     opacity_bound=bound, bound_cell_log2=bs)
-    P.planar_records = 0 if a.gather_interleaved else n * I * world
+    P.planar_records = n * I * world if a.gather_planar else 0
+    # ---- (world > 1, first) photon-sharded gather: own map, whole image, rgb all-reduce -- no photon exchange
+    sharded = None
+    if world > 1:
+        img_w = torch.empty(a.view * a.view * 4, dtype=torch.float32, device=dev)
+        P.planar_records = 0
+        tb, tm, tt = [], [], []
+        for it in range(reps + 1):
+            torch.distributed.barrier()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record(stream)
+            sp, start, end, _ = ctx.build_photon_map(photons, n * I, (g, g, g), torch)
+            if bound is not None:
+                ctx.opacity_bound(vrange, ncell, tf, bound)
+            e[1].record(stream)
+            ctx.gather_raymarch(V, tf, P, sp, start, end, img_w)
+            e[2].record(stream)
+            full_s = sharding.allreduce_image(img_w.view(-1, 4))
+            e[3].record(stream)
+            e[3].synchronize()
+            if it:
+                t = sharding.max_over_ranks([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[0].elapsed_time(e[3])], device=dev)
+                tb.append(t[0]); tm.append(t[1]); tt.append(t[2])
+        sharded = {"frames_per_sec": 1e3 / float(np.median(tt)), "frame_ms": float(np.median(tt)),
+                   "photon_map_build_ms": float(np.median(tb)), "raymarch_ms": float(np.median(tm)),
+                   "image_allreduce_bytes": a.view * a.view * 16, "photons_in_image": n * I * world,
+                   "how": "every rank gathers the whole image against the map of its own photon shard (estimator scale for "
+                          "the total photon count) and the rgb channels are summed with an NCCL all-reduce: radiance is "
+                          "linear in the photon set, the per-rank map stays L2 resident; times are max over ranks"}
+        P.planar_records = n * I * world if a.gather_planar else 0
     first, stride, rows = sharding.image_strips(rank, world, a.view)
     if world > 1:
         P.height, P.strip_first, P.strip_stride = rows, first, stride
@@ -345,7 +374,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
         e[0].record(stream)
         allp = sharding.allgather_photons(photons, allp)
         e[1].record(stream)
-        sp, start, end, _ = ctx.build_photon_map(allp, n * I * world, (g, g, g), torch, planar=not a.gather_interleaved)
+        sp, start, end, _ = ctx.build_photon_map(allp, n * I * world, (g, g, g), torch, planar=a.gather_planar)
         if bound is not None:
             ctx.opacity_bound(vrange, ncell, tf, bound)
         e[2].record(stream)
@@ -385,7 +414,12 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
                    f"{n * I * world} photon records (+ TF classification of the opacity-bound cells); march = step 0.5 voxel, "
                    "Epanechnikov gather r = 1 voxel, transparent cells stepped over, 12 samples gathered per photon pass"}
     if world > 1:
-        out.update({"photon_allgather_ms": x, "frame_ms": tot, "photons_in_map": n * I * world,
+        out = {"frames_per_sec": sharded["frames_per_sec"], "photon_sharded": sharded, "replicated_map": out,
+               "light_volume_raycast_ms": out["light_volume_raycast_ms"], "view": out["view"],
+               "note": "frames_per_sec = the photon-sharded gather (SURVEY 8e: no photon exchange, image all-reduce); "
+                       "replicated_map = option A (photon all-gather, image strips per rank): the map of all ranks' photons "
+                       "outgrows the 126 MB L2, which the latency-bound gather pays for"}
+        out["replicated_map"].update({"photon_allgather_ms": x, "frame_ms": tot, "photons_in_map": n * I * world,
                     "tiling": f"strips of 4 rows dealt round robin over {world} ranks, NCCL all-gather of photon records "
                               f"({32 * n * I * world} B) and of the image strips; times are max over ranks"})
     return out

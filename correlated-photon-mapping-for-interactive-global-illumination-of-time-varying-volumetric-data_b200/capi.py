@@ -358,11 +358,12 @@ def _splat_photons(self, light_volume, channels, tex2idx, idx2tex, out_dims, pho
 
 
 def _splat_photons_update(self, light_volume, channels, tex2idx, idx2tex, out_dims, old_photons, new_photons, indices, n,
-                          per_interaction, n_interactions, radius, scale):
-    self._check(lib().cpm_splat_photons_update(self.h, _p(light_volume), int(channels), _fN(tex2idx, 16), _fN(idx2tex, 16),
-                                               _i3(out_dims), _p(old_photons), _p(new_photons), _p(indices), int(n),
-                                               int(per_interaction), int(n_interactions), C.c_float(radius),
-                                               C.c_float(scale)))
+                          per_interaction, n_interactions, radius, scale, sync=False):
+    """sync=True: cpm_splat_photons_update_sync (old_photons is left holding the new records of the listed ids)"""
+    f = lib().cpm_splat_photons_update_sync if sync else lib().cpm_splat_photons_update
+    self._check(f(self.h, _p(light_volume), int(channels), _fN(tex2idx, 16), _fN(idx2tex, 16),
+        _i3(out_dims), _p(old_photons), _p(new_photons), _p(indices), int(n),
+        int(per_interaction), int(n_interactions), C.c_float(radius), C.c_float(scale)))
 
 
 Context.detect_invalid = _detect_invalid

@@ -27,6 +27,7 @@ struct SplatArgs {
     int dim[3];
     const float4* photons;
     const float4* old_photons;  // cpm_splat_photons_update: records to remove (same ids), or null
+    float4* old_sync;           // cpm_splat_photons_update_sync: == old_photons, overwritten with the new records
     const uint32_t* indices;
     int n;
     int per_interaction;
@@ -96,6 +97,10 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
                 // incremental update: -old +new in one pass; a record the re-trace reproduced bit for bit
                 // contributes nothing and is skipped (the two passes would cancel up to rounding)
                 float4 q0 = A.old_photons[2 * pid], q1 = A.old_photons[2 * pid + 1];
+                if (A.old_sync) {   // leave the copy equal to the new records: no whole-buffer copy after the update
+                    A.old_sync[2 * pid] = p0;
+                    A.old_sync[2 * pid + 1] = p1;
+                }
                 if (q0.x == p0.x && q0.y == p0.y && q0.z == p0.z && q0.w == p0.w && q1.x == p1.x && q1.y == p1.y) continue;
                 splat_one<CH>(A, q0, -(q0.w * s * A.multiplier), -(q1.x * s * A.multiplier), -(q1.y * s * A.multiplier));
             }
@@ -109,7 +114,8 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
 static int splat_common(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
                         const float index_to_texture[16], const int out_dims[3], const float* photons,
                         const float* old_photons, const uint32_t* indices, int n, int photons_per_interaction,
-                        int n_interactions, float radius, float relative_irradiance_scale, float multiplier) {
+                        int n_interactions, float radius, float relative_irradiance_scale, float multiplier,
+                        bool sync_old = false) {
     CPM_REQUIRE(ctx, n >= 0, "negative n");
     if (n == 0) return CPM_OK;
     CPM_REQUIRE(ctx, light_volume && texture_to_index && index_to_texture && out_dims && photons, "null argument");
@@ -124,6 +130,7 @@ static int splat_common(cpm_ctx* ctx, float* light_volume, int channels, const f
     for (int k = 0; k < 3; ++k) a.dim[k] = out_dims[k];
     a.photons = (const float4*)photons;
     a.old_photons = (const float4*)old_photons;
+    a.old_sync = sync_old ? (float4*)const_cast<float*>(old_photons) : nullptr;
     a.indices = indices;
     a.n = n;
     a.per_interaction = photons_per_interaction;
@@ -156,4 +163,16 @@ extern "C" int cpm_splat_photons_update(cpm_ctx* ctx, float* light_volume, int c
     CPM_REQUIRE(ctx, old_photons && indices, "null argument");
     return splat_common(ctx, light_volume, channels, texture_to_index, index_to_texture, out_dims, new_photons, old_photons,
                         indices, n, photons_per_interaction, n_interactions, radius, relative_irradiance_scale, 1.0f);
+}
+
+extern "C" int cpm_splat_photons_update_sync(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
+                                             const float index_to_texture[16], const int out_dims[3], float* old_photons,
+                                             const float* new_photons, const uint32_t* indices, int n,
+                                             int photons_per_interaction, int n_interactions, float radius,
+                                             float relative_irradiance_scale) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, old_photons && indices, "null argument");
+    CPM_REQUIRE(ctx, old_photons != new_photons, "old and new records must be different buffers");
+    return splat_common(ctx, light_volume, channels, texture_to_index, index_to_texture, out_dims, new_photons, old_photons,
+                        indices, n, photons_per_interaction, n_interactions, radius, relative_irradiance_scale, 1.0f, true);
 }

@@ -1302,6 +1302,7 @@ void PhotonToLightVolumeProcessorCL::process() {
     const int nRecomputed = idxData ? idxData->nRecomputedPhotons : -1;
     const float* photonsDev = static_cast<const float*>(photonData->photons_.deviceRead());
     lastPath = "none";
+    bool prevInSync = false;
     if (idxData && prevPhotons_.getSize() == photonData->photons_.getSize() && nRecomputed > 0 && nRecomputed < maxRecomputationPhotons) {
         // incremental: remove the old contribution of the re-traced photons, add the new one (:262-274)
         auto* idxBuf = const_cast<Buffer<unsigned int>*>(&idxData->indicesToRecomputedPhotons);
@@ -1309,10 +1310,12 @@ void PhotonToLightVolumeProcessorCL::process() {
         float* lv = static_cast<float*>(const_cast<void*>(lightVolume_->deviceRead()));
         lightVolume_->deviceWrite();
         ScopedStage st("splat");
-        rt.check(cpm_splat_photons_update(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim,
-                                          static_cast<const float*>(prevPhotons_.deviceRead()), photonsDev, idx, nRecomputed, N, I,
-                                          radius, scale));
+        // (the kernel leaves prevPhotons_ equal to the new records of the listed ids: no whole-buffer copy below)
+        rt.check(cpm_splat_photons_update_sync(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim,
+                                               static_cast<float*>(prevPhotons_.deviceWrite()), photonsDev, idx, nRecomputed, N, I,
+                                               radius, scale));
         lastPath = "incremental";
+        prevInSync = true;
     } else if (prevPhotons_.getSize() != photonData->photons_.getSize() || nRecomputed < 0 || nRecomputed >= maxRecomputationPhotons) {
         float* lv = static_cast<float*>(lightVolume_->deviceWrite());
         ScopedStage st("splat");
@@ -1321,7 +1324,7 @@ void PhotonToLightVolumeProcessorCL::process() {
         rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, photonsDev, nullptr, n, N, I, radius, scale, 1.f));
         lastPath = "full";
     }
-    if (idxData && nRecomputed != 0) {
+    if (idxData && nRecomputed != 0 && !prevInSync) {
         // keep a copy of the photons so that the next incremental update can subtract them (:488-497)
         if (prevPhotons_.getSize() != photonData->photons_.getSize()) prevPhotons_.setSize(photonData->photons_.getSize());
         ScopedStage st("copyprev");

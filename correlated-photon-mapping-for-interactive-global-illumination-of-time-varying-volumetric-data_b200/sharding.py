@@ -150,6 +150,20 @@ def allgather_image(local: torch.Tensor, width: int, height: int, group=None) ->
     return assemble_image(parts.reshape(world, -1, width, 4), world, width, height)
 
 
+# ---- photon-sharded gathering: the estimator is linear in the photon set -------------------------------------------------
+def allreduce_image(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Every rank gathers the WHOLE image against the map of its own photon shard (cpm_gather_params.scale set for the
+    total photon count); radiance is a sum over photons -- compositing weights, opacity and early ray termination depend
+    on the volume and the transfer function only -- so the image of the union is the sum of the ranks' images in the
+    rgb channels, and the opacity channel is every rank's own.  local: [..., 4]; returns a new tensor."""
+    if not is_distributed():
+        return local
+    out = local.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    out.view(-1, 4)[:, 3] = local.reshape(-1, 4)[:, 3]
+    return out
+
+
 def max_over_ranks(values, device="cpu"):
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
     if is_distributed():

@@ -354,6 +354,16 @@ CPM_API int cpm_splat_photons_update(cpm_ctx* ctx, float* light_volume, int chan
                                      const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
                                      float radius, float relative_irradiance_scale);
 
+/* The same update, and afterwards old_photons holds the NEW records of every listed id (all interactions): the copy of
+ * the photon buffer that the next incremental update subtracts (ppm/processor/photontolightvolumeprocessorcl.cpp:
+ * 488-497 copies the whole buffer after every frame) stays current without a pass over all photons.  Ids must be
+ * unique, as the tracer's recomputed-index list is. */
+CPM_API int cpm_splat_photons_update_sync(cpm_ctx* ctx, float* light_volume, int channels,
+                                          const float texture_to_index[16], const float index_to_texture[16],
+                                          const int out_dims[3], float* old_photons, const float* new_photons,
+                                          const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
+                                          float radius, float relative_irradiance_scale);
+
 /* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
 /* Not launched anywhere in the reference; the estimator is the reference's
  * (Epanechnikov kernel, ppm/cl/densityestimationkernel.cl:56-60; power * 1/(4 pi) * relativeIrradianceScale,

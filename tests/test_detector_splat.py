@@ -174,6 +174,18 @@ def test_cuda_splat_update_equals_remove_then_add(cpm, orc, ctx, torch_cuda, syn
     got = lv.cpu().numpy().astype(np.float64)
     assert np.abs(want - base).max() > 0
     assert np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
+    # the _sync variant: same light volume, and the old-record buffer ends up holding the new records of the listed
+    # ids (both interactions) and its own records everywhere else
+    lv3 = torch.from_numpy(base.astype(np.float32)).cuda()
+    dold = torch.from_numpy(old).cuda()
+    ctx.splat_photons_update(lv3, channels, t2i, i2t, od, dold, torch.from_numpy(new).cuda(),
+                             torch.from_numpy(idx.view(np.int32)).cuda(), idx.size, n, 2, radius, scale, sync=True)
+    ctx.sync()
+    g3 = lv3.cpu().numpy().astype(np.float64)
+    assert np.sqrt(((g3 - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
+    expect = old.reshape(2, n, 8).copy()
+    expect[:, idx] = new.reshape(2, n, 8)[:, idx]
+    assert np.array_equal(dold.cpu().numpy().reshape(2, n, 8).view(np.uint32), expect.view(np.uint32))
     # no listed record changed: the light volume is untouched bit for bit
     lv2 = torch.from_numpy(base.astype(np.float32)).cuda()
     ctx.splat_photons_update(lv2, channels, t2i, i2t, od, torch.from_numpy(old).cuda(), torch.from_numpy(old).cuda(),

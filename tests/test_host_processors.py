@@ -128,6 +128,42 @@ def test_network_correlated_retrace(host, cpm, orc, synth, torch_cuda):
 
 
 @pytest.mark.gpu
+def test_network_consecutive_incremental_updates_do_not_drift(host, cpm, synth, torch_cuda):
+    """Four transfer-function changes in a row, each an incremental -old/+new update: the copy of the previous records
+    that the update subtracts is kept current by the update itself (cpm_splat_photons_update_sync), so after the last
+    change the light volume still equals a from-scratch network's (a stale copy would subtract the wrong records)."""
+    dims, ns, I = (64, 64, 64), 96, 2
+    d = (0.2, 0.3, 0.9)
+    vol = synth.volume_u8(dims, 8)
+    kw = dict(max_scattering_events=I, light_volume_option=2, with_importance_grid=True, reference_full_splat_bound=False,
+              incremental_threshold=100.0)
+    net = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], **kw)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_volume_host(vol)
+    net.evaluate()
+    pts = list(synth.WS_TF_POINTS)
+    paths = []
+    for alpha in (0.9, 0.3, 0.7, 0.45):
+        pts[-1] = (pts[-1][0], (0.1, 0.6, 0.65, alpha))
+        net.set_transfer_function(pts)
+        net.evaluate()
+        paths.append(net.last_splat_path)
+        assert 0 < net.n_recomputed < net.n_photons
+    assert paths == ["incremental"] * 4
+    lv_inc = net.read_light_volume().astype(np.float64)
+    ref = host.Network(dims, cpm.CPM_FMT_U8, ns, [d], **kw)
+    ref.set_transfer_function(pts)
+    ref.set_volume_host(vol)
+    ref.evaluate()
+    lv_full = ref.read_light_volume().astype(np.float64)
+    same = np.all(ref.read_photons(I).view(np.uint32) == net.read_photons(I).view(np.uint32), axis=1)
+    assert same.mean() > 0.999, same.mean()
+    rmse = np.sqrt(((lv_inc - lv_full) ** 2).mean()) / np.sqrt((lv_full ** 2).mean())
+    assert rmse < 4e-3, rmse
+    net.close(); ref.close()
+
+
+@pytest.mark.gpu
 def test_network_budgeted_batches(host, cpm, synth, torch_cuda):
     """maxIncrementalPhotonsToUpdate < 100: the re-trace is spread over several evaluations"""
     dims, ns = (48, 48, 48), 64

@@ -51,6 +51,11 @@ def _worker(rank, world, port, q):
     mine = cam_row[:, None, None].expand(rows, W, 4).contiguous()
     img = sh.allgather_image(mine, W, H)
     ok = ok and img.shape == (H, W, 4) and bool(torch.equal(img[:, 0, 0], torch.arange(H, dtype=torch.float32)))
+    # photon-sharded gather: rgb summed over ranks, the opacity channel stays the rank's own
+    part = torch.tensor([[1.0, 2.0, 3.0, 0.5], [0.0, 0.25, 0.0, 0.75]]) * torch.tensor([rank + 1.0, rank + 1.0, rank + 1.0, 1.0])
+    tot = sh.allreduce_image(part)
+    k = float(sum(range(1, world + 1)))
+    ok = ok and bool(torch.equal(tot, torch.tensor([[k, 2 * k, 3 * k, 0.5], [0.0, 0.25 * k, 0.0, 0.75]]))) and tot.data_ptr() != part.data_ptr()
     mx = sh.max_over_ranks([float(rank), 5.0 - rank])
     sm = sh.sum_over_ranks([float(rank + 1)])
     first, count = sh.photon_shard(rank, world, 4096)
