@@ -575,12 +575,29 @@ def run_b200(a):
             first += max(a.warmup, 2)
             host.Network.transfer_bytes(reset=True)
             d2h_extra[0] = 0
+            host.profile_enable(True)
+            host.profile_reset()
             ms_e, wall_e, traced_e = time_loop(net, a.steps, first, step_e2e)
+            st_e = {s: (host.profile_total_ms(s), host.profile_count(s)) for s in host.profile_stages()}
+            host.profile_enable(False)
             h2d, d2h = host.Network.transfer_bytes()
             d2h += d2h_extra[0]
+            # the per-step grid builders run once per uploaded volume here: live HBM figures for them
+            vox_bytes = D ** 3 * 4
+            grid_kernels = {}
+            for stage, kname, nbytes in (("minmax", "minmax8_kernel (volumeMinMaxKernel)", vox_bytes),
+                                         ("voldiff", "diff8_kernel (DynamicVolumeDifferenceAnalysis)", 2 * vox_bytes),
+                                         ("range", "range8_kernel (opacity-bound value range)", vox_bytes)):
+                tot, cnt = st_e.get(stage, (0.0, 0))
+                if cnt:
+                    gbs = nbytes / (tot / cnt * 1e-3) / 1e9
+                    grid_kernels[stage] = {"kernel": kname, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": nbytes,
+                                           "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak()[0]}
             e2e = {"value": traced_e / (wall_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                    "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": wall_e / a.steps,
                    "frames_per_sec": a.steps / (wall_e * 1e-3),
+                   "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
+                   "grid_kernels": grid_kernels,
                    "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume; the next step's "
                            "upload is announced with cpmh_network_prefetch_timestep_host and overlaps this step) -> "
                            "cpmh_network_evaluate -> cpmh_network_read_light_volume(pinned host buffer)"}

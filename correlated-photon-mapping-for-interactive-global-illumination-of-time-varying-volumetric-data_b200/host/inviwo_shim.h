@@ -136,9 +136,7 @@ private:
     cpm_event* take();
     std::vector<cpm_event*> pool_;
     std::vector<Pending> pending_;
-    std::string open_;
-    cpm_event* openEv_ = nullptr;
-    int depth_ = 0;
+    std::vector<std::pair<std::string, cpm_event*>> open_;   // stages nest: an outer stage's time includes its inner stages
     struct Acc { double total = 0, last = 0; int n = 0; };
     std::map<std::string, Acc> acc_;
 };

@@ -80,18 +80,16 @@ cpm_event* StageProfiler::take() {
 }
 void StageProfiler::begin(const char* stage) {
     if (!enabled) return;
-    if (depth_++ > 0) return;   // stages do not nest: the outermost wins
-    open_ = stage;
-    openEv_ = take();
-    CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), openEv_));
+    cpm_event* e = take();
+    CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), e));
+    open_.emplace_back(stage, e);
 }
 void StageProfiler::end() {
-    if (!enabled || depth_ == 0) return;
-    if (--depth_ > 0 || !openEv_) return;
+    if (!enabled || open_.empty()) return;
     cpm_event* b = take();
     CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), b));
-    pending_.push_back({open_, openEv_, b});
-    openEv_ = nullptr;
+    pending_.push_back({open_.back().first, open_.back().second, b});
+    open_.pop_back();
     if (pending_.size() >= 4096) resolve();
 }
 void StageProfiler::resolve() {
@@ -110,9 +108,8 @@ void StageProfiler::resolve() {
 }
 void StageProfiler::reset() {
     resolve();
-    if (openEv_) pool_.push_back(openEv_);   // a stage left open by an exception
-    openEv_ = nullptr;
-    depth_ = 0;
+    for (auto& o : open_) pool_.push_back(o.second);   // stages left open by an exception
+    open_.clear();
     acc_.clear();
 }
 double StageProfiler::totalMs(const std::string& s) { resolve(); auto it = acc_.find(s); return it == acc_.end() ? 0.0 : it->second.total; }
@@ -128,8 +125,8 @@ void StageProfiler::releaseEvents() {
     cpm_ctx* c = g_runtime.ctx();
     for (auto& p : pending_) { cpm_event_destroy(c, p.a); cpm_event_destroy(c, p.b); }
     pending_.clear();
-    if (openEv_) cpm_event_destroy(c, openEv_);
-    openEv_ = nullptr;
+    for (auto& o : open_) cpm_event_destroy(c, o.second);
+    open_.clear();
     for (auto* e : pool_) cpm_event_destroy(c, e);
     pool_.clear();
 }
