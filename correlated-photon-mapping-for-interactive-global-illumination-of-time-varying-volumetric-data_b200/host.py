@@ -143,6 +143,15 @@ def workspace_config(path, basis=None) -> HostConfig:
     return cfg
 
 
+def random_numbers(nx, ny=0, seed=0, evaluations=1):
+    """RandomNumberGeneratorCL (ny = 0) / RandomNumberGenerator2DCL evaluated `evaluations` times: the last numbers"""
+    out = np.empty(nx * max(ny, 1), np.float32)
+    rc = lib().cpmh_random_numbers(int(nx), int(ny), int(seed), int(evaluations), out.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+    return out.reshape(ny, nx) if ny else out
+
+
 def describe_processors() -> dict:
     """{classIdentifier: (set(port ids), set(property ids))} of the drop-in processors"""
     out = {}

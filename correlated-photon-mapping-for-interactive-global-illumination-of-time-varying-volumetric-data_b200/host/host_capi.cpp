@@ -618,6 +618,29 @@ int cpmh_network_get_property(cpmh_network* net, const char* class_id, int k, co
     });
 }
 
+int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_host) {
+    return guarded([&]() {
+        if (!out_host || nx < 1 || ny < 0 || evaluations < 1) throw std::invalid_argument("bad argument");
+        CpmRuntime::init(0);
+        if (ny == 0) {
+            RandomNumberGeneratorCL p;
+            p.seed_.set(seed);
+            p.nRandomNumbers_.set(nx);
+            for (int k = 0; k < evaluations; ++k) p.process();
+            auto data = p.randomNumbersPort_.getData();
+            std::memcpy(out_host, const_cast<Buffer<float>*>(data.get())->getRAMRepresentation()->data(), (size_t)nx * sizeof(float));
+        } else {
+            RandomNumberGenerator2DCL p;
+            p.seed_.set(seed);                       // before nSamples: the streams are seeded when nSamples changes
+            p.nRandomNumbers_.set(ivec2{nx, ny});
+            for (int k = 0; k < evaluations; ++k) p.process();
+            auto img = p.randomNumbersPort_.getData();
+            std::memcpy(out_host, const_cast<ImageF32*>(img.get())->data.getRAMRepresentation()->data(), (size_t)nx * ny * sizeof(float));
+        }
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_fit_light_plane(const float* points, int n, const float P[3], const float N[3], float out[9]) {
     return guarded([&]() {
         std::vector<vec3> pts;
@@ -650,6 +673,7 @@ const char* cpmh_describe_processors(void) {
     { MinMaxUniformGrid3DImportanceCLProcessor p; dump(p); }
     { RadixSortCL p; dump(p); }
     { RandomNumberGeneratorCL p; dump(p); }
+    { RandomNumberGenerator2DCL p; dump(p); }
     s = os.str();
     return s.c_str();
 }

@@ -143,6 +143,9 @@ CPMH_API int cpmh_network_load_workspace(cpmh_network* net, const char* path);
 CPMH_API int cpmh_network_set_samples_per_side(cpmh_network* net, int n);
 CPMH_API int cpmh_network_get_property(cpmh_network* net, const char* class_id, int k, const char* property, double* out);
 
+/* RandomNumberGeneratorCL (ny == 0: nSamples = nx) or RandomNumberGenerator2DCL (nSamples = (nx, ny)) evaluated
+ * `evaluations` times with the given seed; the numbers of the last evaluation are read back (nx * max(ny, 1) floats). */
+CPMH_API int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_host);
 CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
                                   const float plane_normal[3], float out[9]);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */

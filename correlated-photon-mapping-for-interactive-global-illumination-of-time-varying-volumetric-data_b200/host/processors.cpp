@@ -1630,4 +1630,41 @@ void RandomNumberGeneratorCL::process() {
     randomNumbersPort_.setData(randomNumbers_);
 }
 
+const ProcessorInfo RandomNumberGenerator2DCL::processorInfo_{"org.inviwo.RandomNumberGenerator2DCL", "Random Number Generator 2D",
+                                                              "Random numbers", "Stable", "CL"};
+RandomNumberGenerator2DCL::RandomNumberGenerator2DCL()
+    : randomNumbersPort_("samples")
+    , nRandomNumbers_("nSamples", "N samples", ivec2{128, 128}, ivec2{2, 2}, ivec2{2048, 2048})
+    , regenerateNumbers_("genRnd", "Regenerate")
+    , seed_("seed", "Seed number", 0, 0, 2147483647)
+    , workGroupSize_("wgsize", "Work group size", 256, 1, 2048)
+    , useGLSharing_("glsharing", "Use OpenGL sharing", true)
+    , image_(std::make_shared<ImageF32>()) {
+    addPort(randomNumbersPort_);
+    addProperty(nRandomNumbers_);
+    addProperty(regenerateNumbers_);
+    addProperty(seed_);
+    addProperty(workGroupSize_);
+    addProperty(useGLSharing_);
+    nRandomNumbers_.onChange([this]() { nRandomNumbersChanged(); });
+    randomNumbersPort_.setData(image_);
+}
+void RandomNumberGenerator2DCL::nRandomNumbersChanged() {
+    const ivec2 n = nRandomNumbers_.get();
+    if (n.x < 2 || n.y < 2 || n.x > 2048 || n.y > 2048) throw std::invalid_argument("nSamples out of range");
+    randomState_.setSize((size_t)n.x * (size_t)n.y);
+    MWC64XSeedGenerator().generateRandomSeeds(&randomState_, (unsigned)seed_.get(), false);
+    image_->dims = n;
+    image_->data.setSize((size_t)n.x * (size_t)n.y);
+}
+void RandomNumberGenerator2DCL::process() {
+    if (image_->dims.x != nRandomNumbers_.get().x || image_->dims.y != nRandomNumbers_.get().y || randomState_.getSize() == 0)
+        nRandomNumbersChanged();
+    auto& rt = CpmRuntime::get();
+    uint32_t* st = static_cast<uint32_t*>(const_cast<void*>(randomState_.deviceRead()));
+    randomState_.deviceWrite();
+    rt.check(cpm_rng_uniform(rt.ctx(), st, image_->data.getSize(), 1, static_cast<float*>(image_->data.deviceWrite())));
+    randomNumbersPort_.setData(image_);
+}
+
 }  // namespace inviwo

@@ -479,4 +479,29 @@ private:
     MWC64XRandomNumberGenerator randomNumberGenerator_;
 };
 
+// org.inviwo.RandomNumberGenerator2DCL -- rng/processors/randomnumbergenerator2dcl.cpp:44-136.  One MWC64X stream per
+// pixel, one number per stream and evaluation (N_NUMBERS_PER_THREAD = 1, rng/cl/randomnumbergenerator.cl:32,51-71): pixel
+// (x, y) is number y * width + x of the 1-D generator with the same seed.  As in the reference the streams are seeded
+// when nSamples changes (nRandomNumbersChanged), not when `seed` changes.
+struct ImageF32 {
+    ivec2 dims{0, 0};
+    Buffer<float> data;     // row-major, dims.x * dims.y
+};
+class RandomNumberGenerator2DCL : public Processor {
+public:
+    RandomNumberGenerator2DCL();
+    void process() override;
+    const ProcessorInfo getProcessorInfo() const override { return processorInfo_; }
+    static const ProcessorInfo processorInfo_;
+    DataOutport<ImageF32> randomNumbersPort_;
+    IntVec2Property nRandomNumbers_;
+    ButtonProperty regenerateNumbers_;
+    IntProperty seed_, workGroupSize_;
+    BoolProperty useGLSharing_;
+private:
+    void nRandomNumbersChanged();
+    std::shared_ptr<ImageF32> image_;
+    Buffer<uvec2> randomState_;
+};
+
 }  // namespace inviwo

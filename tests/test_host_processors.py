@@ -33,6 +33,7 @@ CONTRACT = {
     "org.inviwo.DynamicVolumeDifferenceAnalysis": ({"data", "DynamicDataInfo"}, {"region"}),
     "org.inviwo.RadixSortCL": ({"unsortedKeys", "unsortedData", "sortedData"}, set()),
     "org.inviwo.RandomNumberGeneratorCL": ({"samples"}, {"nSamples", "genRnd", "seed", "wgsize", "glsharing"}),
+    "org.inviwo.RandomNumberGenerator2DCL": ({"samples"}, {"nSamples", "genRnd", "seed", "wgsize", "glsharing"}),
 }
 
 
@@ -184,3 +185,20 @@ def test_network_budgeted_batches(host, cpm, synth, torch_cuda):
     assert rounds >= 1 and total > 0
     assert net.n_recomputed <= int(0.10 * net.n_photons)
     net.close()
+
+
+@pytest.mark.gpu
+def test_random_number_generator_processors_match_oracle(host, orc, torch_cuda):
+    """RandomNumberGeneratorCL / RandomNumberGenerator2DCL: stream i seeded from the host base offset of `seed`
+    (rng/mwc64xseedgenerator.cpp:56-64), one number per stream and evaluation; pixel (x, y) of the 2-D generator is
+    number y * width + x (rng/cl/randomnumbergenerator.cl:51-71).  Bit-exact."""
+    for seed, evals in ((0, 1), (7, 3)):
+        n = 96 * 40
+        st = orc.rng_seed_streams(orc.rng_host_base_offsets(seed, n))
+        want = None
+        for _ in range(evals):
+            want = orc.rng_uniform(st, 1)
+        got1 = host.random_numbers(n, 0, seed, evals)
+        got2 = host.random_numbers(96, 40, seed, evals)
+        assert np.array_equal(got1.view(np.uint32), np.asarray(want, np.float32).reshape(-1).view(np.uint32))
+        assert got2.shape == (40, 96) and np.array_equal(got2.reshape(-1).view(np.uint32), got1.view(np.uint32))

@@ -1,8 +1,12 @@
-# session 5, run P: full GPU parity suite, smoke, default bench line, reference arm
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/s5p_pytest.log 2>&1
-tail -5 gpurun_out/s5p_pytest.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/s5p_smoke.log 2>&1; tail -2 gpurun_out/s5p_smoke.log
-python bench.py > gpurun_out/s5p_bench.json 2> gpurun_out/s5p_bench.err
-tail -c 5000 gpurun_out/s5p_bench.json; tail -3 gpurun_out/s5p_bench.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s5p_bench_ref.json 2> gpurun_out/s5p_bench_ref.err
-tail -c 1500 gpurun_out/s5p_bench_ref.json
+# session 5, run Q (8 GPUs): scaling check of the whole bench line
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 16 --warmup 3 > gpurun_out/s5q_bench_n8.json 2> gpurun_out/s5q_bench_n8.err
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/s5q_bench_n8.json").read().strip().splitlines()[-1])
+    g=d["gather"]
+    print(d["n_gpus"], d["value"], round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["stages_ms_per_step"].items()}, "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"])
+    print("sharded", g["photon_sharded"]["frames_per_sec"], g["photon_sharded"]["frame_ms"], "replicated", g["replicated_map"]["frames_per_sec"], g["replicated_map"]["frame_ms"], g["replicated_map"]["photon_allgather_ms"])
+except Exception as e:
+    print("failed", e); print(open("gpurun_out/s5q_bench_n8.err").read()[-2500:])
+PY
