@@ -200,12 +200,17 @@ int cpm_volume_create(cpm_ctx* ctx, const void* data, const int dims[3], int for
         cudaChannelFormatDesc cd = format == CPM_FMT_U8    ? cudaCreateChannelDesc<unsigned char>()
                                    : format == CPM_FMT_U16 ? cudaCreateChannelDesc<unsigned short>()
                                                            : cudaCreateChannelDesc<float>();
-        cudaError_t e = cudaMalloc3DArray(&v->array, &cd, make_cudaExtent(dims[0], dims[1], dims[2]),
-                                          cudaArrayLayered | cudaArrayTextureGather);
+        // The gather flag is documented for plain 2-D arrays; tld4.a2d itself only needs a layered array.  Drivers
+        // that reject the combination do so for every array: ask once per process, then go straight to the plain
+        // layered array.
+        static bool gather_flag_ok = true;
+        cudaError_t e = cudaErrorInvalidValue;
+        if (gather_flag_ok)
+            e = cudaMalloc3DArray(&v->array, &cd, make_cudaExtent(dims[0], dims[1], dims[2]),
+                                  cudaArrayLayered | cudaArrayTextureGather);
         if (e == cudaErrorInvalidValue) {
-            // The gather flag is documented for plain 2-D arrays; tld4.a2d itself only needs a
-            // layered array, so retry without it.
-            (void)cudaGetLastError();
+            if (gather_flag_ok) (void)cudaGetLastError();
+            gather_flag_ok = false;
             e = cudaMalloc3DArray(&v->array, &cd, make_cudaExtent(dims[0], dims[1], dims[2]), cudaArrayLayered);
             if (e == cudaSuccess && getenv("CPM_DEBUG")) fprintf(stderr, "cpm: layered array created without gather flag\n");
         }

@@ -37,3 +37,18 @@ def test_glibc_rand_reproduced(cpm):
         want = [libc.rand() for _ in range(1000)]
         assert got[:, 0].tolist() == want
         assert (got[:, 1] == 0).all()
+
+
+def test_host_header_symbols_exported():
+    """libcpm_host.so (the reference-facing plugin layer) exports every CPMH_API function host_capi.h declares"""
+    import importlib
+    import re
+    from conftest import PKG_NAME, ROOT
+    host = importlib.import_module(PKG_NAME + ".host")
+    text = (ROOT / PKG_NAME / "host" / "host_capi.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"CPMH_API\s+[\w\s\*]+?\b(cpmh_\w+)\s*\(", text)))
+    assert len(names) >= 40
+    lib = host.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in host/host_capi.h but not exported: {missing}"

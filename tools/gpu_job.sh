@@ -1,12 +1,4 @@
-# session 5, run Q (8 GPUs): scaling check of the whole bench line
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 16 --warmup 3 > gpurun_out/s5q_bench_n8.json 2> gpurun_out/s5q_bench_n8.err
-python - <<PY
-import json
-try:
-    d=json.loads(open("gpurun_out/s5q_bench_n8.json").read().strip().splitlines()[-1])
-    g=d["gather"]
-    print(d["n_gpus"], d["value"], round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["stages_ms_per_step"].items()}, "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"])
-    print("sharded", g["photon_sharded"]["frames_per_sec"], g["photon_sharded"]["frame_ms"], "replicated", g["replicated_map"]["frames_per_sec"], g["replicated_map"]["frame_ms"], g["replicated_map"]["photon_allgather_ms"])
-except Exception as e:
-    print("failed", e); print(open("gpurun_out/s5q_bench_n8.err").read()[-2500:])
-PY
+# session 5, run S: compute-sanitizer memcheck over the kernels written this session
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_grid.py tests/test_bound.py tests/test_gather.py tests/test_raycast.py tests/test_detector_splat.py -m gpu -x -q -k "minmax or diff or value_range or strips or linear or splat_update or raycast_matches or gather_raymarch" > gpurun_out/s5s_memcheck.log 2>&1
+echo "memcheck exit: $?"
+grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/s5s_memcheck.log | head -20
