@@ -61,6 +61,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--exchange", choices=["auto", "multimem", "p2p", "nccl"], default="auto",
+                    help="N > 1: how the per-rank light volumes are summed (auto: peer kernel with multimem where available)")
+    ap.add_argument("--exchange-ctas", type=int, default=0, help="grid of the peer exchange kernel (0 = default)")
+    ap.add_argument("--exchange-eager-wait", action="store_true",
+                    help="the launch stream waits for the snapshot copy right after the frame (A/B; default: only the next splat waits)")
+    ap.add_argument("--check-exchange", action="store_true", help="compare the first exchanged sum with NCCL's")
     ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
     return ap.parse_args()
@@ -505,7 +511,22 @@ def run_b200(a):
         net.set_timestep(0)
         net.evaluate()                         # first frame: full trace + full splat
 
-        exchange = sharding.LightVolumeExchange()
+        exchange, exchange_kind = sharding.LightVolumeExchange(), "NCCL all-reduce"
+        if world > 1 and a.exchange != "nccl":
+            # one kernel over NVLink peer memory (csrc/exchange.cu); NCCL stays the fallback where symmetric memory
+            # cannot be set up
+            try:
+                lvd0 = net.light_volume_dims
+                exchange = sharding.PeerLightVolumeExchange(cpm, lvd0[0] * lvd0[1] * lvd0[2], dev, max_ctas=a.exchange_ctas,
+                                                            use_multicast=(a.exchange != "p2p"))
+                exchange_kind = ("cpm_allreduce_peer_f32, NVSwitch multimem.ld_reduce/st" if exchange.multicast
+                                 else "cpm_allreduce_peer_f32, peer loads / stores")
+            except Exception as ex:   # noqa: BLE001 -- any set-up failure means: use NCCL
+                sys.stderr.write(f"[rank {rank}] peer exchange unavailable ({type(ex).__name__}: {ex}); using NCCL\n")
+            ok = torch.tensor([1.0 if exchange_kind.startswith("cpm") else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0.0 and exchange_kind.startswith("cpm"):
+                exchange, exchange_kind = sharding.LightVolumeExchange(), "NCCL all-reduce"
 
         def step_resident(t):
             net.set_timestep(t % T)
@@ -517,7 +538,7 @@ def run_b200(a):
                 if lv_view.get("ptr") != ptr:
                     lv_view["ptr"], lv_view["t"] = ptr, torch.as_tensor(DevTensorView(ptr, n), device=dev)
                     lv_view["sum"] = torch.empty_like(lv_view["t"])
-                exchange.submit(lv_view["t"])
+                exchange.submit(lv_view["t"], None if a.exchange_eager_wait else net.wait_before_light_volume_write)
             return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
 
         def drain_resident():
@@ -527,6 +548,14 @@ def run_b200(a):
         for k in range(a.warmup):
             step_resident(1 + k)
         drain_resident()
+        if world > 1 and a.check_exchange:
+            got = exchange.result().clone()
+            want = sharding.allreduce_light_volume(lv_view["t"])
+            torch.cuda.synchronize()
+            err = float((got - want).abs().max().item())
+            ref = float(want.abs().max().item())
+            sys.stderr.write(f"[rank {rank}] exchange check ({exchange_kind}): max |diff| = {err:.3e} of max {ref:.3e}\n")
+            assert err <= 1e-5 * ref + 1e-12, "peer exchange differs from the NCCL sum"
         net.read_collision_tests(reset=True)
         host.profile_enable(True)
         host.profile_reset()
@@ -651,7 +680,7 @@ def run_b200(a):
             "config": {"workload": workload_name(a), "photons_total": n_photons * world,
                        "light_volume": f"{D // 2}^3 f32", "volume_layout": "2-D layered CUDA array (tld4)",
                        "l2": "inputs larger than L2: a different 512 MB volume every step, 128 MB photon records",
-                       "parallelism": f"photon shards x{world}, NCCL all-reduce of the light volume on a side stream (overlaps the next frame)" if world > 1 else "1 GPU"},
+                       "parallelism": f"photon shards x{world}, light volumes summed on a side stream (overlaps the next frame): {exchange_kind}" if world > 1 else "1 GPU"},
             "frames_per_sec": a.steps / (ms * 1e-3), "retrace_fraction": traced / (a.steps * n_photons * world),
             "collision_tests_per_sec": float(tests_t[0]) / (ms * 1e-3),
             "tests_fetching_voxels": fetched / tests if tests else None,

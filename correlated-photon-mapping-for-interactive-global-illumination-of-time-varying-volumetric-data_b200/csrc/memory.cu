@@ -84,6 +84,13 @@ int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev) {
     return CPM_OK;
 }
 
+int cpm_ctx_wait_cuda_event(cpm_ctx* ctx, void* cuda_event) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, cuda_event != nullptr, "null argument");
+    CPM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)cuda_event, 0));
+    return CPM_OK;
+}
+
 int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return CPM_E_INVALID;
     if (bytes == 0) return CPM_OK;

@@ -283,6 +283,11 @@ class Network:
         self._check(lib().cpmh_network_light_volume_device(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def wait_before_light_volume_write(self, event):
+        """the next write to the light volume waits for `event` (torch.cuda.Event recorded on another stream)"""
+        self._keep_event = event
+        self._check(lib().cpmh_network_wait_before_light_volume_write(self.h, C.c_void_p(event.cuda_event)))
+
     def photons_device(self):
         """(device pointer, number of floats) of the photon records"""
         p, n = C.c_void_p(), C.c_size_t()

@@ -272,6 +272,12 @@ int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_fl
     });
 }
 
+int cpmh_network_wait_before_light_volume_write(cpmh_network* net, void* cuda_event) {
+    if (!net) return CPM_E_INVALID;
+    net->toLightVolume.waitBeforeLightVolumeWrite = cuda_event;
+    return CPM_OK;
+}
+
 int cpmh_network_photons_device(cpmh_network* net, void** ptr, size_t* n_floats) {
     return guarded([&]() {
         auto p = std::const_pointer_cast<PhotonData>(net->tracer.outport_.getData());

@@ -72,6 +72,10 @@ CPMH_API int cpmh_network_sync(cpmh_network* net);
 CPMH_API int cpmh_network_light_volume_device(cpmh_network* net, void** ptr, size_t* n_floats);
 /* device pointer of the photon records (float8 x N x maxScatteringEvents) for zero-copy consumers (the
  * photon-map gather) */
+/* The next evaluation's first write to the light volume waits for `cuda_event` (a cudaEvent_t recorded on another
+ * stream by a consumer that is still reading the volume -- the multi-GPU exchange's snapshot); everything before that
+ * write (detector, selection, re-trace) is not held up.  One-shot. */
+CPMH_API int cpmh_network_wait_before_light_volume_write(cpmh_network* net, void* cuda_event);
 CPMH_API int cpmh_network_photons_device(cpmh_network* net, void** ptr, size_t* n_floats);
 /* count delta-tracking collision tests of every trace from now on (device counter); read = sync */
 CPMH_API int cpmh_network_count_collision_tests(cpmh_network* net, int on);

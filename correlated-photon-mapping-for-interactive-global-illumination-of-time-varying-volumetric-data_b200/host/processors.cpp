@@ -1300,6 +1300,12 @@ void PhotonToLightVolumeProcessorCL::process() {
     const float* photonsDev = static_cast<const float*>(photonData->photons_.deviceRead());
     lastPath = "none";
     bool prevInSync = false;
+    auto beforeWrite = [&]() {
+        if (waitBeforeLightVolumeWrite) {
+            rt.check(cpm_ctx_wait_cuda_event(rt.ctx(), waitBeforeLightVolumeWrite));
+            waitBeforeLightVolumeWrite = nullptr;
+        }
+    };
     if (idxData && prevPhotons_.getSize() == photonData->photons_.getSize() && nRecomputed > 0 && nRecomputed < maxRecomputationPhotons) {
         // incremental: remove the old contribution of the re-traced photons, add the new one (:262-274)
         auto* idxBuf = const_cast<Buffer<unsigned int>*>(&idxData->indicesToRecomputedPhotons);
@@ -1307,6 +1313,7 @@ void PhotonToLightVolumeProcessorCL::process() {
         float* lv = static_cast<float*>(const_cast<void*>(lightVolume_->deviceRead()));
         lightVolume_->deviceWrite();
         ScopedStage st("splat");
+        beforeWrite();
         // (the kernel leaves prevPhotons_ equal to the new records of the listed ids: no whole-buffer copy below)
         rt.check(cpm_splat_photons_update_sync(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim,
                                                static_cast<float*>(prevPhotons_.deviceWrite()), photonsDev, idx, nRecomputed, N, I,
@@ -1316,6 +1323,7 @@ void PhotonToLightVolumeProcessorCL::process() {
     } else if (prevPhotons_.getSize() != photonData->photons_.getSize() || nRecomputed < 0 || nRecomputed >= maxRecomputationPhotons) {
         float* lv = static_cast<float*>(lightVolume_->deviceWrite());
         ScopedStage st("splat");
+        beforeWrite();
         rt.check(cpm_mem_fill_u32(rt.ctx(), lv, 0u, od.x * od.y * od.z * (size_t)channels));
         const int n = referenceFullSplatBound ? N : N * I;
         rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, photonsDev, nullptr, n, N, I, radius, scale, 1.f));

@@ -365,6 +365,9 @@ public:
     DataInport<Volume> volumeInport_;
     DataInport<PhotonData> photons_;
     DataInport<RecomputedPhotonIndices> recomputedPhotonIndicesPort_;
+    // one-shot: a cudaEvent_t the next write to the light volume waits for (a consumer on another stream, e.g. the
+    // multi-GPU exchange, is still reading the volume); cleared once waited for
+    void* waitBeforeLightVolumeWrite = nullptr;
     DataOutport<Volume> outport_;
     FloatProperty incrementalRecomputationThreshold_;
     OptionProperty<int> volumeSizeOption_;

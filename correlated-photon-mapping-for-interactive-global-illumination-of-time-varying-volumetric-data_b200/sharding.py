@@ -60,7 +60,10 @@ class LightVolumeExchange:
         self.side = None
         self.copied = None
 
-    def submit(self, local: torch.Tensor) -> None:
+    def submit(self, local: torch.Tensor, defer_wait=None) -> None:
+        """defer_wait(event): instead of making the launch stream wait for the snapshot copy right away, hand the event
+        to the only writer of `local` (host.Network.wait_before_light_volume_write): the next frame's detector and
+        re-trace then start at once and only its splat waits -- by then the copy is long done."""
         if not is_distributed():
             self.pending = (None, local)
             return
@@ -86,7 +89,10 @@ class LightVolumeExchange:
             b.copy_(local, non_blocking=True)
             self.copied.record(self.side)
             work = dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        cur.wait_event(self.copied)             # the next frame may touch `local` once the snapshot is taken
+        if defer_wait is not None:
+            defer_wait(self.copied)
+        else:
+            cur.wait_event(self.copied)         # the next frame may touch `local` once the snapshot is taken
         b.record_stream(self.side)
         self.pending = (work, b)
 
@@ -99,6 +105,81 @@ class LightVolumeExchange:
             work.wait()                          # current stream waits for the collective
             self.pending = (None, b)
         return b
+
+
+class PeerLightVolumeExchange:
+    """LightVolumeExchange with the sum done by cpm_allreduce_peer_f32 (csrc/exchange.cu) instead of NCCL: the snapshot
+    buffers are symmetric memory (torch.distributed._symmetric_memory: one allocation per rank, peer and NVSwitch
+    multicast mappings exchanged once), and one small kernel per rank reduces its slice over NVLink -- in the switch
+    (multimem.ld_reduce / multimem.st) where the node has multicast support, with peer loads in rank order otherwise.
+    On the side stream: snapshot copy -> barrier (all snapshots written) -> kernel -> barrier (all slices stored);
+    the barriers are the symmetric-memory signal-pad barriers, the kernel itself never waits on another GPU.
+    Same interface and result semantics as LightVolumeExchange; raises at construction if symmetric memory cannot be
+    set up on this node (the caller falls back to NCCL)."""
+
+    def __init__(self, cpm, n_floats: int, device, group=None, max_ctas: int = 0, use_multicast: bool = True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        if not is_distributed():
+            raise RuntimeError("PeerLightVolumeExchange needs an initialised process group with world size > 1")
+        if n_floats % 4:
+            raise ValueError("the light volume must hold a multiple of 4 floats")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("at most 8 peers (one NVLink domain)")
+        self.n = n_floats
+        self.max_ctas = max_ctas
+        self.side = torch.cuda.Stream(device=device)
+        self.copied = torch.cuda.Event()
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ctx = cpm.Context(device.index, self.side.cuda_stream)      # launches on the side stream
+        self.bufs, self.hdls, self.peer_arrays, self.mc = [], [], [], []
+        for _ in range(2):
+            b = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(b, self.group.group_name)
+            ptrs = (C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+            mc = int(h.multicast_ptr) if (use_multicast and h.has_multicast_support and h.multicast_ptr) else 0
+            self.bufs.append(b); self.hdls.append(h); self.peer_arrays.append(ptrs); self.mc.append(mc)
+        self.multicast = all(m != 0 for m in self.mc)
+        self.turn = 0
+        self.pending = None
+        self._lib = cpm.lib()
+        self._C = C
+
+    def submit(self, local: torch.Tensor, defer_wait=None) -> None:
+        i = self.turn
+        self.turn ^= 1
+        b, h = self.bufs[i], self.hdls[i]
+        cur = torch.cuda.current_stream(local.device)
+        self.side.wait_stream(cur)              # this frame's splat has to be complete
+        with torch.cuda.stream(self.side):
+            b.copy_(local.reshape(-1), non_blocking=True)
+            self.copied.record(self.side)
+            h.barrier(channel=i)                # every rank's snapshot is in place
+            rc = self._lib.cpm_allreduce_peer_f32(self.ctx.h, self.peer_arrays[i], self._C.c_void_p(self.mc[i] if self.multicast else 0),
+                                                  self._C.c_size_t(self.n), self.rank, self.world, int(self.max_ctas))
+            if rc != 0:
+                raise RuntimeError(f"cpm_allreduce_peer_f32 failed: {rc}")
+            h.barrier(channel=i)                # every rank's slice is stored everywhere
+            self.done[i].record(self.side)
+        if defer_wait is not None:
+            defer_wait(self.copied)             # only the next write to `local` waits (see LightVolumeExchange.submit)
+        else:
+            cur.wait_event(self.copied)         # the next frame may touch `local` once the snapshot is taken
+        self.pending = i
+
+    def result(self) -> torch.Tensor:
+        """the most recently submitted sum; the current stream is made to wait for it"""
+        if self.pending is None:
+            raise RuntimeError("PeerLightVolumeExchange.result() before submit()")
+        i = self.pending
+        torch.cuda.current_stream(self.bufs[i].device).wait_event(self.done[i])
+        return self.bufs[i]
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.ctx.close()
 
 
 # ---- option A of SURVEY 8e: replicated photon map, image tiles per GPU --------------------------------------------

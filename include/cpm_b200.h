@@ -364,6 +364,19 @@ CPM_API int cpm_splat_photons_update_sync(cpm_ctx* ctx, float* light_volume, int
                                           const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
                                           float radius, float relative_irradiance_scale);
 
+/* ---- multi-GPU exchange (option B) --------------------------------------------------------------- */
+/* Sum of the per-GPU light volumes over NVLink peer memory, in place: peer_buffers[r] (r < world; host array of device
+ * pointers, this GPU's mapping of rank r's buffer, all n_floats long) each hold one rank's volume on entry and the sum
+ * on return.  Rank `rank` reduces the rank-th slice and stores it to every buffer.  multicast != NULL: the NVSwitch
+ * multicast mapping of the same buffers -- the reduction and the broadcast are done by the switch (multimem.ld_reduce /
+ * multimem.st) and peer_buffers may be NULL; otherwise peer loads in rank order (every rank gets the same bits) and peer
+ * stores.  No inter-GPU synchronisation inside: the caller orders "all ranks wrote their buffer" -> this call -> "all
+ * ranks finished" with barriers on the same stream.  max_ctas <= 0: default (48).  Replaces nothing in the reference
+ * (single GPU); the role of the proposed cpm_allreduce_lightvol. */
+#define CPM_MAX_PEERS 8
+CPM_API int cpm_allreduce_peer_f32(cpm_ctx* ctx, float* const* peer_buffers, float* multicast, size_t n_floats,
+                                   int rank, int world, int max_ctas);
+
 /* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
 /* Not launched anywhere in the reference; the estimator is the reference's
  * (Epanechnikov kernel, ppm/cl/densityestimationkernel.cl:56-60; power * 1/(4 pi) * relativeIrradianceScale,
@@ -453,6 +466,8 @@ CPM_API int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size
  * cpm_ctx_wait_event makes the context stream wait for before dst is consumed.  src_host must be pinned. */
 CPM_API int cpm_mem_prefetch_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes, cpm_event** done);
 CPM_API int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev);
+/* the same for an event owned by the caller's runtime (a cudaEvent_t, e.g. torch.cuda.Event.cuda_event) */
+CPM_API int cpm_ctx_wait_cuda_event(cpm_ctx* ctx, void* cuda_event);
 /* overlapping ranges are allowed when dst < src (the index-list slide-down of
  * ppm/processor/progressivephotontracercl.cpp:389-419) */
 CPM_API int cpm_mem_copy_d2d(cpm_ctx* ctx, void* dst, const void* src, size_t bytes);

@@ -152,3 +152,29 @@ def test_photon_shards_equal_one_large_photon_set(cpm, orc, synth, torch_cuda):
         host.set_photon_shard_offset(0)
     rel = np.sqrt(((lv_sum - 2.0 * big_lv) ** 2).mean()) / np.sqrt(((2.0 * big_lv) ** 2).mean())
     assert rel < 1e-5, rel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n", [(2, 4096), (3, 1000 * 4), (8, 4 * 12345)])
+def test_cuda_peer_allreduce_kernel_single_gpu(cpm, ctx, torch_cuda, world, n):
+    """cpm_allreduce_peer_f32 (csrc/exchange.cu), peer-load path, with all `world` buffers on one GPU and the ranks'
+    calls issued one after the other: every rank reduces its slice in rank order and stores it to every buffer, so
+    afterwards all buffers hold the same sum, bit for bit the rank-ordered fp32 sum.  (The NVSwitch multimem path and
+    real peer mappings are exercised by bench.py --gpus N --check-exchange.)"""
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bufs = [torch.rand(n, dtype=torch.float32, device="cuda", generator=g) * (r + 1) for r in range(world)]
+    want = bufs[0].clone()
+    for r in range(1, world):
+        want = want + bufs[r]
+    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    for r in range(world):
+        rc = cpm.lib().cpm_allreduce_peer_f32(ctx.h, ptrs, C.c_void_p(0), C.c_size_t(n), r, world, 0)
+        assert rc == 0
+    ctx.sync()
+    for b in bufs:
+        assert torch.equal(b, want)
+    # argument errors
+    assert cpm.lib().cpm_allreduce_peer_f32(ctx.h, ptrs, C.c_void_p(0), C.c_size_t(n + 1), 0, world, 0) < 0
+    assert cpm.lib().cpm_allreduce_peer_f32(ctx.h, ptrs, C.c_void_p(0), C.c_size_t(n), world, world, 0) < 0
+    assert cpm.lib().cpm_allreduce_peer_f32(ctx.h, ptrs, C.c_void_p(0), C.c_size_t(n), 0, 9, 0) < 0
