@@ -23,6 +23,8 @@ struct cpm_ctx {
     void* comm = nullptr;  // ncclComm_t when multi-GPU is initialised
     cudaStream_t xfer_stream = nullptr;  // transfer stream of cpm_mem_prefetch_h2d (lazy)
     cudaEvent_t xfer_fence = nullptr;
+    cudaEvent_t select_done = nullptr;   // cpm_select_below_begin / _end
+    bool select_pending = false;
 };
 
 struct cpm_event {

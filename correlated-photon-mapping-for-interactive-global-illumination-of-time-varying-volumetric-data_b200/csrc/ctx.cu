@@ -94,6 +94,7 @@ void cpm_ctx_destroy(cpm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->select_done) cudaEventDestroy(ctx->select_done);
     if (ctx->xfer_stream) {
         cudaStreamSynchronize(ctx->xfer_stream);
         cudaStreamDestroy(ctx->xfer_stream);

@@ -514,11 +514,9 @@ static int reduce_common(cpm_ctx* ctx, bool count_below, const uint32_t* data, u
     return CPM_OK;
 }
 
-int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out,
-                     long long* count_host) {
+int cpm_select_below_begin(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out) {
     if (!ctx) return CPM_E_INVALID;
-    CPM_REQUIRE(ctx, count_host != nullptr, "result pointer is NULL");
-    *count_host = 0;
+    ctx->select_pending = false;
     if (n == 0) return CPM_OK;
     CPM_REQUIRE(ctx, data && ids_out, "null buffer");
     if (n >= (1ull << 30)) return cpm_fail(ctx, CPM_E_UNSUPPORTED, "cpm_select_below: n must be < 2^30");
@@ -534,9 +532,31 @@ int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t thre
                (unsigned)tiles);
     unsigned long long* pinned = (unsigned long long*)ctx->pinned;
     CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
-    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *count_host = (long long)*pinned;
+    if (!ctx->select_done) CPM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->select_done, cudaEventDisableTiming));
+    CPM_CUDA(ctx, cudaEventRecord(ctx->select_done, ctx->stream));
+    ctx->select_pending = true;
     return CPM_OK;
+}
+
+int cpm_select_below_end(cpm_ctx* ctx, long long* count_host) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, count_host != nullptr, "result pointer is NULL");
+    *count_host = 0;
+    if (!ctx->select_pending) return CPM_OK;   // n == 0
+    ctx->select_pending = false;
+    CPM_CUDA(ctx, cudaEventSynchronize(ctx->select_done));
+    *count_host = (long long)*(unsigned long long*)ctx->pinned;
+    return CPM_OK;
+}
+
+int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out,
+                     long long* count_host) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, count_host != nullptr, "result pointer is NULL");
+    *count_host = 0;
+    int rc = cpm_select_below_begin(ctx, data, n, threshold, ids_out);
+    if (rc != CPM_OK) return rc;
+    return cpm_select_below_end(ctx, count_host);
 }
 
 int cpm_reduce_sum_i32(cpm_ctx* ctx, const int32_t* data, size_t n, long long* result_host) {

@@ -654,6 +654,23 @@ void PhotonTracerCL::setRandomSeedSize(size_t nPhotons) {
         MWC64XSeedGenerator().generateRandomSeeds(&randomState_, 0, false);   // seed 0: ppm/photontracercl.cpp:180
     }
 }
+void PhotonTracerCL::prepareOpacityBound(const Volume* volume, TransferFunction& tf) {
+    if (!useOpacityBound) return;
+    auto& rt = CpmRuntime::get();
+    // per-cell opacity bound of (this volume, this transfer function): refreshed when either changed
+    size_t nCells = 0;
+    const float* range = const_cast<Volume*>(volume)->valueRange(boundCellLog2, &nCells);
+    if (opacityBound_.getSize() != nCells || boundVolumeVersion_ != volume->dataVersion() || boundTfVersion_ != tf.version()) {
+        ScopedStage st("bound");
+        float scale, offset;
+        volume->formatScaleOffset(scale, offset);
+        opacityBound_.setSize(nCells);
+        float* bound = static_cast<float*>(opacityBound_.deviceWrite());
+        rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tf.deviceData(), (int)tf.getTextureSize(), bound));
+        boundVolumeVersion_ = volume->dataVersion();
+        boundTfVersion_ = tf.version();
+    }
+}
 void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, const vec4 aabb[2],
                                   const AdvancedMaterialProperty& material, float stepSize, const LightSamples* lightSamples,
                                   Buffer<unsigned int>* recomputeIdx, int nInvalidPhotons, int photonOffset, int /*batch*/,
@@ -689,20 +706,7 @@ void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, co
     photons = static_cast<float*>(photonOutData->photons_.deviceWrite());
     const float* tfData = tf.deviceData();
     if (useOpacityBound) {
-        // per-cell opacity bound of (this volume, this transfer function): refreshed when either changed
-        size_t nCells = 0;
-        const float* range = const_cast<Volume*>(volume)->valueRange(boundCellLog2, &nCells);
-        if (opacityBound_.getSize() != nCells || boundVolumeVersion_ != volume->dataVersion() || boundTfVersion_ != tf.version()) {
-            ScopedStage st("bound");
-            float scale, offset;
-            volume->formatScaleOffset(scale, offset);
-            opacityBound_.setSize(nCells);
-            float* bound = static_cast<float*>(opacityBound_.deviceWrite());
-            rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tfData, (int)tf.getTextureSize(), bound));
-
-            boundVolumeVersion_ = volume->dataVersion();
-            boundTfVersion_ = tf.version();
-        }
+        prepareOpacityBound(volume, tf);
         p.opacity_bound = static_cast<const float*>(opacityBound_.deviceRead());
         p.bound_cell_log2 = boundCellLog2;
     }
@@ -1001,8 +1005,12 @@ void ProgressivePhotonTracerCL::process() {
             StageProfiler::get().begin("select");
             long long nInvalid = 0;
             const uint32_t* keys = static_cast<const uint32_t*>(photonRecomputationImportance_.deviceRead());
-            rt.check(cpm_select_below(rt.ctx(), keys, N, 2147483647u, static_cast<uint32_t*>(indices.deviceWrite()), &nInvalid));
+            rt.check(cpm_select_below_begin(rt.ctx(), keys, N, 2147483647u, static_cast<uint32_t*>(indices.deviceWrite())));
             StageProfiler::get().end();
+            // the count is on its way to the host: the device meanwhile refreshes the tracer's opacity bound, which
+            // the re-trace needs whatever the count is
+            photonTracer_.prepareOpacityBound(volume, transferFunction_.get());
+            rt.check(cpm_select_below_end(rt.ctx(), &nInvalid));
             const long long budget = static_cast<long long>((maxIncrementalPhotonsToUpdate_.get() / 100.f) * (float)N);
             selectionIsSorted_ = spatialSorting_.get() && nInvalid <= budget;
             if (!selectionIsSorted_) {

@@ -222,6 +222,9 @@ public:
                       const AdvancedMaterialProperty& material, float stepSize, const LightSamples* lightSamples,
                       Buffer<unsigned int>* photonsToRecomputeIndices, int nInvalidPhotons, int photonOffset, int batch,
                       int maxInteractions, PhotonData* photonOutData);
+    // refresh of the per-cell opacity bound of (volume, transfer function) if either changed; tracePhotons calls it,
+    // and a caller may do so earlier to overlap it with something else (idempotent)
+    void prepareOpacityBound(const Volume* volume, TransferFunction& transferFunction);
     void setRandomSeedSize(size_t nPhotons);
     void setNoSingleScattering(bool v) { onlyMultipleScattering_ = v; }
     void setProgressive(bool v) { progressive_ = v; }

@@ -267,6 +267,12 @@ CPM_API int cpm_count_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32
  * sorts.  SYNCHRONOUS (returns the count). */
 CPM_API int cpm_select_below(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out,
                              long long* count_host);
+/* The same in two halves, so that the caller can enqueue work that does not depend on the count (e.g. the tracer's
+ * opacity-bound refresh) while the count travels to the host: _begin launches the selection and the copy of the count,
+ * _end waits for that copy only -- not for work enqueued after _begin -- and returns the count.  No other call that
+ * returns a value synchronously (cpm_count_below, cpm_reduce_sum_i32, cpm_select_below) may come in between. */
+CPM_API int cpm_select_below_begin(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_t threshold, uint32_t* ids_out);
+CPM_API int cpm_select_below_end(cpm_ctx* ctx, long long* count_host);
 
 /* clogs::Radixsort::enqueue (rsc/ext/clogs/radixsort.h:227-262, src/radixsort.cpp:169-259) for
  * TYPE_UINT keys with TYPE_UINT values (values == NULL: keys only, as recomputationIndexSorter_).
