@@ -68,6 +68,7 @@ def parse():
                     help="the launch stream waits for the snapshot copy right after the frame (A/B; default: only the next splat waits)")
     ap.add_argument("--check-exchange", action="store_true", help="compare the first exchanged sum with NCCL's")
     ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
+    ap.add_argument("--gather-grid-scale", type=float, default=1.0, help="photon-map cells per 2r along an axis (tuning sweeps)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
     return ap.parse_args()
 
@@ -321,7 +322,7 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
     synth = importlib.import_module(PKG + ".synth")
     tf = torch.from_numpy(synth.rasterise_tf(width=1024)).to(dev)
     radius = float(np.float32(np.sqrt(3.0) / D))                       # the tracer's 1-voxel photon radius
-    g = int(min(512, max(1, int(1.0 / (2.0 * radius)))))                # cell edge >= 2 r: at most 8 cells per gather
+    g = int(min(512, max(1, int(a.gather_grid_scale / (2.0 * radius)))))   # scale 1: cell edge >= 2 r (at most 8 cells per point)
     scale = float((1.0 / np.pi) / (4.0 / 3.0 * np.pi * radius ** 3 * n * world))
     # per-cell opacity bound of (this volume, this TF), as the tracer keeps it: the value-range grid is per-step data
     # like the min-max grid (untimed), the TF classification of its cells belongs to the frame (timed with the build)
