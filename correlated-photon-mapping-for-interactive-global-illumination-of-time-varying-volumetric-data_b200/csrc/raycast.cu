@@ -60,7 +60,39 @@ __device__ __forceinline__ void sample_light(const RaycastArgs& A, float px, flo
     }
 }
 
-template <int FMT, int LAYOUT, int NCH>
+// the same sample for the one-channel light volume in two steps, so that the taps of several samples can be in flight
+struct LightTaps {
+    float t[8];   // t000 t100 t010 t110 t001 t101 t011 t111
+    float a, b, c;
+};
+__device__ __forceinline__ LightTaps fetch_light1(const RaycastArgs& A, float px, float py, float pz) {
+    LightTaps T;
+    const float fx = (float)A.lx, fy = (float)A.ly, fz = (float)A.lz;
+    float u = fmaf(px, fx, -0.5f), v = fmaf(py, fy, -0.5f), w = fmaf(pz, fz, -0.5f);
+    float fu = floorf(u), fv = floorf(v), fw = floorf(w);
+    T.a = u - fu; T.b = v - fv; T.c = w - fw;
+    int i0 = (int)cpm_clamp(fu, -1.0f, fx - 1.0f), j0 = (int)cpm_clamp(fv, -1.0f, fy - 1.0f), k0 = (int)cpm_clamp(fw, -1.0f, fz - 1.0f);
+    int i1 = min(i0 + 1, A.lx - 1), j1 = min(j0 + 1, A.ly - 1), k1 = min(k0 + 1, A.lz - 1);
+    i0 = max(i0, 0); j0 = max(j0, 0); k0 = max(k0, 0);
+    const size_t sy = (size_t)A.lx, sz = (size_t)A.lx * A.ly;
+    const size_t b00 = (size_t)k0 * sz + (size_t)j0 * sy, b10 = (size_t)k0 * sz + (size_t)j1 * sy;
+    const size_t b01 = (size_t)k1 * sz + (size_t)j0 * sy, b11 = (size_t)k1 * sz + (size_t)j1 * sy;
+    const float* L = A.lv;
+    T.t[0] = __ldg(L + b00 + i0); T.t[1] = __ldg(L + b00 + i1); T.t[2] = __ldg(L + b10 + i0); T.t[3] = __ldg(L + b10 + i1);
+    T.t[4] = __ldg(L + b01 + i0); T.t[5] = __ldg(L + b01 + i1); T.t[6] = __ldg(L + b11 + i0); T.t[7] = __ldg(L + b11 + i1);
+    return T;
+}
+__device__ __forceinline__ float blend_light1(const LightTaps& T) {   // the arithmetic of sample_light<1>, same order
+    float x00 = lerpf(T.t[0], T.t[1], T.a), x10 = lerpf(T.t[2], T.t[3], T.a);
+    float x01 = lerpf(T.t[4], T.t[5], T.a), x11 = lerpf(T.t[6], T.t[7], T.a);
+    return lerpf(lerpf(x00, x10, T.b), lerpf(x01, x11, T.b), T.c);
+}
+
+// Samples are taken RB at a time: the voxel taps of the whole batch are requested together, then the light-volume taps
+// of its visible samples, then the batch is composited in order.  A sample in a transparent cell that a one-at-a-time
+// march would have stepped over has opacity exactly 0 and contributes nothing, and samples behind the one that ends the
+// ray are dropped: the image is that of the plain loop, bit for bit.
+template <int FMT, int LAYOUT, int NCH, int RB>
 __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs A, unsigned* __restrict__ tile_counter) {
     extern __shared__ float4 s_tf[];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_tf[i] = A.tf[i];
@@ -91,36 +123,65 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs A, unsig
                 ix = 1.0f / R.dx; iy = 1.0f / R.dy; iz = 1.0f / R.dz;
             }
             int k = 0;
-            while (true) {
+            bool done = false;
+            while (!done) {
                 float t = fmaf((float)k + 0.5f, P.step, t0);
                 if (A.bound.g) k = skip_transparent(A.bound, R, ix, iy, iz, t0, t1, P.step, inv_step, k, t);
                 if (!(t < t1)) break;
-                float x = fmaf(t, d.x, o.x), y = fmaf(t, d.y, o.y), z = fmaf(t, d.z, o.z);
-                float v = sample_volume<FMT, LAYOUT>(A.vol, x, y, z);
-                float4 c = sample_tf_rgba(s_tf, A.tf_width, ftfw, v);
-                if (c.w > 0.0f) {
-                    float e[3];
-                    sample_light<NCH>(A, x, y, z, e);
-                    float Ts = cpm_expf(-(c.w * P.sigma_scale) * P.step);
-                    float wgt = T * (1.0f - Ts);
-                    lr = fmaf(wgt * c.x, e[0], lr);
-                    lg = fmaf(wgt * c.y, e[1], lg);
-                    lb = fmaf(wgt * c.z, e[2], lb);
-                    T *= Ts;
-                    if (T < 1e-4f) break;
+                float tj[RB];
+                Taps tp[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    tj[j] = fmaf((float)(k + j) + 0.5f, P.step, t0);
+                    tp[j] = fetch_taps<FMT, LAYOUT>(A.vol, fmaf(tj[j], d.x, o.x), fmaf(tj[j], d.y, o.y), fmaf(tj[j], d.z, o.z));
                 }
-                ++k;
+                float4 c[RB];
+                bool vis[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    c[j] = sample_tf_rgba(s_tf, A.tf_width, ftfw, blend_taps<FMT>(A.vol, tp[j]));
+                    vis[j] = tj[j] < t1 && c[j].w > 0.0f;
+                }
+                LightTaps lt[NCH == 1 ? RB : 1];
+                if (NCH == 1) {
+#pragma unroll
+                    for (int j = 0; j < RB; ++j)
+                        if (vis[j]) lt[j] = fetch_light1(A, fmaf(tj[j], d.x, o.x), fmaf(tj[j], d.y, o.y), fmaf(tj[j], d.z, o.z));
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    if (done) continue;
+                    if (!(tj[j] < t1)) {
+                        done = true;
+                        continue;
+                    }
+                    if (vis[j]) {
+                        float e[3];
+                        if (NCH == 1)
+                            e[0] = e[1] = e[2] = blend_light1(lt[j]);
+                        else
+                            sample_light<NCH>(A, fmaf(tj[j], d.x, o.x), fmaf(tj[j], d.y, o.y), fmaf(tj[j], d.z, o.z), e);
+                        float Ts = cpm_expf(-(c[j].w * P.sigma_scale) * P.step);
+                        float wgt = T * (1.0f - Ts);
+                        lr = fmaf(wgt * c[j].x, e[0], lr);
+                        lg = fmaf(wgt * c[j].y, e[1], lg);
+                        lb = fmaf(wgt * c[j].z, e[2], lb);
+                        T *= Ts;
+                        if (T < 1e-4f) done = true;
+                    }
+                }
+                k += RB;
             }
         }
         A.image[(size_t)py * P.width + px] = make_float4(lr, lg, lb, 1.0f - T);
     }
 }
 
-template <int FMT, int LAYOUT, int NCH>
-int launch_raycast(cpm_ctx* ctx, const RaycastArgs& a) {
+template <int FMT, int LAYOUT, int NCH, int RB>
+int launch_raycast_rb(cpm_ctx* ctx, const RaycastArgs& a) {
     size_t smem = (size_t)a.tf_width * sizeof(float4);
     if (smem > 48 * 1024)
-        CPM_CUDA(ctx, cudaFuncSetAttribute(raycast_kernel<FMT, LAYOUT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPM_CUDA(ctx, cudaFuncSetAttribute(raycast_kernel<FMT, LAYOUT, NCH, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* scratch;
     int rc = cpm_scratch(ctx, 4096, &scratch);
     if (rc != CPM_OK) return rc;
@@ -128,13 +189,24 @@ int launch_raycast(cpm_ctx* ctx, const RaycastArgs& a) {
     CPM_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
     int tiles = ((a.p.width + 7) / 8) * ((a.p.height + 3) / 4);
     int per_sm = 0;
-    CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<FMT, LAYOUT, NCH>, 128, smem));
+    CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raycast_kernel<FMT, LAYOUT, NCH, RB>, 128, smem));
     unsigned grid = (unsigned)std::min<long long>((long long)ctx->sm_count * std::max(per_sm, 1), (long long)cpm_div_up(tiles, 4));
-    CPM_LAUNCH(ctx, (raycast_kernel<FMT, LAYOUT, NCH>), grid, 128, smem, a, counter);
+    CPM_LAUNCH(ctx, (raycast_kernel<FMT, LAYOUT, NCH, RB>), grid, 128, smem, a, counter);
     return CPM_OK;
 }
 
 }  // namespace
+
+#ifndef CPM_RAYCAST_BATCH
+#define CPM_RAYCAST_BATCH 4   // samples whose taps are in flight together
+#endif
+template <int FMT, int LAYOUT, int NCH>
+int launch_raycast(cpm_ctx* ctx, const RaycastArgs& a) {
+    static const int rb = getenv("CPM_RAYCAST_BATCH") ? atoi(getenv("CPM_RAYCAST_BATCH")) : CPM_RAYCAST_BATCH;   // tuning sweeps only
+    if (rb >= 4) return launch_raycast_rb<FMT, LAYOUT, NCH, 4>(ctx, a);
+    if (rb >= 2) return launch_raycast_rb<FMT, LAYOUT, NCH, 2>(ctx, a);
+    return launch_raycast_rb<FMT, LAYOUT, NCH, 1>(ctx, a);
+}
 
 extern "C" int cpm_raycast_light_volume(cpm_ctx* ctx, const cpm_volume* vol, const float* tf_rgba, int tf_width,
                                         const cpm_gather_params* params, const float* light_volume, const int lv_dims[3],
