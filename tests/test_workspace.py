@@ -139,3 +139,36 @@ def test_network_from_workspace_equals_network_configured_by_hand(host, cpm, syn
         a.load_workspace(f.name)
     assert "maxScatteringEvents" in str(e.value)
     a.close(); b.close()
+
+
+def test_generated_workspaces_round_trip_through_describe(host, tmp_path):
+    """structure check on machine-written files: comments, declarations, single-quoted and escaped attribute values,
+    deep property nesting, ports that carry ids on either end of a connection"""
+    import random
+    rnd = random.Random(7)
+    for case in range(20):
+        n = rnd.randint(1, 6)
+        procs, names = [], []
+        for i in range(n):
+            name = f"P {i} <&> 'q'"
+            esc = name.replace("&", "&amp;").replace("<", "&lt;").replace(">", "&gt;").replace("'", "&apos;")
+            names.append(name)
+            depth = rnd.randint(0, 4)
+            inner = '<Property type="t" identifier="leaf"><value content="1.5" /></Property>'
+            for d in range(depth):
+                inner = f'<Property type="c" identifier="c{d}"><Properties>{inner}</Properties><!-- c --></Property>'
+            procs.append(f"""<Processor type='org.test.T{i % 2}' identifier="{esc}">
+                <InPorts><InPort type="x" identifier="in" id="refi{i}" /></InPorts>
+                <OutPorts><OutPort type="x" identifier="out" id="refo{i}" /></OutPorts>
+                <Properties>{inner}<Property type="b" identifier="flag" /></Properties></Processor>""")
+        conns = "".join(f'<Connection><OutPort type="x" identifier="out" reference="refo{i}" />'
+                        f'<InPort type="x" identifier="in" reference="refi{i + 1}" /></Connection>' for i in range(n - 1))
+        text = ('<?xml version="1.0" ?>\n<!-- generated -->\n<InviwoTreeData version="1.0"><Processors>' + "".join(procs) +
+                f"</Processors><Connections>{conns}</Connections></InviwoTreeData>\n")
+        p = tmp_path / f"gen{case}.inv"
+        p.write_text(text)
+        d = host.workspace_describe(p)
+        assert [q[1] for q in d["processors"]] == names
+        assert len(d["connections"]) == n - 1 and all("?" not in a + b for a, b in d["connections"])
+        for q in d["processors"]:
+            assert len(q[2]) == 1 and q[2][0].endswith("leaf") and q[2][0].count(".") <= 4
