@@ -626,6 +626,7 @@ def run_b200(a):
             e2e = {"value": traced_e / (wall_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                    "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": wall_e / a.steps,
                    "frames_per_sec": a.steps / (wall_e * 1e-3),
+                   "h2d_gbs": (h2d / a.steps) / (wall_e / a.steps * 1e-3) / 1e9,   # per rank: the step is PCIe bound
                    "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
                    "grid_kernels": grid_kernels,
                    "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume; the next step's "
