@@ -1,6 +1,9 @@
-# round-1 final state: ncu launch list of the bench command + full captures of the frame's kernels
-K='regex:(trace|onesweep|histogram|hist_scan|detect|splat|classify|minmax|minmax8|diff|diff8|range|range8|bound|tf_summary|select|reduce|seed_streams|fill_u32|scatter_fill|directional|mesh_intersect|uniform2d|cell_range|hash|gather|raycast|reorder|photon_cell_keys|mix)_kernel'
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 800 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/final_launches.log 2>&1
-python tools/launch_summary.py gpurun_out/final_launches.csv "python bench.py --steps 4 --warmup 3 --no-cpu   (-k <our kernels> -c 800; C4: resident leg = first frame + 3 warm-up + 4 timed frames, gather / final-image leg, e2e leg)" > gpurun_out/final_launches_summary.txt 2>&1; head -16 gpurun_out/final_launches_summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:(trace|detect|splat|select)_kernel' -s 8 -c 8 -o gpurun_out/final_frame -f python bench.py --steps 4 --warmup 3 --timesteps 8 --no-e2e --no-cpu --no-gather > gpurun_out/final_ncu_frame.log 2>&1
-tail -2 gpurun_out/final_ncu_frame.log
+# what the round-end driver does, in one gpurun call: full GPU parity suite, smoke, default bench line, reference arm
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/gpu_job.sh'
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/final_pytest.log 2>&1
+tail -5 gpurun_out/final_pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/final_smoke.log 2>&1; tail -2 gpurun_out/final_smoke.log
+python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
+tail -c 3000 gpurun_out/final_bench.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err
+tail -c 1200 gpurun_out/final_bench_ref.json
