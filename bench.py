@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU (A/B)")
     ap.add_argument("--exchange", choices=["auto", "multimem", "p2p", "nccl"], default="auto",
                     help="N > 1: how the per-rank light volumes are summed (auto: peer kernel with multimem where available)")
     ap.add_argument("--exchange-ctas", type=int, default=0, help="grid of the peer exchange kernel (0 = default)")
@@ -432,6 +433,27 @@ def gather_leg(a, cpm, torch, stream, net, vol_host, dev, sharding, rank=0, worl
     return out
 
 
+def bind_to_gpu_numa(torch, local):
+    """Multi-GPU runs: keep this rank's threads (and with them its pinned host buffers, first-touch) on the CPUs next
+    to its GPU -- /sys/bus/pci/devices/<bdf>/local_cpulist -- so that eight ranks uploading 512 MB per step do not all
+    cross the same socket link.  Returns the cpulist applied, or None (no sysfs entry, restricted cpuset, ...)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:   # noqa: BLE001 -- best effort
+        return None
+
+
 def run_b200(a):
     import ctypes as C
 
@@ -442,6 +464,7 @@ def run_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpulist = bind_to_gpu_numa(torch, local) if (world > 1 and not a.no_numa_bind) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cpm = importlib.import_module(PKG)
@@ -629,6 +652,7 @@ def run_b200(a):
                    "h2d_gbs": (h2d / a.steps) / (wall_e / a.steps * 1e-3) / 1e9,   # per rank: the step is PCIe bound
                    "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
                    "grid_kernels": grid_kernels,
+                   "cpu_affinity": cpulist,
                    "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume; the next step's "
                            "upload is announced with cpmh_network_prefetch_timestep_host and overlaps this step) -> "
                            "cpmh_network_evaluate -> cpmh_network_read_light_volume(pinned host buffer)"}
