@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[3], "C4" of SURVEY.md section 8d): a synthetic 5
 volume with 32 time steps, 2048^2 = 4 194 304 photons from one directional light, correlated re-tracing.
 A *step* is one time-step change handled the way the reference handles it (call stack D):
 importance classify -> photon re-computation detector -> count -> key/value radix sort -> index sort ->
-re-trace of the invalidated photons -> -old/+new splat into the light volume.  Everything goes through the
+re-trace of the invalidated photons -> -old/+new splat into the light volume (with the default budget the count,
+both sorts and the index sort collapse into one stable compaction).  Everything goes through the
 reference-facing host layer (libcpm_host.so, the drop-in Inviwo processor mirror) on top of the C ABI.
 
   value     photons (re)traced per second, whole job, the time series resident in HBM
@@ -18,8 +19,12 @@ reference-facing host layer (libcpm_host.so, the drop-in Inviwo processor mirror
             the CPU oracle (oracle/, a restatement of the reference's OpenCL kernels; the reference itself
             needs Inviwo + an OpenCL device, neither exists here) on all host cores, on a bounded photon sample
 
+  gather    gathered frames/s: photon-map build + view-ray-march gather (north-star 5-7), and the light-volume
+            ray caster (the reference network's own final image step)
+
 N > 1 (torchrun, one rank per GPU): weak scaling -- every GPU traces its own 4 Mi photons on disjoint MWC64X
-substreams against the replicated volume and the per-GPU light volumes are summed with an NCCL all-reduce.
+substreams against the replicated volume and the per-GPU light volumes are summed on a side stream by one kernel
+over NVLink peer memory (cpm_allreduce_peer_f32; NCCL all-reduce as the fallback and as --exchange nccl).
 """
 from __future__ import annotations
 
