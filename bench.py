@@ -72,7 +72,8 @@ def parse():
     ap.add_argument("--exchange-ctas", type=int, default=0, help="grid of the peer exchange kernel (0 = default)")
     ap.add_argument("--exchange-eager-wait", action="store_true",
                     help="the launch stream waits for the snapshot copy right after the frame (A/B; default: only the next splat waits)")
-    ap.add_argument("--check-exchange", action="store_true", help="compare the first exchanged sum with NCCL's")
+    ap.add_argument("--no-check-exchange", action="store_true",
+                    help="N > 1: skip the comparison of the first exchanged sum with NCCL's (untimed, on by default)")
     ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
     ap.add_argument("--gather-grid-scale", type=float, default=1.0, help="photon-map cells per 2r along an axis (tuning sweeps)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
@@ -127,6 +128,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_sources_sha():
+    """sha256 over the CUDA sources of the library: ties a committed ncu capture to the code it measured"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / PKG / "csrc").glob("*.cu*")) + [ROOT / "include" / "cpm_detmath.h", ROOT / "Makefile"]:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def profile_counters():
+    """DRAM traffic and issue counters of trace_kernel from the committed ncu capture (profiles/roofline_traffic.json,
+    written by tools/update_roofline_traffic.py from a `ncu --set full` run of this benchmark).  Only reported when the
+    capture was taken from the kernel sources being run; otherwise null + the reason."""
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    try:
+        d = json.loads(tp.read_text())
+    except Exception:   # noqa: BLE001
+        return {"traffic": None, "counters": None, "traffic_source": "no profiles/roofline_traffic.json"}
+    sha = kernel_sources_sha()
+    if d.get("kernel_sources_sha") != sha:
+        return {"traffic": None, "counters": None,
+                "traffic_source": f"stale: capture of sources {d.get('kernel_sources_sha')}, running {sha}"}
+    return {"traffic": d.get("trace_kernel_dram_bytes_per_launch"), "counters": d.get("counters"),
+            "traffic_source": d.get("source")}
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -143,115 +171,67 @@ def hbm_peak():
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's correlated frame on a photon sample
 class CpuArm:
-    """The reference's per-frame algorithm executed by the CPU oracle with OpenMP."""
+    """The reference's per-frame algorithm executed by the CPU oracle with OpenMP
+    (oracle/frame.py: the same class the parity tests check the GPU network against).  Light set-up, transfer-function
+    rasterisation and photon streams are the GPU arm's, so on the full photon grid both arms re-trace the same photons."""
 
     def __init__(self, a, volumes, n_side):
-        from oracle import orc
+        from oracle import frame, orc
         self.orc, self.a, self.vols = orc, a, volumes
         synth = importlib.import_module(PKG + ".synth")
-        self.synth = synth
-        self.dims = (a.dims,) * 3
-        self.I = a.max_interactions
-        self.tf = synth.rasterise_tf(width=1024)
-        d = synth.normalize(LIGHT_DIR)
-        o, u, v = orc.fit_light_plane(synth.CUBE_VERTICES, np.float32([0.5, 0.5, 0.5]) - 2 * d, d)
-        area = float(np.float32(np.linalg.norm(u)) * np.float32(np.linalg.norm(v)))
-        n = n_side * n_side
-        s = orc.sample_uniform2d(n_side, n_side, n)
-        self.ls = orc.light_sample_directional(s, (1, 1, 1), d, o, u, v, area)
-        self.isect = orc.light_mesh_intersect(synth.CUBE_VERTICES, synth.CUBE_INDICES, self.ls)
-        self.n = n
-        self.rng = orc.rng_seed_streams(orc.rng_host_base_offsets(0, n))
-        self.photons = np.zeros((n * self.I, 8), np.float32)
-        self.prev = np.zeros_like(self.photons)
-        self.keys = np.full(n, 0x7FFFFFFF, np.uint32)
-        pts = synth.WS_TF_POINTS
-        self.tfpos = np.array([0.0] + [p[0] for p in pts] + [1.0], np.float32)
-        self.tfcol = np.ascontiguousarray(np.array([pts[0][1]] + [p[1] for p in pts] + [pts[-1][1]], np.float32))
+        dims = (a.dims,) * 3
+        light = frame.directional_light(n_side, LIGHT_DIR)
+        self.net = frame.OracleNetwork(dims, [light], frame.rasterise_tf(synth.WS_TF_POINTS), synth.WS_TF_POINTS,
+                                       max_interactions=a.max_interactions)
+        self.n = self.net.n
         self.region = 8
-        self.gd = tuple(-(-x // self.region) for x in self.dims)
-        lv = a.dims // 2
-        self.lvdims = (lv, lv, lv)
-        self.lightvol = np.zeros(lv * lv * lv, np.float64)
-        cpm = importlib.import_module(PKG)
-        self.t2i_vol = cpm.capi.texture_to_index_matrix(self.dims)
-        self.t2i_lv = cpm.capi.texture_to_index_matrix(self.lvdims)
-        self.i2t_lv = cpm.capi.index_to_texture_matrix(self.lvdims)
-        self.radius = float(np.float32(np.sqrt(3.0) / a.dims))   # |indexToTexture * (1,1,1)| for radius = 1 voxel
         self.mm, self.diff = {}, {}
-
-    def params(self):
-        return self.orc.trace_params(n_light_samples=self.n, max_interactions=self.I, step_size=1.0 / self.a.dims)
-
-    def scale(self):
-        vol = 4.0 / 3.0 * np.pi * self.radius ** 3
-        return float((1.0 / np.pi) / (vol * self.n))
 
     def prepare(self, t):
         """untimed, as in the GPU arm's resident mode: min-max grid of step t and difference grid (t-1 -> t)"""
         T = len(self.vols)
-        if t % T not in self.mm:
-            self.mm[t % T] = self.orc.volume_minmax(self.vols[t % T], self.region)
-        if (t - 1) % T not in self.mm:
-            self.mm[(t - 1) % T] = self.orc.volume_minmax(self.vols[(t - 1) % T], self.region)
+        for k in (t % T, (t - 1) % T):
+            if k not in self.mm:
+                self.mm[k] = self.orc.volume_minmax(self.vols[k], self.region)
         if (t - 1) % T not in self.diff:
             self.diff[(t - 1) % T] = self.orc.volume_diff_bricks(self.vols[(t - 1) % T], self.vols[t % T], self.region)
 
     def first_frame(self, t=0):
-        orc = self.orc
-        self.tests = orc.trace_photons(orc.volume(self.vols[t]), self.tf, self.params(), self.ls, self.isect,
-                                       self.photons, self.rng.copy())
-        self.lightvol[:] = 0
-        orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, None, self.n, self.n, self.I,
-                  self.radius, self.scale())
-        self.prev[:] = self.photons
+        self.net.first_frame(self.vols[t])
 
     def frame(self, t):
         """one time-step change; returns (photons re-traced, collision tests)"""
-        orc, T = self.orc, len(self.vols)
-        imp = orc.classify_importance(self.mm[t % T], self.tfpos, self.tfcol, (0, 0, 0, 1), False,
-                                      prev=self.mm[(t - 1) % T], diff=self.diff[(t - 1) % T].reshape(-1))
-        orc.detect_invalid(imp, self.gd, (self.region,) * 3, self.t2i_vol, self.photons, 0, self.ls, self.isect, self.n,
-                           self.I, self.n, self.keys)
-        n_inv = orc.count_below(self.keys, 0x7FFFFFFF)
-        ids = np.arange(self.n, dtype=np.uint32)
-        sk = self.keys.copy()
-        orc.radix_sort(sk, ids)
-        sel = np.ascontiguousarray(ids[:n_inv])
-        tests = 0
-        if n_inv:
-            orc.radix_sort(sel, None)
-            tests = orc.trace_photons(orc.volume(self.vols[t % T]), self.tf, self.params(), self.ls, self.isect,
-                                      self.photons, self.rng.copy(), recompute=sel, n_recompute=n_inv)
-            self.keys[sel] = 0x7FFFFFFF
-            if n_inv < 0.5 * self.n:      # incrementalRecomputationThreshold = 50 %: remove old, add new
-                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.prev, sel, n_inv, self.n, self.I,
-                          self.radius, self.scale(), -1.0)
-                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, sel, n_inv, self.n,
-                          self.I, self.radius, self.scale(), 1.0)
-            else:                         # above the threshold the reference clears and splats everything
-                self.lightvol[:] = 0
-                allp = np.arange(self.n, dtype=np.uint32)
-                orc.splat(self.lightvol, 1, self.t2i_lv, self.i2t_lv, self.lvdims, self.photons, allp, self.n, self.n,
-                          self.I, self.radius, self.scale(), 1.0)
-            self.prev[:] = self.photons
-        return n_inv, tests
+        T = len(self.vols)
+        imp = self.net.importance_time_varying(self.mm[t % T], self.mm[(t - 1) % T], self.diff[(t - 1) % T])
+        ids = self.net.frame(self.vols[t % T], imp)
+        return int(ids.size), (self.net.tests if ids.size else 0)
 
 
-def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False):
-    """times `steps` CPU frames after `warmup`, the photon sample sized to fit budget_s"""
+def host_threads():
+    """host cores this process may use (the cpuset, not what OMP_NUM_THREADS says: torchrun exports 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False, full_grid=False):
+    """times `steps` CPU frames after `warmup`, the photon sample sized to fit budget_s (full_grid: always the
+    whole light-sample grid, so that the arm is the same job for every --gpus N)"""
     from oracle import orc
-    cores = orc.num_threads()
-    # calibrate: trace rate on a 128^2 sample
-    cal = CpuArm(a, volumes, 256)
-    cal.first_frame(0)
-    cal.prepare(1)
-    t0 = time.perf_counter()
-    cal.frame(1)
-    rate = cal.n / max(time.perf_counter() - t0, 1e-6)          # photons in the map per second of frame time
-    frames = steps + warmup + 1
-    side = int(np.sqrt(max(rate * budget_s / frames, 64.0 * 64.0)))
-    side = int(min(a.photons_side, max(64, side // 32 * 32)))
+    cores = orc.set_num_threads(host_threads())
+    side = a.photons_side
+    if not full_grid:
+        # calibrate: trace rate on a 256^2 sample
+        cal = CpuArm(a, volumes, 256)
+        cal.first_frame(0)
+        cal.prepare(1)
+        t0 = time.perf_counter()
+        cal.frame(1)
+        rate = cal.n / max(time.perf_counter() - t0, 1e-6)          # photons in the map per second of frame time
+        frames = steps + warmup + 1
+        side = int(np.sqrt(max(rate * budget_s / frames, 64.0 * 64.0)))
+        side = int(min(a.photons_side, max(64, side // 32 * 32)))
     arm = CpuArm(a, volumes, side)
     arm.first_frame(0)
     for t in range(1, warmup + 1):
@@ -276,7 +256,32 @@ def cpu_run(a, volumes, steps, warmup, budget_s, grow_steps=False):
                       f"frames ({elapsed:.2f} s CPU) on the full {a.dims}^3 volumes; min-max / difference grids "
                       f"precomputed untimed as in the resident GPU run",
             "ms_per_step": elapsed / steps * 1e3, "retrace_fraction": traced / (steps * arm.n),
+            "n_recomputed_total": int(traced), "photon_grid": f"{side}x{side}",
             "collision_tests_per_sec": tests / elapsed if elapsed > 0 else 0.0, "frames_per_sec": steps / elapsed}
+
+
+def probe_opencl():
+    """the preferred CPU baseline is the reference's own OpenCL kernels on a PoCL CPU device.  That route
+    needs (a) an OpenCL ICD with a CPU device and (b) an Inviwo checkout (commit 989dc16e) for the 13 un-vendored .cl
+    headers; this probe records what the box has, and the arm falls back to the oracle port (always the case so far)."""
+    import ctypes.util
+    import glob
+    import shutil
+    out = {"clinfo": shutil.which("clinfo") is not None, "icd_files": sorted(glob.glob("/etc/OpenCL/vendors/*.icd")),
+           "libOpenCL": ctypes.util.find_library("OpenCL"), "libpocl": ctypes.util.find_library("pocl"),
+           "cpu_device": None, "inviwo_cl_headers": False}
+    if out["clinfo"]:
+        try:
+            txt = subprocess.run(["clinfo", "-l"], capture_output=True, text=True, timeout=20).stdout
+            out["cpu_device"] = any(k in txt.lower() for k in ("pocl", "cpu", "portable computing"))
+        except Exception:   # noqa: BLE001
+            out["cpu_device"] = False
+    for root in (os.environ.get("INVIWO_HOME"), "/opt/inviwo", "/usr/share/inviwo"):
+        if root and os.path.exists(os.path.join(root, "modules", "opencl", "cl", "samplers.cl")):
+            out["inviwo_cl_headers"] = True
+    usable = bool(out["cpu_device"]) and out["inviwo_cl_headers"]
+    out["route"] = "reference OpenCL kernels on PoCL" if usable else "oracle port (no CPU OpenCL device and/or no Inviwo headers)"
+    return out
 
 
 def make_volumes_numpy(a, n_steps, device):
@@ -292,7 +297,9 @@ def run_reference(a):
     import torch
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     vols = make_volumes_numpy(a, a.steps + a.warmup + 2, dev)
-    r = cpu_run(a, vols, a.steps, a.warmup, a.ref_seconds)
+    # always the whole light-sample grid and every host core, whatever the launcher's OMP_NUM_THREADS says: the arm is
+    # the same job (cores, sample) for every --gpus N
+    r = cpu_run(a, vols, a.steps, a.warmup, a.ref_seconds, full_grid=True)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -301,7 +308,8 @@ def run_reference(a):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "frames_per_sec": r["frames_per_sec"], "retrace_fraction": r["retrace_fraction"],
-            "collision_tests_per_sec": r["collision_tests_per_sec"], "gpu_launches": 0}
+            "n_recomputed_total": r["n_recomputed_total"], "photon_grid": r["photon_grid"],
+            "collision_tests_per_sec": r["collision_tests_per_sec"], "gpu_launches": 0, "opencl_probe": probe_opencl()}
     print(json.dumps(line), flush=True)
 
 
@@ -577,13 +585,16 @@ def run_b200(a):
         for k in range(a.warmup):
             step_resident(1 + k)
         drain_resident()
-        if world > 1 and a.check_exchange:
+        exchange_check = None
+        if world > 1 and not a.no_check_exchange:
+            # untimed: the sum the exchange kernel produced for the last warm-up frame against NCCL's all-reduce
             got = exchange.result().clone()
             want = sharding.allreduce_light_volume(lv_view["t"])
             torch.cuda.synchronize()
             err = float((got - want).abs().max().item())
             ref = float(want.abs().max().item())
-            sys.stderr.write(f"[rank {rank}] exchange check ({exchange_kind}): max |diff| = {err:.3e} of max {ref:.3e}\n")
+            worst = sharding.max_over_ranks([err], device=dev)[0]
+            exchange_check = {"max_abs_diff": worst, "max_abs_value": ref, "against": "NCCL all-reduce of the same per-rank volumes"}
             assert err <= 1e-5 * ref + 1e-12, "peer exchange differs from the NCCL sum"
         net.read_collision_tests(reset=True)
         host.profile_enable(True)
@@ -674,31 +685,29 @@ def run_b200(a):
     dom = max(stages.items(), key=lambda kv: kv[1][0])[0] if stages else "trace"
     tests_rank0 = float(tests)
     traced_rank0 = traced / world
-    # stream part 48 + 32 I + 4 (index) B per traced photon; sampling part 8 * sizeof(voxel) per
-    # collision test THAT FETCHES VOXELS (the opacity bound decides the others from one 4 B cell look-up; the 2 x 4 B
-    # transfer-function taps come from shared memory: not counted)
     fetched_rank0 = float(fetched)
-    alg_bytes = traced_rank0 * (48 + 32 * I + 4) + fetched_rank0 * 8 * 4 + (tests_rank0 * 4 if a.bound_log2 >= 0 else 0)
+    # HBM-algorithmic bytes, SURVEY.md 8(d): stream part 48 + 32 I + 4 (index) B per traced photon + 8 * sizeof(voxel)
+    # per collision test THAT FETCHES VOXELS.  The 4 B opacity-bound look-up every test makes hits a ~1 MB table that
+    # lives in L1 / L2: reported separately (l2_lookup_bytes_per_launch), not as HBM traffic.  The 2 x 4 B
+    # transfer-function taps come from shared memory.
+    hbm_bytes = traced_rank0 * (48 + 32 * I + 4) + fetched_rank0 * 8 * 4
     ref_bytes = traced_rank0 * (48 + 32 * I + 4) + tests_rank0 * 8 * 4     # what the reference's loop touches
-    roof = {"bound": "hbm", "kernel": "trace_kernel (photonTracerKernel -D PHOTON_RECOMPUTATION)",
-            "achieved": alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None, "peak": peak, "unit": "GB/s",
-            "frac": (alg_bytes / (trace_ms * 1e-3) / 1e9 / peak) if trace_ms > 0 else None, "peak_source": peak_src,
+    ach = hbm_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+    roof = {"bound": "issue", "kernel": "trace_kernel (photonTracerKernel -D PHOTON_RECOMPUTATION)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "peak_source": peak_src,
             "traffic": None, "launches": trace_n, "avg_launch_ms": trace_ms / trace_n if trace_n else None,
-            "algorithmic_bytes_per_launch": alg_bytes / trace_n if trace_n else None,
+            "algorithmic_bytes_per_launch": hbm_bytes / trace_n if trace_n else None,
+            "l2_lookup_bytes_per_launch": (tests_rank0 * 4 / trace_n) if (trace_n and a.bound_log2 >= 0) else 0,
             "reference_algorithm_bytes_per_launch": ref_bytes / trace_n if trace_n else None,
+            "collision_tests_per_launch": tests_rank0 / trace_n if trace_n else None,
             "dominant_stage_by_time": dom,
-            "note": "algorithmic bytes = 84 B/photon stream + 4 B bound look-up per collision test + 32 B (8 f32 taps) "
-                    "per test that fetches voxels; the reference's loop fetches for every test "
-                    "(reference_algorithm_bytes_per_launch).  With the bound the kernel is instruction-issue bound "
-                    "(ncu: issue slots busy, profiles/), not HBM bound: frac is small by construction and the "
-                    "meaningful figures are collision_tests_per_sec and the issue utilisation"}
-    tp = ROOT / "profiles" / "roofline_traffic.json"
-    if tp.exists():
-        try:
-            roof["traffic"] = json.loads(tp.read_text()).get("trace_kernel_dram_bytes_per_launch")
-        except Exception:
-            pass
-
+            "note": "frac = HBM-algorithmic bytes (84 B per re-traced photon + 32 B per collision test that fetches "
+                    "voxels) / launch time / measured HBM peak.  The kernel is instruction-issue bound, not HBM bound: "
+                    "the opacity-bound grid decides ~98 % of the reference's per-test fetches from an L1/L2-resident "
+                    "table (reference_algorithm_bytes_per_launch is what the reference loop would move), so HBM is "
+                    "the wrong roof and `counters` (ncu, same kernel sources) carries the binding ones: issue slots "
+                    "busy, active lanes per instruction, resident warps"}
+    roof.update(profile_counters())
     cpu = None
     if world == 1 and not a.no_cpu:
         vols = [p.numpy() for p in pinned]
@@ -713,6 +722,8 @@ def run_b200(a):
                        "l2": "inputs larger than L2: a different 512 MB volume every step, 128 MB photon records",
                        "parallelism": f"photon shards x{world}, light volumes summed on a side stream (overlaps the next frame): {exchange_kind}" if world > 1 else "1 GPU"},
             "frames_per_sec": a.steps / (ms * 1e-3), "retrace_fraction": traced / (a.steps * n_photons * world),
+            "n_recomputed_total": int(traced), "photon_grid": f"{a.photons_side}x{a.photons_side}" + (f" x {world} shards" if world > 1 else ""),
+            "exchange_check": exchange_check,
             "collision_tests_per_sec": float(tests_t[0]) / (ms * 1e-3),
             "tests_fetching_voxels": fetched / tests if tests else None,
             "wall_ms_per_step": wall_ms / a.steps,

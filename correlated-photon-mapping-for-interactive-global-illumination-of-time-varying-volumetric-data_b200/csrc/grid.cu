@@ -113,62 +113,6 @@ __global__ void __launch_bounds__(256) minmax_kernel(const void* __restrict__ vo
     }
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(256) diff_kernel(const void* __restrict__ va, const void* __restrict__ vb, int nx,
-                                                   int ny, int nz, int region, int nbx, double scaling, double rmin,
-                                                   double rmax, float* __restrict__ out, int vec_ok) {
-    typedef typename Vox<FMT>::T T;
-    constexpr int K = Vox<FMT>::PER16;
-    extern __shared__ double s_sum[];
-    const int by = blockIdx.x, bz = blockIdx.y;
-    for (int i = threadIdx.x; i < nbx; i += blockDim.x) s_sum[i] = 0.0;
-    __syncthreads();
-    const int y0 = by * region, z0 = bz * region;
-    const int ry = min(region, ny - y0), rz = min(region, nz - z0);
-    const int rows = ry * rz;
-    const T *A = (const T*)va, *B = (const T*)vb;
-    if (vec_ok) {
-        const int chunks = nx / K;
-        const int items = rows * chunks;
-        for (int w = threadIdx.x; w < items; w += blockDim.x) {
-            int r = w / chunks, c = w - r * chunks;
-            int y = y0 + r % ry, z = z0 + r / ry;
-            size_t ro = ((size_t)z * ny + y) * nx;
-            uint4 ra = __ldg(reinterpret_cast<const uint4*>(A + ro) + c);
-            uint4 rb = __ldg(reinterpret_cast<const uint4*>(B + ro) + c);
-            const T* ea = reinterpret_cast<const T*>(&ra);
-            const T* eb = reinterpret_cast<const T*>(&rb);
-            int x = c * K;
-            int cur = x / region;
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                int b = (x + k) / region;
-                if (b != cur) {
-                    atomicAdd(&s_sum[cur], acc);
-                    cur = b;
-                    acc = 0.0;
-                }
-                acc += fabs(scaling * ((double)eb[k] - (double)ea[k]));
-            }
-            atomicAdd(&s_sum[cur], acc);
-        }
-    } else {
-        const int items = rows * nx;
-        for (int w = threadIdx.x; w < items; w += blockDim.x) {
-            int r = w / nx, x = w - r * nx;
-            int y = y0 + r % ry, z = z0 + r / ry;
-            size_t p = ((size_t)z * ny + y) * nx + x;
-            atomicAdd(&s_sum[x / region], fabs(scaling * ((double)B[p] - (double)A[p])));
-        }
-    }
-    __syncthreads();
-    const int nby = gridDim.x;
-    const double r3 = (double)region * region * region;
-    for (int i = threadIdx.x; i < nbx; i += blockDim.x)
-        out[((size_t)bz * nby + by) * nbx + i] = (float)((s_sum[i] / r3 - rmin) / (rmax - rmin));
-}
-
 // ---- bricks of 8 voxels (the default region), 16-byte aligned rows: streaming versions ---------------------------
 // Same CTA mapping, but a thread owns one 16-byte chunk COLUMN and walks down the brick row's 64 voxel rows: the
 // brick(s) a chunk feeds are fixed per thread, partial results stay in registers (packed bytes / halves for the
@@ -291,55 +235,93 @@ __global__ void __launch_bounds__(256) minmax8_kernel(const void* __restrict__ v
     }
 }
 
+// ---- inter-step difference bricks --------------------------------------------------------------------------------
+// One THREAD per brick, voxels added in the reference's order (z, then y, then x ascending:
+// ugc/processors/dynamicvolumedifferenceanalysis.h:123-138).  The double-precision sum is then the reference's bit
+// for bit and the same on every run (a sum combined through atomics is neither).  Lanes of a warp own consecutive
+// bricks along x, so a row read by a warp is one contiguous segment of 32 bricks.
+template <int FMT>
+struct BrickRow;   // the 8 voxels of one brick row
+template <>
+struct BrickRow<CPM_FMT_F32> {
+    uint4 a, b;
+    __device__ void load(const void* p) { a = __ldg((const uint4*)p); b = __ldg((const uint4*)p + 1); }
+    __device__ double get(int k) const {
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        return (double)__uint_as_float(w[k]);
+    }
+};
+template <>
+struct BrickRow<CPM_FMT_U16> {
+    uint4 a;
+    __device__ void load(const void* p) { a = __ldg((const uint4*)p); }
+    __device__ double get(int k) const {
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+        return (double)((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+    }
+};
+template <>
+struct BrickRow<CPM_FMT_U8> {
+    uint2 a;
+    __device__ void load(const void* p) { a = __ldg((const uint2*)p); }
+    __device__ double get(int k) const {
+        const uint32_t w[2] = {a.x, a.y};
+        return (double)((w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+    }
+};
+
+// region 8, nx % 8 == 0, 16-byte aligned buffers.  Block (32, 8): 32 bricks along x, 8 along y; grid.z = brick layer.
 template <int FMT>
 __global__ void __launch_bounds__(256) diff8_kernel(const void* __restrict__ va, const void* __restrict__ vb, int nx,
-                                                    int ny, int nz, int nbx, double scaling, double rmin, double rmax,
-                                                    float* __restrict__ out) {
+                                                    int ny, int nz, int nbx, int nby, double scaling, double rmin,
+                                                    double rmax, float* __restrict__ out) {
     typedef typename Vox<FMT>::T T;
-    constexpr int K = Vox<FMT>::PER16;
-    constexpr int NB = K > 8 ? K / 8 : 1;      // bricks per chunk
-    extern __shared__ double s_sum[];
-    __shared__ unsigned long long s_row[64];
-    const int by = blockIdx.x, bz = blockIdx.y;
-    for (int i = threadIdx.x; i < nbx; i += blockDim.x) s_sum[i] = 0.0;
+    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, bz = blockIdx.z;
+    if (bx >= nbx || by >= nby) return;
     const int y0 = by * 8, z0 = bz * 8;
     const int ry = min(8, ny - y0), rz = min(8, nz - z0);
-    const int rows = ry * rz, chunks = nx / K;
-    brick_row_offsets(s_row, rows, ry, y0, z0, ny, chunks);
-    __syncthreads();
-    const uint4 *A = reinterpret_cast<const uint4*>(va), *B = reinterpret_cast<const uint4*>(vb);
-    const int cols = min(chunks, (int)blockDim.x), groups = blockDim.x / cols;
-    const int col = threadIdx.x % cols, rg = threadIdx.x / cols;
-    if (rg < groups) {
-        for (int c = col; c < chunks; c += cols) {
-            double acc[NB];
+    const T *A = (const T*)va, *B = (const T*)vb;
+    double acc = 0.0;
+    for (int z = 0; z < rz; ++z) {
+        const size_t slab = ((size_t)(z0 + z) * ny + y0) * nx + (size_t)bx * 8;
+        for (int y = 0; y < ry; y += 4) {          // four rows of both volumes in flight, added in order
+            BrickRow<FMT> ra[4], rb[4];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.0;
-            auto add = [&](const uint4& ra, const uint4& rb) {
-                const T* ea = reinterpret_cast<const T*>(&ra);
-                const T* eb = reinterpret_cast<const T*>(&rb);
+            for (int j = 0; j < 4; ++j)
+                if (y + j < ry) {
+                    ra[j].load(A + slab + (size_t)(y + j) * nx);
+                    rb[j].load(B + slab + (size_t)(y + j) * nx);
+                }
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[NB > 1 ? k / 8 : 0] += fabs(scaling * ((double)eb[k] - (double)ea[k]));
-            };
-            int r = rg;
-            for (; r + 3 * groups < rows; r += 4 * groups) {
-                const unsigned long long o0 = s_row[r] + c, o1 = s_row[r + groups] + c, o2 = s_row[r + 2 * groups] + c,
-                                         o3 = s_row[r + 3 * groups] + c;
-                uint4 a0 = __ldg(A + o0), b0 = __ldg(B + o0), a1 = __ldg(A + o1), b1 = __ldg(B + o1);
-                uint4 a2 = __ldg(A + o2), b2 = __ldg(B + o2), a3 = __ldg(A + o3), b3 = __ldg(B + o3);
-                add(a0, b0); add(a1, b1); add(a2, b2); add(a3, b3);
-            }
-            for (; r < rows; r += groups) add(__ldg(A + s_row[r] + c), __ldg(B + s_row[r] + c));
-            const int first = (c * K) / 8;
+            for (int j = 0; j < 4; ++j)
+                if (y + j < ry) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (first + b < nbx) atomicAdd(&s_sum[first + b], acc[b]);
+                    for (int k = 0; k < 8; ++k) acc += fabs(scaling * (rb[j].get(k) - ra[j].get(k)));
+                }
         }
     }
-    __syncthreads();
-    const int nby = gridDim.x;
-    for (int i = threadIdx.x; i < nbx; i += blockDim.x)
-        out[((size_t)bz * nby + by) * nbx + i] = (float)((s_sum[i] / 512.0 - rmin) / (rmax - rmin));
+    out[((size_t)bz * nby + by) * nbx + bx] = (float)((acc / 512.0 - rmin) / (rmax - rmin));
+}
+
+// any region / row length: the same order with scalar loads
+template <int FMT>
+__global__ void __launch_bounds__(256) diff_kernel(const void* __restrict__ va, const void* __restrict__ vb, int nx,
+                                                   int ny, int nz, int region, int nbx, int nby, double scaling,
+                                                   double rmin, double rmax, float* __restrict__ out) {
+    typedef typename Vox<FMT>::T T;
+    const int bx = blockIdx.x * 32 + threadIdx.x, by = blockIdx.y * 8 + threadIdx.y, bz = blockIdx.z;
+    if (bx >= nbx || by >= nby) return;
+    const int x0 = bx * region, y0 = by * region, z0 = bz * region;
+    const int x1 = min(x0 + region, nx), y1 = min(y0 + region, ny), z1 = min(z0 + region, nz);
+    const T *A = (const T*)va, *B = (const T*)vb;
+    double acc = 0.0;
+    for (int z = z0; z < z1; ++z)
+        for (int y = y0; y < y1; ++y) {
+            const size_t row = ((size_t)z * ny + y) * nx;
+            for (int x = x0; x < x1; ++x) acc += fabs(scaling * ((double)B[row + x] - (double)A[row + x]));
+        }
+    const double r3 = (double)region * region * region;
+    out[((size_t)bz * nby + by) * nbx + bx] = (float)((acc / r3 - rmin) / (rmax - rmin));
 }
 
 // ---- importance classification ----------------------------------------------------------------
@@ -354,12 +336,12 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 }
 __device__ void rgb2lab(float r, float g, float b, float lab[3]) {
     float c[3] = {r, g, b}, lin[3];
-    for (int k = 0; k < 3; ++k) lin[k] = c[k] > 0.04045f ? powf((c[k] + 0.055f) / 1.055f, 2.4f) : c[k] / 12.92f;
+    for (int k = 0; k < 3; ++k) lin[k] = c[k] > 0.04045f ? cpm_powf((c[k] + 0.055f) / 1.055f, 2.4f) : c[k] / 12.92f;
     float X = 0.4124564f * lin[0] + 0.3575761f * lin[1] + 0.1804375f * lin[2];
     float Y = 0.2126729f * lin[0] + 0.7151522f * lin[1] + 0.0721750f * lin[2];
     float Z = 0.0193339f * lin[0] + 0.1191920f * lin[1] + 0.9503041f * lin[2];
     float xyz[3] = {X / 0.95047f, Y / 1.0f, Z / 1.08883f}, f[3];
-    for (int k = 0; k < 3; ++k) f[k] = xyz[k] > 0.008856f ? cbrtf(xyz[k]) : 7.787f * xyz[k] + 16.0f / 116.0f;
+    for (int k = 0; k < 3; ++k) f[k] = xyz[k] > 0.008856f ? cpm_cbrtf(xyz[k]) : 7.787f * xyz[k] + 16.0f / 116.0f;
     lab[0] = 116.0f * f[1] - 16.0f;
     lab[1] = 500.0f * (f[0] - f[1]);
     lab[2] = 200.0f * (f[1] - f[2]);
@@ -534,17 +516,16 @@ int cpm_volume_diff_bricks(cpm_ctx* ctx, const cpm_volume* a, const cpm_volume* 
     const int nx = a->dims[0], ny = a->dims[1], nz = a->dims[2];
     const int nbx = (nx + region - 1) / region, nby = (ny + region - 1) / region, nbz = (nz + region - 1) / region;
     CPM_REQUIRE(ctx, nbz <= 65535, "too many brick layers");
-    size_t smem = (size_t)nbx * sizeof(double);
-    dim3 grid(nby, nbz);
+    dim3 grid(cpm_div_up(nbx, 32), cpm_div_up(nby, 8), nbz), block(32, 8);
 #define DF(F)                                                                                                      \
     {                                                                                                              \
-        int vec_ok = ((uintptr_t)a->linear % 16 == 0) && ((uintptr_t)b->linear % 16 == 0) && (nx % Vox<F>::PER16 == 0); \
+        int vec_ok = ((uintptr_t)a->linear % 16 == 0) && ((uintptr_t)b->linear % 16 == 0) && (nx % 8 == 0);        \
         if (vec_ok && region == 8 && !grid_generic()) {                                                            \
-            CPM_LAUNCH(ctx, diff8_kernel<F>, grid, 256, smem, a->linear, b->linear, nx, ny, nz, nbx, data_scaling, \
+            CPM_LAUNCH(ctx, diff8_kernel<F>, grid, block, 0, a->linear, b->linear, nx, ny, nz, nbx, nby, data_scaling, \
                        range_min, range_max, out);                                                                 \
         } else {                                                                                                   \
-            CPM_LAUNCH(ctx, diff_kernel<F>, grid, 256, smem, a->linear, b->linear, nx, ny, nz, region, nbx, data_scaling, \
-                       range_min, range_max, out, vec_ok);                                                         \
+            CPM_LAUNCH(ctx, diff_kernel<F>, grid, block, 0, a->linear, b->linear, nx, ny, nz, region, nbx, nby,    \
+                       data_scaling, range_min, range_max, out);                                                   \
         }                                                                                                          \
     }
     switch (a->format) {

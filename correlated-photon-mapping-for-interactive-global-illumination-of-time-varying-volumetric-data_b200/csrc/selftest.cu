@@ -16,6 +16,9 @@ __global__ void math_kernel(int fn, const float* __restrict__ x, const float* __
         case 4: r = cpm_atan2f(a, b); break;
         case 5: r = unorm8(a); break;
         case 6: r = unorm16(a); break;
+        case 7: r = cpm_powf(a, b); break;
+        case 8: r = cpm_cbrtf(a); break;
+        case 9: r = cpm_expf_sym(a); break;
         default: r = 0.0f;
     }
     out[i] = r;
@@ -24,7 +27,7 @@ __global__ void math_kernel(int fn, const float* __restrict__ x, const float* __
 
 extern "C" int cpm_selftest_math(cpm_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n) {
     if (!ctx) return CPM_E_INVALID;
-    CPM_REQUIRE(ctx, fn >= 0 && fn <= 6, "unknown function id");
+    CPM_REQUIRE(ctx, fn >= 0 && fn <= 9, "unknown function id");
     if (n == 0) return CPM_OK;
     CPM_REQUIRE(ctx, x && out, "null buffer");
     CPM_LAUNCH(ctx, math_kernel, cpm_div_up(n, 256), 256, 0, fn, x, y, out, n);

@@ -70,6 +70,11 @@ def lib():
         _lib.cpmh_config_from_workspace.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.POINTER(HostConfig)]
         _lib.cpmh_network_load_workspace.argtypes = [C.c_void_p, C.c_char_p]
         _lib.cpmh_network_get_property.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
+        _lib.cpmh_network_read_importance_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpmh_network_read_recomputed_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpmh_network_read_importance_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpmh_network_light_setup.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        _lib.cpmh_network_read_light_samples.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     return _lib
 
 
@@ -341,6 +346,43 @@ class Network:
         out = np.empty(n, np.float32)
         self._check(lib().cpmh_network_read_photons(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
         return out.reshape(-1, 8)
+
+    def read_importance_keys(self):
+        """the tracer's per-photon importance keys (0x7FFFFFFF = valid), device -> host"""
+        out = np.empty(self.n_photons, np.uint32)
+        self._check(lib().cpmh_network_read_importance_keys(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)))
+        return out
+
+    def read_recomputed_indices(self):
+        """ids re-traced by the last evaluation (empty when it traced everything)"""
+        n = max(self.n_recomputed, 0)
+        out = np.empty(n, np.uint32)
+        if n:
+            m = self._check(lib().cpmh_network_read_recomputed_indices(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+            out = out[:m]
+        return out
+
+    def read_importance_grid(self, n_cells):
+        out = np.empty(int(n_cells), np.float32)
+        self._check(lib().cpmh_network_read_importance_grid(self.h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)))
+        return out
+
+    def light_setup(self, light=0) -> dict:
+        """kernel arguments of one directional light sampler: direction, plane point (before the fit), fitted origin, u, v,
+        radiance (float32 triples) and area"""
+        out = (C.c_float * 19)()
+        self._check(lib().cpmh_network_light_setup(self.h, int(light), out))
+        a = np.array(out[:], np.float32)
+        return dict(dir=a[0:3].copy(), plane_point=a[3:6].copy(), origin=a[6:9].copy(), u=a[9:12].copy(), v=a[12:15].copy(),
+                    radiance=a[15:18].copy(), area=np.float32(a[18]))
+
+    def read_light_samples(self, light=0):
+        """(light samples (n, 8), intersections (n, 2)) of one light sampler, device -> host"""
+        n = self.cfg.samples_per_side ** 2
+        ls, it = np.empty((n, 8), np.float32), np.empty((n, 2), np.float32)
+        self._check(lib().cpmh_network_read_light_samples(self.h, int(light), ls.ctypes.data_as(C.c_void_p),
+                                                          it.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+        return ls, it
 
     @property
     def last_splat_path(self):

@@ -373,7 +373,60 @@ int cpmh_network_read_photons(cpmh_network* net, float* out, size_t n) {
         return (int)CPM_OK;
     });
 }
-int cpmh_network_read_importance_keys(cpmh_network*, uint32_t*, size_t) { return CPM_E_UNSUPPORTED; }
+int cpmh_network_read_importance_keys(cpmh_network* net, uint32_t* out, size_t n) {
+    return guarded([&]() {
+        auto& keys = net->tracer.importanceKeys();
+        if (keys.getSize() != n) throw std::invalid_argument("importance key buffer size mismatch");
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, keys.deviceRead(), n * sizeof(uint32_t)));
+        rt.sync();
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_read_recomputed_indices(cpmh_network* net, uint32_t* out, size_t n) {
+    return guarded([&]() {
+        auto d = std::const_pointer_cast<RecomputedPhotonIndices>(net->tracer.recomputedIndicesPort_.getData());
+        if (!d || d->nRecomputedPhotons <= 0) return 0;
+        const size_t m = (size_t)d->nRecomputedPhotons;
+        if (n < m) throw std::invalid_argument("index buffer too small");
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, d->indicesToRecomputedPhotons.deviceRead(), m * sizeof(uint32_t)));
+        rt.sync();
+        return (int)m;
+    });
+}
+int cpmh_network_read_importance_grid(cpmh_network* net, float* out, size_t n) {
+    return guarded([&]() {
+        auto g = std::dynamic_pointer_cast<const ImportanceUniformGrid3D>(net->importance.importanceUniformGrid3DOutport_.getData());
+        if (!g || g->data.getSize() != n) throw std::invalid_argument("importance grid size mismatch");
+        auto& rt = CpmRuntime::get();
+        rt.check(cpm_mem_copy_d2h(rt.ctx(), out, g->data.deviceRead(), n * sizeof(float)));
+        rt.sync();
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_light_setup(cpmh_network* net, int light, float out[19]) {
+    return guarded([&]() {
+        if (light < 0 || light >= (int)net->lightSamplers.size()) throw std::invalid_argument("no such light");
+        const auto& s = net->lightSamplers[light]->sampler().lastSetup;
+        const vec3 v[6] = {s.direction, s.planePoint, s.origin, s.u, s.v, s.radiance};
+        for (int k = 0; k < 6; ++k) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
+        out[18] = s.area;
+        return (int)CPM_OK;
+    });
+}
+int cpmh_network_read_light_samples(cpmh_network* net, int light, float* samples_out, float* isect_out, size_t n) {
+    return guarded([&]() {
+        if (light < 0 || light >= (int)net->lightSamplers.size()) throw std::invalid_argument("no such light");
+        auto* ls = const_cast<LightSamples*>(net->lightSamplers[light]->lightSamples());
+        if (!ls || ls->getSize() != n) throw std::invalid_argument("light sample count mismatch");
+        auto& rt = CpmRuntime::get();
+        if (samples_out) rt.check(cpm_mem_copy_d2h(rt.ctx(), samples_out, ls->getLightSamples()->deviceRead(), n * 8 * sizeof(float)));
+        if (isect_out) rt.check(cpm_mem_copy_d2h(rt.ctx(), isect_out, ls->getIntersectionPoints()->deviceRead(), n * 2 * sizeof(float)));
+        rt.sync();
+        return (int)CPM_OK;
+    });
+}
 const char* cpmh_network_last_splat_path(cpmh_network* net) { return net->toLightVolume.lastPath.c_str(); }
 int cpmh_network_set_profile(cpmh_network*, int on) {
     StageProfiler::get().enabled = on != 0;
@@ -656,6 +709,19 @@ int cpmh_fit_light_plane(const float* points, int n, const float P[3], const flo
         for (int k = 0; k < 3; ++k) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
         return (int)CPM_OK;
     });
+}
+
+int cpmh_convex_hull2d(const float* pts, int n, float* hull_out) {
+    int m = 0;
+    int rc = guarded([&]() {
+        std::vector<vec2> p;
+        for (int i = 0; i < n; ++i) p.push_back(vec2{pts[2 * i], pts[2 * i + 1]});
+        auto h = geometry::convexHull2D(p);
+        for (size_t i = 0; i < h.size(); ++i) { hull_out[2 * i] = h[i].x; hull_out[2 * i + 1] = h[i].y; }
+        m = (int)h.size();
+        return (int)CPM_OK;
+    });
+    return rc == CPM_OK ? m : rc;
 }
 
 const char* cpmh_describe_processors(void) {

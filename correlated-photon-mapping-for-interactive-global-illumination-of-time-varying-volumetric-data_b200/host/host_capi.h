@@ -93,6 +93,16 @@ CPMH_API int cpmh_network_light_volume_dims(cpmh_network* net, int dims[3]);
 CPMH_API int cpmh_network_read_light_volume(cpmh_network* net, float* out_host, size_t n_floats);
 CPMH_API int cpmh_network_read_photons(cpmh_network* net, float* out_host, size_t n_floats);
 CPMH_API int cpmh_network_read_importance_keys(cpmh_network* net, uint32_t* out_host, size_t n);
+/* the ids the tracer re-traced in its last evaluation (RecomputedPhotonIndices, ppm/photondata.h:58-63): out_host holds
+ * cpmh_network_n_recomputed() entries; returns the number written (0 when the last evaluation traced everything) */
+CPMH_API int cpmh_network_read_recomputed_indices(cpmh_network* net, uint32_t* out_host, size_t n);
+/* the importance grid the tracer's detector last saw (float per brick of `region` voxels) */
+CPMH_API int cpmh_network_read_importance_grid(cpmh_network* net, float* out_host, size_t n);
+/* kernel arguments of light sampler `light` (lcl/directionallightsamplercl.cpp:66-73), for parity checks:
+ * out = direction[3], plane point before the fit[3], fitted origin[3], u[3], v[3], radiance[3], area */
+CPMH_API int cpmh_network_light_setup(cpmh_network* net, int light, float out[19]);
+/* light samples (float8 per sample) and (tStart, tEnd) intersections of light sampler `light`, device -> host */
+CPMH_API int cpmh_network_read_light_samples(cpmh_network* net, int light, float* samples_out, float* isect_out, size_t n);
 CPMH_API const char* cpmh_network_last_splat_path(cpmh_network* net);
 /* stage timing of the tracer's last process(): "detector","count+iota","sort","indexsort","trace" */
 CPMH_API int cpmh_network_set_profile(cpmh_network* net, int on);
@@ -152,6 +162,8 @@ CPMH_API int cpmh_network_get_property(cpmh_network* net, const char* class_id, 
 CPMH_API int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_host);
 CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
                                   const float plane_normal[3], float out[9]);
+/* the 2-D convex hull alone (lcl/convexhull2d.cpp:38-130): hull_out holds up to 2 * n + 2 points; returns the hull size */
+CPMH_API int cpmh_convex_hull2d(const float* points_xy, int n_points, float* hull_out);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */
 CPMH_API const char* cpmh_describe_processors(void);
 #ifdef __cplusplus

@@ -61,7 +61,9 @@ inline vec3 operator*(float s, vec3 a) { return a * s; }
 inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline vec3 cross(vec3 a, vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
 inline float length(vec3 a) { return std::sqrt(dot(a, a)); }
-inline vec3 normalize(vec3 a) { float l = length(a); return {a.x / l, a.y / l, a.z / l}; }
+// glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x) (GLM 0.9.7 func_geometric.inl): the rounding
+// of the reference's CPU light-plane fit depends on it (tests/test_ref_geometry.py pins it against the reference's files)
+inline vec3 normalize(vec3 a) { float inv = 1.0f / std::sqrt(dot(a, a)); return {a.x * inv, a.y * inv, a.z * inv}; }
 
 // column-major 4x4, m[c][r] like glm
 struct mat4 {

@@ -589,8 +589,8 @@ PlaneFit fitPlaneAlignedOrientedBoundingBox2D(const std::vector<vec3>& points, v
     const size_t nh = hull.size();
     for (size_t i = 0, j = nh - 1; i < nh; j = i, ++i) {
         float ex = hull[i].x - hull[j].x, ey = hull[i].y - hull[j].y;
-        float len = std::sqrt(ex * ex + ey * ey);
-        vec2 e0{ex / len, ey / len};
+        float inv = 1.0f / std::sqrt(ex * ex + ey * ey);   // glm::normalize
+        vec2 e0{ex * inv, ey * inv};
         if (e0.x != e0.x || e0.y != e0.y) continue;
         vec2 e1{-e0.y, e0.x};
         float min0 = 0, min1 = 0, max0 = 0, max1 = 0;
@@ -634,6 +634,13 @@ void DirectionalLightSamplerCL::sampleLightSource(const Mesh* mesh, const Sample
     float area = length(fit.u) * length(fit.v);
     auto& rt = CpmRuntime::get();
     const float rad[3] = {lightBase.radiance.x, lightBase.radiance.y, lightBase.radiance.z};
+    lastSetup.direction = lightDirection;
+    lastSetup.planePoint = vec3(o4.x, o4.y, o4.z);
+    lastSetup.origin = fit.origin;
+    lastSetup.u = fit.u;
+    lastSetup.v = fit.v;
+    lastSetup.radiance = vec3(rad[0], rad[1], rad[2]);
+    lastSetup.area = area;
     rt.check(cpm_light_sample_directional(rt.ctx(), static_cast<const float*>(samplesNC->deviceRead()), rad, &lightDirection.x,
                                           &fit.origin.x, &fit.u.x, &fit.v.x, area, (int)samples->getSize(),
                                           static_cast<float*>(out.getLightSamples()->deviceWrite())));

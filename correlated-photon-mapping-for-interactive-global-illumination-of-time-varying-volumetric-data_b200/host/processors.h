@@ -207,6 +207,8 @@ std::vector<vec2> convexHull2D(std::vector<vec2> points);
 class DirectionalLightSamplerCL {
 public:
     void sampleLightSource(const Mesh* mesh, const SampleBuffer* samples, const LightSource* light, LightSamples& lightSamplesOut);
+    // the kernel arguments of the last call (lcl/directionallightsamplercl.cpp:66-73), kept for parity checks
+    struct Setup { vec3 direction, planePoint, origin, u, v, radiance; float area = 0.f; } lastSetup;
 };
 // lcl/lightsamplemeshintersectioncl.h:64
 class LightSampleMeshIntersectionCL {
@@ -296,6 +298,8 @@ public:
     DataOutport<LightSamples> lightSamplesOutport_;
     IntProperty workGroupSize_;
     BoolProperty useGLSharing_;
+    const DirectionalLightSamplerCL& sampler() const { return lightSampler_; }
+    const LightSamples* lightSamples() const { return lightSamples_.get(); }
 private:
     std::shared_ptr<LightSamples> lightSamples_;
     DirectionalLightSamplerCL lightSampler_;
@@ -335,6 +339,7 @@ public:
     void onTimerEvent();    // the reference's 100 ms Timer callback; call it to step progressive work
     PhotonTracerCL& tracer() { return photonTracer_; }
     int remainingPhotonsToUpdate() const { return remainingPhotonsToUpdate_; }
+    Buffer<unsigned int>& importanceKeys() { return photonRecomputationImportance_; }   // for parity checks
     // stage timings (detector, count+iota, sort, indexsort, trace), like the reference's
     // IVW_DETAILED_PROFILING log (:562-598), are collected by StageProfiler when it is enabled
 private:

@@ -493,7 +493,8 @@ CPM_API int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t 
 
 /* ---- self test ----------------------------------------------------------------------- */
 /* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,
- * 3 acos, 4 atan2(x, y), 5 v/255, 6 v/65535 (x holds the integer value as float).  Lets the
+ * 3 acos, 4 atan2(x, y), 5 v/255, 6 v/65535 (x holds the integer value as float), 7 pow(x, y), 8 cbrt,
+ * 9 exp on [-87, 87].  Lets the
  * tests prove that the host and sm_100a compilations of the math layer agree bit for bit. */
 CPM_API int cpm_selftest_math(cpm_ctx* ctx, int fn, const float* x, const float* y, float* out,
                               size_t n);

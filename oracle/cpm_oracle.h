@@ -129,7 +129,9 @@ void orc_sample_importance2d(const float* importance, int w, int h, float floor_
                              int n, float* out);
 
 void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_t n);
+int orc_convex_hull2d(const float* pts, int n, float* hull_out);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,18 @@ def ref():
     return _ref
 
 
+_ref_libs = {}
+
+
+def ref_lib(name):
+    """oracle/_ref/lib<name>.so -- the reference's own sources compiled for the host (oracle/Makefile `ref`), or None
+    when it was not built (no /root/reference at build time and no prebuilt copy)"""
+    if name not in _ref_libs:
+        so = HERE / "_ref" / f"lib{name}.so"
+        _ref_libs[name] = C.CDLL(str(so)) if so.exists() else None
+    return _ref_libs[name]
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -129,6 +141,13 @@ def fit_light_plane(points, plane_point, plane_normal):
     return out[0:3].copy(), out[3:6].copy(), out[6:9].copy()
 
 
+def convex_hull2d(points_xy):
+    pts = np.ascontiguousarray(points_xy, np.float32)
+    hull = np.zeros((2 * len(pts) + 2, 2), np.float32)
+    n = lib().orc_convex_hull2d(_ptr(pts), int(len(pts)), _ptr(hull))
+    return hull[:n].copy()
+
+
 def trace_params(**kw) -> OrcTraceParams:
     p = OrcTraceParams()
     p.aabb_min[:] = [float(x) for x in kw.get("aabb_min", (0, 0, 0))]
@@ -153,6 +172,12 @@ def trace_photons(vol: OrcVolume, tf_rgba, params: OrcTraceParams, light_samples
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of every later oracle call (torchrun exports OMP_NUM_THREADS=1); returns the count in effect"""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def selftest_math(fn, x, y=None):

@@ -154,9 +154,19 @@ static int convexHull2D(v2* points, int n, v2* hull) {
     return h;
 }
 
+/* glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x) (GLM 0.9.7, Inviwo's ext/glm) */
+/* exposed for the golden-vector test of the hull alone; hull_out holds 2*n+2 points, returns the hull size */
+int orc_convex_hull2d(const float* pts, int n, float* hull_out) {
+    v2* p = (v2*)malloc(sizeof(v2) * (size_t)(n > 0 ? n : 1));
+    memcpy(p, pts, sizeof(v2) * (size_t)n);
+    int h = convexHull2D(p, n, (v2*)hull_out);
+    free(p);
+    return h;
+}
+
 static v3 v3_normalize(v3 a) {
-    float l = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-    return v3_make(a.x / l, a.y / l, a.z / l);
+    float inv = 1.0f / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+    return v3_make(a.x * inv, a.y * inv, a.z * inv);
 }
 static float dot_glm(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static v3 cross_glm(v3 a, v3 b) { return v3_make(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
@@ -194,8 +204,8 @@ void orc_fit_light_plane(const float* pts, int n_points, const float plane_point
     v2 origin = {0, 0}, bu = {0, 0}, bv = {0, 0};
     for (int i = 0, j = nh - 1; i < nh; j = i, ++i) {
         float ex = hull[i].x - hull[j].x, ey = hull[i].y - hull[j].y;
-        float len = sqrtf(ex * ex + ey * ey);
-        v2 e0 = {ex / len, ey / len};
+        float inv = 1.0f / sqrtf(ex * ex + ey * ey); /* glm::normalize */
+        v2 e0 = {ex * inv, ey * inv};
         if (e0.x != e0.x || e0.y != e0.y) continue;
         v2 e1 = {-e0.y, e0.x};
         float min0 = 0.f, min1 = 0.f, max0 = 0.f, max1 = 0.f;
@@ -240,6 +250,9 @@ void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_
             case 4: r = cpm_atan2f(a, b); break;
             case 5: r = a / 255.0f; break;
             case 6: r = a / 65535.0f; break;
+            case 7: r = cpm_powf(a, b); break;
+            case 8: r = cpm_cbrtf(a); break;
+            case 9: r = cpm_expf_sym(a); break;
             default: r = 0.0f;
         }
         out[i] = r;

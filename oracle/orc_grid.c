@@ -86,20 +86,20 @@ static v4 v4_mix(v4 a, v4 b, float t) { /* mix(x,y,a) = x + (y-x)*a */
 static v4 v4_min(v4 a, v4 b) { v4 r = {cpm_fmin(a.x, b.x), cpm_fmin(a.y, b.y), cpm_fmin(a.z, b.z), cpm_fmin(a.w, b.w)}; return r; }
 static v4 v4_max(v4 a, v4 b) { v4 r = {cpm_fmax(a.x, b.x), cpm_fmax(a.y, b.y), cpm_fmax(a.z, b.z), cpm_fmax(a.w, b.w)}; return r; }
 
-/* rgb2lab (Inviwo colorconversion.cl, un-vendored): sRGB (D65) -> XYZ -> CIE L*a*b*.  libm powf/cbrtf:
- * this branch is compared with a tolerance, not bit for bit. */
+/* rgb2lab (Inviwo colorconversion.cl, un-vendored): sRGB (D65) -> XYZ -> CIE L*a*b*.  pow and cbrt come from
+ * include/cpm_detmath.h (shared with the CUDA kernel), so this branch is compared bit for bit as well. */
 static void rgb2lab(const float rgb[3], float lab[3]) {
     float lin[3];
     for (int k = 0; k < 3; ++k) {
         float c = rgb[k];
-        lin[k] = c > 0.04045f ? powf((c + 0.055f) / 1.055f, 2.4f) : c / 12.92f;
+        lin[k] = c > 0.04045f ? cpm_powf((c + 0.055f) / 1.055f, 2.4f) : c / 12.92f;
     }
     float X = 0.4124564f * lin[0] + 0.3575761f * lin[1] + 0.1804375f * lin[2];
     float Y = 0.2126729f * lin[0] + 0.7151522f * lin[1] + 0.0721750f * lin[2];
     float Z = 0.0193339f * lin[0] + 0.1191920f * lin[1] + 0.9503041f * lin[2];
     float xyz[3] = {X / 0.95047f, Y / 1.0f, Z / 1.08883f};
     float f[3];
-    for (int k = 0; k < 3; ++k) f[k] = xyz[k] > 0.008856f ? cbrtf(xyz[k]) : 7.787f * xyz[k] + 16.0f / 116.0f;
+    for (int k = 0; k < 3; ++k) f[k] = xyz[k] > 0.008856f ? cpm_cbrtf(xyz[k]) : 7.787f * xyz[k] + 16.0f / 116.0f;
     lab[0] = 116.0f * f[1] - 16.0f;
     lab[1] = 500.0f * (f[0] - f[1]);
     lab[2] = 200.0f * (f[1] - f[2]);

@@ -9,6 +9,8 @@
 #include "orc_common.h"
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the CPU arm of bench.py sets its thread count explicitly */
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 static float fetch(const orc_volume* v, int i, int j, int k) {
     size_t idx = ((size_t)k * v->dims[1] + (size_t)j) * v->dims[0] + (size_t)i;

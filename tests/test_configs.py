@@ -1,6 +1,7 @@
 """BASELINE.json configs at (or near) full size on the GPU: parity against the oracle on a bounded photon sample
 plus size-independent properties (replay determinism, sortedness + stability + permutation checksum,
-energy bookkeeping).  C4 is bench.py's workload; C1, C2, C3 and C5 are exercised here."""
+energy bookkeeping).  C1, C2, C3 and C5 call the C ABI directly; C4 (bench.py's workload) goes through the drop-in
+host network and is compared frame by frame with the oracle's network (oracle/frame.py)."""
 import importlib
 
 import numpy as np
@@ -216,3 +217,114 @@ def test_c5_1024cube_four_lights_sharded_ranges(cpm, orc, synth, ctx, torch_cuda
     got = full[2 * n:2 * n + m].cpu().numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     V.destroy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C4: time-varying f32 volume, correlated re-tracing through the drop-in host network, against the oracle's network
+def oracle_lights_from_host(orc, synth, net, ns):
+    """The oracle's light samples built from the kernel arguments the host layer derived (direction and plane point
+    through the light's transform matrix, lcl/directionallightsamplercl.cpp:66-73).  Asserts on the way that the host's
+    CPU plane fit equals the oracle's (== the reference's own files, tests/test_ref_geometry.py) and that the emitted
+    light samples / intersections are bit-identical."""
+    lights = []
+    f = np.float32
+    for l in range(net.cfg.n_lights):
+        S = net.light_setup(l)
+        o, u, v = orc.fit_light_plane(synth.CUBE_VERTICES, S["plane_point"], S["dir"])
+        for got, want in ((S["origin"], o), (S["u"], u), (S["v"], v)):
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (l, got, want)
+        lu = np.sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2])
+        lv = np.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+        assert f(lu * lv) == S["area"]
+        samples = orc.sample_uniform2d(float(ns), float(ns), ns * ns)
+        ls = orc.light_sample_directional(samples, S["radiance"], S["dir"], o, u, v, float(S["area"]))
+        isect = orc.light_mesh_intersect(synth.CUBE_VERTICES, synth.CUBE_INDICES, ls)
+        got_ls, got_it = net.read_light_samples(l)
+        assert np.array_equal(got_ls.view(np.uint32), ls.view(np.uint32)), l
+        assert np.array_equal(got_it.view(np.uint32), isect.view(np.uint32)), l
+        lights.append(dict(light_samples=ls, isect=isect))
+    return lights
+
+
+def _rel_rmse(got, want):
+    return float(np.sqrt(((got.astype(np.float64) - want) ** 2).mean()) / max(np.sqrt((want ** 2).mean()), 1e-300))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("I,n_lights", [(1, 1), (2, 2)])
+def test_c4_correlated_frames_match_oracle(cpm, orc, synth, torch_cuda, I, n_lights):
+    """C4-shaped case (f32 time series, time-varying Lab classify + volume difference + detector + selection +
+    indexed re-trace + -old/+new splat) through libcpm_host.so, four time-step changes incl. the wrap-around:
+    per frame equal re-trace count, equal id list, bit-equal importance grid and photon records, light volume
+    within 1e-5 relative RMSE of the oracle's float64 accumulation."""
+    from oracle import frame
+    host = importlib.import_module(PKG_NAME + ".host")
+    D, ns, T = 128, 256, 4
+    dims = (D, D, D)
+    vols = [synth.volume_f32(dims, 4, t / 32.0) for t in range(T)]
+    dirs = [(0.3, -0.5, 0.8), (-0.6, 0.2, 0.77)][:n_lights]
+    net = host.Network(dims, cpm.CPM_FMT_F32, ns, dirs, max_scattering_events=I, light_volume_option=2,
+                       with_importance_grid=True, reference_full_splat_bound=False)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_sequence_host(vols)
+    net.set_timestep(0)
+    net.evaluate()
+    assert net.n_recomputed == -1
+    O = frame.OracleNetwork(dims, oracle_lights_from_host(orc, synth, net, ns), frame.rasterise_tf(synth.WS_TF_POINTS),
+                            synth.WS_TF_POINTS, max_interactions=I)
+    O.first_frame(vols[0])
+    assert np.array_equal(net.read_photons(I).view(np.uint32), O.photons.view(np.uint32))
+    assert _rel_rmse(net.read_light_volume(), O.lightvol) <= 1e-5
+    mm = [orc.volume_minmax(v, 8) for v in vols]
+    diff = [orc.volume_diff_bricks(vols[t], vols[(t + 1) % T], 8) for t in range(T)]
+    n_cells = mm[0].size // 2
+    total = 0
+    for step in range(1, T + 2):              # 1, 2, 3, 0 (wrap: (t + 1) % T, dynamicvolumedifferenceanalysis.cpp:64), 1
+        t, tp = step % T, (step - 1) % T
+        net.set_timestep(t)
+        net.evaluate()
+        imp = O.importance_time_varying(mm[t], mm[tp], diff[tp])
+        assert np.array_equal(net.read_importance_grid(n_cells).view(np.uint32), imp.view(np.uint32)), step
+        ids = O.frame(vols[t], imp)
+        assert net.n_recomputed == ids.size, (step, net.n_recomputed, ids.size)
+        assert np.array_equal(net.read_recomputed_indices(), ids), step
+        assert np.array_equal(net.read_photons(I).view(np.uint32), O.photons.view(np.uint32)), step
+        assert np.array_equal(net.read_importance_keys(), O.keys), step
+        assert net.last_splat_path == O.last_splat_path, (step, net.last_splat_path, O.last_splat_path)
+        assert _rel_rmse(net.read_light_volume(), O.lightvol) <= 1e-5, step
+        total += ids.size
+    assert 0 < total < (T + 1) * O.n          # something was re-traced, and not everything
+    net.close()
+
+
+@pytest.mark.gpu
+def test_c4_full_size_retrace_counts_match_oracle(cpm, orc, synth, torch_cuda):
+    """C4 at BASELINE size (512^3 f32, 2048^2 photons): the number of photons the network re-traces per time step and
+    the re-traced id lists equal the oracle's for two consecutive steps (the records themselves are compared at
+    128^3 above and, sampled, here)."""
+    from oracle import frame
+    torch = torch_cuda
+    host = importlib.import_module(PKG_NAME + ".host")
+    D, ns, T = 512, 2048, 3
+    dims = (D, D, D)
+    vols = [synth.volume_field_torch(dims, 4, t / 32.0, device="cuda").cpu().numpy() for t in range(T)]
+    net = host.Network(dims, cpm.CPM_FMT_F32, ns, [(0.3, -0.5, 0.8)], max_scattering_events=1, light_volume_option=2,
+                       with_importance_grid=True, reference_full_splat_bound=False)
+    net.set_transfer_function(synth.WS_TF_POINTS)
+    net.set_sequence_host(vols)
+    net.set_timestep(0)
+    net.evaluate()
+    O = frame.OracleNetwork(dims, oracle_lights_from_host(orc, synth, net, ns), frame.rasterise_tf(synth.WS_TF_POINTS),
+                            synth.WS_TF_POINTS, max_interactions=1)
+    O.first_frame(vols[0])
+    mm = [orc.volume_minmax(v, 8) for v in vols]
+    for t in (1, 2):
+        net.set_timestep(t)
+        net.evaluate()
+        imp = O.importance_time_varying(mm[t], mm[t - 1], orc.volume_diff_bricks(vols[t - 1], vols[t], 8))
+        ids = O.frame(vols[t], imp)
+        assert net.n_recomputed == ids.size, (t, net.n_recomputed, ids.size)
+        assert 0.05 * O.n < ids.size < 0.95 * O.n
+        assert np.array_equal(net.read_recomputed_indices(), ids), t
+        assert np.array_equal(net.read_photons(1).view(np.uint32), O.photons.view(np.uint32)), t
+    net.close()

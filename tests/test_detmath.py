@@ -35,6 +35,16 @@ def test_accuracy_against_libm(orc):
     sp = orc.selftest_math(0, np.array([0.0, 1.0], np.float32))
     assert np.isneginf(sp[0]) and sp[1] == 0.0
     assert orc.selftest_math(3, np.array([1.0], np.float32))[0] == 0.0
+    # pow / cbrt / exp of rgb2lab (isc/cl/minmaxuniformgrid3dimportance.cl:174-175 through Inviwo's colorconversion.cl)
+    rng = np.random.default_rng(5)
+    base = rng.uniform(0.05, 1.2, 200_000).astype(np.float32)
+    p24 = np.full_like(base, 2.4)
+    assert _ulps(orc.selftest_math(7, base, p24), np.power(base.astype(np.float64), np.float64(np.float32(2.4)))).max() <= 8.0
+    cb = np.concatenate([rng.uniform(1e-6, 8.0, 200_000), 10.0 ** rng.uniform(-30, 30, 20_000)]).astype(np.float32)
+    assert _ulps(orc.selftest_math(8, cb), np.cbrt(cb.astype(np.float64))).max() <= 1.0
+    ex = rng.uniform(-87, 87, 200_000).astype(np.float32)
+    assert _ulps(orc.selftest_math(9, ex), np.exp(ex.astype(np.float64))).max() <= 3.0
+    assert orc.selftest_math(8, np.array([0.0, 1.0, 8.0, 27.0], np.float32)).tolist() == [0.0, 1.0, 2.0, 3.0]
 
 
 @pytest.mark.gpu
@@ -43,6 +53,11 @@ def test_host_and_device_agree_bitwise(orc, ctx, torch_cuda):
     u, ang, cz, y, x = _inputs()
     cases = [(0, u, None), (1, ang, None), (2, ang, None), (3, cz, None), (4, y, x),
              (5, np.arange(256, dtype=np.float32), None), (6, np.arange(65536, dtype=np.float32), None)]
+    rng = np.random.default_rng(5)
+    base = rng.uniform(0.0, 1.5, 200_000).astype(np.float32)
+    cases += [(7, base, np.full_like(base, 2.4)), (7, base, rng.uniform(-3, 3, 200_000).astype(np.float32)),
+              (8, np.concatenate([rng.uniform(0, 8.0, 200_000), 10.0 ** rng.uniform(-44, 36, 20_000)]).astype(np.float32), None),
+              (9, rng.uniform(-90, 90, 200_000).astype(np.float32), None)]
     for fn, a, b in cases:
         da = torch.from_numpy(a).cuda()
         db = torch.from_numpy(b).cuda() if b is not None else None

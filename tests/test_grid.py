@@ -81,30 +81,31 @@ def test_cuda_minmax_bit_exact(cpm, orc, ctx, torch_cuda, fmt, dims, region):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fmt", ["u8", "f32"])
-@pytest.mark.parametrize("dims", [(72, 40, 36), (80, 37, 19), (1040, 8, 9)])
-def test_cuda_diff_bricks(cpm, orc, ctx, torch_cuda, synth, fmt, dims):
-    """(72: the generic kernel for u8, 16-byte chunks do not tile the rows; 80 / 1040: the streaming kernels, ragged
-    y / z, more chunk columns than threads)"""
+@pytest.mark.parametrize("fmt", ["u8", "u16", "f32"])
+@pytest.mark.parametrize("dims,region", [((72, 40, 36), 8), ((80, 37, 19), 8), ((1040, 8, 9), 8), ((75, 41, 19), 8),
+                                         ((64, 48, 40), 5), ((33, 20, 17), 16)])
+def test_cuda_diff_bricks(cpm, orc, ctx, torch_cuda, synth, fmt, dims, region):
+    """One thread per brick adds the voxels in the reference's order (z, y, x; dynamicvolumedifferenceanalysis.h:123-138):
+    the double sum -- and with it the float result -- equals the oracle's bit for bit for every format.
+    (rows that are a multiple of 8 voxels: the vector-load kernel, ragged y / z; 75 / 33 and regions 5 / 16: the scalar one)"""
     torch = torch_cuda
     if fmt == "u8":
         a, b = synth.volume_u8(dims, 1), synth.volume_u8(dims, 2)
         rng = (1.0, 0.0, 255.0)
+    elif fmt == "u16":
+        a, b = synth.volume_u16(dims, 1), synth.volume_u16(dims, 2)
+        rng = (65535.0 / 4095.0, 0.0, 4095.0)      # 12-bit data in a 16-bit volume: a scaling that is not 1
     else:
         a, b = synth.volume_f32(dims, 4, 0.0), synth.volume_f32(dims, 4, 1.0 / 32)
         rng = (1.0, 0.0, 1.0)
-    want = orc.volume_diff_bricks(a, b, 8, *rng)
+    want = orc.volume_diff_bricks(a, b, region, *rng)
     Va, ka = _dev_vol(cpm, ctx, torch, a)
     Vb, kb = _dev_vol(cpm, ctx, torch, b)
     out = torch.zeros(want.size, dtype=torch.float32, device="cuda")
-    ctx.volume_diff_bricks(Va, Vb, 8, *rng, out)
+    ctx.volume_diff_bricks(Va, Vb, region, *rng, out)
     ctx.sync()
     got = out.cpu().numpy()
-    if fmt == "u8":
-        assert np.array_equal(got.view(np.uint32), want.reshape(-1).view(np.uint32))   # integer sums: exact
-    else:
-        # double sums in a different order: at most one float ulp
-        assert np.allclose(got, want.reshape(-1), rtol=2e-7, atol=1e-12)
+    assert np.array_equal(got.view(np.uint32), want.reshape(-1).view(np.uint32))
     Va.destroy(); Vb.destroy()
 
 
@@ -127,13 +128,13 @@ def test_cuda_classify_importance(cpm, orc, ctx, torch_cuda, synth):
     ctx.sync()
     want = orc.classify_importance(mm, pos, col, w, True)
     assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
-    # time-varying, Lab formula (powf/cbrtf from two different libms): tolerance
+    # time-varying, Lab formula: pow / cbrt of rgb2lab come from include/cpm_detmath.h on both sides -> bit exact
     norm = 1.0 / np.sqrt(100.0 ** 2 + 500.0 ** 2 + 400.0 ** 2)
     w = (0.5 * norm / 2.0, 0.5 * norm / 2.0, 0.5 / 2.0, 0.5 / 2.0)   # ws:472-483, normalised as the host does
     ctx.classify_importance(dmm, n, dpos, dcol, len(pos), w, False, out, prev=dprev, diff=ddiff)
     ctx.sync()
     want = orc.classify_importance(mm, pos, col, w, False, prev=prev, diff=diff.reshape(-1))
-    assert np.allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-9)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
     assert want.max() > 0
 
 

@@ -58,5 +58,60 @@ def mwc64x():
     print("wrote tests/golden/mwc64x.json")
 
 
+def _hex(a):
+    return [float(x).hex() for x in np.asarray(a, np.float32).reshape(-1)]
+
+
+def geometry_cases():
+    """seeded inputs of the light-plane fit: the unit-cube proxy under many directions (incl. axis-aligned ones, where
+    hull points share x), random point clouds, degenerate sets (collinear, duplicates, < 4 points)"""
+    rng = np.random.default_rng(11)
+    cube = np.array([[x, y, z] for z in (0.0, 1.0) for y in (0.0, 1.0) for x in (0.0, 1.0)], np.float32)
+    cases = []
+    dirs = [(0, 0, 1), (1, 0, 0), (0, 1, 0), (0, -1, 0), (0.3, -0.5, 0.8), (-0.36, 0.48, 0.8), (0.5, -0.3, 0.81), (1, 1, 0),
+            (1, 1, 1), (-1, 2, -3)]
+    for k in range(30):
+        d = np.array(dirs[k], np.float64) if k < len(dirs) else rng.normal(size=3)
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        cases.append((cube, (np.float32([0.5, 0.5, 0.5]) - 2 * d).astype(np.float32), d))
+    for k in range(20):
+        n = int(rng.integers(3, 24))
+        pts = rng.uniform(-1, 2, (n, 3)).astype(np.float32)
+        if k % 5 == 0:
+            pts[n // 2:] = pts[: n - n // 2]            # duplicates
+        if k % 7 == 0:
+            pts = (pts[:1] + np.outer(np.linspace(0, 1, n), [1, 2, 3])).astype(np.float32)   # collinear
+        d = rng.normal(size=3)
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        cases.append((np.ascontiguousarray(pts), rng.uniform(-1, 1, 3).astype(np.float32), d))
+    return cases
+
+
+def geometry():
+    """tests/golden/lightplane.json from the reference's own lcl/{convexhull2d,orientedboundingbox2d,pointplaneprojection}.cpp
+    (oracle/_ref/libgeometry_ref.so): plane fit, plus the 2-D hull and minimum rectangle of the projected points"""
+    ref = orc.ref_lib("geometry_ref")
+    if ref is None:
+        raise SystemExit("oracle/_ref/libgeometry_ref.so missing: run `make -C oracle ref` first")
+    P = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    out = {"source": "reference lcl/convexhull2d.cpp, lcl/orientedboundingbox2d.cpp, lcl/pointplaneprojection.cpp compiled "
+                     "via oracle/Makefile (GLM / Inviwo Plane stand-ins: oracle/ref_shim/host)", "cases": []}
+    for pts, pp, d in geometry_cases():
+        fit = np.zeros(9, np.float32)
+        ref.ref_fit_plane_aligned_obb2d(P(pts), len(pts), P(pp), P(d), P(fit))
+        # the hull / rectangle of an arbitrary 2-D set: the points' xy
+        xy = np.ascontiguousarray(pts[:, :2])
+        hull = np.zeros((2 * len(pts) + 2, 2), np.float32)
+        nh = ref.ref_convex_hull2d(P(xy), len(xy), P(hull))
+        rect = np.zeros(6, np.float32)
+        ref.ref_minimum_bounding_rectangle(P(hull), nh, P(rect))
+        out["cases"].append({"points": _hex(pts), "plane_point": _hex(pp), "normal": _hex(d), "fit": _hex(fit),
+                             "hull_xy": _hex(hull[:nh]), "rect_xy": _hex(rect)})
+    (ROOT / "tests" / "golden" / "lightplane.json").write_text(json.dumps(out, indent=0))
+    print("wrote tests/golden/lightplane.json")
+
+
 if __name__ == "__main__":
-    mwc64x()
+    which = sys.argv[1:] or ["mwc64x", "geometry"]
+    for w in which:
+        {"mwc64x": mwc64x, "geometry": geometry}[w]()
