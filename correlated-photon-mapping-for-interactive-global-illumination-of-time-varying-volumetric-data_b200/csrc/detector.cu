@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) detect_kernel(const DetectArgs A) {
         float2 ip = A.isect[tid];
         float tStart = ip.x, tEnd = ip.y;
         if (tStart < tEnd) {
-            float3_ entry = {fmaf(tStart, dir.x, origin.x), fmaf(tStart, dir.y, origin.y), fmaf(tStart, dir.z, origin.z)};
+            float3_ entry = ray_at(origin, tStart, dir);
             for (int k = 0; k < A.max_interactions; ++k) {
                 size_t pid = (size_t)A.photon_offset + (size_t)k * A.total_photons + tid;
                 float4 p0 = A.photons[2 * pid], p1 = A.photons[2 * pid + 1];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128) detect_kernel(const DetectArgs A) {
                 if (p0.x == CPM_FLT_MAX || p0.y == CPM_FLT_MAX || p0.z == CPM_FLT_MAX) {
                     if (k == 0) {
                         if (A.fix_exit)
-                            exit = {fmaf(tEnd, dir.x, origin.x), fmaf(tEnd, dir.y, origin.y), fmaf(tEnd, dir.z, origin.z)};
+                            exit = ray_at(origin, tEnd, dir);
                         else
                             exit = {tEnd * dir.x, tEnd * dir.y, tEnd * dir.z};  // reference quirk (:128)
                     } else if (entry.x == CPM_FLT_MAX || entry.y == CPM_FLT_MAX || entry.z == CPM_FLT_MAX) {
@@ -138,7 +138,15 @@ __global__ void __launch_bounds__(128) detect_kernel(const DetectArgs A) {
                         float t0 = 0.0f, t1 = CPM_FLT_MAX;
                         float3_ pd = decode_direction(p1.z, p1.w);
                         if (p0.w != CPM_FLT_MAX && ray_box(bmin, bmax, entry, pd, t0, t1)) {
-                            exit = {fmaf(t1, pd.x, entry.x), fmaf(t1, pd.y, entry.y), fmaf(t1, pd.z, entry.z)};
+                            if (A.fix_exit) {
+                                exit = ray_at(entry, t1, pd);   // the evidently intended exit point
+                            } else {
+                                // reference (:137): `exit += photonDirection*tEnd` on exit == (FLT_MAX, FLT_MAX, FLT_MAX):
+                                // x2 becomes +inf on every axis, the DDA sums val * 0 and scales by length(x2 - x1) == inf,
+                                // i.e. NaN, and convert_uint_sat_rtp(NaN) == 0: the photon is not flagged (see orc_grid.c)
+                                imp = __uint_as_float(0x7fc00000u);
+                                break;
+                            }
                         } else {
                             break;
                         }

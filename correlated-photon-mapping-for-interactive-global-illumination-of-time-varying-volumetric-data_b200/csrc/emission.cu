@@ -27,9 +27,11 @@ __global__ void __launch_bounds__(256) directional_kernel(const float4* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 s = samples[i];  // u, v, w, pdf
-    float ox = fmaf(L.v[0], s.y, fmaf(L.u[0], s.x, L.origin[0]));
-    float oy = fmaf(L.v[1], s.y, fmaf(L.u[1], s.x, L.origin[1]));
-    float oz = fmaf(L.v[2], s.y, fmaf(L.u[2], s.x, L.origin[2]));
+    // planeOrigin + planeTangentU * s.x + planeTangentV * s.y as written (lcl/cl/directionallightsampler.cl:56): rounded
+    // products and sums, left to right
+    float ox = __fadd_rn(__fadd_rn(L.origin[0], __fmul_rn(L.u[0], s.x)), __fmul_rn(L.v[0], s.y));
+    float oy = __fadd_rn(__fadd_rn(L.origin[1], __fmul_rn(L.u[1], s.x)), __fmul_rn(L.v[1], s.y));
+    float oz = __fadd_rn(__fadd_rn(L.origin[2], __fmul_rn(L.u[2], s.x)), __fmul_rn(L.v[2], s.y));
     float pdf = s.w / L.area;
     float2 ang = encode_direction({L.dir[0], L.dir[1], L.dir[2]});
     out[2 * (size_t)i] = make_float4(ox, oy, oz, L.radiance[0] / pdf);

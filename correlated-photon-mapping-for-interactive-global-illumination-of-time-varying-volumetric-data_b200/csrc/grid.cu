@@ -354,9 +354,10 @@ __device__ float tf_points_importance(float4 color, float4 next, const float* w,
         rgb2lab(color.x, color.y, color.z, la);
         rgb2lab(next.x, next.y, next.z, lb);
         float d0 = lb[0] - la[0], d1 = lb[1] - la[1], d2 = lb[2] - la[2];
-        float lenN = sqrtf(lb[0] * lb[0] + lb[1] * lb[1] + lb[2] * lb[2]);
-        float lenC = sqrtf(la[0] * la[0] + la[1] * la[1] + la[2] * la[2]);
-        float lenD = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+        // length(): the definition used everywhere on the path (fma chain from x)
+        float lenN = sqrtf(fmaf(lb[2], lb[2], fmaf(lb[1], lb[1], lb[0] * lb[0])));
+        float lenC = sqrtf(fmaf(la[2], la[2], fmaf(la[1], la[1], la[0] * la[0])));
+        float lenD = sqrtf(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
         imp = w[0] * fmaxf(lenN, lenC) + w[1] * lenD + w[2] * fabsf(next.w - color.w) + w[3] * fmaxf(color.w, next.w);
     }
     return imp;
@@ -436,7 +437,8 @@ __global__ void __launch_bounds__(128) hash_kernel(const float4* __restrict__ ls
     float4 l0 = ls[2 * (size_t)id], l1 = ls[2 * (size_t)id + 1];
     float3_ d = decode_direction(l1.z, l1.w);
     float ts = isect[id].x;
-    float px = fmaf(ts, d.x, l0.x), py = fmaf(ts, d.y, l0.y), pz = fmaf(ts, d.z, l0.z);
+    // lightSample.origin + tStart * lightSample.direction as written (ppm/cl/hashlightsample.cl:56)
+    float px = __fadd_rn(l0.x, __fmul_rn(ts, d.x)), py = __fadd_rn(l0.y, __fmul_rn(ts, d.y)), pz = __fadd_rn(l0.z, __fmul_rn(ts, d.z));
     uint32_t hx = (uint32_t)cpm_clamp(truncf(px * cx), 0.f, 4294967040.f);
     uint32_t hy = (uint32_t)cpm_clamp(truncf(py * cy), 0.f, 4294967040.f);
     uint32_t hz = (uint32_t)cpm_clamp(truncf(pz * cz), 0.f, 4294967040.f);

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ x, const
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float fx = (float)x[i], fy = (float)y[i];
-    float m = fx + (fy - fx) * a;
+    float m = fmaf(fy - fx, a, fx);   // mix(): one definition on the whole path (grid.cu mix4, the oracle's v4_mix)
     if (sizeof(T) == 4) {
         out[i] = (T)m;
     } else {

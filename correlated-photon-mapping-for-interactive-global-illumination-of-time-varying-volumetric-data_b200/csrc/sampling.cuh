@@ -15,6 +15,16 @@ struct float3_ {
     float x, y, z;
 };
 
+// `origin + t*direction` as the reference's kernels write it (ppm/cl/transmittance.cl:136, photontracer.cl:165,
+// photonrecomputationdetector.cl:122 ...): a rounded product and a rounded sum per component, never a fused
+// multiply-add -- what the reference's .cl files give under strict IEEE evaluation (oracle/_ref/libcl_ref.so), which
+// the oracle and these kernels match bit for bit.  The intrinsics keep the two roundings whatever -fmad says.
+__device__ __forceinline__ float3_ ray_at(const float3_& o, float t, const float3_& d) {
+    return {__fadd_rn(o.x, __fmul_rn(t, d.x)), __fadd_rn(o.y, __fmul_rn(t, d.y)), __fadd_rn(o.z, __fmul_rn(t, d.z))};
+}
+// `t += -native_log(u) * invTauMaxSampleBaseInterval` (ppm/cl/transmittance.cl:135), as written
+__device__ __forceinline__ float advance_t(float t, float log_u, float inv) { return __fadd_rn(t, __fmul_rn(-log_u, inv)); }
+
 struct VolumeView {
     const void* lin;
     cudaTextureObject_t tex;

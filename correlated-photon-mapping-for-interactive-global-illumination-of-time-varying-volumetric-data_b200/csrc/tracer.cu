@@ -60,8 +60,9 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
     // tauMax = 1 (photontracer.cl:160): invTauMaxSampleBaseInterval = 1/(1*150), invTauMax = 1
     const float inv = 1.0f / 150.0f;
     cpm_rng spec = rng;
-    float tA = fmaf(-cpm_logf(cpm_rng_01(spec)), inv, tStart), tB;
-    Taps A = fetch_taps<FMT, LAYOUT>(V, fmaf(tA, d.x, o.x), fmaf(tA, d.y, o.y), fmaf(tA, d.z, o.z)), B;
+    float tA = advance_t(tStart, cpm_logf(cpm_rng_01(spec)), inv), tB;
+    float3_ pA = ray_at(o, tA, d);
+    Taps A = fetch_taps<FMT, LAYOUT>(V, pA.x, pA.y, pA.z), B;
     float t;
     // one test: CUR is in flight since the previous test, NXT is requested here (the loop body is written
     // twice with the roles of A and B swapped so that no register moves are needed)
@@ -70,8 +71,9 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
         rng = spec;                 /* commit the first number of this test */                             \
         float u2 = cpm_rng_01(rng); /* second number of this test */                                       \
         spec = rng;                                                                                        \
-        TNXT = fmaf(-cpm_logf(cpm_rng_01(spec)), inv, TCUR);                                               \
-        NXT = fetch_taps<FMT, LAYOUT>(V, fmaf(TNXT, d.x, o.x), fmaf(TNXT, d.y, o.y), fmaf(TNXT, d.z, o.z)); \
+        TNXT = advance_t(TCUR, cpm_logf(cpm_rng_01(spec)), inv);                                           \
+        const float3_ pn = ray_at(o, TNXT, d);                                                             \
+        NXT = fetch_taps<FMT, LAYOUT>(V, pn.x, pn.y, pn.z);                                                \
         float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, blend_taps<FMT>(V, CUR));                      \
         ++tests;                                                                                           \
         if (!(u2 >= opacity && TCUR <= tEnd)) {                                                            \
@@ -133,7 +135,7 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
         float u2 = 0.0f;
 #pragma unroll 1
         for (int k = 0; k < A.scan; ++k) {
-            t = fmaf(-log_unit(cpm_rng_01(rng)), inv, t);
+            t = advance_t(t, log_unit(cpm_rng_01(rng)), inv);
             u2 = cpm_rng_01(rng);
             ++tests;
             if (!(t <= tEnd)) {
@@ -151,7 +153,8 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
         }
         if (cand) {
             ++fetched;
-            float v = sample_volume<FMT, LAYOUT>(V, fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+            const float3_ pc = ray_at(o, t, d);
+            float v = sample_volume<FMT, LAYOUT>(V, pc.x, pc.y, pc.z);
             float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
             done = !(u2 >= opacity);
         }
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
             float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT>(A, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
                               : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             if (scatter) {
-                o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+                o = ray_at(o, t, d);
                 tStart = 0.0f;
                 tEnd = CPM_FLT_MAX;
                 float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
                               : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             scatter = t <= tEnd;
             if (scatter) {
-                o = {fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)};
+                o = ray_at(o, t, d);
                 size_t pid = (size_t)P.photon_offset + (size_t)n * P.total_photons + tid;
                 float2 ang = encode_direction(d);
                 float vs = sample_volume<FMT, LAYOUT>(A.vol, o.x, o.y, o.z);

@@ -740,7 +740,7 @@ void PhotonRecomputationDetector::photonRecomputationImportance(const PhotonData
                                 static_cast<const float*>(ls.getLightSamples()->deviceRead()),
                                 static_cast<const float*>(ls.getIntersectionPoints()->deviceRead()), (int)lightSamples.getSize(),
                                 photonData->getMaxPhotonInteractions(), (int)photonData->getNumberOfPhotons(), keys,
-                                equalImportance_ ? 1 : 0, percentage_, iteration_, 0));
+                                equalImportance_ ? 1 : 0, percentage_, iteration_, fixExitPoint_ ? CPM_DETECT_FIX_EXIT : 0));
 }
 
 void Radixsort::enqueue(Buffer<unsigned int>& keys, Buffer<unsigned int>* values, size_t elements, unsigned int maxBits) {
@@ -845,6 +845,7 @@ ProgressivePhotonTracerCL::ProgressivePhotonTracerCL()
     , clipX_("clipX", "Clip X Slices", ivec2{0, 256}, ivec2{0, 0}, ivec2{256, 256})
     , clipY_("clipY", "Clip Y Slices", ivec2{0, 256}, ivec2{0, 0}, ivec2{256, 256})
     , clipZ_("clipZ", "Clip Z Slices", ivec2{0, 256}, ivec2{0, 0}, ivec2{256, 256})
+    , fixDetectorExitPoint_("fixDetectorExitPoint", "Detector: repaired exit points (not in the reference)", false)
     , photonData_(std::make_shared<PhotonData>())
     , recomputedPhotonIndices_(std::make_shared<RecomputedPhotonIndices>()) {
     using R = PhotonData::InvalidationReason;
@@ -898,6 +899,8 @@ ProgressivePhotonTracerCL::ProgressivePhotonTracerCL()
     addProperty(clipX_);
     addProperty(clipY_);
     addProperty(clipZ_);
+    addProperty(fixDetectorExitPoint_);
+    fixDetectorExitPoint_.onChange([this]() { photonRecomputationDetector_.setFixExitPoint(fixDetectorExitPoint_.get()); });
     clipX_.setVisible(false);
     clipY_.setVisible(false);
     clipZ_.setVisible(false);

@@ -254,9 +254,14 @@ public:
     void setPercentage(int v) { percentage_ = v; }
     int getIteration() const { return iteration_; }
     void setIteration(int v) { iteration_ = v; }
+    // not in the reference: CPM_DETECT_FIX_EXIT -- exit points of photons that left the volume are computed as intended
+    // (origin + tEnd * dir for interaction 0, entry + t * dir later) instead of the reference's
+    // ppm/cl/photonrecomputationdetector.cl:128 / :137 arithmetic
+    bool getFixExitPoint() const { return fixExitPoint_; }
+    void setFixExitPoint(bool v) { fixExitPoint_ = v; }
     bool isValid() const { return true; }
 private:
-    bool equalImportance_ = false;
+    bool equalImportance_ = false, fixExitPoint_ = false;
     int percentage_ = 100, iteration_ = 0;
 };
 // clogs::Radixsort (rsc/ext/clogs/radixsort.h) for uint keys / uint-or-no values
@@ -334,6 +339,7 @@ public:
     ButtonProperty invalidateRendering_;
     BoolProperty enableProgressiveRefinement_, enableProgressivePhotonRecomputation_;
     IntMinMaxProperty clipX_, clipY_, clipZ_;
+    BoolProperty fixDetectorExitPoint_;   // extension (default off = the reference's arithmetic): see PhotonRecomputationDetector
 
     void invalidateProgressiveRendering(PhotonData::InvalidationReason r) { invalidationFlag_ |= r; }
     void onTimerEvent();    // the reference's 100 ms Timer callback; call it to step progressive work

@@ -16,8 +16,12 @@ static inline v3 v3_cross(v3 a, v3 b) {
     return v3_make(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 static inline v3 v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
-/* origin + t*direction, one fused multiply-add per component */
+/* origin + t*direction, one fused multiply-add per component (the oracle's own marchers: gather, ray caster) */
 static inline v3 v3_madd(v3 o, float t, v3 d) { return v3_make(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)); }
+/* `origin + t*direction` as the reference's kernels WRITE it: a rounded product, then a rounded sum per component
+ * (built with -ffp-contract=off).  This is what oracle/_ref/libcl_ref.so -- the reference's .cl files compiled with
+ * strict IEEE evaluation -- computes, so the oracle matches it bit for bit (tests/test_ref_kernels.py). */
+static inline v3 v3_ray(v3 o, float t, v3 d) { return v3_make(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z); }
 
 static inline float lerpf_(float p, float q, float a) { return fmaf(a, q - p, p); }
 

@@ -26,7 +26,8 @@ void orc_light_sample_directional(const float* samples, const float radiance[3],
     for (int i = 0; i < n; ++i) {
         const float* s = samples + 4 * i;
         float* o = out + 8 * (size_t)i;
-        for (int k = 0; k < 3; ++k) o[k] = fmaf(v[k], s[1], fmaf(u[k], s[0], origin[k]));
+        /* planeOrigin + planeTangentU * s.x + planeTangentV * s.y, evaluated as written (rounded products and sums) */
+        for (int k = 0; k < 3; ++k) o[k] = (origin[k] + u[k] * s[0]) + v[k] * s[1];
         float pdf = s[3] / area;
         for (int k = 0; k < 3; ++k) o[3 + k] = radiance[k] / pdf;
         o[6] = theta;

@@ -114,9 +114,10 @@ static float tfPointsImportance(v4 color, v4 nextColor, const float w[4], int in
         rgb2lab(a, la);
         rgb2lab(b, lb);
         float dl[3] = {lb[0] - la[0], lb[1] - la[1], lb[2] - la[2]};
-        float lenN = sqrtf(lb[0] * lb[0] + lb[1] * lb[1] + lb[2] * lb[2]);
-        float lenC = sqrtf(la[0] * la[0] + la[1] * la[1] + la[2] * la[2]);
-        float lenD = sqrtf(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+        /* length(): the same definition as everywhere else in the oracle (fma chain from x) */
+        float lenN = sqrtf(fmaf(lb[2], lb[2], fmaf(lb[1], lb[1], lb[0] * lb[0])));
+        float lenC = sqrtf(fmaf(la[2], la[2], fmaf(la[1], la[1], la[0] * la[0])));
+        float lenD = sqrtf(fmaf(dl[2], dl[2], fmaf(dl[1], dl[1], dl[0] * dl[0])));
         float opacityDiff = nextColor.w - color.w;
         /* weights: colorWeight, colorDiffWeight, opacityDiffWeight, opacityWeight */
         importance = w[0] * fmaxf(lenN, lenC) + w[1] * lenD + w[2] * fabsf(opacityDiff) + w[3] * fmaxf(color.w, nextColor.w);
@@ -253,14 +254,14 @@ void orc_detect_invalid(const float* grid, const int grid_dims[3], const float c
             v3 direction = decodeDirection(ls[6], ls[7]);
             float tStart = isect[2 * (size_t)threadId], tEnd = isect[2 * (size_t)threadId + 1];
             if (tStart < tEnd) {
-                v3 entry = v3_madd(origin, tStart, direction);
+                v3 entry = v3_ray(origin, tStart, direction);
                 for (int interaction = 0; interaction < max_interactions; ++interaction) {
                     size_t photonId = (size_t)photon_offset + (size_t)interaction * total_photons + threadId;
                     const float* ph = photons + 8 * photonId;
                     v3 exit = v3_make(ph[0], ph[1], ph[2]);
                     if (ph[0] == FLT_MAX || ph[1] == FLT_MAX || ph[2] == FLT_MAX) {
                         if (interaction == 0) {
-                            exit = fix_exit ? v3_madd(origin, tEnd, direction)
+                            exit = fix_exit ? v3_ray(origin, tEnd, direction)
                                             : v3_make(tEnd * direction.x, tEnd * direction.y, tEnd * direction.z);
                         } else if (entry.x == FLT_MAX || entry.y == FLT_MAX || entry.z == FLT_MAX) {
                             break;
@@ -269,9 +270,19 @@ void orc_detect_invalid(const float* grid, const int grid_dims[3], const float c
                             float t0 = 0.f, t1 = FLT_MAX;
                             v3 pd = decodeDirection(ph[6], ph[7]);
                             if (ph[3] != FLT_MAX && rayBoxIntersection(bmin, bmax, entry, pd, &t0, &t1)) {
-                                /* the reference adds to photon.xyz == FLT_MAX here, which overflows and is
-                                 * implementation-defined; restated as the evidently intended entry + d*tEnd */
-                                exit = v3_madd(entry, t1, pd);
+                                if (fix_exit) {
+                                    exit = v3_ray(entry, t1, pd); /* the evidently intended exit point */
+                                } else {
+                                    /* reference (:137): `exit += photonDirection*tEnd` with exit == photon.xyz ==
+                                     * (FLT_MAX, FLT_MAX, FLT_MAX).  The sum stays FLT_MAX (or overflows), the index
+                                     * coordinate x2 = textureToIndex * exit is +inf on every axis, the DDA then walks
+                                     * along x with dt == 0 (every cell contributes val * 0) and multiplies the sum by
+                                     * length(x2 - x1) == inf: the segment's importance is 0 * inf = NaN, the photon's
+                                     * total is NaN, and convert_uint_sat_rtp(NaN) == 0 -- the photon is NOT flagged.
+                                     * Checked against the reference's own kernel (oracle/_ref/libcl_ref.so). */
+                                    recomputationImportance = NAN;
+                                    break;
+                                }
                             } else {
                                 break;
                             }
@@ -303,7 +314,7 @@ void orc_hash_light_samples(const float* light_samples, const float* isect, int 
         v3 origin = v3_make(ls[0], ls[1], ls[2]);
         v3 direction = decodeDirection(ls[6], ls[7]);
         float tStart = isect[2 * (size_t)id];
-        v3 pos = v3_madd(origin, tStart, direction);
+        v3 pos = v3_ray(origin, tStart, direction);
         /* convert_uint3: truncation; clamp in float so the conversion is defined */
         uint32_t hx = (uint32_t)cpm_clamp(truncf(pos.x * cell_size[0]), 0.f, 4294967040.f);
         uint32_t hy = (uint32_t)cpm_clamp(truncf(pos.y * cell_size[1]), 0.f, 4294967040.f);

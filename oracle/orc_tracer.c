@@ -67,8 +67,8 @@ static float woodcockTracking(const orc_volume* vol, const float* tf, int tfw, v
     float opacity;
     float r;
     do {
-        t = fmaf(-cpm_logf(random_01(rs)), invTauMaxSampleBaseInterval, t);
-        v3 pos = v3_madd(origin, t, direction);
+        t += -cpm_logf(random_01(rs)) * invTauMaxSampleBaseInterval;
+        v3 pos = v3_ray(origin, t, direction);
         float volumeSample = orc_sample_volume(vol, pos.x, pos.y, pos.z);
         opacity = orc_sample_tf_alpha(tf, tfw, volumeSample);
         r = random_01(rs);
@@ -128,7 +128,7 @@ static unsigned long long trace_one(const orc_volume* vol, const float* tf, int 
     if (P->flags & 2u) { /* NO_SINGLE_SCATTERING, photontracer.cl:143-157 */
         float t = woodcockTracking(vol, tf, tfw, origin, direction, tStart, tEnd, 1.f, &rs, &tests);
         if (scatterEvent) {
-            origin = v3_madd(origin, t, direction);
+            origin = v3_ray(origin, t, direction);
             tStart = 0.f;
             tEnd = FLT_MAX;
             float u1 = random_01(&rs), u2 = random_01(&rs);
@@ -142,7 +142,7 @@ static unsigned long long trace_one(const orc_volume* vol, const float* tf, int 
         float t = woodcockTracking(vol, tf, tfw, origin, direction, tStart, tEnd, 1.f, &rs, &tests);
         scatterEvent = t <= tEnd;
         if (scatterEvent) {
-            origin = v3_madd(origin, t, direction);
+            origin = v3_ray(origin, t, direction);
             size_t photonId = (size_t)P->photon_offset + (size_t)nInteractions * P->total_photons + threadId;
             float th, ph;
             encodeDirection(direction, &th, &ph);

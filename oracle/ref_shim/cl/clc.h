@@ -145,38 +145,60 @@ struct float16 {
 };
 
 // vector literals: "(typeN)(...)" is rewritten to "make_typeN(...)" by the Makefile (section 6.1.6: a single scalar
-// is replicated, otherwise the operands are concatenated)
-#define CLC_MAKE2(NAME, T)                                    \
-    inline NAME make_##NAME(T a) { return NAME(a); }          \
-    inline NAME make_##NAME(T a, T b) { return NAME(a, b); }  \
-    inline NAME make_##NAME(const NAME& v) { return v; }
-CLC_MAKE2(float2, float)
-CLC_MAKE2(int2, int)
-CLC_MAKE2(uint2, uint)
-CLC_MAKE2(ushort2, ushort)
-#define CLC_MAKE3(NAME, T, V2)                                            \
-    inline NAME make_##NAME(T a) { return NAME(a); }                      \
-    inline NAME make_##NAME(T a, T b, T c) { return NAME(a, b, c); }      \
-    inline NAME make_##NAME(const V2& v, T c) { return NAME(v.s[0], v.s[1], c); } \
-    inline NAME make_##NAME(const NAME& v) { return v; }
-CLC_MAKE3(float3, float, float2)
-CLC_MAKE3(int3, int, int2)
-CLC_MAKE3(uint3, uint, uint2)
-#define CLC_MAKE4(NAME, T, V2, V3)                                                          \
-    inline NAME make_##NAME(T a) { return NAME(a); }                                        \
-    inline NAME make_##NAME(T a, T b, T c, T d) { return NAME(a, b, c, d); }                \
-    inline NAME make_##NAME(const V3& v, T d) { return NAME(v.s[0], v.s[1], v.s[2], d); }   \
-    inline NAME make_##NAME(const V2& v, T c, T d) { return NAME(v.s[0], v.s[1], c, d); }   \
-    inline NAME make_##NAME(const NAME& v) { return v; }
-CLC_MAKE4(float4, float, float2, float3)
-CLC_MAKE4(int4, int, int2, int3)
-CLC_MAKE4(uint4, uint, uint2, uint3)
-inline float8 make_float8(float a, float b, float c, float d, float e, float f, float g, float h) {
-    return float8(a, b, c, d, e, f, g, h);
-}
-inline float8 make_float8(const float3& a, const float3& b, const float2& c) {
-    return float8(a.s[0], a.s[1], a.s[2], b.s[0], b.s[1], b.s[2], c.s[0], c.s[1]);
-}
+// is replicated, otherwise the operands are concatenated).  make_typeN is a MACRO over a braced initialiser so that the
+// operands are evaluated LEFT TO RIGHT (C++ [dcl.init.list]/4) -- `(float2)(random_01(s), random_01(s))`
+// (ppm/cl/photontracer.cl:53) must draw its first number into .x, as OpenCL compilers (clang) do; a plain function
+// call would leave the order to the host compiler (gcc evaluates arguments right to left).
+#define CLC_MK2(NAME, T)                          \
+    struct mk_##NAME {                            \
+        NAME v;                                   \
+        mk_##NAME(T a) : v(a) {}                  \
+        mk_##NAME(T a, T b) : v(a, b) {}          \
+        mk_##NAME(const NAME& a) : v(a) {}        \
+    };
+CLC_MK2(float2, float)
+CLC_MK2(int2, int)
+CLC_MK2(uint2, uint)
+CLC_MK2(ushort2, ushort)
+#define CLC_MK3(NAME, T, V2)                                          \
+    struct mk_##NAME {                                                \
+        NAME v;                                                       \
+        mk_##NAME(T a) : v(a) {}                                      \
+        mk_##NAME(T a, T b, T c) : v(a, b, c) {}                      \
+        mk_##NAME(const V2& a, T c) : v(a.s[0], a.s[1], c) {}         \
+        mk_##NAME(const NAME& a) : v(a) {}                            \
+    };
+CLC_MK3(float3, float, float2)
+CLC_MK3(int3, int, int2)
+CLC_MK3(uint3, uint, uint2)
+#define CLC_MK4(NAME, T, V2, V3)                                                  \
+    struct mk_##NAME {                                                            \
+        NAME v;                                                                   \
+        mk_##NAME(T a) : v(a) {}                                                  \
+        mk_##NAME(T a, T b, T c, T d) : v(a, b, c, d) {}                          \
+        mk_##NAME(const V3& a, T d) : v(a.s[0], a.s[1], a.s[2], d) {}             \
+        mk_##NAME(const V2& a, T c, T d) : v(a.s[0], a.s[1], c, d) {}             \
+        mk_##NAME(const NAME& a) : v(a) {}                                        \
+    };
+CLC_MK4(float4, float, float2, float3)
+CLC_MK4(int4, int, int2, int3)
+CLC_MK4(uint4, uint, uint2, uint3)
+struct mk_float8 {
+    float8 v;
+    mk_float8(float a, float b, float c, float d, float e, float f, float g, float h) : v(a, b, c, d, e, f, g, h) {}
+    mk_float8(const float3& a, const float3& b, const float2& c) : v(a.s[0], a.s[1], a.s[2], b.s[0], b.s[1], b.s[2], c.s[0], c.s[1]) {}
+};
+#define make_float2(...) (mk_float2{__VA_ARGS__}.v)
+#define make_int2(...) (mk_int2{__VA_ARGS__}.v)
+#define make_uint2(...) (mk_uint2{__VA_ARGS__}.v)
+#define make_ushort2(...) (mk_ushort2{__VA_ARGS__}.v)
+#define make_float3(...) (mk_float3{__VA_ARGS__}.v)
+#define make_int3(...) (mk_int3{__VA_ARGS__}.v)
+#define make_uint3(...) (mk_uint3{__VA_ARGS__}.v)
+#define make_float4(...) (mk_float4{__VA_ARGS__}.v)
+#define make_int4(...) (mk_int4{__VA_ARGS__}.v)
+#define make_uint4(...) (mk_uint4{__VA_ARGS__}.v)
+#define make_float8(...) (mk_float8{__VA_ARGS__}.v)
 
 // ---- operators (section 6.3): component-wise; relational operators give -1 (true) / 0 per component ---------------
 #define CLC_ARITH(V, T, N)                                                                                         \
@@ -186,11 +208,9 @@ inline float8 make_float8(const float3& a, const float3& b, const float2& c) {
     inline V operator/(const V& a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] / b.s[i]; return r; } \
     inline V operator+(const V& a, T b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] + b; return r; }         \
     inline V operator-(const V& a, T b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] - b; return r; }         \
-    inline V operator*(const V& a, T b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] * b; return r; }         \
     inline V operator/(const V& a, T b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] / b; return r; }         \
     inline V operator+(T a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a + b.s[i]; return r; }         \
     inline V operator-(T a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a - b.s[i]; return r; }         \
-    inline V operator*(T a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a * b.s[i]; return r; }         \
     inline V operator/(T a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a / b.s[i]; return r; }         \
     inline V operator-(const V& a) { V r; for (int i = 0; i < N; ++i) r.s[i] = -a.s[i]; return r; }                 \
     inline V& operator+=(V& a, const V& b) { return a = a + b; }                                                    \
@@ -201,6 +221,9 @@ inline float8 make_float8(const float3& a, const float3& b, const float2& c) {
     inline V& operator-=(V& a, T b) { return a = a - b; }                                                           \
     inline V& operator*=(V& a, T b) { return a = a * b; }                                                           \
     inline V& operator/=(V& a, T b) { return a = a / b; }
+#define CLC_SCALE(V, T, N)                                                                                      \
+    inline V operator*(const V& a, T b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] * b; return r; }      \
+    inline V operator*(T a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = a * b.s[i]; return r; }
 #define CLC_REL(V, IV, N)                                                                                              \
     inline IV operator<(const V& a, const V& b) { IV r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] < b.s[i] ? -1 : 0; return r; }   \
     inline IV operator>(const V& a, const V& b) { IV r; for (int i = 0; i < N; ++i) r.s[i] = a.s[i] > b.s[i] ? -1 : 0; return r; }   \
@@ -211,6 +234,35 @@ inline float8 make_float8(const float3& a, const float3& b, const float2& c) {
 CLC_ARITH(float2, float, 2)
 CLC_ARITH(float3, float, 3)
 CLC_ARITH(float4, float, 4)
+CLC_SCALE(float2, float, 2)
+CLC_SCALE(float4, float, 4)
+CLC_SCALE(int2, int, 2)
+CLC_SCALE(int3, int, 3)
+CLC_SCALE(int4, int, 4)
+CLC_SCALE(uint3, uint, 3)
+#ifndef CLC_CONTRACT
+CLC_SCALE(float3, float, 3)
+#else
+// FP_CONTRACT ON (the OpenCL C default, section 6.12.2... #pragma OPENCL FP_CONTRACT): a product that directly feeds a
+// sum may be evaluated as one fused multiply-add.  Scalar expressions are contracted by the host compiler
+// (-ffp-contract=fast); for `vector + scalar * vector` the fusion is spelled out here, because the compiler does not see
+// through the vector classes reliably: scalar * float3 yields a lazy product that + / - / += consume with fmaf.
+struct Prod3 {
+    float3 v;
+    float k;
+    operator float3() const { return float3(v.s[0] * k, v.s[1] * k, v.s[2] * k); }
+};
+inline Prod3 operator*(float k, const float3& v) { Prod3 p; p.v = v; p.k = k; return p; }
+inline Prod3 operator*(const float3& v, float k) { Prod3 p; p.v = v; p.k = k; return p; }
+inline float3 operator*(const Prod3& p, float k) { return float3(p) * float3(k); }
+inline float3 operator/(const Prod3& p, float k) { return float3(p) / k; }
+inline float3 operator-(const Prod3& p) { return -float3(p); }
+inline float3 operator+(const float3& a, const Prod3& p) { return float3(fmaf(p.k, p.v.s[0], a.s[0]), fmaf(p.k, p.v.s[1], a.s[1]), fmaf(p.k, p.v.s[2], a.s[2])); }
+inline float3 operator+(const Prod3& p, const float3& a) { return a + p; }
+inline float3 operator-(const float3& a, const Prod3& p) { return float3(fmaf(-p.k, p.v.s[0], a.s[0]), fmaf(-p.k, p.v.s[1], a.s[1]), fmaf(-p.k, p.v.s[2], a.s[2])); }
+inline float3& operator+=(float3& a, const Prod3& p) { return a = a + p; }
+inline float3& operator-=(float3& a, const Prod3& p) { return a = a - p; }
+#endif
 CLC_ARITH(int2, int, 2)
 CLC_ARITH(int3, int, 3)
 CLC_ARITH(int4, int, 4)
@@ -347,8 +399,11 @@ struct clc_image {
     int dims[3];      // width, height, depth
     int format;       // 0 = UNORM_INT8, 1 = UNORM_INT16, 2 = FLOAT (1 channel); 3 = RGBA FLOAT (transfer functions)
 };
+struct clc_image2d : clc_image {};
 typedef const clc_image* image3d_t;
-typedef const clc_image* image2d_t;
+typedef const clc_image2d* image2d_t;
 typedef int sampler_t;
 inline int4 get_image_dim(image3d_t img) { return int4(img->dims[0], img->dims[1], img->dims[2], 0); }
+inline int2 get_image_dim(image2d_t img) { return int2(img->dims[0], img->dims[1]); }
 inline int get_image_width(image2d_t img) { return img->dims[0]; }
+inline int get_image_height(image2d_t img) { return img->dims[1]; }

@@ -170,8 +170,24 @@ def test_cuda_hash_and_cell_ranges(cpm, orc, ctx, torch_cuda, synth):
 
 @pytest.mark.gpu
 def test_cuda_mix_kernel(cpm, ctx, torch_cuda, synth):
-    """mixKernel (ugc/cl/buffermixer.cl:37-48): x + (y - x) * a; integer formats truncate toward zero"""
+    """mixKernel (ugc/cl/buffermixer.cl:37-48): x + (y - x) * a; integer formats truncate toward zero.  First against the
+    reference's own kernel (tests/golden/ref_kernels.npz: float and uchar buffers), then at size against numpy."""
     torch = torch_cuda
+    from conftest import GOLDEN
+    gold = np.load(GOLDEN / "ref_kernels.npz")
+    x = synth.volume_f32((8, 8, 8), 1).reshape(-1)
+    y = synth.volume_f32((8, 8, 8), 2).reshape(-1)
+    out = torch.zeros(x.size, dtype=torch.float32, device="cuda")
+    ctx.mix(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), 0.3, x.size, cpm.CPM_FMT_F32, out)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), gold["mix_f32"].view(np.uint32))
+    bx = (synth.splitmix64(3, 4096) & np.uint64(255)).astype(np.uint8)
+    by = (synth.splitmix64(4, 4096) & np.uint64(255)).astype(np.uint8)
+    for k, a in enumerate((0.0, 0.3, 0.5, 1.0)):
+        ob = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+        ctx.mix(torch.from_numpy(bx).cuda(), torch.from_numpy(by).cuda(), a, 4096, cpm.CPM_FMT_U8, ob)
+        ctx.sync()
+        assert np.array_equal(ob.cpu().numpy(), gold[f"mix_u8_{k}"]), a
     n = 100_003
     for a in (0.0, 0.25, 1.0):
         fx = synth.uniform01(1, n).astype(np.float32)
@@ -179,12 +195,12 @@ def test_cuda_mix_kernel(cpm, ctx, torch_cuda, synth):
         out = torch.zeros(n, dtype=torch.float32, device="cuda")
         ctx.mix(torch.from_numpy(fx).cuda(), torch.from_numpy(fy).cuda(), a, n, cpm.CPM_FMT_F32, out)
         ctx.sync()
-        want = (fx + (fy - fx) * np.float32(a)).astype(np.float32)
-        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        want = (fx.astype(np.float64) + (fy - fx).astype(np.float64) * np.float64(np.float32(a))).astype(np.float32)   # fma
+        assert np.abs(out.cpu().numpy().view(np.int32) - want.view(np.int32)).max() <= 1      # (double rounding: <= 1 ulp)
         bx = (synth.splitmix64(3, n) & np.uint64(255)).astype(np.uint8)
         by = (synth.splitmix64(4, n) & np.uint64(255)).astype(np.uint8)
         ob = torch.zeros(n, dtype=torch.uint8, device="cuda")
         ctx.mix(torch.from_numpy(bx).cuda(), torch.from_numpy(by).cuda(), a, n, cpm.CPM_FMT_U8, ob)
         ctx.sync()
-        wb = np.trunc(bx.astype(np.float32) + (by.astype(np.float32) - bx.astype(np.float32)) * np.float32(a)).astype(np.uint8)
+        wb = np.trunc(bx.astype(np.float64) + (by.astype(np.float64) - bx.astype(np.float64)) * np.float64(np.float32(a))).astype(np.uint8)
         assert np.array_equal(ob.cpu().numpy(), wb)

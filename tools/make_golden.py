@@ -111,7 +111,20 @@ def geometry():
     print("wrote tests/golden/lightplane.json")
 
 
+def kernels():
+    """tests/golden/ref_kernels.npz: the outputs of the reference's own OpenCL kernels (oracle/_ref/libcl_ref.so: the .cl
+    files compiled for the host, strict IEEE evaluation) on the seeded cases of tests/ref_cases.py"""
+    ref = orc.ref_lib("cl_ref")
+    if ref is None:
+        raise SystemExit("oracle/_ref/libcl_ref.so missing: run `make -C oracle ref` first")
+    sys.path.insert(0, str(ROOT / "tests"))
+    import ref_cases
+    out = ref_cases.ref_outputs(ref)
+    np.savez_compressed(ROOT / "tests" / "golden" / "ref_kernels.npz", **out)
+    print("wrote tests/golden/ref_kernels.npz:", len(out), "arrays,", (ROOT / "tests" / "golden" / "ref_kernels.npz").stat().st_size, "bytes")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mwc64x", "geometry"]
+    which = sys.argv[1:] or ["mwc64x", "geometry", "kernels"]
     for w in which:
-        {"mwc64x": mwc64x, "geometry": geometry}[w]()
+        {"mwc64x": mwc64x, "geometry": geometry, "kernels": kernels}[w]()
