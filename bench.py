@@ -67,8 +67,11 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU (A/B)")
-    ap.add_argument("--exchange", choices=["auto", "multimem", "p2p", "nccl"], default="auto",
-                    help="N > 1: how the per-rank light volumes are summed (auto: peer kernel with multimem where available)")
+    ap.add_argument("--exchange", choices=["auto", "multimem", "p2p", "cabi", "nccl"], default="auto",
+                    help="N > 1: how the per-rank light volumes are summed (auto: peer kernel with multimem where available; "
+                         "cabi: the C-ABI communicator alone -- cpm_comm_split + cpm_allreduce_lightvol_begin/_end)")
+    ap.add_argument("--no-sharded-ingest", action="store_true",
+                    help="N > 1: every rank uploads the whole time step over PCIe instead of its slab + NVLink all-gather (A/B)")
     ap.add_argument("--exchange-ctas", type=int, default=0, help="grid of the peer exchange kernel (0 = default)")
     ap.add_argument("--exchange-eager-wait", action="store_true",
                     help="the launch stream waits for the snapshot copy right after the frame (A/B; default: only the next splat waits)")
@@ -489,6 +492,12 @@ def run_b200(a):
     T, D, I = a.timesteps, a.dims, a.max_interactions
     n_photons = a.photons_side ** 2
     host.runtime_init(local, stream.cuda_stream, sharding.photon_shard(rank, world, n_photons)[0])
+    hcomm = None
+    if world > 1:
+        # the C-ABI communicator of this process (cpm_comm_init on the host layer's context; torch.distributed only carries
+        # the NCCL id): sharded ingest of host volumes and the frame sum of the e2e leg go through it
+        hcomm = sharding.bootstrap_comm(cpm, host.runtime_ctx())
+        host.runtime_set_comm(hcomm.h.value, not a.no_sharded_ingest)
 
     # ---- the time series: generated on the device, staged in pinned host memory (the e2e source) ----
     pinned = []
@@ -549,7 +558,11 @@ def run_b200(a):
         net.evaluate()                         # first frame: full trace + full splat
 
         exchange, exchange_kind = sharding.LightVolumeExchange(), "NCCL all-reduce"
-        if world > 1 and a.exchange != "nccl":
+        if world > 1 and a.exchange == "cabi":
+            lvd0 = net.light_volume_dims
+            exchange = sharding.CommLightVolumeExchange(cpm, hcomm, lvd0[0] * lvd0[1] * lvd0[2], dev)
+            exchange_kind = "cpm_allreduce_lightvol_begin/_end on a cpm_comm_split side-stream communicator"
+        elif world > 1 and a.exchange != "nccl":
             # one kernel over NVLink peer memory (csrc/exchange.cu); NCCL stays the fallback where symmetric memory
             # cannot be set up
             try:
@@ -630,9 +643,9 @@ def run_b200(a):
                 net.prefetch_timestep_host(pinned[(t + 1) % T])    # next step's 512 MB: overlaps this evaluation
                 net.evaluate()
                 if world > 1:
-                    out_host.copy_(allreduce_light_volume(), non_blocking=True)   # D2H of the summed volume
-                    stream.synchronize()
-                    d2h_extra[0] += out_host.numel() * 4
+                    # frame result = sum over ranks (cpm_allreduce_lightvol through the host layer's communicator);
+                    # rank 0 -- the process that shows the image -- reads it back
+                    net.sum_light_volume(out_host if rank == 0 else None)
                 else:
                     net.read_light_volume(out_host)
                 return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
@@ -662,8 +675,17 @@ def run_b200(a):
                     gbs = nbytes / (tot / cnt * 1e-3) / 1e9
                     grid_kernels[stage] = {"kernel": kname, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": nbytes,
                                            "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak()[0]}
+            if rank != 0:
+                stream.synchronize()
+            tot = sharding.sum_over_ranks([h2d, d2h], device=dev)
             e2e = {"value": traced_e / (wall_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                    "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": wall_e / a.steps,
+                   "h2d_bytes_per_step_all_ranks": int(tot[0]) // a.steps, "d2h_bytes_per_step_all_ranks": int(tot[1]) // a.steps,
+                   "ingest": ("sharded: rank r uploads slab r of the step (1/N of it) from pinned host memory, the slabs are "
+                              "all-gathered over NVLink on the transfer stream (cpm_comm_upload_volume_sharded); rank 0 reads "
+                              "the summed light volume back" if (world > 1 and not a.no_sharded_ingest) else
+                              "every rank uploads the whole step from pinned host memory" if world > 1 else
+                              "whole step from pinned (cudaHostAlloc) host memory"),
                    "frames_per_sec": a.steps / (wall_e * 1e-3),
                    "h2d_gbs": (h2d / a.steps) / (wall_e / a.steps * 1e-3) / 1e9,   # per rank: the step is PCIe bound
                    "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
@@ -673,6 +695,11 @@ def run_b200(a):
                            "upload is announced with cpmh_network_prefetch_timestep_host and overlaps this step) -> "
                            "cpmh_network_evaluate -> cpmh_network_read_light_volume(pinned host buffer)"}
         net.close()
+        if hcomm is not None:
+            if hasattr(exchange, "close"):
+                exchange.close()
+            host.runtime_set_comm(None, False)
+            hcomm.close()
 
     if rank != 0:
         if world > 1:

@@ -76,6 +76,20 @@ def lib() -> C.CDLL:
         _lib.cpm_ctx_destroy.argtypes = [C.c_void_p]
         _lib.cpm_volume_destroy.restype = None
         _lib.cpm_volume_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.cpm_comm_destroy.restype = None
+        _lib.cpm_comm_destroy.argtypes = [C.c_void_p]
+        _lib.cpm_comm_transport.restype = C.c_char_p
+        _lib.cpm_comm_transport.argtypes = [C.c_void_p]
+        _lib.cpm_comm_rank.argtypes = [C.c_void_p]
+        _lib.cpm_comm_world.argtypes = [C.c_void_p]
+        _lib.cpm_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        _lib.cpm_comm_split.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib.cpm_allreduce_lightvol.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpm_allreduce_lightvol_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpm_allreduce_lightvol_end.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpm_allgather_photons.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        _lib.cpm_allgather_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.cpm_comm_barrier.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -492,3 +506,70 @@ def _mix(self, x, y, a, n, fmt, out):
 
 
 Context.mix = _mix
+
+
+# -- multi-GPU communicator (cpm_comm_*: NCCL resolved at run time, own peer kernel for the light-volume sum) ---------
+CPM_COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """rank 0: the 128-byte id every rank passes to Comm() (hand it over by any transport)"""
+    buf = C.create_string_buffer(CPM_COMM_ID_BYTES)
+    rc = lib().cpm_comm_unique_id(buf)
+    if rc != 0:
+        raise CpmError(rc, "cpm_comm_unique_id: NCCL not available")
+    return buf.raw
+
+
+class Comm:
+    """One per process / GPU: cpm_comm_init on a Context.  All methods are collective and asynchronous on the context's
+    stream; tensors are device tensors."""
+
+    def __init__(self, ctx: Context, unique_id: bytes = None, rank: int = 0, world: int = 1, handle=None):
+        self.ctx = ctx
+        self.h = C.c_void_p(handle) if handle is not None else C.c_void_p()
+        if handle is None:
+            ctx._check(lib().cpm_comm_init(ctx.h, C.c_char_p(unique_id), int(rank), int(world), C.byref(self.h)))
+
+    def split(self, other_ctx: Context) -> "Comm":
+        """a second communicator over the same ranks bound to another context (stream) of this process"""
+        h = C.c_void_p()
+        other_ctx._check(lib().cpm_comm_split(self.h, other_ctx.h, C.byref(h)))
+        return Comm(other_ctx, handle=h.value)
+
+    @property
+    def rank(self):
+        return lib().cpm_comm_rank(self.h)
+
+    @property
+    def world(self):
+        return lib().cpm_comm_world(self.h)
+
+    @property
+    def transport(self):
+        return lib().cpm_comm_transport(self.h).decode()
+
+    def allreduce_lightvol(self, local, out):
+        self.ctx._check(lib().cpm_allreduce_lightvol(self.h, _p(local), _p(out), C.c_size_t(local.numel())))
+        return out
+
+    def allreduce_lightvol_begin(self, local, out):
+        self.ctx._check(lib().cpm_allreduce_lightvol_begin(self.h, _p(local), _p(out), C.c_size_t(local.numel())))
+
+    def allreduce_lightvol_end(self, out):
+        self.ctx._check(lib().cpm_allreduce_lightvol_end(self.h, _p(out), C.c_size_t(out.numel())))
+
+    def allgather_photons(self, local, out):
+        self.ctx._check(lib().cpm_allgather_photons(self.h, _p(local), C.c_size_t(local.numel()), _p(out)))
+        return out
+
+    def allgather_volume(self, volume, slab_bytes):
+        self.ctx._check(lib().cpm_allgather_volume(self.h, _p(volume), C.c_size_t(slab_bytes)))
+
+    def barrier(self):
+        self.ctx._check(lib().cpm_comm_barrier(self.h))
+
+    def close(self):
+        if self.h:
+            lib().cpm_comm_destroy(self.h)
+            self.h = C.c_void_p()

@@ -70,6 +70,9 @@ def lib():
         _lib.cpmh_config_from_workspace.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.POINTER(HostConfig)]
         _lib.cpmh_network_load_workspace.argtypes = [C.c_void_p, C.c_char_p]
         _lib.cpmh_network_get_property.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
+        _lib.cpmh_runtime_ctx.restype = C.c_void_p
+        _lib.cpmh_runtime_set_comm.argtypes = [C.c_void_p, C.c_int]
+        _lib.cpmh_network_sum_light_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         _lib.cpmh_network_read_importance_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_recomputed_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_importance_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -88,6 +91,19 @@ def runtime_init(device=0, stream=None, photon_shard_offset=0):
 def set_photon_shard_offset(offset: int):
     """first global photon id of this process (used by the next RNG seeding); see cpmh_runtime_init"""
     rc = lib().cpmh_runtime_set_photon_shard_offset(C.c_uint64(offset))
+    if rc < 0:
+        raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+
+
+def runtime_ctx() -> int:
+    """the process's cpm_ctx* (create the multi-GPU communicator on it: capi.Comm(handle=...) / cpm_comm_init)"""
+    return lib().cpmh_runtime_ctx()
+
+
+def runtime_set_comm(comm_handle, sharded_ingest=True):
+    """hand the process's cpm_comm* to the host layer; sharded_ingest: host volumes are uploaded as this rank's slab and
+    completed over NVLink (see cpmh_runtime_set_comm).  None detaches."""
+    rc = lib().cpmh_runtime_set_comm(C.c_void_p(comm_handle or 0), int(bool(sharded_ingest)))
     if rc < 0:
         raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
 
@@ -340,6 +356,16 @@ class Network:
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
         self._check(lib().cpmh_network_read_light_volume(self.h, C.c_void_p(ptr), C.c_size_t(n)))
         return out
+
+    def sum_light_volume(self, out_host=None):
+        """sum over ranks of the light volumes (cpm_allreduce_lightvol through the host layer's communicator); returns the
+        device pointer of the sum; out_host (pinned tensor / array): also read back into it, synchronously"""
+        d = self.light_volume_dims
+        n = d[0] * d[1] * d[2] * self.cfg.light_volume_channels
+        ptr = C.c_void_p()
+        hp = 0 if out_host is None else (out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data)
+        self._check(lib().cpmh_network_sum_light_volume(self.h, C.c_void_p(hp), C.c_size_t(n), C.byref(ptr)))
+        return ptr.value
 
     def read_photons(self, max_interactions):
         n = self.n_photons * max_interactions * 8

@@ -38,6 +38,7 @@ struct cpmh_network {
     std::shared_ptr<DynamicVolumeInfoUniformGrid3D> streamDiff[3];
     int streamSlot = -1;
     unsigned long long* collisionCounter = nullptr;
+    Buffer<float> lightVolumeSum;   // cpmh_network_sum_light_volume
 };
 
 template <typename F>
@@ -68,6 +69,46 @@ int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset) {
 int cpmh_runtime_set_photon_shard_offset(uint64_t photon_shard_offset) {
     return guarded([&]() {
         CpmRuntime::get().photonShardOffset = photon_shard_offset;
+        return (int)CPM_OK;
+    });
+}
+
+void* cpmh_runtime_ctx(void) {
+    void* c = nullptr;
+    guarded([&]() { c = CpmRuntime::get().ctx(); return (int)CPM_OK; });
+    return c;
+}
+
+int cpmh_runtime_set_comm(void* comm, int sharded_ingest) {
+    return guarded([&]() {
+        auto& rt = CpmRuntime::get();
+        rt.sync();
+        rt.comm = static_cast<cpm_comm*>(comm);
+        rt.shardedIngest = comm != nullptr && sharded_ingest != 0;
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_sum_light_volume(cpmh_network* net, float* out_host, size_t n_floats, void** sum_device) {
+    return guarded([&]() {
+        auto v = std::const_pointer_cast<Volume>(net->toLightVolume.outport_.getData());
+        if (!v || v->getSizeInBytes() != n_floats * sizeof(float)) throw std::invalid_argument("light volume size mismatch");
+        auto& rt = CpmRuntime::get();
+        const float* local = static_cast<const float*>(v->deviceRead());
+        const float* result = local;
+        if (rt.comm && cpm_comm_world(rt.comm) > 1) {
+            if (net->lightVolumeSum.getSize() != n_floats) net->lightVolumeSum.setSize(n_floats);
+            float* sum = static_cast<float*>(net->lightVolumeSum.deviceWrite());
+            ScopedStage st("exchange");
+            rt.check(cpm_allreduce_lightvol(rt.comm, local, sum, n_floats));
+            result = sum;
+        }
+        if (sum_device) *sum_device = const_cast<float*>(result);
+        if (out_host) {
+            rt.check(cpm_mem_copy_d2h(rt.ctx(), out_host, result, n_floats * sizeof(float)));
+            rt.sync();
+            BufferBase::d2hBytes() += n_floats * sizeof(float);
+        }
         return (int)CPM_OK;
     });
 }

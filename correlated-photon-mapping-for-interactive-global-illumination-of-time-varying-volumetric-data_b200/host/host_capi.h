@@ -45,6 +45,18 @@ typedef struct cpmh_config {
  * is photon photon_shard_offset + i of the global photon set (MWC64X stream and host base offset). */
 CPMH_API int cpmh_runtime_init(int device, void* stream, uint64_t photon_shard_offset);
 CPMH_API int cpmh_runtime_set_photon_shard_offset(uint64_t photon_shard_offset);
+/* Multi-GPU (one process per GPU).  cpmh_runtime_ctx() is the process's cpm_ctx*: create the communicator on it with
+ * cpm_comm_unique_id / cpm_comm_init (include/cpm_b200.h) and hand it over with cpmh_runtime_set_comm.  sharded_ingest != 0:
+ * every volume that arrives from HOST memory (cpmh_network_set_volume_host with pinned memory, _stream_timestep_host,
+ * _prefetch_timestep_host; every rank passes a buffer holding the whole time step) is uploaded as this rank's slab only
+ * and completed over NVLink -- 1 / world of the PCIe traffic per GPU.  Pass NULL to detach before destroying the
+ * communicator. */
+CPMH_API void* cpmh_runtime_ctx(void);
+CPMH_API int cpmh_runtime_set_comm(void* cpm_comm_handle, int sharded_ingest);
+/* frame result across GPUs: sum over ranks of the networks' light volumes (cpm_allreduce_lightvol) into a device buffer
+ * owned by the network (*sum_device, valid until the next call); out_host != NULL: also read back into it (n_floats),
+ * synchronously -- typically on rank 0 only */
+CPMH_API int cpmh_network_sum_light_volume(cpmh_network* net, float* out_host, size_t n_floats, void** sum_device);
 CPMH_API int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out);
 CPMH_API void cpmh_network_destroy(cpmh_network* net);
 CPMH_API const char* cpmh_last_error(void);

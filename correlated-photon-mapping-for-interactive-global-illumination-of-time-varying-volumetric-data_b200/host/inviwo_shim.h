@@ -108,6 +108,16 @@ public:
     // process uses MWC64X stream photonShardOffset + i (and the matching host base offset), so that the
     // shards of all GPUs together are the streams of one large single-GPU photon set.
     uint64_t photonShardOffset = 0;
+    // multi-GPU: the communicator of this process (cpm_comm_init on ctx()) and whether volumes are ingested sharded --
+    // rank r uploads slab r of a time step and the slabs are all-gathered over NVLink (cpm_comm_upload_volume_sharded)
+    cpm_comm* comm = nullptr;
+    bool shardedIngest = false;
+    // slab upload possible for a volume of `bytes`?
+    bool shardedUpload(size_t bytes) const {
+        if (!comm || !shardedIngest) return false;
+        const size_t w = (size_t)cpm_comm_world(comm);
+        return w > 1 && bytes % w == 0 && (bytes / w) % 16 == 0;
+    }
     cpm_ctx* ctx() { return ctx_; }
     void check(int rc) const {
         if (rc != CPM_OK) throw CpmError(rc, cpm_last_error(ctx_));

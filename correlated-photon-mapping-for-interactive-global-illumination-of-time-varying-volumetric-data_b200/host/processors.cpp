@@ -245,8 +245,14 @@ void Volume::prefetchExternalRAMData(void* ptr) {
         cpm_event_destroy(rt.ctx(), prefetchDone_);
         prefetchDone_ = nullptr;
     }
-    rt.check(cpm_mem_prefetch_h2d(rt.ctx(), dev_, ptr, devBytes_, &prefetchDone_));
-    BufferBase::h2dBytes() += devBytes_;
+    if (rt.shardedUpload(devBytes_)) {
+        // this rank's slab over PCIe, the other slabs over NVLink, both on the transfer stream
+        rt.check(cpm_comm_upload_volume_sharded(rt.comm, dev_, ptr, devBytes_, 1, &prefetchDone_));
+        BufferBase::h2dBytes() += devBytes_ / (size_t)cpm_comm_world(rt.comm);
+    } else {
+        rt.check(cpm_mem_prefetch_h2d(rt.ctx(), dev_, ptr, devBytes_, &prefetchDone_));
+        BufferBase::h2dBytes() += devBytes_;
+    }
     prefetched_ = ptr;
     devValid_ = false;
     texValid_ = false; touch();
@@ -269,9 +275,15 @@ const void* Volume::deviceRead() {
     if (!devValid_ && devBytes_) {
         const void* p = ext_ ? ext_ : (const void*)ram_.data();
         ScopedStage st("h2d");
-        CPM_CHECK(cpm_mem_copy_h2d(CpmRuntime::get().ctx(), dev_, p, devBytes_));
-        if (!ext_) CpmRuntime::get().sync();   // external (pinned) sources stay valid; stream order suffices
-        BufferBase::h2dBytes() += devBytes_;
+        auto& rt = CpmRuntime::get();
+        if (ext_ && rt.shardedUpload(devBytes_)) {
+            rt.check(cpm_comm_upload_volume_sharded(rt.comm, dev_, p, devBytes_, 0, nullptr));
+            BufferBase::h2dBytes() += devBytes_ / (size_t)cpm_comm_world(rt.comm);
+        } else {
+            CPM_CHECK(cpm_mem_copy_h2d(rt.ctx(), dev_, p, devBytes_));
+            if (!ext_) rt.sync();   // external (pinned) sources stay valid; stream order suffices
+            BufferBase::h2dBytes() += devBytes_;
+        }
         texValid_ = false; touch();
     }
     devValid_ = true;

@@ -107,6 +107,73 @@ class LightVolumeExchange:
         return b
 
 
+def bootstrap_comm(cpm, ctx_or_handle, group=None):
+    """The C-ABI communicator (cpm_comm_init) of this process: rank 0 makes the NCCL id, torch.distributed carries the 128
+    bytes to the other ranks (a C++ host would use MPI or a socket for this one message), every rank initialises.
+    ctx_or_handle: a cpm.Context, or the raw cpm_ctx* of the host layer (host.runtime_ctx())."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [cpm.capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    if isinstance(ctx_or_handle, int):
+        class _Raw:                      # a Context-like view of a cpm_ctx* owned elsewhere
+            def __init__(self, h):
+                import ctypes as C
+                self.h = C.c_void_p(h)
+
+            def _check(self, rc):
+                if rc != 0:
+                    raise cpm.capi.CpmError(rc, cpm.lib().cpm_last_error(self.h).decode())
+        ctx_or_handle = _Raw(ctx_or_handle)
+    return cpm.capi.Comm(ctx_or_handle, box[0], rank, world)
+
+
+class CommLightVolumeExchange:
+    """LightVolumeExchange on the C ABI alone (what a C++ host does): a side-stream context with its own communicator
+    (cpm_comm_split); submit() = wait for the frame's splat, cpm_allreduce_lightvol_begin (snapshot), event,
+    cpm_allreduce_lightvol_end (the library's peer kernel over CUDA IPC symmetric memory, or NCCL) on the side stream."""
+
+    def __init__(self, cpm, comm, n_floats: int, device):
+        self.side = torch.cuda.Stream(device=device)
+        self.ctx = cpm.Context(device.index, self.side.cuda_stream)
+        self.comm = comm.split(self.ctx)
+        self.bufs = [torch.empty(n_floats, dtype=torch.float32, device=device) for _ in range(2)]
+        self.copied = torch.cuda.Event()
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.turn, self.pending = 0, None
+
+    @property
+    def transport(self):
+        return self.comm.transport
+
+    def submit(self, local: torch.Tensor, defer_wait=None) -> None:
+        i = self.turn
+        self.turn ^= 1
+        cur = torch.cuda.current_stream(local.device)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            self.comm.allreduce_lightvol_begin(local.reshape(-1), self.bufs[i])
+            self.copied.record(self.side)
+            self.comm.allreduce_lightvol_end(self.bufs[i])
+            self.done[i].record(self.side)
+        if defer_wait is not None:
+            defer_wait(self.copied)
+        else:
+            cur.wait_event(self.copied)
+        self.pending = i
+
+    def result(self) -> torch.Tensor:
+        if self.pending is None:
+            raise RuntimeError("CommLightVolumeExchange.result() before submit()")
+        i = self.pending
+        torch.cuda.current_stream(self.bufs[i].device).wait_event(self.done[i])
+        return self.bufs[i]
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.comm.close()
+        self.ctx.close()
+
+
 class PeerLightVolumeExchange:
     """LightVolumeExchange with the sum done by cpm_allreduce_peer_f32 (csrc/exchange.cu) instead of NCCL: the snapshot
     buffers are symmetric memory (torch.distributed._symmetric_memory: one allocation per rank, peer and NVSwitch

@@ -383,6 +383,56 @@ CPM_API int cpm_splat_photons_update_sync(cpm_ctx* ctx, float* light_volume, int
 CPM_API int cpm_allreduce_peer_f32(cpm_ctx* ctx, float* const* peer_buffers, float* multicast, size_t n_floats,
                                    int rank, int world, int max_ctas);
 
+/* ---- multi-GPU communicator (cpm_comm_init / cpm_allreduce_lightvol / cpm_allgather_photons) ----------- */
+/* One communicator per process (= per GPU, one cpm_ctx).  A C / C++ host runs the sharded path with these calls alone:
+ *   rank 0: cpm_comm_unique_id(id); the application hands the 128 bytes to every rank (MPI, a file, a socket ...);
+ *   every rank: cpm_comm_init(ctx, id, rank, world, &comm).
+ * NCCL is loaded at run time (libnccl.so.2; CPM_NCCL_LIBRARY overrides the name) -- no link-time dependency, single-GPU
+ * users never load it.  cpm_comm_init_nccl adopts a communicator the application already owns (an ncclComm_t).
+ * Nothing in the reference corresponds to these (it is a single-GPU program); photon ranges per rank come from its own
+ * photonOffset / totalPhotons kernel arguments (ppm/cl/photontracer.cl:123,166), see cpmh_runtime_init.
+ * All calls are collective over the communicator and asynchronous on the context's stream. */
+typedef struct cpm_comm cpm_comm;
+#define CPM_COMM_ID_BYTES 128
+CPM_API int cpm_comm_unique_id(void* id_out /* CPM_COMM_ID_BYTES */);
+CPM_API int cpm_comm_init(cpm_ctx* ctx, const void* unique_id, int rank, int world, cpm_comm** out);
+CPM_API int cpm_comm_init_nccl(cpm_ctx* ctx, void* nccl_comm, int rank, int world, cpm_comm** out);
+CPM_API void cpm_comm_destroy(cpm_comm* comm);
+CPM_API int cpm_comm_rank(const cpm_comm* comm);
+CPM_API int cpm_comm_world(const cpm_comm* comm);
+/* "nccl" or "peer kernel over CUDA IPC symmetric memory": what cpm_allreduce_lightvol last used */
+CPM_API const char* cpm_comm_transport(const cpm_comm* comm);
+/* sum_out = sum over ranks of `local` (n_floats each; sum_out may equal local).  Option B of SURVEY 8e: every rank
+ * splats its photon shard into its own light volume, the frame's result is the sum.  When the GPUs can map each other's
+ * memory (CUDA IPC; CPM_COMM_TRANSPORT=nccl switches it off) the sum is formed by the library's own kernel over NVLink
+ * peer memory -- snapshot into a symmetric staging buffer, flag barrier, cpm_allreduce_peer_f32 (rank r reduces slice r
+ * with peer loads in rank order: every rank gets the same bits), flag barrier -- otherwise by ncclAllReduce. */
+CPM_API int cpm_allreduce_lightvol(cpm_comm* comm, const float* local, float* sum_out, size_t n_floats);
+/* The same in two halves for pipelining (cpm_allreduce_lightvol = _begin + _end): _begin snapshots `local` -- record an
+ * event after it; once that event has completed the next frame may overwrite `local` --, _end forms the sum in sum_out.
+ * Typical use: a communicator on a side-stream context (cpm_comm_split), so that the exchange runs next to the following
+ * frame's detector / re-trace and only that frame's splat waits for the snapshot event. */
+CPM_API int cpm_allreduce_lightvol_begin(cpm_comm* comm, const float* local, float* sum_out, size_t n_floats);
+CPM_API int cpm_allreduce_lightvol_end(cpm_comm* comm, float* sum_out, size_t n_floats);
+/* a second communicator over the same ranks, bound to another context (another stream) of this process; collective */
+CPM_API int cpm_comm_split(cpm_comm* comm, cpm_ctx* other_ctx, cpm_comm** out);
+/* all_out = every rank's n_floats_per_rank photon-record floats in rank order (option A of SURVEY 8e: the replicated
+ * photon map for gathering) */
+CPM_API int cpm_allgather_photons(cpm_comm* comm, const float* local, size_t n_floats_per_rank, float* all_out);
+/* Sharded ingest of a time step ("broadcast once per time step over NVLink"): on entry rank r holds slab r
+ * (bytes [r * slab_bytes, (r + 1) * slab_bytes) of `volume`, e.g. uploaded from its host), on return every rank holds
+ * all world * slab_bytes bytes.  In place. */
+CPM_API int cpm_allgather_volume(cpm_comm* comm, void* volume, size_t slab_bytes);
+/* The same with the upload: this rank copies ITS slab of the host buffer `src_host` (the whole time step, total_bytes) to
+ * the same offset of `volume` and the slabs are all-gathered, so a step costs total_bytes / world of PCIe traffic per
+ * GPU instead of total_bytes.  on_transfer_stream = 0: on the context stream.  on_transfer_stream = 1: both the copy and
+ * the all-gather run on the context's transfer stream (its own NCCL communicator where ncclCommSplit exists) after the
+ * work already submitted to the context stream, and *done is an event to hand to cpm_ctx_wait_event before the volume is
+ * used -- the pendant of cpm_mem_prefetch_h2d.  total_bytes must split into `world` equal 16-byte aligned slabs. */
+CPM_API int cpm_comm_upload_volume_sharded(cpm_comm* comm, void* volume, const void* src_host, size_t total_bytes,
+                                           int on_transfer_stream, cpm_event** done);
+CPM_API int cpm_comm_barrier(cpm_comm* comm);
+
 /* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
 /* Not launched anywhere in the reference; the estimator is the reference's
  * (Epanechnikov kernel, ppm/cl/densityestimationkernel.cl:56-60; power * 1/(4 pi) * relativeIrradianceScale,
