@@ -356,7 +356,7 @@ def test_cuda_equals_reference_golden(cpm, ctx, torch_cuda):
         # the kernel weights with the squared distance (1 - d^2 / r^2, no sqrt / division per voxel) where the reference
         # has 1 - (d / r)^2: a few ulp of the photon's peak contribution per voxel, relatively more towards the rim
         assert ((got != 0) == (w != 0)).mean() > 0.999, k
-        assert np.abs(got - w).max() <= 1e-6 * np.abs(w).max(), (k, np.abs(got - w).max(), np.abs(w).max())
+        assert np.abs(got - w).max() <= 4e-6 * np.abs(w).max(), (k, np.abs(got - w).max(), np.abs(w).max())
     dph = T(ph)
     v = torch.zeros(nv, dtype=torch.float32, device=dev)
     ctx.splat_photons(v, 1, t2, i2, rc.LV, dph, None, N * 3, N, 3, radius, scale)
