@@ -157,7 +157,8 @@ def main():
     (ra, sa, la, ha), (rb, sb, lb, hb) = results[False], results[True]
     for (na, pa), (nb, pb) in zip(ra, rb):
         assert na == nb and np.array_equal(pa.view(np.uint32), pb.view(np.uint32)), "sharded ingest changes the photons"
-    assert np.array_equal(la.view(np.uint32), lb.view(np.uint32))
+    # (the splat adds with fp32 atomics: two runs agree to rounding, not bit for bit)
+    assert np.sqrt(((la.astype(np.float64) - lb) ** 2).mean()) <= 1e-5 * np.sqrt((la.astype(np.float64) ** 2).mean())
     assert hb < ha and abs(hb * world - ha) <= 0.05 * ha + 4 * 16 * 1024 * 1024, (ha, hb)
     # the summed light volume = rank-ordered sum of the per-rank volumes
     mine = torch.from_numpy(lb).to(dev)
