@@ -80,6 +80,8 @@ def parse():
     ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
     ap.add_argument("--gather-grid-scale", type=float, default=1.0, help="photon-map cells per 2r along an axis (tuning sweeps)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
+    ap.add_argument("--volume-layout", choices=["texture", "linear"], default="texture",
+                    help="layout the tracer samples: 2-D layered CUDA array (tld4) or the caller's linear buffer (A/B)")
     return ap.parse_args()
 
 
@@ -537,7 +539,8 @@ def run_b200(a):
 
     with torch.cuda.stream(stream):
         net = host.Network((D, D, D), cpm.CPM_FMT_F32, a.photons_side, [LIGHT_DIR], max_scattering_events=I,
-                           light_volume_option=2, with_importance_grid=True, volume_layout=cpm.CPM_VOLUME_TEXTURE,
+                           light_volume_option=2, with_importance_grid=True,
+                           volume_layout=cpm.CPM_VOLUME_TEXTURE if a.volume_layout == "texture" else cpm.CPM_VOLUME_LINEAR,
                            reference_full_splat_bound=False, device=local, opacity_bound_cell_log2=a.bound_log2)
         net.set_transfer_function(synth.WS_TF_POINTS)
         net.count_collision_tests(True)
@@ -638,16 +641,19 @@ def run_b200(a):
             lvd = net.light_volume_dims
             out_host = torch.empty(lvd[0] * lvd[1] * lvd[2], dtype=torch.float32, pin_memory=True)
 
+            out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+            e2e_k = [0]
+
             def step_e2e(t):
                 net.stream_timestep_host(pinned[t % T])            # adopts the upload announced one step earlier
-                net.prefetch_timestep_host(pinned[(t + 1) % T])    # next step's 512 MB: overlaps this evaluation
+                net.prefetch_timestep_host(pinned[(t + 1) % T])    # next step's 512 MB (N > 1: this rank's slab + NVLink all-gather)
                 net.evaluate()
-                if world > 1:
-                    # frame result = sum over ranks (cpm_allreduce_lightvol through the host layer's communicator);
-                    # rank 0 -- the process that shows the image -- reads it back
-                    net.sum_light_volume(out_host if rank == 0 else None)
-                else:
-                    net.read_light_volume(out_host)
+                # frame result -> host: the sum over ranks (cpm_allreduce_lightvol through the host layer's communicator) is
+                # read back by rank 0 -- the process that shows the image -- on the read-back stream; the copy of frame k
+                # travels while frame k + 1 is computed and is waited for before the buffer pair is reused
+                net.wait_readback()
+                net.read_light_volume_async(out_hosts[e2e_k[0] & 1] if rank == 0 else None)
+                e2e_k[0] += 1
                 return max(net.n_recomputed, 0) if net.n_recomputed >= 0 else net.n_photons
 
             d2h_extra = [0]
@@ -659,7 +665,7 @@ def run_b200(a):
             d2h_extra[0] = 0
             host.profile_enable(True)
             host.profile_reset()
-            ms_e, wall_e, traced_e = time_loop(net, a.steps, first, step_e2e)
+            ms_e, wall_e, traced_e = time_loop(net, a.steps, first, step_e2e, net.wait_readback)   # the last result lands inside the timed region
             st_e = {s: (host.profile_total_ms(s), host.profile_count(s)) for s in host.profile_stages()}
             host.profile_enable(False)
             h2d, d2h = host.Network.transfer_bytes()
@@ -693,7 +699,9 @@ def run_b200(a):
                    "cpu_affinity": cpulist,
                    "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume; the next step's "
                            "upload is announced with cpmh_network_prefetch_timestep_host and overlaps this step) -> "
-                           "cpmh_network_evaluate -> cpmh_network_read_light_volume(pinned host buffer)"}
+                           "cpmh_network_evaluate -> cpmh_network_read_light_volume_async(pinned host buffer; lands while "
+                           "the next step is computed, cpmh_network_wait_readback before the buffer pair is reused and at "
+                           "the end of the timed region)"}
         net.close()
         if hcomm is not None:
             if hasattr(exchange, "close"):
@@ -745,7 +753,7 @@ def run_b200(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "photons_total": n_photons * world,
-                       "light_volume": f"{D // 2}^3 f32", "volume_layout": "2-D layered CUDA array (tld4)",
+                       "light_volume": f"{D // 2}^3 f32", "volume_layout": "2-D layered CUDA array (tld4)" if a.volume_layout == "texture" else "linear buffer (8 x LDG)",
                        "l2": "inputs larger than L2: a different 512 MB volume every step, 128 MB photon records",
                        "parallelism": f"photon shards x{world}, light volumes summed on a side stream (overlaps the next frame): {exchange_kind}" if world > 1 else "1 GPU"},
             "frames_per_sec": a.steps / (ms * 1e-3), "retrace_fraction": traced / (a.steps * n_photons * world),

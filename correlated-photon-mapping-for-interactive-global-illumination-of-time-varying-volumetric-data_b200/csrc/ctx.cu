@@ -95,6 +95,11 @@ void cpm_ctx_destroy(cpm_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->select_done) cudaEventDestroy(ctx->select_done);
+    if (ctx->d2h_stream) {
+        cudaStreamSynchronize(ctx->d2h_stream);
+        cudaStreamDestroy(ctx->d2h_stream);
+        if (ctx->d2h_fence) cudaEventDestroy(ctx->d2h_fence);
+    }
     if (ctx->xfer_stream) {
         cudaStreamSynchronize(ctx->xfer_stream);
         cudaStreamDestroy(ctx->xfer_stream);

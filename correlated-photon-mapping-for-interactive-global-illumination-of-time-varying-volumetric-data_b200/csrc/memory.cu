@@ -77,6 +77,37 @@ int cpm_mem_prefetch_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t b
     return CPM_OK;
 }
 
+// The mirror image of cpm_mem_prefetch_h2d: device -> (pinned) host on a read-back stream of its own, after the work
+// already submitted to the context stream; the context stream does not wait.  *done: hand it to cpm_event_sync before
+// the host reads dst_host, and to cpm_ctx_wait_event before src is overwritten.
+int cpm_mem_readback_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes, cpm_event** done) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, dst_host && src && done && bytes > 0, "null argument");
+    if (!ctx->d2h_stream) {
+        CPM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        CPM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->d2h_fence, cudaEventDisableTiming));
+    }
+    CPM_CUDA(ctx, cudaEventRecord(ctx->d2h_fence, ctx->stream));
+    CPM_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->d2h_fence, 0));
+    CPM_CUDA(ctx, cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    cpm_event* e = new cpm_event();
+    cudaError_t rc = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+    if (rc != cudaSuccess) {
+        delete e;
+        return cpm_fail(ctx, CPM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(rc));
+    }
+    CPM_CUDA(ctx, cudaEventRecord(e->ev, ctx->d2h_stream));
+    *done = e;
+    return CPM_OK;
+}
+
+int cpm_event_sync(cpm_ctx* ctx, cpm_event* ev) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, ev != nullptr, "null argument");
+    CPM_CUDA(ctx, cudaEventSynchronize(ev->ev));
+    return CPM_OK;
+}
+
 int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev) {
     if (!ctx) return CPM_E_INVALID;
     CPM_REQUIRE(ctx, ev != nullptr, "null argument");

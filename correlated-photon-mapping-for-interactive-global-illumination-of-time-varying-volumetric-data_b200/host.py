@@ -73,6 +73,8 @@ def lib():
         _lib.cpmh_runtime_ctx.restype = C.c_void_p
         _lib.cpmh_runtime_set_comm.argtypes = [C.c_void_p, C.c_int]
         _lib.cpmh_network_sum_light_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        _lib.cpmh_network_read_light_volume_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        _lib.cpmh_network_wait_readback.argtypes = [C.c_void_p]
         _lib.cpmh_network_read_importance_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_recomputed_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_importance_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -366,6 +368,19 @@ class Network:
         hp = 0 if out_host is None else (out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data)
         self._check(lib().cpmh_network_sum_light_volume(self.h, C.c_void_p(hp), C.c_size_t(n), C.byref(ptr)))
         return ptr.value
+
+    def read_light_volume_async(self, out_host=None, sum_over_ranks=True):
+        """start the read-back of the frame result (summed over ranks when a communicator is set) into a pinned buffer on
+        the read-back stream and return at once; out_host None: only form the sum (ranks that do not display)"""
+        d = self.light_volume_dims
+        n = d[0] * d[1] * d[2] * self.cfg.light_volume_channels
+        hp = 0 if out_host is None else (out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data)
+        self._keep_readback = out_host
+        self._check(lib().cpmh_network_read_light_volume_async(self.h, C.c_void_p(hp), C.c_size_t(n), int(bool(sum_over_ranks))))
+
+    def wait_readback(self):
+        """block until the most recent read_light_volume_async has landed in its host buffer"""
+        self._check(lib().cpmh_network_wait_readback(self.h))
 
     def read_photons(self, max_interactions):
         n = self.n_photons * max_interactions * 8

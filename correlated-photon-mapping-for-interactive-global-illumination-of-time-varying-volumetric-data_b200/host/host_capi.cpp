@@ -39,6 +39,9 @@ struct cpmh_network {
     int streamSlot = -1;
     unsigned long long* collisionCounter = nullptr;
     Buffer<float> lightVolumeSum;   // cpmh_network_sum_light_volume
+    Buffer<float> readbackStage[2];  // cpmh_network_read_light_volume_async
+    cpm_event* readbackDone[2] = {nullptr, nullptr};
+    int readbackTurn = 0, readbackLast = -1;
 };
 
 template <typename F>
@@ -113,6 +116,47 @@ int cpmh_network_sum_light_volume(cpmh_network* net, float* out_host, size_t n_f
     });
 }
 
+int cpmh_network_read_light_volume_async(cpmh_network* net, float* out_host, size_t n_floats, int sum_over_ranks) {
+    return guarded([&]() {
+        auto v = std::const_pointer_cast<Volume>(net->toLightVolume.outport_.getData());
+        if (!v || v->getSizeInBytes() != n_floats * sizeof(float)) throw std::invalid_argument("light volume size mismatch");
+        auto& rt = CpmRuntime::get();
+        const int i = net->readbackTurn;
+        net->readbackTurn ^= 1;
+        if (net->readbackDone[i]) {
+            // the staging buffer is reused: its previous read-back must have left it
+            rt.check(cpm_ctx_wait_event(rt.ctx(), net->readbackDone[i]));
+            cpm_event_destroy(rt.ctx(), net->readbackDone[i]);
+            net->readbackDone[i] = nullptr;
+        }
+        if (net->readbackStage[i].getSize() != n_floats) net->readbackStage[i].setSize(n_floats);
+        float* stage = static_cast<float*>(net->readbackStage[i].deviceWrite());
+        const float* local = static_cast<const float*>(v->deviceRead());
+        if (sum_over_ranks && rt.comm && cpm_comm_world(rt.comm) > 1) {
+            ScopedStage st("exchange");
+            rt.check(cpm_allreduce_lightvol(rt.comm, local, stage, n_floats));
+        } else if (out_host) {
+            rt.check(cpm_mem_copy_d2d(rt.ctx(), stage, local, n_floats * sizeof(float)));   // the next frame updates `local`
+        }
+        net->readbackLast = -1;
+        if (out_host) {
+            rt.check(cpm_mem_readback_d2h(rt.ctx(), out_host, stage, n_floats * sizeof(float), &net->readbackDone[i]));
+            BufferBase::d2hBytes() += n_floats * sizeof(float);
+            net->readbackLast = i;
+        }
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_network_wait_readback(cpmh_network* net) {
+    return guarded([&]() {
+        auto& rt = CpmRuntime::get();
+        const int i = net->readbackLast;
+        if (i >= 0 && net->readbackDone[i]) rt.check(cpm_event_sync(rt.ctx(), net->readbackDone[i]));
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out) {
     return guarded([&]() {
         if (!cfg || !out) throw std::invalid_argument("null argument");
@@ -177,6 +221,11 @@ void cpmh_network_destroy(cpmh_network* net) {
     if (!net) return;
     try {
         CpmRuntime::get().sync();
+        for (int i = 0; i < 2; ++i)
+            if (net->readbackDone[i]) {
+                cpm_event_sync(CpmRuntime::get().ctx(), net->readbackDone[i]);
+                cpm_event_destroy(CpmRuntime::get().ctx(), net->readbackDone[i]);
+            }
     } catch (...) {
     }
     delete net;

@@ -57,6 +57,13 @@ CPMH_API int cpmh_runtime_set_comm(void* cpm_comm_handle, int sharded_ingest);
  * owned by the network (*sum_device, valid until the next call); out_host != NULL: also read back into it (n_floats),
  * synchronously -- typically on rank 0 only */
 CPMH_API int cpmh_network_sum_light_volume(cpmh_network* net, float* out_host, size_t n_floats, void** sum_device);
+/* The frame result on its way to the host WITHOUT stalling the next frame: the light volume (sum_over_ranks != 0 and a
+ * communicator set: its sum over ranks; out_host == NULL: the sum is formed, nothing is read back -- the ranks that do not
+ * display) is snapshotted into one of two staging buffers and copied to out_host (pinned) on a read-back stream; the call
+ * returns at once.  cpmh_network_wait_readback blocks until the most recent read-back has landed.  Pattern:
+ *   evaluate(k); read_light_volume_async(out[k & 1]); ... evaluate(k+1) ...; wait_readback(); use out[k & 1] */
+CPMH_API int cpmh_network_read_light_volume_async(cpmh_network* net, float* out_host, size_t n_floats, int sum_over_ranks);
+CPMH_API int cpmh_network_wait_readback(cpmh_network* net);
 CPMH_API int cpmh_network_create(const cpmh_config* cfg, cpmh_network** out);
 CPMH_API void cpmh_network_destroy(cpmh_network* net);
 CPMH_API const char* cpmh_last_error(void);

@@ -1067,6 +1067,10 @@ void ProgressivePhotonTracerCL::process() {
                 recomputationIndexSorter_.enqueue(indices, nullptr, nPhotonsToCompute, 0);
                 StageProfiler::get().end();
             }
+            // the tracer's volume layout and opacity bound are refreshed before the stage clock starts ("texcopy" and
+            // "bound" are stages of their own; nested inside "trace" they were counted twice)
+            volume->handle(photonTracer_.volumeLayout);
+            photonTracer_.prepareOpacityBound(volume, transferFunction_.get());
             StageProfiler::get().begin("trace");
             int offset = 0;
             for (auto& l : lights) {
@@ -1090,6 +1094,8 @@ void ProgressivePhotonTracerCL::process() {
             enableProgressiveRefinement_.set(false);
         }
     } else {
+        volume->handle(photonTracer_.volumeLayout);
+        photonTracer_.prepareOpacityBound(volume, transferFunction_.get());
         StageProfiler::get().begin("trace");
         int offset = 0;
         for (auto& l : lights) {

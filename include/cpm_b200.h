@@ -522,6 +522,12 @@ CPM_API int cpm_mem_copy_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size
  * cpm_ctx_wait_event makes the context stream wait for before dst is consumed.  src_host must be pinned. */
 CPM_API int cpm_mem_prefetch_h2d(cpm_ctx* ctx, void* dst, const void* src_host, size_t bytes, cpm_event** done);
 CPM_API int cpm_ctx_wait_event(cpm_ctx* ctx, cpm_event* ev);
+/* The mirror image: device -> pinned host on the context's READ-BACK stream (created on first use), after the work
+ * already submitted to the context stream; the context stream itself does not wait, so the next frame's kernels run
+ * while the result travels.  *done: cpm_event_sync before the host reads dst_host, cpm_ctx_wait_event before `src` is
+ * overwritten. */
+CPM_API int cpm_mem_readback_d2h(cpm_ctx* ctx, void* dst_host, const void* src, size_t bytes, cpm_event** done);
+CPM_API int cpm_event_sync(cpm_ctx* ctx, cpm_event* ev); /* cudaEventSynchronize */
 /* the same for an event owned by the caller's runtime (a cudaEvent_t, e.g. torch.cuda.Event.cuda_event) */
 CPM_API int cpm_ctx_wait_cuda_event(cpm_ctx* ctx, void* cuda_event);
 /* overlapping ranges are allowed when dst < src (the index-list slide-down of
