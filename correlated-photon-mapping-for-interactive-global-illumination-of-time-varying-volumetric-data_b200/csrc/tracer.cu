@@ -17,6 +17,8 @@
 //    Hardware-filtered taps are not used: their 1.8 fixed-point weights flip accept/reject
 //    decisions, which breaks the replay property the correlated re-trace depends on.
 //  * Photon records are 32 B: written as two 16 B stores (STG.128).
+#include <algorithm>
+
 #include "sampling.cuh"
 
 namespace {
@@ -267,6 +269,176 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
     }
 }
 
+// ---- the bounded walk with LANE REFILL ---------------------------------------------------------------------------------
+// trace_kernel gives every photon a thread for its whole life: a warp runs until its longest walk ends, and the scan
+// loop -- 98 % of the instructions -- executes with 19.6 of 32 lanes on C4 (ncu).  Photons are independent (per-photon
+// RNG stream, result independent of lane / warp / GPU), so here warps are PERSISTENT and lanes are re-used: a lane
+// whose walk has ended waits until REFILL lanes of its warp are in that state, then the warp handles all of them
+// together -- store the interaction (or the empty slots), start the next walk of a scattered photon, or fetch a new
+// photon from a global cursor -- and returns to the scan loop with (almost) all lanes walking.  Batching matters: the
+// end-of-walk / set-up code is ~300 instructions per photon and would otherwise run with one or two lanes at a time.
+// Same draws, same positions, same records as trace_kernel and the oracle (tests/test_bound.py runs both).
+struct RefillArgs {
+    unsigned* cursor;      // next unclaimed work item (device counter, zeroed before the launch)
+    int refill_min;        // lanes that must be waiting before the warp leaves the scan loop for them
+};
+
+template <int FMT, int LAYOUT>
+__global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, const RefillArgs Q) {
+    extern __shared__ float s_alpha[];
+    for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
+    __syncthreads();
+    const cpm_trace_params& P = A.p;
+    const VolumeView& V = A.vol;
+    const int tfw = A.tf_width;
+    const float ftfw = (float)tfw;
+    const float inv = 1.0f / 150.0f;
+    const unsigned maxI = (unsigned)P.max_interactions;
+    const unsigned lane = threadIdx.x & 31u;
+    enum { EMPTY = 0, WALK = 1, ENDED = 2 };
+    int state = EMPTY, tid = -1;
+    bool exhausted = false;                 // warp-uniform: the cursor has passed n_work
+    float3_ o = {0.f, 0.f, 0.f}, d = {0.f, 0.f, 1.f};
+    float t = 0.f, tEnd = 0.f, pr = 0.f, pg = 0.f, pb = 0.f;
+    unsigned n = 0, tests = 0, fetched = 0;
+    cpm_rng rng{0u, 0u};
+    CellRay R = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+    while (true) {
+        const unsigned walking = __ballot_sync(0xffffffffu, state == WALK);
+        const unsigned todo = __ballot_sync(0xffffffffu, state == ENDED || (state == EMPTY && !exhausted));
+        if (walking == 0u && todo == 0u) break;
+        if (__popc(todo) >= Q.refill_min || walking == 0u) {
+            // ---- (1) walks that ended: photontracer.cl:161-197 ------------------------------------------------------
+            if (state == ENDED) {
+                bool scatter = t <= tEnd;
+                if (scatter) {
+                    o = ray_at(o, t, d);
+                    size_t pid = (size_t)P.photon_offset + (size_t)n * P.total_photons + tid;
+                    float2 ang = encode_direction(d);
+                    float vs = sample_volume<FMT, LAYOUT>(V, o.x, o.y, o.z);
+                    float ca = sample_tf_alpha(s_alpha, tfw, ftfw, vs);   // color.w == scattering.w
+                    float albedo = ca / (ca + ca);
+                    float den = cpm_fmax(ca, 0.01f);
+                    pr = pr / den; pg = pg / den; pb = pb / den;
+                    ++n;
+                    if (n < maxI && cpm_rng_01(rng) < albedo) {
+                        pr *= albedo; pg *= albedo; pb *= albedo;
+                        store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+                        float tStart = 0.0f;
+                        tEnd = CPM_FLT_MAX;
+                        float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
+                        d = (P.phase_function == CPM_PHASE_HENYEY_GREENSTEIN) ? sample_henyey_greenstein(d, P.material[0], u1, u2)
+                                                                              : uniform_sample_sphere(u1, u2);
+                        scatter = ray_box(P.aabb_min, P.aabb_max, o, d, tStart, tEnd);
+                        tStart += 0.5f * P.step_size;
+                        t = tStart;
+                    } else {
+                        store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+                        pr = pg = pb = CPM_FLT_MAX;
+                        scatter = false;
+                    }
+                }
+                if (scatter) {
+                    R = cell_ray(A.bound, o, d);
+                    state = WALK;
+                } else {
+                    float2 ang = encode_direction(d);
+                    for (unsigned i = n; i < maxI; ++i) {
+                        size_t pid = (size_t)P.photon_offset + (size_t)i * P.total_photons + tid;
+                        store_photon(A.photons, pid, CPM_FLT_MAX, CPM_FLT_MAX, CPM_FLT_MAX, pr, CPM_FLT_MAX, CPM_FLT_MAX, ang.x, ang.y);
+                    }
+                    if (P.flags & CPM_TRACE_PROGRESSIVE) A.rng[P.photon_offset + tid] = make_uint2(rng.x, rng.c);
+                    state = EMPTY;
+                    tid = -1;
+                }
+            }
+            // ---- (2) free lanes take new photons --------------------------------------------------------------------------
+            if (!exhausted) {
+                const unsigned freem = __ballot_sync(0xffffffffu, state == EMPTY);
+                if (freem) {
+                    unsigned base = 0;
+                    if (lane == (unsigned)(__ffs(freem) - 1)) base = atomicAdd(Q.cursor, (unsigned)__popc(freem));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(freem) - 1);
+                    exhausted = base + (unsigned)__popc(freem) >= (unsigned)A.n_work;
+                    if (state == EMPTY) {
+                        const unsigned g = base + (unsigned)__popc(freem & ((1u << lane) - 1u));
+                        if (g < (unsigned)A.n_work) {
+                            int cand = (int)g;
+                            if (A.recompute) {
+                                cand = (int)A.recompute[g] - P.photon_offset;
+                                if (cand < 0 || cand >= P.n_light_samples) cand = -1;   // not this light's photon
+                            }
+                            if (cand >= 0) {
+                                tid = cand;
+                                uint2 st = A.rng[P.photon_offset + tid];
+                                rng = cpm_rng{st.x, st.y};
+                                float4 l0 = A.light_samples[2 * (size_t)tid], l1 = A.light_samples[2 * (size_t)tid + 1];
+                                o = {l0.x, l0.y, l0.z};
+                                float fmaxi = (float)P.max_interactions;
+                                pr = l0.w / fmaxi; pg = l1.x / fmaxi; pb = l1.y / fmaxi;
+                                d = decode_direction(l1.z, l1.w);
+                                float2 ip = A.isect[tid];
+                                t = ip.x;
+                                tEnd = ip.y;
+                                n = 0;
+                                if (ip.x < ip.y) {
+                                    R = cell_ray(A.bound, o, d);
+                                    state = WALK;
+                                } else {
+                                    // the ray misses the volume: empty slots only (t > tEnd makes step (1) write them)
+                                    state = ENDED;
+                                    t = CPM_FLT_MAX;
+                                    tEnd = -CPM_FLT_MAX;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        // ---- (3) the scan loop of woodcock_bounded for the walking lanes --------------------------------------------------
+        if (state == WALK) {
+            bool cand = false, done = false;
+            float u2 = 0.0f;
+#pragma unroll 1
+            for (int k = 0; k < A.scan; ++k) {
+                t = advance_t(t, log_unit(cpm_rng_01(rng)), inv);
+                u2 = cpm_rng_01(rng);
+                ++tests;
+                if (!(t <= tEnd)) {
+                    done = true;
+                    break;
+                }
+                float m = bound_at(A.bound, R, t);
+                if (!(u2 >= m)) {
+                    cand = true;
+                    break;
+                }
+            }
+            if (cand) {
+                ++fetched;
+                const float3_ pc = ray_at(o, t, d);
+                float v = sample_volume<FMT, LAYOUT>(V, pc.x, pc.y, pc.z);
+                float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
+                done = !(u2 >= opacity);
+            }
+            if (done) state = ENDED;
+        }
+    }
+    if (A.tests) {
+        unsigned long long v = tests;
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && v) atomicAdd(A.tests, v);
+        if (P.flags & CPM_TRACE_STATS) {
+            unsigned long long f = fetched;
+            for (int off = 16; off; off >>= 1) f += __shfl_xor_sync(0xffffffffu, f, off);
+            if (lane == 0 && f) atomicAdd(A.tests + 1, f);
+        }
+    }
+}
+
 template <int FMT, int LAYOUT, bool BOUNDED>
 int launch2(cpm_ctx* ctx, const TraceArgs& a) {
     size_t smem = (size_t)a.tf_width * sizeof(float);
@@ -276,7 +448,33 @@ int launch2(cpm_ctx* ctx, const TraceArgs& a) {
     return CPM_OK;
 }
 template <int FMT, int LAYOUT>
+int launch_refill(cpm_ctx* ctx, const TraceArgs& a, int refill_min) {
+    size_t smem = (size_t)a.tf_width * sizeof(float);
+    if (smem > 48 * 1024)
+        CPM_CUDA(ctx, cudaFuncSetAttribute(trace_refill_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int per_sm = 0;
+    if (!per_sm) {
+        CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_refill_kernel<FMT, LAYOUT>, 128, smem));
+        per_sm = per_sm > 0 ? per_sm : 1;
+    }
+    if (!ctx->trace_cursor) CPM_CUDA(ctx, cudaMalloc((void**)&ctx->trace_cursor, 256));
+    RefillArgs q;
+    q.cursor = ctx->trace_cursor;
+    q.refill_min = refill_min;
+    CPM_CUDA(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(unsigned), ctx->stream));
+    // persistent grid: every resident CTA slot of the device, but no more warps than work items / 32
+    unsigned grid = (unsigned)(ctx->sm_count * per_sm);
+    grid = std::max(1u, std::min(grid, cpm_div_up(a.n_work, 128)));
+    CPM_LAUNCH(ctx, (trace_refill_kernel<FMT, LAYOUT>), grid, 128, smem, a, q);
+    return CPM_OK;
+}
+template <int FMT, int LAYOUT>
 int launch(cpm_ctx* ctx, const TraceArgs& a) {
+    // lane refill (trace_refill_kernel): bounded walks that start at the light sample; CPM_TRACE_REFILL=0 switches it off
+    // (A/B), =n sets the batch size.  NO_SINGLE_SCATTERING walks start differently and stay on trace_kernel.
+    static const int refill_env = getenv("CPM_TRACE_REFILL") ? atoi(getenv("CPM_TRACE_REFILL")) : 8;
+    if (a.bound.g && refill_env > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING) && a.n_work >= 256)
+        return launch_refill<FMT, LAYOUT>(ctx, a, std::min(refill_env, 32));
     return a.bound.g ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
 }
 
