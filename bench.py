@@ -80,6 +80,8 @@ def parse():
     ap.add_argument("--gather-planar", action="store_true", help="photon map as planar halves instead of 32-byte records (A/B)")
     ap.add_argument("--gather-grid-scale", type=float, default=1.0, help="photon-map cells per 2r along an axis (tuning sweeps)")
     ap.add_argument("--view", type=int, default=1024, help="side of the gathered view image")
+    ap.add_argument("--e2e-layout", choices=["auto", "texture", "linear"], default="auto",
+                    help="layout the tracer samples in the e2e leg (auto: linear -- a streamed step is sampled where it lands)")
     ap.add_argument("--volume-layout", choices=["texture", "linear"], default="texture",
                     help="layout the tracer samples: 2-D layered CUDA array (tld4) or the caller's linear buffer (A/B)")
     return ap.parse_args()
@@ -641,6 +643,9 @@ def run_b200(a):
             lvd = net.light_volume_dims
             out_host = torch.empty(lvd[0] * lvd[1] * lvd[2], dtype=torch.float32, pin_memory=True)
 
+            # a streamed step is sampled where it lands (the linear buffer): no linear -> CUDA-array copy per step
+            e2e_layout = "linear" if a.e2e_layout == "auto" else a.e2e_layout
+            net.set_volume_layout(cpm.CPM_VOLUME_LINEAR if e2e_layout == "linear" else cpm.CPM_VOLUME_TEXTURE)
             out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
             e2e_k = [0]
 
@@ -696,7 +701,7 @@ def run_b200(a):
                    "h2d_gbs": (h2d / a.steps) / (wall_e / a.steps * 1e-3) / 1e9,   # per rank: the step is PCIe bound
                    "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
                    "grid_kernels": grid_kernels,
-                   "cpu_affinity": cpulist,
+                   "cpu_affinity": cpulist, "volume_layout": e2e_layout,
                    "path": "libcpm_host.so: cpmh_network_stream_timestep_host(pinned host volume; the next step's "
                            "upload is announced with cpmh_network_prefetch_timestep_host and overlaps this step) -> "
                            "cpmh_network_evaluate -> cpmh_network_read_light_volume_async(pinned host buffer; lands while "

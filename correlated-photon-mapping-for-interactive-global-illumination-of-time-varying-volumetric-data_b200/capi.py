@@ -304,6 +304,7 @@ Context.radix_sort = _radix_sort
 
 # -- detector / grids / splat ------------------------------------------------------------------
 CPM_DETECT_FIX_EXIT = 1
+CPM_TRACE_LANE_REFILL = 8
 
 
 def _fN(v, n):

@@ -470,11 +470,13 @@ int launch_refill(cpm_ctx* ctx, const TraceArgs& a, int refill_min) {
 }
 template <int FMT, int LAYOUT>
 int launch(cpm_ctx* ctx, const TraceArgs& a) {
-    // lane refill (trace_refill_kernel): bounded walks that start at the light sample; CPM_TRACE_REFILL=0 switches it off
-    // (A/B), =n sets the batch size.  NO_SINGLE_SCATTERING walks start differently and stay on trace_kernel.
-    static const int refill_env = getenv("CPM_TRACE_REFILL") ? atoi(getenv("CPM_TRACE_REFILL")) : 8;
-    if (a.bound.g && refill_env > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING) && a.n_work >= 256)
-        return launch_refill<FMT, LAYOUT>(ctx, a, std::min(refill_env, 32));
+    // lane refill (trace_refill_kernel): opt-in through CPM_TRACE_LANE_REFILL or CPM_TRACE_REFILL=<batch> in the
+    // environment (A/B runs).  Bounded walks that start at the light sample only: NO_SINGLE_SCATTERING walks start
+    // differently and stay on trace_kernel.
+    static const int refill_env = getenv("CPM_TRACE_REFILL") ? atoi(getenv("CPM_TRACE_REFILL")) : 0;
+    const int refill = refill_env > 0 ? refill_env : ((a.p.flags & CPM_TRACE_LANE_REFILL) ? 12 : 0);
+    if (a.bound.g && refill > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING))
+        return launch_refill<FMT, LAYOUT>(ctx, a, std::min(refill, 32));
     return a.bound.g ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
 }
 

@@ -282,6 +282,10 @@ class Network:
         ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data for a in arrays])
         self._check(lib().cpmh_network_set_sequence_host(self.h, ptrs, len(arrays)))
 
+    def set_volume_layout(self, layout):
+        """CPM_VOLUME_TEXTURE / CPM_VOLUME_LINEAR for the tracer from now on (see cpmh_network_set_volume_layout)"""
+        self._check(lib().cpmh_network_set_volume_layout(self.h, int(layout)))
+
     def set_timestep(self, t):
         self._check(lib().cpmh_network_set_timestep(self.h, int(t)))
 

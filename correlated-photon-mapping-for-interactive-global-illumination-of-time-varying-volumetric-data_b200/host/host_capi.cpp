@@ -295,6 +295,14 @@ int cpmh_network_set_timestep(cpmh_network* net, int t) {
     });
 }
 
+int cpmh_network_set_volume_layout(cpmh_network* net, int layout) {
+    return guarded([&]() {
+        if (layout != CPM_VOLUME_TEXTURE && layout != CPM_VOLUME_LINEAR) throw std::invalid_argument("unknown volume layout");
+        net->tracer.tracer().volumeLayout = layout;
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
     return guarded([&]() {
         if (!voxels) throw std::invalid_argument("null voxel buffer");

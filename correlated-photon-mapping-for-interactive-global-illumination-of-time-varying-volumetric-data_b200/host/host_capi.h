@@ -76,6 +76,10 @@ CPMH_API int cpmh_network_set_volume_host(cpmh_network* net, const void* voxels_
  * device for all steps (VolumeMinMaxCL on the sequence + DynamicVolumeDifferenceAnalysis) */
 CPMH_API int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels_host, int n_steps);
 CPMH_API int cpmh_network_set_timestep(cpmh_network* net, int t);
+/* layout the tracer samples from now on (CPM_VOLUME_TEXTURE / CPM_VOLUME_LINEAR; same photons either way).  A resident
+ * series is best kept as CUDA arrays (built once, 12 % faster walks); a series that streams from the host is best
+ * sampled where it lands -- the linear buffer -- which saves the 0.54 ms linear -> array copy of a 512^3 f32 step. */
+CPMH_API int cpmh_network_set_volume_layout(cpmh_network* net, int layout);
 /* Streaming variant for data that does not stay resident: upload the next time step from a HOST buffer
  * (pinned memory: asynchronous), compute its min-max grid and the per-brick difference to the previously
  * streamed step on the device, and mark volume / grids changed.  The buffer must stay valid until the

@@ -159,11 +159,12 @@ def test_cuda_bounded_tracer_bit_exact(cpm, orc, ctx, torch_cuda, synth, fmt, la
     L = scenes.directional_light(96, (0.25, -0.4, 0.85))
     for I, flags in ((1, 0), (4, cpm.CPM_TRACE_PROGRESSIVE)):
         want, want_rng, want_tests = oracle_trace(orc, vol, tf, L, max_interactions=I, flags=flags)
-        for s in (0, 2, 3, 6):
+        for s, refill in ((0, 0), (2, 0), (3, 0), (6, 0), (3, cpm.capi.CPM_TRACE_LANE_REFILL), (1, cpm.capi.CPM_TRACE_LANE_REFILL)):
+            # (refill: the persistent-warp scheduling of trace_refill_kernel -- same photons, same counters)
             got, got_rng, got_tests, fetched = _bounded_trace(cpm, ctx, torch_cuda, vol, tf, L, lay, s,
-                                                              max_interactions=I, flags=flags)
+                                                              max_interactions=I, flags=flags | refill)
             assert got_tests == want_tests
-            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (I, s)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (I, s, refill)
             assert np.array_equal(got_rng, want_rng)
             assert 0 < fetched < want_tests
 
@@ -186,10 +187,17 @@ def test_cuda_bounded_tracer_variants_bit_exact(cpm, orc, ctx, torch_cuda, synth
         dict(L=Ld, max_interactions=2, total_photons=3 * n, photon_offset=n),
         dict(L=Ld, max_interactions=2, total_photons=2 * n, photon_offset=n, recompute=idx,
              photons=np.full((2 * n * 2, 8), -3.0, np.float32), rng=scenes.rng_states(2 * n)),
+        # the same index-list re-trace and the clip box / Henyey-Greenstein walk with lane refill
+        dict(L=Ld, max_interactions=2, total_photons=2 * n, photon_offset=n, recompute=idx, cuda_flags=cpm.capi.CPM_TRACE_LANE_REFILL,
+             photons=np.full((2 * n * 2, 8), -3.0, np.float32), rng=scenes.rng_states(2 * n)),
+        dict(L=Ld, max_interactions=5, phase=1, material=(0.6, 0, 0, 0), aabb=aabb, cuda_flags=cpm.capi.CPM_TRACE_LANE_REFILL),
     ]
     for kw in cases:
         L = kw.pop("L")
+        cuda_flags = kw.pop("cuda_flags", 0)
         want, want_rng, wt = oracle_trace(orc, vol, tf, L, **{k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()})
+        if cuda_flags:
+            kw["flags"] = kw.get("flags", 0) | cuda_flags
         got, got_rng, gt, fetched = _bounded_trace(cpm, ctx, torch_cuda, vol, tf, L, cpm.CPM_VOLUME_TEXTURE, 3, **kw)
         assert gt == wt, kw
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), kw
