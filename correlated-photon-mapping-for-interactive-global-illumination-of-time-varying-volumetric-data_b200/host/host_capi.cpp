@@ -315,7 +315,67 @@ int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
         Volume* v = net->streamVol[cur].get();
         v->setExternalRAMData(const_cast<void*>(voxels));
         const size_t r = (size_t)net->minMax.volumeRegionSize_.get();
-        if (c.with_importance_grid) {
+        // multi-GPU with sharded ingest: every rank builds the min-max and difference bricks of ITS z-slab only and the
+        // slices are all-gathered (2 x ~1 MB) -- the grid passes cost 1 / world of a whole-volume pass
+        const int W = rt.comm ? cpm_comm_world(rt.comm) : 1, R = rt.comm ? cpm_comm_rank(rt.comm) : 0;
+        const size_t nz = (size_t)c.dims[2];
+        const bool shardGrids = c.with_importance_grid && W > 1 && rt.shardedIngest && nz % ((size_t)W * r) == 0 &&
+                                (size_t)c.dims[0] % r == 0 && (size_t)c.dims[1] % r == 0 &&
+                                (((size_t)c.dims[0] / r) * ((size_t)c.dims[1] / r) * (nz / W / r) * 4) % 16 == 0;
+        auto slabView = [&](Volume* vol, cpm_volume** out) {
+            const char* base = static_cast<const char*>(vol->deviceRead());
+            const size_t slabBytes = vol->getSizeInBytes() / (size_t)W;
+            const int dims[3] = {c.dims[0], c.dims[1], (int)(nz / W)};
+            float scale, offset;
+            vol->formatScaleOffset(scale, offset);
+            rt.check(cpm_volume_create(rt.ctx(), base + slabBytes * (size_t)R, dims, c.format, scale, offset, CPM_VOLUME_LINEAR, out));
+        };
+        const size_t cellsPerSlab = ((size_t)c.dims[0] / r) * ((size_t)c.dims[1] / r) * (nz / (size_t)W / r);
+        if (c.with_importance_grid && shardGrids) {
+            if (!net->streamMinMax[cur]) {
+                const size3_t outDim((size_t)c.dims[0] / r, (size_t)c.dims[1] / r, nz / r);
+                auto g = std::make_shared<MinMaxUniformGrid3D>(size3_t(r));
+                g->setModelMatrix(v->getModelMatrix());
+                g->setWorldMatrix(v->getWorldMatrix());
+                g->setDimensions(outDim);
+                net->streamMinMax[cur] = g;
+            }
+            cpm_volume* sv = nullptr;
+            slabView(v, &sv);
+            uint16_t* mm = static_cast<uint16_t*>(net->streamMinMax[cur]->data.deviceWrite());
+            {
+                ScopedStage st("minmax");
+                rt.check(cpm_volume_minmax(rt.ctx(), sv, (int)r, mm + 2 * cellsPerSlab * (size_t)R, nullptr));
+                rt.check(cpm_allgather_volume(rt.comm, mm, cellsPerSlab * 4));
+            }
+            if (prev >= 0) {
+                Volume* pv = net->streamVol[prev].get();
+                if (!net->streamDiff[cur]) {
+                    auto g = std::make_shared<DynamicVolumeInfoUniformGrid3D>(size3_t(r));
+                    g->setModelMatrix(v->getModelMatrix());
+                    g->setWorldMatrix(v->getWorldMatrix());
+                    g->setDimensions(net->streamMinMax[cur]->getDimensions());
+                    net->streamDiff[cur] = g;
+                }
+                cpm_volume* pvw = nullptr;
+                slabView(pv, &pvw);
+                dvec2 dataRange = pv->dataMap_.dataRange;
+                const double defaultToDataRange = pv->getDataFormat()->maxValue / (dataRange.y - dataRange.x);
+                float* df = static_cast<float*>(net->streamDiff[cur]->data.deviceWrite());
+                {
+                    ScopedStage st("voldiff");
+                    rt.check(cpm_volume_diff_bricks(rt.ctx(), pvw, sv, (int)r, defaultToDataRange, dataRange.x, dataRange.y,
+                                                    df + cellsPerSlab * (size_t)R));
+                    rt.check(cpm_allgather_volume(rt.comm, df, cellsPerSlab * 4));
+                }
+                cpm_volume_destroy(rt.ctx(), pvw);
+                net->diffSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->streamDiff[cur]));
+                net->importance.volumeDifferenceInfoInport_.connectTo(&net->diffSelector);
+            }
+            cpm_volume_destroy(rt.ctx(), sv);
+            net->importance.minMaxUniformGrid3DInport_.connectTo(&net->minMaxSelector);
+            net->minMaxSelector.setData(std::shared_ptr<const UniformGrid3DBase>(net->streamMinMax[cur]));
+        } else if (c.with_importance_grid) {
             if (!net->streamMinMax[cur]) {
                 net->streamMinMax[cur] = std::shared_ptr<MinMaxUniformGrid3D>(net->minMax.compute(v).release());
             } else {
