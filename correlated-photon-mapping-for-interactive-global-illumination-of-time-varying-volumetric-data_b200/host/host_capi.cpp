@@ -315,11 +315,14 @@ int cpmh_network_stream_timestep_host(cpmh_network* net, const void* voxels) {
         Volume* v = net->streamVol[cur].get();
         v->setExternalRAMData(const_cast<void*>(voxels));
         const size_t r = (size_t)net->minMax.volumeRegionSize_.get();
-        // multi-GPU with sharded ingest: every rank builds the min-max and difference bricks of ITS z-slab only and the
-        // slices are all-gathered (2 x ~1 MB) -- the grid passes cost 1 / world of a whole-volume pass
+        // multi-GPU with sharded ingest, opt-in (CPM_SHARD_GRIDS=1): every rank builds the min-max and difference bricks of ITS
+        // z-slab only and the slices are all-gathered (2 x ~1 MB).  Measured at N = 8 on C4: the two extra rank
+        // synchronisations cost what the 7/8 smaller passes save (min-max 0.117 vs 0.104 ms, difference 0.20 vs 0.16 ms
+        // per step), so whole-volume passes on every rank stay the default.
+        static const bool shardGridsEnv = std::getenv("CPM_SHARD_GRIDS") && std::atoi(std::getenv("CPM_SHARD_GRIDS")) > 0;
         const int W = rt.comm ? cpm_comm_world(rt.comm) : 1, R = rt.comm ? cpm_comm_rank(rt.comm) : 0;
         const size_t nz = (size_t)c.dims[2];
-        const bool shardGrids = c.with_importance_grid && W > 1 && rt.shardedIngest && nz % ((size_t)W * r) == 0 &&
+        const bool shardGrids = shardGridsEnv && c.with_importance_grid && W > 1 && rt.shardedIngest && nz % ((size_t)W * r) == 0 &&
                                 (size_t)c.dims[0] % r == 0 && (size_t)c.dims[1] % r == 0 &&
                                 (((size_t)c.dims[0] / r) * ((size_t)c.dims[1] / r) * (nz / W / r) * 4) % 16 == 0;
         auto slabView = [&](Volume* vol, cpm_volume** out) {
