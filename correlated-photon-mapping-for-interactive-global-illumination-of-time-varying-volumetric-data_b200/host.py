@@ -75,6 +75,11 @@ def lib():
         _lib.cpmh_network_sum_light_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         _lib.cpmh_network_read_light_volume_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         _lib.cpmh_network_wait_readback.argtypes = [C.c_void_p]
+        _lib.cpmh_network_importance_tf_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.cpmh_network_set_property.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_double]
+        _lib.cpmh_photondata_progress.argtypes = [C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_double)]
+        _lib.cpmh_network_photon_state.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _lib.cpmh_network_set_data_range.argtypes = [C.c_void_p, C.c_double, C.c_double]
         _lib.cpmh_network_read_importance_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_recomputed_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.cpmh_network_read_importance_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -248,6 +253,28 @@ class Network:
         self._check(lib().cpmh_network_get_property(self.h, class_id.encode(), int(k), prop.encode(), C.byref(v)))
         return v.value
 
+    def set_property(self, class_id, prop, value, k=0):
+        """scalar / bool / option property of the k-th processor of a class, e.g.
+        ("org.inviwo.ProgressivePhotonTracerCL", "equalImportance", True)"""
+        self._check(lib().cpmh_network_set_property(self.h, class_id.encode(), int(k), prop.encode(), C.c_double(float(value))))
+
+    def importance_tf_points(self):
+        """(positions (n,), colors (n, 4)) of the point list the importance classifier last used"""
+        pos, col = np.zeros(256, np.float32), np.zeros((256, 4), np.float32)
+        n = self._check(lib().cpmh_network_importance_tf_points(self.h, pos.ctypes.data_as(C.c_void_p),
+                                                                col.ctypes.data_as(C.c_void_p), 256))
+        return pos[:n].copy(), col[:n].copy()
+
+    def tracer_timer_event(self):
+        """one tick of the tracer's progressive-refinement timer (onTimerEvent)"""
+        self._check(lib().cpmh_network_timer_event(self.h))
+
+    def photon_state(self) -> dict:
+        """PhotonData after the last evaluation: iteration, radius (world), scene radius, relative radius, irradiance scale"""
+        out = (C.c_double * 5)()
+        self._check(lib().cpmh_network_photon_state(self.h, out))
+        return dict(iteration=int(out[0]), radius=out[1], scene_radius=out[2], radius_rel=out[3], irradiance_scale=out[4])
+
     def set_samples_per_side(self, n):
         self._check(lib().cpmh_network_set_samples_per_side(self.h, int(n)))
 
@@ -281,6 +308,10 @@ class Network:
         self._seq = list(arrays)
         ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data for a in arrays])
         self._check(lib().cpmh_network_set_sequence_host(self.h, ptrs, len(arrays)))
+
+    def set_data_range(self, lo, hi):
+        """Volume::dataMap_.dataRange, e.g. (0, 4095) for 12-bit data in a 16-bit volume"""
+        self._check(lib().cpmh_network_set_data_range(self.h, float(lo), float(hi)))
 
     def set_volume_layout(self, layout):
         """CPM_VOLUME_TEXTURE / CPM_VOLUME_LINEAR for the tracer from now on (see cpmh_network_set_volume_layout)"""

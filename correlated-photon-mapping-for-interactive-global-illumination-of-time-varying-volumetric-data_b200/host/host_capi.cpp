@@ -295,6 +295,19 @@ int cpmh_network_set_timestep(cpmh_network* net, int t) {
     });
 }
 
+int cpmh_network_set_data_range(cpmh_network* net, double lo, double hi) {
+    return guarded([&]() {
+        if (!(hi > lo)) throw std::invalid_argument("empty data range");
+        auto apply = [&](Volume* v) { if (v) v->dataMap_.dataRange = dvec2{lo, hi}; };
+        apply(net->volume.get());
+        if (net->sequence)
+            for (auto& v : *net->sequence) apply(v.get());
+        for (auto& v : net->streamVol) apply(v.get());
+        if (!net->useSequence) net->volumeSource.setData(net->volume);   // notifies the connected inports: Volume invalidation
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_set_volume_layout(cpmh_network* net, int layout) {
     return guarded([&]() {
         if (layout != CPM_VOLUME_TEXTURE && layout != CPM_VOLUME_LINEAR) throw std::invalid_argument("unknown volume layout");
@@ -496,6 +509,12 @@ int cpmh_network_evaluate(cpmh_network* net) {
     return rc == CPM_OK ? ran : rc;
 }
 
+int cpmh_network_timer_event(cpmh_network* net) {
+    return guarded([&]() {
+        net->tracer.onTimerEvent();
+        return (int)CPM_OK;
+    });
+}
 int cpmh_network_remaining_photons(cpmh_network* net) { return net->tracer.remainingPhotonsToUpdate(); }
 int cpmh_network_n_photons(cpmh_network* net) {
     auto d = net->tracer.outport_.getData();
@@ -838,6 +857,41 @@ int cpmh_network_get_property(cpmh_network* net, const char* class_id, int k, co
     });
 }
 
+int cpmh_network_set_property(cpmh_network* net, const char* class_id, int k, const char* property, double value) {
+    return guarded([&]() {
+        if (!net || !class_id || !property) throw std::invalid_argument("null argument");
+        for (auto& entry : network_processors(net)) {
+            if (entry.first != class_id) continue;
+            if (k < 0 || k >= (int)entry.second.size()) throw std::invalid_argument("no such processor instance");
+            Property* p = entry.second[k]->getPropertyByIdentifier(property);
+            if (!p) throw std::invalid_argument(std::string("no property ") + property);
+            if (auto* f = dynamic_cast<FloatProperty*>(p)) f->set((float)value);
+            else if (auto* i = dynamic_cast<IntProperty*>(p)) i->set((int)value);
+            else if (auto* b = dynamic_cast<BoolProperty*>(p)) b->set(value != 0.0);
+            else if (auto* o = dynamic_cast<OptionProperty<int>*>(p)) o->setSelectedValue((int)value);
+            else throw std::invalid_argument(std::string("property ") + property + " is not scalar");
+            return (int)CPM_OK;
+        }
+        throw std::invalid_argument(std::string("no processor of class ") + class_id);
+    });
+}
+
+int cpmh_network_importance_tf_points(cpmh_network* net, float* positions, float* colors, int capacity) {
+    int n = 0;
+    int rc = guarded([&]() {
+        n = net->importance.tfPointImportanceSize();
+        if (n > capacity) throw std::invalid_argument("capacity too small");
+        const auto& P = net->importance.tfPointPositions();
+        const auto& C = net->importance.tfPointColors();
+        for (int i = 0; i < n; ++i) {
+            positions[i] = P[i];
+            for (int k = 0; k < 4; ++k) colors[4 * i + k] = C[i][k];
+        }
+        return (int)CPM_OK;
+    });
+    return rc == CPM_OK ? n : rc;
+}
+
 int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_host) {
     return guarded([&]() {
         if (!out_host || nx < 1 || ny < 0 || evaluations < 1) throw std::invalid_argument("bad argument");
@@ -857,6 +911,77 @@ int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_ho
             auto img = p.randomNumbersPort_.getData();
             std::memcpy(out_host, const_cast<ImageF32*>(img.get())->data.getRAMRepresentation()->data(), (size_t)nx * ny * sizeof(float));
         }
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_tf_difference_points(const float* cur, int n_cur, const float* prev, int n_prev, float epsilon, int associated,
+                              float* positions, float* colors, int capacity) {
+    int n = 0;
+    int rc = guarded([&]() {
+        TransferFunction a, b;
+        for (int i = 0; i < n_cur; ++i) a.add(cur[5 * i], vec4(cur[5 * i + 1], cur[5 * i + 2], cur[5 * i + 3], cur[5 * i + 4]));
+        for (int i = 0; i < n_prev; ++i) b.add(prev[5 * i], vec4(prev[5 * i + 1], prev[5 * i + 2], prev[5 * i + 3], prev[5 * i + 4]));
+        MinMaxUniformGrid3DImportanceCLProcessor p;
+        p.TFPointEpsilon_.set(epsilon);
+        p.useAssociatedColor_.set(associated != 0);
+        p.buildDifferenceLists(a, b);
+        n = p.tfPointImportanceSize();
+        if (n > capacity) throw std::invalid_argument("capacity too small");
+        const auto& P = p.tfPointPositions();
+        const auto& C = p.tfPointColors();
+        for (int i = 0; i < n; ++i) {
+            positions[i] = P[i];
+            for (int k = 0; k < 4; ++k) colors[4 * i + k] = C[i][k];
+        }
+        return (int)CPM_OK;
+    });
+    return rc == CPM_OK ? n : rc;
+}
+
+int cpmh_photondata_progress(size_t n_photons, int max_interactions, double radius_rel, double scene_radius, int iterations,
+                             double alpha, double out[4]) {
+    return guarded([&]() {
+        // (sizes only: PhotonData::setSize would allocate the record buffer; the arithmetic needs the count alone)
+        struct Sized : PhotonData {
+            void sizeOnly(size_t n, int I) { maxPhotonInteractions_ = I; count_ = n; }
+            size_t count_ = 0;
+        } d;
+        d.sizeOnly(n_photons, max_interactions);
+        d.setRadius(radius_rel, scene_radius);
+        for (int i = 0; i < iterations; ++i) d.advanceToNextIteration(alpha);
+        out[0] = d.getRadius();
+        out[1] = d.getRadiusRelativeToSceneSize();
+        // getRelativeIrradianceScale with the photon count given (ppm/photondata.cpp:84-94)
+        out[2] = PhotonData::sphereVolume(d.getRadiusRelativeToSceneSize()) / PhotonData::sphereVolume(PhotonData::defaultRadiusRelativeToSceneRadius) *
+                 ((double)n_photons / (double)PhotonData::defaultNumberOfPhotons);
+        out[3] = d.iteration();
+        return (int)CPM_OK;
+    });
+}
+int cpmh_photon_encode_direction(const float dir[3], float out[2]) {
+    Photon p;
+    p.setDirection(vec3(dir[0], dir[1], dir[2]));
+    out[0] = p.encodedDirection.x;
+    out[1] = p.encodedDirection.y;
+    return CPM_OK;
+}
+int cpmh_photon_decode_direction(const float enc[2], float out[3]) {
+    Photon p;
+    p.encodedDirection = vec2{enc[0], enc[1]};
+    vec3 d = p.getDirection();
+    out[0] = d.x; out[1] = d.y; out[2] = d.z;
+    return CPM_OK;
+}
+int cpmh_network_photon_state(cpmh_network* net, double out[5]) {
+    return guarded([&]() {
+        auto d = net->tracer.outport_.getData();
+        if (!d) throw std::invalid_argument("no photons yet");
+        out[0] = d->iteration();
+        out[1] = d->getRadius();
+        out[2] = d->getSceneRadius();
+        out[3] = d->getRadiusRelativeToSceneSize();
+        out[4] = d->getRelativeIrradianceScale();
         return (int)CPM_OK;
     });
 }

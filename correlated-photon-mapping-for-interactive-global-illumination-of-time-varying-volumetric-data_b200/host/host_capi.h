@@ -75,6 +75,9 @@ CPMH_API int cpmh_network_set_volume_host(cpmh_network* net, const void* voxels_
 /* a time series: T host buffers; min-max grids and inter-step difference grids are computed on the
  * device for all steps (VolumeMinMaxCL on the sequence + DynamicVolumeDifferenceAnalysis) */
 CPMH_API int cpmh_network_set_sequence_host(cpmh_network* net, const void* const* voxels_host, int n_steps);
+/* Volume::dataMap_.dataRange of the network's volume(s), e.g. (0, 4095) for 12-bit data in a 16-bit volume ("scaling for
+ * 12-bit data", ugc/processors/volumeminmaxclprocessor.cpp:134-136); marks the volume changed */
+CPMH_API int cpmh_network_set_data_range(cpmh_network* net, double lo, double hi);
 CPMH_API int cpmh_network_set_timestep(cpmh_network* net, int t);
 /* layout the tracer samples from now on (CPM_VOLUME_TEXTURE / CPM_VOLUME_LINEAR; same photons either way).  A resident
  * series is best kept as CUDA arrays (built once, 12 % faster walks); a series that streams from the host is best
@@ -109,6 +112,9 @@ CPMH_API int cpmh_network_read_collision_stats(cpmh_network* net, unsigned long 
 CPMH_API int cpmh_network_evaluate(cpmh_network* net);
 /* progressive work left (budgeted re-trace batches): call evaluate again while > 0 */
 CPMH_API int cpmh_network_remaining_photons(cpmh_network* net);
+/* the tracer's 100 ms progressive-refinement timer tick (ProgressivePhotonTracerCL::onTimerEvent,
+ * ppm/processor/progressivephotontracercl.cpp:186-190): marks the tracer invalid for reason Progressive */
+CPMH_API int cpmh_network_timer_event(cpmh_network* net);
 CPMH_API int cpmh_network_n_photons(cpmh_network* net);
 CPMH_API int cpmh_network_n_recomputed(cpmh_network* net);
 CPMH_API int cpmh_network_light_volume_dims(cpmh_network* net, int dims[3]);
@@ -121,6 +127,12 @@ CPMH_API int cpmh_network_read_importance_keys(cpmh_network* net, uint32_t* out_
 CPMH_API int cpmh_network_read_recomputed_indices(cpmh_network* net, uint32_t* out_host, size_t n);
 /* the importance grid the tracer's detector last saw (float per brick of `region` voxels) */
 CPMH_API int cpmh_network_read_importance_grid(cpmh_network* net, float* out_host, size_t n);
+/* the transfer-function point list the importance classifier last used (host side: the points with end points, or the
+ * |new - old| difference list after a transfer-function change): positions[capacity], colors[4 * capacity]; returns the
+ * number of points (tfPointImportanceSize_) */
+CPMH_API int cpmh_network_importance_tf_points(cpmh_network* net, float* positions, float* colors, int capacity);
+/* properties of the network's processors by class id / occurrence / identifier (bool, int, float and option values) */
+CPMH_API int cpmh_network_set_property(cpmh_network* net, const char* class_id, int k, const char* property, double value);
 /* kernel arguments of light sampler `light` (lcl/directionallightsamplercl.cpp:66-73), for parity checks:
  * out = direction[3], plane point before the fit[3], fitted origin[3], u[3], v[3], radiance[3], area */
 CPMH_API int cpmh_network_light_setup(cpmh_network* net, int light, float out[19]);
@@ -183,6 +195,21 @@ CPMH_API int cpmh_network_get_property(cpmh_network* net, const char* class_id, 
 /* RandomNumberGeneratorCL (ny == 0: nSamples = nx) or RandomNumberGenerator2DCL (nSamples = (nx, ny)) evaluated
  * `evaluations` times with the given seed; the numbers of the last evaluation are read back (nx * max(ny, 1) floats). */
 CPMH_API int cpmh_random_numbers(int nx, int ny, int seed, int evaluations, float* out_host);
+/* host only: the |new - old| transfer-function point list of MinMaxUniformGrid3DImportanceCLProcessor
+ * (isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:364-501) for two point sets of (pos, r, g, b, a); returns the
+ * number of points written to positions[capacity] / colors[4 * capacity] */
+CPMH_API int cpmh_tf_difference_points(const float* cur, int n_cur, const float* prev, int n_prev, float epsilon, int associated,
+                                       float* positions, float* colors, int capacity);
+/* host only, for parity tests against the reference's ppm/photondata.cpp: PhotonData after setSize / setRadius(radius_rel,
+ * scene_radius) / `iterations` x advanceToNextIteration(alpha): out = {getRadius, getRadiusRelativeToSceneSize,
+ * getRelativeIrradianceScale, iteration}; and Photon::setDirection / getDirection */
+CPMH_API int cpmh_photondata_progress(size_t n_photons, int max_interactions, double radius_rel, double scene_radius, int iterations,
+                                      double alpha, double out[4]);
+CPMH_API int cpmh_photon_encode_direction(const float dir[3], float out[2]);
+CPMH_API int cpmh_photon_decode_direction(const float enc[2], float out[3]);
+/* state of the network's PhotonData after the last evaluation: out = {iteration, getRadius, getSceneRadius,
+ * getRadiusRelativeToSceneSize, getRelativeIrradianceScale} */
+CPMH_API int cpmh_network_photon_state(cpmh_network* net, double out[5]);
 CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float plane_point[3],
                                   const float plane_normal[3], float out[9]);
 /* the 2-D convex hull alone (lcl/convexhull2d.cpp:38-130): hull_out holds up to 2 * n + 2 points; returns the hull size */

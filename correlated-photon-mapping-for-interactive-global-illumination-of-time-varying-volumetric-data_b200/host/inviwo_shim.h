@@ -291,6 +291,9 @@ private:
     cpm_volume* lin_ = nullptr;
     cpm_volume* tex_ = nullptr;
     bool texValid_ = false;
+    // format scale / offset the handles were created with (dataMap_.dataRange is a public member, as in Inviwo: a change
+    // of the data range must reach the sampling arithmetic and everything derived from it, e.g. the opacity bound)
+    float handleScale_ = 0.f, handleOffset_ = 0.f;
     void* prefetched_ = nullptr;
     cpm_event* prefetchDone_ = nullptr;
 };
@@ -446,6 +449,11 @@ public:
     void addOption(std::string id, std::string name, T value) { options_.push_back({std::move(id), std::move(name), value}); }
     const T& get() const { return options_[selected_].value; }
     const std::string& getSelectedIdentifier() const { return options_[selected_].id; }
+    void setSelectedValue(const T& v) {
+        for (size_t i = 0; i < options_.size(); ++i)
+            if (options_[i].value == v) { selected_ = i; propertyModified(); return; }
+        throw std::invalid_argument("no option with that value");
+    }
     void setSelectedIdentifier(const std::string& id) {
         for (size_t i = 0; i < options_.size(); ++i)
             if (options_[i].id == id) { selected_ = i; propertyModified(); return; }

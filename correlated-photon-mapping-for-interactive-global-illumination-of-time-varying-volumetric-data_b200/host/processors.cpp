@@ -304,6 +304,15 @@ const cpm_volume* Volume::handle(int layout) {
     if (format_->id == DataFormatId::Vec4Float32) throw CpmError(CPM_E_UNSUPPORTED, "vec4 volumes cannot be sampled");
     float scale, offset;
     formatScaleOffset(scale, offset);
+    if ((lin_ || tex_) && (scale != handleScale_ || offset != handleOffset_)) {
+        // dataMap_.dataRange changed since the handles were made (e.g. 12-bit data declared in a 16-bit volume): new
+        // handles, and a new data version so that value ranges / opacity bounds derived with the old scaling are rebuilt
+        if (lin_) { cpm_volume_destroy(c, lin_); lin_ = nullptr; }
+        if (tex_) { cpm_volume_destroy(c, tex_); tex_ = nullptr; }
+        touch();
+    }
+    handleScale_ = scale;
+    handleOffset_ = offset;
     if (layout == CPM_VOLUME_LINEAR) {
         if (!lin_) CPM_CHECK(cpm_volume_create(c, d, dims, fmt, scale, offset, CPM_VOLUME_LINEAR, &lin_));
         return lin_;
@@ -478,8 +487,10 @@ const float PhotonData::defaultSceneRadius = 1.1447142425533318678080422119397f;
 const double PhotonData::scaleToMakeLightPowerOfOneVisibleForDirectionalLightSource = 1.0 / 3.14159265358979323846;
 
 void Photon::setDirection(vec3 dir) {
-    float phi = std::atan2(dir.y, dir.x);
-    float theta = std::acos(std::min(1.f, std::max(-1.f, dir.z)));
+    // ppm/photondata.cpp:100-109 calls unqualified atan2 / acos on float arguments: with GCC's <cmath> those are the C
+    // double functions, the result is rounded to float (pinned against the reference's file: tests/test_ref_photondata.py)
+    float phi = (float)::atan2((double)dir.y, (double)dir.x);
+    float theta = (float)::acos((double)std::min(std::max(dir.z, -1.f), 1.f));
     encodedDirection = vec2{theta, phi};
 }
 vec3 Photon::getDirection() const {
@@ -1531,37 +1542,86 @@ void MinMaxUniformGrid3DImportanceCLProcessor::updateTransferFunctionData() {
     std::copy(col.begin(), col.end(), C->begin());
 }
 void MinMaxUniformGrid3DImportanceCLProcessor::updateTransferFunctionDifferenceData() {
-    // |TF_new - TF_old| as a point list: both piecewise-linear functions are evaluated at the union of their
-    // break points (plus 0 and 1); where the difference stays below TFPointEpsilon the importance is zero.
-    // Same information as the reference's merge walk (:364-501), built by direct evaluation.
-    TransferFunction& cur = transferFunction_.get();
-    TransferFunction& prev = prevTransferFunction_;
-    auto eval = [](TransferFunction& tf, double x) {
-        if (tf.size() == 0) return vec4(0.f);
-        if (x <= tf.get(0).getPosition()) return tf.get(0).getColor();
-        if (x >= tf.get(tf.size() - 1).getPosition()) return tf.get(tf.size() - 1).getColor();
-        size_t k = 1;
-        while (tf.get(k).getPosition() < x) ++k;
-        double p0 = tf.get(k - 1).getPosition(), p1 = tf.get(k).getPosition(), t = (x - p0) / (p1 - p0);
-        vec4 a = tf.get(k - 1).getColor(), b = tf.get(k).getColor(), r;
-        for (int c = 0; c < 4; ++c) r[c] = (float)((1.0 - t) * a[c] + t * b[c]);
-        return r;
-    };
-    std::vector<double> xs{0.0, 1.0};
-    for (size_t i = 0; i < cur.size(); ++i) xs.push_back(cur.get(i).getPosition());
-    for (size_t i = 0; i < prev.size(); ++i) xs.push_back(prev.get(i).getPosition());
-    std::sort(xs.begin(), xs.end());
-    xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
-    const float eps = TFPointEpsilon_.get();
+    // |TF_new - TF_old| as a point list for the incremental classifier: a merge walk over the break points of both
+    // functions, with the reference's rules for what is stored -- a pair of points only where the difference exceeds
+    // TFPointEpsilon and one of them is visible, the moved zero-opacity first point, the last point of either function
+    // replaced by (1, its colour), zero-difference end points at 0 and 1
+    // (isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:364-501; oracle/frame.py tf_difference_lists is the
+    // checker's restatement, tests/test_host_processors.py compares the two lists).
+    const TransferFunction& cur = transferFunction_.get();
+    const TransferFunction& prev = prevTransferFunction_;
+    const int nC = (int)cur.size(), nP = (int)prev.size();
     std::vector<float> pos;
     std::vector<vec4> col;
-    for (double x : xs) {
-        vec4 a = eval(cur, x), b = eval(prev, x);
-        vec4 d = tfPointColorDiff(a, b);
-        bool visible = a.w > 0.f || b.w > 0.f;
-        bool changed = d.x > eps || d.y > eps || d.z > eps || d.w > eps;
-        pos.push_back((float)x);
-        col.push_back(visible && changed ? d : vec4(0.f));
+    const float eps = TFPointEpsilon_.get();
+    auto differs = [eps](const vec4& c) {   // glm::any(glm::epsilonNotEqual(c, vec4(0), eps)): |c_k| >= eps
+        return std::fabs(c.x) >= eps || std::fabs(c.y) >= eps || std::fabs(c.z) >= eps || std::fabs(c.w) >= eps;
+    };
+    // mix(a, b, t): the colour of the segment a -> b at t's position; glm::mix(vec4, vec4, double) = vec4(dvec4(x) + a * dvec4(y - x))
+    auto colourAt = [](const TFPrimitive& a, const TFPrimitive& b, const TFPrimitive& t) {
+        const double w = (t.getPosition() - a.getPosition()) / (b.getPosition() - a.getPosition());
+        const vec4 x = a.getColor(), y = b.getColor();
+        vec4 r;
+        for (int k = 0; k < 4; ++k) r[k] = (float)((double)x[k] + w * (double)(y[k] - x[k]));
+        return r;
+    };
+    if (nC == 0 || nP == 0) {
+        // the reference reads point 0 of both functions; with both empty it stores two zero points at position 0
+        pos = {0.f, nC == 0 && nP == 0 ? 0.f : 1.f};
+        col = {vec4(0.f), vec4(0.f)};
+    } else {
+        const TFPrimitive first = cur.get(0), pfirst = prev.get(0);
+        TFPrimitive p1(first < pfirst ? first.getPosition() : pfirst.getPosition(), tfPointColorDiff(first.getColor(), pfirst.getColor()));
+        TFPrimitive p2 = p1;
+        if (first.getPosition() != pfirst.getPosition() && first.getAlpha() == 0.f && pfirst.getAlpha() == 0.f) {
+            // a moved first point with zero opacity
+            if (first < pfirst) {
+                const TFPrimitive a2 = cur.get((size_t)std::min(1, nC - 1));
+                p2 = TFPrimitive(pfirst.getPosition(), tfPointColorDiff(pfirst.getColor(), colourAt(first, a2, pfirst)));
+            } else {
+                const TFPrimitive a2 = prev.get((size_t)std::min(1, nP - 1));
+                p2 = TFPrimitive(first.getPosition(), tfPointColorDiff(first.getColor(), colourAt(pfirst, a2, first)));
+            }
+        }
+        pos.push_back(0.f);
+        col.push_back(p1.getPosition() > 0.0 && (first.getAlpha() > 0.f || pfirst.getAlpha() > 0.f) && differs(p1.getColor())
+                          ? p1.getColor() : vec4(0.f));
+        int id = 0, prevId = 0;
+        while (id < nC || prevId < nP) {
+            if ((differs(p1.getColor()) || differs(p2.getColor())) && (p1.getAlpha() > 0.f || p2.getAlpha() > 0.f)) {
+                if (pos.size() == 1) {   // everything before was equal: open the segment
+                    pos.push_back((float)p1.getPosition());
+                    col.push_back(p1.getColor());
+                }
+                pos.push_back((float)p2.getPosition());
+                col.push_back(p2.getColor());
+            }
+            const TFPrimitive a1 = cur.get((size_t)std::min(id, nC - 1));
+            const TFPrimitive a2 = id + 1 < nC - 1 ? cur.get((size_t)id + 1) : TFPrimitive(1.0, cur.get((size_t)nC - 1).getColor());
+            const TFPrimitive b1 = prev.get((size_t)std::min(prevId, nP - 1));
+            const TFPrimitive b2 = prevId + 1 < nP - 1 ? prev.get((size_t)prevId + 1) : TFPrimitive(1.0, prev.get((size_t)nP - 1).getColor());
+            p1 = p2;
+            if (a2 < b2) {
+                p2 = TFPrimitive(a2.getPosition(), tfPointColorDiff(a2.getColor(), colourAt(b1, b2, a2)));
+                ++id;
+            } else if (b2 < a2) {
+                p2 = TFPrimitive(b2.getPosition(), tfPointColorDiff(b2.getColor(), colourAt(a1, a2, b2)));
+                ++prevId;
+            } else {
+                p2 = TFPrimitive(a2.getAlpha() < b2.getAlpha() ? b2.getPosition() : a2.getPosition(),
+                                 tfPointColorDiff(a2.getColor(), b2.getColor()));
+                ++id;
+                ++prevId;
+            }
+        }
+        if (p2.getPosition() < 1.0 && p2.getAlpha() > 0.f) {
+            pos.push_back((float)p2.getPosition());
+            col.push_back(p2.getColor());
+        }
+        if (pos.back() < 1.f) {
+            pos.push_back(1.f);
+            col.push_back(vec4(0.f));
+        }
     }
     tfPointImportanceSize_ = (int)pos.size();
     if ((int)tfPointPositions_.getSize() < tfPointImportanceSize_) {
@@ -1588,7 +1648,7 @@ void MinMaxUniformGrid3DImportanceCLProcessor::process() {
     }
     bool incrementalFormula = true;   // the static kernel is built with -D INCREMENTAL_TF_IMPORTANCE (:99-101)
     if ((int)invalidationFlag_ & (int)InvalidationReason::TransferFunction) {
-        if (!prevTransferFunctionValid_ || !incrementalImportance.get())
+        if (!prevTransferFunctionValid_ || prevTransferFunction_.size() == 0 || !incrementalImportance.get())
             updateTransferFunctionData();
         else
             updateTransferFunctionDifferenceData();

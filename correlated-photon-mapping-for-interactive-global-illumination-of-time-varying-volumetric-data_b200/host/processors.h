@@ -452,6 +452,13 @@ public:
     const std::vector<float>& tfPointPositions() { return *tfPointPositions_.getRAMRepresentation(); }
     const std::vector<vec4>& tfPointColors() { return *tfPointColors_.getRAMRepresentation(); }
     int tfPointImportanceSize() const { return tfPointImportanceSize_; }
+    // host-only hook for parity tests: the difference list of (cur, prev) as a transfer-function change would build it
+    void buildDifferenceLists(const TransferFunction& cur, const TransferFunction& prev) {
+        transferFunction_.set(cur);
+        prevTransferFunction_ = prev;
+        prevTransferFunctionValid_ = true;
+        updateTransferFunctionDifferenceData();
+    }
 private:
     void updateTransferFunctionData();
     void updateTransferFunctionDifferenceData();

@@ -75,6 +75,74 @@ def tf_point_lists(points):
     return np.array(pos, np.float32), np.ascontiguousarray(np.array(col, np.float32))
 
 
+def tf_difference_lists(cur_points, prev_points, eps=1e-4, associated=False):
+    """updateTransferFunctionDifferenceData (isc/processors/minmaxuniformgrid3dimportanceclprocessor.cpp:364-501): the
+    |new - old| point list the incremental classifier gets after a transfer-function change -- a merge walk over the break
+    points of both functions.  Restated statement by statement (the checker's copy; the host layer has its own).  Points:
+    [(pos, (r, g, b, a))], positions double, colours float32."""
+    f = np.float32
+
+    def col(c):
+        return np.array([f(x) for x in c], np.float32)
+
+    def diff(c1, c2):   # tfPointColorDiff: |p2 * (assoc ? p2.w : 1) - p1 * (assoc ? p1.w : 1)| in fp32
+        a1, a2 = (c1[3], c2[3]) if associated else (f(1), f(1))
+        return np.abs(c2 * a2 - c1 * a1).astype(np.float32)
+
+    def differs(c):     # glm::any(glm::epsilonNotEqual(c, 0, eps))
+        return bool((np.abs(c) >= f(eps)).any())
+
+    def colour_at(a, b, t):   # mix(a, b, t): vec4(dvec4(x) + w * dvec4(y - x)), w in double
+        with np.errstate(all="ignore"):      # coincident points divide by zero, as in the reference (inf / NaN propagate)
+            w = np.float64(t[0] - a[0]) / np.float64(b[0] - a[0])
+            return (a[1].astype(np.float64) + w * (b[1] - a[1]).astype(np.float64)).astype(np.float32)
+
+    cur = [(float(f(p)), col(c)) for p, c in cur_points]
+    prev = [(float(f(p)), col(c)) for p, c in prev_points]
+    nC, nP = len(cur), len(prev)
+    zero = np.zeros(4, np.float32)
+    if nC == 0 or nP == 0:
+        return np.array([0.0, 0.0 if (nC == 0 and nP == 0) else 1.0], np.float32), np.zeros((2, 4), np.float32)
+    first, pfirst = cur[0], prev[0]
+    p1 = (first[0] if first[0] < pfirst[0] else pfirst[0], diff(first[1], pfirst[1]))
+    p2 = p1
+    if first[0] != pfirst[0] and first[1][3] == 0 and pfirst[1][3] == 0:
+        if first[0] < pfirst[0]:
+            a2 = cur[min(1, nC - 1)]
+            p2 = (pfirst[0], diff(pfirst[1], colour_at(first, a2, pfirst)))
+        else:
+            a2 = prev[min(1, nP - 1)]
+            p2 = (first[0], diff(first[1], colour_at(pfirst, a2, first)))
+    pos, cols = [0.0], []
+    cols.append(p1[1] if (p1[0] > 0 and (first[1][3] > 0 or pfirst[1][3] > 0) and differs(p1[1])) else zero)
+    i = j = 0
+    while i < nC or j < nP:
+        if (differs(p1[1]) or differs(p2[1])) and (p1[1][3] > 0 or p2[1][3] > 0):
+            if len(pos) == 1:
+                pos.append(p1[0]); cols.append(p1[1])
+            pos.append(p2[0]); cols.append(p2[1])
+        a1 = cur[min(i, nC - 1)]
+        a2 = cur[i + 1] if i + 1 < nC - 1 else (1.0, cur[nC - 1][1])
+        b1 = prev[min(j, nP - 1)]
+        b2 = prev[j + 1] if j + 1 < nP - 1 else (1.0, prev[nP - 1][1])
+        p1 = p2
+        if a2[0] < b2[0]:
+            p2 = (a2[0], diff(a2[1], colour_at(b1, b2, a2)))
+            i += 1
+        elif b2[0] < a2[0]:
+            p2 = (b2[0], diff(b2[1], colour_at(a1, a2, b2)))
+            j += 1
+        else:
+            p2 = (b2[0] if a2[1][3] < b2[1][3] else a2[0], diff(a2[1], b2[1]))
+            i += 1
+            j += 1
+    if p2[0] < 1.0 and p2[1][3] > 0:
+        pos.append(p2[0]); cols.append(p2[1])
+    if f(pos[-1]) < 1:
+        pos.append(1.0); cols.append(zero)
+    return np.array(pos, np.float32), np.ascontiguousarray(np.array(cols, np.float32))
+
+
 def importance_weights(color=0.0, color_diff=0.0, opacity_diff=0.0, opacity=1.0):
     """the four kernel weights as MinMaxUniformGrid3DImportanceCLProcessor::process normalises them (fp32)"""
     f = np.float32
@@ -131,6 +199,7 @@ class OracleNetwork:
         self.I = int(max_interactions)
         self.tf = tf_rgba
         self.tfpos, self.tfcol = tf_point_lists(tf_points)
+        self.tf_points_ = list(tf_points)
         self.weights = weights if weights is not None else importance_weights()
         self.region = int(region)
         self.gd = tuple(-(-d // self.region) for d in self.dims)
@@ -210,12 +279,16 @@ class OracleNetwork:
                                        self.tfcol if colors is None else colors, self.weights, True)
 
     # -- the correlated branch -----------------------------------------------------------------------------------
-    def detect(self, importance_grid):
+    def detect(self, importance_grid, equal_importance=False):
+        """one detector launch per light (progressivephotontracercl.cpp:306-325); equal importance: every
+        (100 / percentage)-th photon, shifted by the detector's iteration counter, gets importance 1"""
         offset = 0
+        self.detector_iteration = getattr(self, "detector_iteration", 0) + 1
         for L in self.lights:
             nl = L["light_samples"].shape[0]
             orc.detect_invalid(importance_grid, self.gd, (self.region,) * 3, self.t2i_vol, self.photons, offset,
-                               L["light_samples"], L["isect"], nl, self.I, self.n, self.keys)
+                               L["light_samples"], L["isect"], nl, self.I, self.n, self.keys,
+                               equal_importance=equal_importance, percentage=int(self.budget), iteration=self.detector_iteration)
             offset += nl
 
     def select(self):
@@ -261,9 +334,18 @@ class OracleNetwork:
         if m:
             self.prev[:] = self.photons
 
-    def frame(self, vol_np, importance_grid):
+    def frame(self, vol_np, importance_grid, equal_importance=False):
         """one change handled in one evaluation (budget permitting): returns the re-traced ids (ascending when
         spatial sorting is on)"""
-        self.detect(importance_grid)
+        self.detect(importance_grid, equal_importance)
         self.select()
         return self.retrace_batch(vol_np)
+
+    def set_transfer_function(self, tf_points, width=1024):
+        """a transfer-function change: new raster for the tracer, the |new - old| point list for the importance classifier
+        (returned as (positions, colours) for importance_static)"""
+        lists = tf_difference_lists(tf_points, self.tf_points_)
+        self.tf = rasterise_tf(tf_points, width)
+        self.tf_points_ = list(tf_points)
+        self.tfpos, self.tfcol = tf_point_lists(tf_points)
+        return lists

@@ -9,6 +9,7 @@
 // TEST INFRASTRUCTURE: lets oracle/Makefile compile lcl/convexhull2d.cpp, orientedboundingbox2d.cpp and
 // pointplaneprojection.cpp where they lie.
 #pragma once
+#include <algorithm>
 #include <cmath>
 namespace glm {
 struct vec2 {
@@ -22,6 +23,16 @@ struct vec3 {
     vec3() : x(0.f), y(0.f), z(0.f) {}
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
     explicit vec3(float a) : x(a), y(a), z(a) {}
+};
+struct vec4 {
+    float x, y, z, w;
+    vec4() : x(0.f), y(0.f), z(0.f), w(0.f) {}
+    vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
+    explicit vec4(float a) : x(a), y(a), z(a), w(a) {}
+};
+struct uvec3 {
+    unsigned x, y, z;
+    uvec3(unsigned a, unsigned b, unsigned c) : x(a), y(b), z(c) {}
 };
 struct bvec2 { bool x, y; };
 inline vec2 operator+(vec2 a, vec2 b) { return vec2(a.x + b.x, a.y + b.y); }
@@ -42,6 +53,10 @@ inline float length(vec3 v) { return std::sqrt(dot(v, v)); }
 inline vec2 normalize(vec2 v) { return v * inversesqrt(dot(v, v)); }
 inline vec3 normalize(vec3 v) { return v * inversesqrt(dot(v, v)); }
 inline vec3 cross(vec3 x, vec3 y) { return vec3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+// component-wise std functions on vec2 (func_trigonometric.inl: functor1 over the scalar function)
+inline vec2 cos(vec2 v) { return vec2(std::cos(v.x), std::cos(v.y)); }
+inline vec2 sin(vec2 v) { return vec2(std::sin(v.x), std::sin(v.y)); }
+inline float clamp(float x, float lo, float hi) { return std::min(std::max(x, lo), hi); }   // min(max(x, minVal), maxVal)
 inline bvec2 isnan(vec2 v) { bvec2 r; r.x = std::isnan(v.x); r.y = std::isnan(v.y); return r; }
 inline bool any(bvec2 b) { return b.x || b.y; }
 }  // namespace glm

@@ -124,7 +124,46 @@ def kernels():
     print("wrote tests/golden/ref_kernels.npz:", len(out), "arrays,", (ROOT / "tests" / "golden" / "ref_kernels.npz").stat().st_size, "bytes")
 
 
+def photondata_cases():
+    rng = np.random.default_rng(17)
+    cases = []
+    for k in range(40):
+        n = int(rng.choice([256 * 256, 1024 * 1024, 2048 * 2048, 131072, 4 * 2048 * 2048]))
+        cases.append((n, int(rng.integers(1, 9)), float(rng.uniform(1e-3, 0.1)), float(rng.uniform(0.3, 400.0)), int(rng.integers(0, 60)),
+                      float(rng.choice([0.5, 0.7, 0.9, 1e-4, 1.0]))))
+    cases.append((256 * 256, 1, float(np.float32(0.0153866)), float(np.float32(1.1447142425533318678080422119397)), 0, 0.5))
+    dirs = rng.normal(size=(64, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs = np.vstack([dirs, [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0], [0, 0, 1.0000001]]]).astype(np.float32)
+    return cases, dirs
+
+
+def photondata():
+    """tests/golden/photondata.json from the reference's own ppm/photondata.cpp (oracle/_ref/libphotondata_ref.so)"""
+    ref = orc.ref_lib("photondata_ref")
+    if ref is None:
+        raise SystemExit("oracle/_ref/libphotondata_ref.so missing: run `make -C oracle ref` first")
+    ref.ref_photondata_progress.argtypes = [C.c_size_t, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    cases, dirs = photondata_cases()
+    out = {"source": "reference ppm/photondata.cpp compiled via oracle/Makefile (GLM / Inviwo Buffer stand-ins: oracle/ref_shim/host)",
+           "progress": [], "directions": []}
+    for c in cases:
+        o = (C.c_double * 4)()
+        ref.ref_photondata_progress(*c, o)
+        out["progress"].append({"in": [c[0], c[1], c[2].hex(), c[3].hex(), c[4], c[5].hex()], "out": [float(x).hex() for x in o]})
+    k = (C.c_double * 4)()
+    ref.ref_photondata_constants(k)
+    out["constants"] = [float(x).hex() for x in k]
+    for d in dirs:
+        enc, dec = (C.c_float * 2)(), (C.c_float * 3)()
+        ref.ref_photon_encode_direction((C.c_float * 3)(*d), enc)
+        ref.ref_photon_decode_direction(enc, dec)
+        out["directions"].append({"dir": _hex(d), "encoded": _hex(enc[:]), "decoded": _hex(dec[:])})
+    (ROOT / "tests" / "golden" / "photondata.json").write_text(json.dumps(out, indent=0))
+    print("wrote tests/golden/photondata.json")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mwc64x", "geometry", "kernels"]
+    which = sys.argv[1:] or ["mwc64x", "geometry", "kernels", "photondata"]
     for w in which:
-        {"mwc64x": mwc64x, "geometry": geometry, "kernels": kernels}[w]()
+        {"mwc64x": mwc64x, "geometry": geometry, "kernels": kernels, "photondata": photondata}[w]()
