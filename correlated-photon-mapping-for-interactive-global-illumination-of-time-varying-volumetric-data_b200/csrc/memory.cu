@@ -172,9 +172,36 @@ __global__ void __launch_bounds__(256) mix_kernel(const T* __restrict__ x, const
         out[i] = (T)(int)cpm_clamp(truncf(m), 0.0f, hi);
     }
 }
+// volume_mix.frag of VolumeSequencePlayer: integer volumes are NORMALISED textures there -- the shader mixes v / max and
+// the render target converts back with round-to-nearest (OpenGL 4.x 2.3.5.2), unlike mixKernel's truncation
+template <typename T>
+__global__ void __launch_bounds__(256) mix_unorm_kernel(const T* __restrict__ x, const T* __restrict__ y, float a, size_t n,
+                                                        T* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float hi = sizeof(T) == 1 ? 255.0f : 65535.0f;
+    float fx = (float)x[i] / hi, fy = (float)y[i] / hi;
+    float m = fmaf(fy - fx, a, fx);
+    out[i] = (T)(int)rintf(cpm_clamp(m, 0.0f, 1.0f) * hi);
+}
 }  // namespace
 
 extern "C" {
+
+int cpm_mix_unorm(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out) {
+    if (format == CPM_FMT_F32) return cpm_mix(ctx, x, y, a, n, format, out);
+    if (!ctx) return CPM_E_INVALID;
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, x && y && out, "null pointer");
+    unsigned grid = cpm_div_up(n, 256);
+    if (format == CPM_FMT_U8)
+        CPM_LAUNCH(ctx, mix_unorm_kernel<unsigned char>, grid, 256, 0, (const unsigned char*)x, (const unsigned char*)y, a, n, (unsigned char*)out);
+    else if (format == CPM_FMT_U16)
+        CPM_LAUNCH(ctx, mix_unorm_kernel<unsigned short>, grid, 256, 0, (const unsigned short*)x, (const unsigned short*)y, a, n, (unsigned short*)out);
+    else
+        return cpm_fail(ctx, CPM_E_INVALID, "cpm_mix_unorm: unknown format");
+    return CPM_OK;
+}
 
 int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out) {
     if (!ctx) return CPM_E_INVALID;

@@ -1,6 +1,8 @@
 // host_capi.cpp -- headless driver of the drop-in processor network (see host_capi.h).
 #include "host_capi.h"
+#include "players.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1010,6 +1012,93 @@ int cpmh_convex_hull2d(const float* pts, int n, float* hull_out) {
     return rc == CPM_OK ? m : rc;
 }
 
+int cpmh_player_clock(int n_elements, float time_per_element, int frame_rate, int ticks, float* times_out, int* index_out) {
+    return guarded([&]() {
+        if (n_elements < 1 || !times_out || !index_out) throw std::invalid_argument("bad argument");
+        SequenceClock c("timePerElement", "Time Per element (s)", "frameRate");
+        c.timePerElement_.set(time_per_element);
+        c.frameRate_.set(frame_rate);
+        c.onSequenceChange((size_t)n_elements);
+        for (int k = 0; k < ticks; ++k) {
+            c.onSequenceTimerEvent();
+            times_out[k] = c.time_.get();
+            index_out[k] = c.index_.get();
+        }
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_player_grids_f32(const float* grids, int n_grids, size_t n_cells, float time_per_element, const float* times, int n_times,
+                          float* out_host, int* out_index, int* out_buffer) {
+    return guarded([&]() {
+        if (!grids || n_grids < 1 || !times || !out_host) throw std::invalid_argument("bad argument");
+        auto seq = std::make_shared<UniformGrid3DVector>();
+        for (int g = 0; g < n_grids; ++g) {
+            auto grid = std::make_shared<UniformGrid3D<float>>(size3_t(n_cells, 1, 1), size3_t(8));
+            std::memcpy(grid->getData(), grids + (size_t)g * n_cells, n_cells * sizeof(float));
+            seq->push_back(grid);
+        }
+        DataOutport<UniformGrid3DVector> src("Sequence");
+        UniformGrid3DPlayerProcessor player;
+        player.inport_.connectTo(&src);
+        src.setData(std::shared_ptr<const UniformGrid3DVector>(seq));
+        player.clock_.timePerElement_.set(time_per_element);
+        std::vector<const UniformGrid3DBase*> seen;
+        for (int k = 0; k < n_times; ++k) {
+            player.clock_.time_.set(times[k]);
+            player.process();
+            auto out = player.outport_.getData();
+            auto* g = dynamic_cast<const UniformGrid3D<float>*>(out.get());
+            if (!g) throw std::invalid_argument("player produced no float grid");
+            const std::vector<float>* ram = const_cast<UniformGrid3D<float>*>(g)->data.getRAMRepresentation();
+            std::memcpy(out_host + (size_t)k * n_cells, ram->data(), n_cells * sizeof(float));
+            if (out_index) out_index[k] = player.clock_.index_.get();
+            if (out_buffer) {
+                int id = -1;
+                bool isInput = false;
+                for (auto& e : *seq) isInput = isInput || e.get() == out.get();
+                if (!isInput) {
+                    auto it = std::find(seen.begin(), seen.end(), out.get());
+                    if (it == seen.end()) { seen.push_back(out.get()); it = seen.end() - 1; }
+                    id = (int)(it - seen.begin());
+                }
+                out_buffer[k] = id;
+            }
+        }
+        return (int)CPM_OK;
+    });
+}
+
+int cpmh_player_volumes(const void* volumes, int n_volumes, const int dims[3], int format, float time_per_volume, const float* times,
+                        int n_times, void* out_host, int* out_index) {
+    return guarded([&]() {
+        if (!volumes || n_volumes < 1 || !dims || !times || !out_host) throw std::invalid_argument("bad argument");
+        DataFormatId fid = format == CPM_FMT_U8 ? DataFormatId::UInt8 : (format == CPM_FMT_U16 ? DataFormatId::UInt16 : DataFormatId::Float32);
+        auto seq = std::make_shared<VolumeSequence>();
+        const size3_t d(dims[0], dims[1], dims[2]);
+        size_t bytes = 0;
+        for (int v = 0; v < n_volumes; ++v) {
+            auto vol = std::make_shared<Volume>(d, DataFormatBase::get(fid));
+            bytes = vol->getSizeInBytes();
+            std::memcpy(vol->getEditableRAMData(), static_cast<const char*>(volumes) + (size_t)v * bytes, bytes);
+            seq->push_back(vol);
+        }
+        DataOutport<VolumeSequence> src("volumeSequence");
+        VolumeSequencePlayer player;
+        player.inport_.connectTo(&src);
+        src.setData(std::shared_ptr<const VolumeSequence>(seq));
+        player.clock_.timePerElement_.set(time_per_volume);
+        for (int k = 0; k < n_times; ++k) {
+            player.clock_.time_.set(times[k]);
+            player.process();
+            auto out = std::const_pointer_cast<Volume>(player.outport_.getData());
+            std::memcpy(static_cast<char*>(out_host) + (size_t)k * bytes, out->getRAMData(), bytes);
+            if (out_index) out_index[k] = player.clock_.index_.get();
+        }
+        return (int)CPM_OK;
+    });
+}
+
 const char* cpmh_describe_processors(void) {
     static std::string s;
     std::ostringstream os;
@@ -1032,6 +1121,8 @@ const char* cpmh_describe_processors(void) {
     { RadixSortCL p; dump(p); }
     { RandomNumberGeneratorCL p; dump(p); }
     { RandomNumberGenerator2DCL p; dump(p); }
+    { UniformGrid3DPlayerProcessor p; dump(p); }
+    { VolumeSequencePlayer p; dump(p); }
     s = os.str();
     return s.c_str();
 }

@@ -214,6 +214,16 @@ CPMH_API int cpmh_fit_light_plane(const float* points, int n_points, const float
                                   const float plane_normal[3], float out[9]);
 /* the 2-D convex hull alone (lcl/convexhull2d.cpp:38-130): hull_out holds up to 2 * n + 2 points; returns the hull size */
 CPMH_API int cpmh_convex_hull2d(const float* points_xy, int n_points, float* hull_out);
+/* The sequence players, headless.  cpmh_player_clock: host only -- `ticks` timer events of a player over a
+ * sequence of n_elements (time and selectedSequenceIndex after each tick).  cpmh_player_grids_f32: UniformGrid3DPlayerProcessor
+ * over n_grids float grids of n_cells (host memory, back to back); for every entry of `times`: set time, evaluate, read the
+ * interpolated grid back (out_host: n_times x n_cells), report the sequence index and which of the two ping-pong output
+ * grids carried it (0 / 1; -1: an input grid passed through).  cpmh_player_volumes: VolumeSequencePlayer likewise. */
+CPMH_API int cpmh_player_clock(int n_elements, float time_per_element, int frame_rate, int ticks, float* times_out, int* index_out);
+CPMH_API int cpmh_player_grids_f32(const float* grids_host, int n_grids, size_t n_cells, float time_per_element, const float* times,
+                                   int n_times, float* out_host, int* out_index, int* out_buffer);
+CPMH_API int cpmh_player_volumes(const void* volumes_host, int n_volumes, const int dims[3], int format, float time_per_volume,
+                                 const float* times, int n_times, void* out_host, int* out_index);
 /* introspection for drop-in checks: "classId|port,port,...|prop,prop,..." per processor, newline separated */
 CPMH_API const char* cpmh_describe_processors(void);
 #ifdef __cplusplus

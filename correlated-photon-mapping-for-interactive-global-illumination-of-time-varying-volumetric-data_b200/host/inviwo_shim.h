@@ -410,8 +410,13 @@ public:
     void set(const T& v) { value_ = v; propertyModified(); }
     T getMinValue() const { return min_; }
     T getMaxValue() const { return max_; }
+    void setMinValue(const T& v) { min_ = v; }
+    void setMaxValue(const T& v) { max_ = v; }
+    void setReadOnly(bool v) { readOnly_ = v; }
+    bool getReadOnly() const { return readOnly_; }
 private:
     T value_, min_, max_;
+    bool readOnly_ = false;
 };
 using FloatProperty = OrdinalProperty<float>;
 using IntProperty = OrdinalProperty<int>;

@@ -550,6 +550,10 @@ CPM_API int cpm_mem_scatter_fill_u32(cpm_ctx* ctx, void* dst, const uint32_t* in
  * out[i] = x[i] + (y[i] - x[i]) * a over n scalars of format CPM_FMT_* (float2/3/4 buffers: n = elements *
  * components); u8 / u16 are mixed in float and converted back with round-toward-zero. */
 CPM_API int cpm_mix(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out);
+/* the same through normalised textures, as VolumeSequencePlayer's fragment shader sees integer volumes
+ * (ugc/glsl/volume_mix.frag:44-52): out = round(clamp(mix(x / max, y / max, a), 0, 1) * max); identical to cpm_mix for f32.
+ * OpenGL arithmetic: parity unpinned. */
+CPM_API int cpm_mix_unorm(cpm_ctx* ctx, const void* x, const void* y, float a, size_t n, int format, void* out);
 
 /* ---- self test ----------------------------------------------------------------------- */
 /* Evaluates one function of include/cpm_detmath.h on the device: fn 0 log, 1 sin, 2 cos,
