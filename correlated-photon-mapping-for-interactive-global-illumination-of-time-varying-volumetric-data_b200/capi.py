@@ -44,6 +44,7 @@ class TraceParams(C.Structure):
         ("opacity_bound", C.c_void_p),
         ("bound_cell_log2", C.c_int32),
         ("reserved_", C.c_int32),
+        ("opacity_bound_tex", C.c_void_p),
     ]
 
 
@@ -206,12 +207,40 @@ class Context:
         self._check(lib().cpm_opacity_bound_clearance(self.h, _p(bound), (C.c_int * 3)(*[int(x) for x in grid_dims]),
                                                       int(max_radius)))
 
+    def bound_texture(self, grid_dims, bound=None):
+        """the bound grid as a 3-D texture (cpm_bound_tex_*): returns a BoundTexture, filled from `bound` if given"""
+        t = BoundTexture(self, grid_dims)
+        if bound is not None:
+            t.update(bound)
+        return t
+
     # -- tracer ------------------------------------------------------------------------
     def trace_photons(self, vol: Volume, tf_rgba, params: TraceParams, light_samples, intersections, photons,
                       rng_state, recompute_index=None, n_recompute=0, collision_tests=None):
         self._check(lib().cpm_trace_photons(self.h, vol.handle, _p(tf_rgba), int(tf_rgba.numel() // 4), C.byref(params),
                                             _p(light_samples), _p(intersections), _p(recompute_index),
                                             int(n_recompute), _p(photons), _p(rng_state), _p(collision_tests)))
+
+
+class BoundTexture:
+    def __init__(self, ctx, grid_dims):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        ctx._check(lib().cpm_bound_tex_create(ctx.h, (C.c_int * 3)(*[int(x) for x in grid_dims]), C.byref(self.handle)))
+
+    def update(self, bound):
+        self.ctx._check(lib().cpm_bound_tex_update(self.ctx.h, self.handle, _p(bound)))
+
+    def close(self):
+        if self.handle:
+            lib().cpm_bound_tex_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def rng_host_base_offsets(seed: int, n: int):
@@ -226,7 +255,7 @@ def rng_host_base_offsets(seed: int, n: int):
 
 def make_trace_params(n_light_samples, total_photons=None, photon_offset=0, max_interactions=1, step_size=1.0 / 256,
                       aabb_min=(0, 0, 0), aabb_max=(1, 1, 1), phase=CPM_PHASE_ISOTROPIC, material=(0, 0, 0, 0),
-                      flags=0, opacity_bound=None, bound_cell_log2=3) -> TraceParams:
+                      flags=0, opacity_bound=None, bound_cell_log2=3, opacity_bound_tex=None) -> TraceParams:
     p = TraceParams()
     p.aabb_min[:] = [float(x) for x in aabb_min]
     p.aabb_max[:] = [float(x) for x in aabb_max]
@@ -240,6 +269,7 @@ def make_trace_params(n_light_samples, total_photons=None, photon_offset=0, max_
     p.flags = flags
     p.opacity_bound = opacity_bound.data_ptr() if opacity_bound is not None else None
     p.bound_cell_log2 = bound_cell_log2
+    p.opacity_bound_tex = opacity_bound_tex.handle if opacity_bound_tex is not None else None
     return p
 
 
@@ -381,6 +411,12 @@ def _splat_photons_update(self, light_volume, channels, tex2idx, idx2tex, out_di
         int(per_interaction), int(n_interactions), C.c_float(radius), C.c_float(scale)))
 
 
+def _copy_index_photons(self, photons, indices, n, multiplier, per_interaction, n_interactions, out, out_offset=0):
+    self._check(lib().cpm_copy_index_photons(self.h, _p(photons), _p(indices), int(n), C.c_float(multiplier), int(per_interaction),
+                                             int(n_interactions), _p(out), C.c_size_t(out_offset)))
+
+
+Context.copy_index_photons = _copy_index_photons
 Context.detect_invalid = _detect_invalid
 Context.splat_photons_update = _splat_photons_update
 Context.volume_minmax = _volume_minmax

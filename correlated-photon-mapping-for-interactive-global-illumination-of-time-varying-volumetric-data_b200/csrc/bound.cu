@@ -486,4 +486,63 @@ int cpm_opacity_bound(cpm_ctx* ctx, const float* range, size_t n_cells, float fo
     return CPM_OK;
 }
 
+// ---- the bound grid as a 3-D texture -------------------------------------------------------------------------------------
+// One look-up per collision test is the tracer's hottest load.  From a linear buffer it costs, per test, three floor
+// conversions, two multiply-adds for the index, the bias, the address and the load -- plus one constant-bank load per
+// grid parameter, because sm_100 ALU instructions take no constant operands and uniform registers do not live across the
+// divergent scan loop.  As a point-sampled 3-D texture with clamped, unnormalised coordinates it is three FFMA (the ray
+// in cell coordinates) and one TEX: the texture unit floors, clamps and addresses.
+int cpm_bound_tex_create(cpm_ctx* ctx, const int grid_dims[3], cpm_bound_tex** out) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, grid_dims && out, "null argument");
+    CPM_REQUIRE(ctx, grid_dims[0] >= 1 && grid_dims[1] >= 1 && grid_dims[2] >= 1, "grid dims must be positive");
+    CPM_REQUIRE(ctx, grid_dims[0] <= 16384 && grid_dims[1] <= 16384 && grid_dims[2] <= 16384, "grid too large for a 3-D texture");
+    cpm_bound_tex* t = new cpm_bound_tex();
+    for (int k = 0; k < 3; ++k) t->dims[k] = grid_dims[k];
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+    cudaError_t e = cudaMalloc3DArray(&t->array, &cd, make_cudaExtent(grid_dims[0], grid_dims[1], grid_dims[2]), 0);
+    if (e != cudaSuccess) {
+        delete t;
+        return cpm_fail(ctx, e == cudaErrorMemoryAllocation ? CPM_E_NOMEM : CPM_E_CUDA, "cudaMalloc3DArray: %s", cudaGetErrorString(e));
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = t->array;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    e = cudaCreateTextureObject(&t->tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(t->array);
+        delete t;
+        return cpm_fail(ctx, CPM_E_CUDA, "cudaCreateTextureObject: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return CPM_OK;
+}
+
+int cpm_bound_tex_update(cpm_ctx* ctx, cpm_bound_tex* t, const float* bound) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, t && bound, "null argument");
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(const_cast<float*>(bound), (size_t)t->dims[0] * sizeof(float), (size_t)t->dims[0], (size_t)t->dims[1]);
+    p.dstArray = t->array;
+    p.extent = make_cudaExtent(t->dims[0], t->dims[1], t->dims[2]);
+    p.kind = cudaMemcpyDeviceToDevice;
+    CPM_CUDA(ctx, cudaMemcpy3DAsync(&p, ctx->stream));
+    return CPM_OK;
+}
+
+void cpm_bound_tex_destroy(cpm_bound_tex* t) {
+    if (!t) return;
+    if (t->tex) cudaDestroyTextureObject(t->tex);
+    if (t->array) cudaFreeArray(t->array);
+    delete t;
+}
+
 }  // extern "C"

@@ -94,6 +94,26 @@ __global__ void barrier_kernel(const BarrierArgs A) {
     }
 }
 
+// ---- global (cross-shard) selection ------------------------------------------------------------------------------------
+// out[b] = number of keys below prefix + b * 2^shift (b = 0 ... 256) in an ascending array: one binary search per thread
+__global__ void __launch_bounds__(288) probe_counts_kernel(const uint32_t* __restrict__ sorted, unsigned long long n,
+                                                           unsigned long long prefix, int shift, uint32_t* __restrict__ out) {
+    const unsigned b = threadIdx.x;
+    if (b > 256u) return;
+    const unsigned long long T = prefix + ((unsigned long long)b << shift);
+    unsigned long long lo = 0, hi = n;
+    if (T > 0xffffffffull) {
+        lo = n;
+    } else {
+        const uint32_t t32 = (uint32_t)T;
+        while (lo < hi) {
+            const unsigned long long mid = (lo + hi) >> 1;
+            if (sorted[mid] < t32) lo = mid + 1; else hi = mid;
+        }
+    }
+    out[b] = (uint32_t)lo;
+}
+
 }  // namespace
 
 struct cpm_comm {
@@ -451,6 +471,81 @@ int cpm_comm_barrier(cpm_comm* c) {
     int rc = cpm_scratch(c->ctx, 64, &s);
     if (rc != CPM_OK) return rc;
     return nccl_check(c->ctx, nccl().AllReduce(s, s, 1, ncclFloat32_, ncclSum_, c->nccl, c->ctx->stream), "ncclAllReduce (barrier)");
+}
+
+// ---- host-value collectives and the global selection --------------------------------------------------------------------
+int cpm_comm_allgather_u64(cpm_comm* c, const unsigned long long* values, int count, unsigned long long* all_out) {
+    if (!c) return CPM_E_INVALID;
+    cpm_ctx* ctx = c->ctx;
+    CPM_REQUIRE(ctx, values && all_out && count >= 1 && count <= 64, "bad argument");
+    if (c->world == 1) {
+        memcpy(all_out, values, (size_t)count * sizeof(unsigned long long));
+        return CPM_OK;
+    }
+    const size_t bytes = (size_t)count * sizeof(unsigned long long);
+    void* scr = nullptr;
+    int rc = cpm_scratch(ctx, bytes * (size_t)(c->world + 1), &scr);
+    if (rc != CPM_OK) return rc;
+    unsigned char* mine = (unsigned char*)scr;
+    unsigned char* all = mine + bytes;
+    CPM_CUDA(ctx, cudaMemcpyAsync(mine, values, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = nccl_check(ctx, nccl().AllGather(mine, all, bytes, ncclUint8_, c->nccl, ctx->stream), "ncclAllGather");
+    if (rc != CPM_OK) return rc;
+    CPM_CUDA(ctx, cudaMemcpyAsync(all_out, all, bytes * (size_t)c->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CPM_OK;
+}
+
+int cpm_comm_select_global(cpm_comm* c, const uint32_t* sorted_keys, size_t n_local, unsigned long long position,
+                           unsigned long long* local_count) {
+    if (!c) return CPM_E_INVALID;
+    cpm_ctx* ctx = c->ctx;
+    CPM_REQUIRE(ctx, local_count && (sorted_keys || n_local == 0), "null argument");
+    const int W = c->world;
+    void* scr = nullptr;
+    int rc = cpm_scratch(ctx, 257 * sizeof(uint32_t) * (size_t)(W + 1), &scr);
+    if (rc != CPM_OK) return rc;
+    uint32_t* mine = (uint32_t*)scr;
+    uint32_t* all = mine + 257;
+    std::vector<uint32_t> h((size_t)W * 257);
+    unsigned long long prefix = 0;
+    std::vector<unsigned long long> less((size_t)W, 0), leq((size_t)W, 0);
+    // 256-ary descent over the key bits: after the round with `shift`, prefix holds the bits >= shift of the key T of the
+    // element at `position` of the global order (the largest T with #{keys < T} <= position)
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        CPM_LAUNCH(ctx, probe_counts_kernel, 1, 288, 0, sorted_keys, (unsigned long long)n_local, prefix, shift, mine);
+        if (W > 1) {
+            rc = nccl_check(ctx, nccl().AllGather(mine, all, 257 * sizeof(uint32_t), ncclUint8_, c->nccl, ctx->stream), "ncclAllGather");
+            if (rc != CPM_OK) return rc;
+        }
+        CPM_CUDA(ctx, cudaMemcpyAsync(h.data(), W > 1 ? all : mine, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int pick = 0;
+        for (int b = 0; b <= 255; ++b) {
+            unsigned long long tot = 0;
+            for (int r = 0; r < W; ++r) tot += h[(size_t)r * 257 + b];
+            if (tot <= position) pick = b; else break;
+        }
+        prefix += (unsigned long long)pick << shift;
+        for (int r = 0; r < W; ++r) {
+            less[r] = h[(size_t)r * 257 + pick];
+            leq[r] = h[(size_t)r * 257 + pick + 1];
+        }
+    }
+    // every key < T is taken; the keys == T fill what is left of `position` in rank order (the global order is
+    // (key, rank, local index): what one stable sort over the concatenated shards gives)
+    unsigned long long taken = 0;
+    for (int r = 0; r < W; ++r) taken += less[r];
+    unsigned long long left = position > taken ? position - taken : 0;
+    unsigned long long count = 0;
+    for (int r = 0; r < W; ++r) {
+        const unsigned long long ties = leq[r] - less[r];
+        const unsigned long long take = std::min(ties, left);
+        if (r == c->rank) count = less[r] + take;
+        left -= take;
+    }
+    *local_count = count;
+    return CPM_OK;
 }
 
 }  // extern "C"

@@ -44,6 +44,13 @@ struct cpm_volume {
     cudaTextureObject_t tex;
 };
 
+// the opacity-bound grid as a point-sampled 3-D texture (bound.cu: cpm_bound_tex_*)
+struct cpm_bound_tex {
+    int dims[3];
+    cudaArray_t array;
+    cudaTextureObject_t tex;
+};
+
 int cpm_fail(cpm_ctx* ctx, int code, const char* fmt, ...);
 int cpm_scratch(cpm_ctx* ctx, size_t bytes, void** out);
 
@@ -79,13 +86,14 @@ struct cpm_rng {
 };
 __device__ __forceinline__ uint32_t cpm_rng_next(cpm_rng& s) {
     uint32_t res = s.x ^ s.c;
-    uint64_t t = (uint64_t)CPM_MWC64X_A * s.x + s.c;  // A*X + C: low word = Xn, high = Cn
-    s.x = (uint32_t)t;
-    s.c = (uint32_t)(t >> 32);
+    // A*X + C: low word = Xn, high = Cn -- one mad.wide (the C++ form leaves the compiler adding the zero high word of C
+    // in a separate instruction)
+    asm("{\n\t.reg .u64 t, cc;\n\tcvt.u64.u32 cc, %1;\n\tmad.wide.u32 t, %0, %2, cc;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "+r"(s.x), "+r"(s.c)
+        : "r"(CPM_MWC64X_A));
     return res;
 }
 // random_01 = (float)u / 4294967295.0f ; the divisor rounds to 2^32 in fp32 so the
 // result is (float)u * 2^-32 exactly (can be 1.0f and 0.0f).
-__device__ __forceinline__ float cpm_rng_01(cpm_rng& s) {
-    return __uint2float_rn(cpm_rng_next(s)) * 2.3283064365386963e-10f;
-}
+__device__ __forceinline__ float cpm_u01(uint32_t k) { return __uint2float_rn(k) * 2.3283064365386963e-10f; }
+__device__ __forceinline__ float cpm_rng_01(cpm_rng& s) { return cpm_u01(cpm_rng_next(s)); }

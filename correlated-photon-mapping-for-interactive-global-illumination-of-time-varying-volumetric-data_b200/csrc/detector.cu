@@ -16,6 +16,9 @@
 namespace {
 
 #define CPM_FLT_MAX 3.402823466e+38f
+#ifndef CPM_DETECT_PTX_LOOP
+#define CPM_DETECT_PTX_LOOP 1  // 0: the reference-shaped loop for every segment (A/B builds)
+#endif
 
 struct Mat4 {
     float m[16];
@@ -59,25 +62,76 @@ __device__ float uniform_grid_importance(const GridArgs& G, float3_ x1, float3_ 
     const int s0 = di[0], s1 = di[1] * sy, s2 = di[2] * sz;
     int idx = cell[0] + cell[1] * sy + cell[2] * sz;
     float d0 = dt[0], d1 = dt[1], d2 = dt[2];
-    bool go = true;
-    float importance = 0.0f, dt1 = 0.0f;
-    while (go) {
-        float val = __ldg(G.grid + idx);
-        float dt0 = dt1;
-        bool ax = (d0 <= d1 && d0 <= d2);
-        bool ay = !ax && (d0 > d1 && d1 <= d2);
-        dt1 = ax ? d0 : (ay ? d1 : d2);
-        int rsel = ax ? rem0 : (ay ? rem1 : rem2);
-        if (rsel == 0) {
-            go = false;
-        } else if (ax) {
-            d0 += deltatx[0]; idx += s0; --rem0;
-        } else if (ay) {
-            d1 += deltatx[1]; idx += s1; --rem1;
-        } else {
-            d2 += deltatx[2]; idx += s2; --rem2;
+    float importance = 0.0f;
+    const float del0 = deltatx[0], del1 = deltatx[1], del2 = deltatx[2];
+    const float* __restrict__ grid = G.grid;
+    if (CPM_DETECT_PTX_LOOP && d0 == d0 && d1 == d1 && d2 == d2) {
+        // No NaN among the three parameters (they arise only as 0 * inf at set-up: a segment that lies in a cell face and
+        // does not move along that axis): the reference's comparisons (uniformgrid.cl:163-180) then select the smallest
+        // parameter with ties resolved x before y before z, i.e. dt1 = min(d0, d1, d2), x iff d0 == dt1, else y iff
+        // d1 == dt1.  The loop is branch-free apart from its exit: lanes of a warp step along different axes in the same
+        // iteration, and with a branch per axis every iteration would run all three paths.
+        // Written in PTX: from the C++ form of this loop the compiler builds 34 instructions per step (predicate
+        // shuffles, copies, two-instruction conditional decrements); this is 25, one per line.
+        asm volatile(
+            "{\n\t"
+            ".reg .pred ax, ay, axy, go;\n\t"
+            ".reg .f32 dt0, dt1, c, w, val;\n\t"
+            ".reg .s32 r, st;\n\t"
+            ".reg .u64 addr;\n\t"
+            "mov.f32 dt0, 0f00000000;\n"
+            "DDA_STEP:\n\t"
+            "mad.wide.s32 addr, %0, 4, %8;\n\t"
+            "ld.global.nc.f32 val, [addr];\n\t"
+            "min.f32 dt1, %1, %2;\n\t"
+            "min.f32 dt1, dt1, %3;\n\t"
+            "setp.eq.f32 ax, %1, dt1;\n\t"
+            "setp.eq.and.f32 ay, %2, dt1, !ax;\n\t"
+            "selp.s32 r, %5, %6, ay;\n\t"
+            "selp.s32 r, %4, r, ax;\n\t"
+            "setp.ne.s32 go, r, 0;\n\t"
+            "min.f32 c, dt1, 0f3F800000;\n\t"
+            "sub.rn.f32 w, c, dt0;\n\t"
+            "mul.rn.f32 w, val, w;\n\t"
+            "add.rn.f32 %7, %7, w;\n\t"
+            "@!go bra DDA_DONE;\n\t"
+            "mov.f32 dt0, dt1;\n\t"
+            "selp.s32 st, %13, %14, ay;\n\t"
+            "selp.s32 st, %12, st, ax;\n\t"
+            "add.s32 %0, %0, st;\n\t"
+            "or.pred axy, ax, ay;\n\t"
+            "@ax add.rn.f32 %1, %1, %9;\n\t"
+            "@ay add.rn.f32 %2, %2, %10;\n\t"
+            "@!axy add.rn.f32 %3, %3, %11;\n\t"
+            "@ax sub.s32 %4, %4, 1;\n\t"
+            "@ay sub.s32 %5, %5, 1;\n\t"
+            "@!axy sub.s32 %6, %6, 1;\n\t"
+            "bra DDA_STEP;\n"
+            "DDA_DONE:\n\t"
+            "}"
+            : "+r"(idx), "+f"(d0), "+f"(d1), "+f"(d2), "+r"(rem0), "+r"(rem1), "+r"(rem2), "+f"(importance)
+            : "l"(grid), "f"(del0), "f"(del1), "f"(del2), "r"(s0), "r"(s1), "r"(s2));
+    } else {
+        bool go = true;
+        float dt1 = 0.0f;
+        while (go) {
+            float val = __ldg(grid + idx);
+            float dt0 = dt1;
+            bool ax = (d0 <= d1 && d0 <= d2);
+            bool ay = !ax && (d0 > d1 && d1 <= d2);
+            dt1 = ax ? d0 : (ay ? d1 : d2);
+            int rsel = ax ? rem0 : (ay ? rem1 : rem2);
+            if (rsel == 0) {
+                go = false;
+            } else if (ax) {
+                d0 += del0; idx += s0; --rem0;
+            } else if (ay) {
+                d1 += del1; idx += s1; --rem1;
+            } else {
+                d2 += del2; idx += s2; --rem2;
+            }
+            importance += val * (cpm_fmin(1.0f, dt1) - dt0);
         }
-        importance += val * (cpm_fmin(1.0f, dt1) - dt0);
     }
     float dx = x2.x - x1.x, dy = x2.y - x1.y, dz = x2.z - x1.z;
     float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));

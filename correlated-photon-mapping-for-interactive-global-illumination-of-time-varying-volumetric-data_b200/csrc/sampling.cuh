@@ -184,10 +184,12 @@ __device__ __forceinline__ float sample_volume(const VolumeView& V, float px, fl
 }
 
 // ---- per-cell opacity bound grid (bound.cu) ----------------------------------------------------------------
-// Cell of a sample p, per axis: floor(p * fc + hc) = floor((p * dim + 0.5) / cell), clamped to [0, mx].
+// Cell of a sample p, per axis: floor(p * fc + hc) = floor((p * dim + 0.5) / cell), clamped to [0, gd - 1].
 struct BoundGrid {
     const float* g;   // null: no grid
-    float fc[3], hc, mx[3];
+    float fc[3], hc, mx[3];   // p -> cell coordinate p * fc + hc, last cell per axis (the view ray marchers: raymarch.cuh)
+    float fn[3], hn[3];   // p -> NORMALISED cell coordinate p * fn + hn = (p * dim / cell + 0.5 / cell) / gd (the tracer)
+    float gs[3];          // normalised -> cell: gd * (1 - 2^-22), so that 1.0 still lands in the last cell
     unsigned bias;    // (1 + nx + nxy) * 0x4B400000 mod 2^32: removes the float-bit biases of the three cell coordinates
     int nx, nxy;
 };
@@ -201,6 +203,9 @@ static inline bool make_bound_grid(BoundGrid& B, const float* g, const int dims[
         gd[k] = (dims[k] >> cell_log2) + 1;
         B.fc[k] = (float)dims[k] / cell;   // exact: cell is a power of two
         B.mx[k] = (float)(gd[k] - 1);
+        B.fn[k] = (float)dims[k] / cell / (float)gd[k];
+        B.hn[k] = 0.5f / cell / (float)gd[k];
+        B.gs[k] = (float)gd[k] * (1.0f - 0x1p-22f);
     }
     if ((double)gd[0] * gd[1] * gd[2] >= 2147483648.0) return false;
     B.g = g;
@@ -212,25 +217,34 @@ static inline bool make_bound_grid(BoundGrid& B, const float* g, const int dims[
     return true;
 }
 // Opacity bound of the cell that holds the trilinear footprint of the sample at parameter t of the ray
-// w(t) = wo + t * wd, the ray in CELL coordinates (set up once per walk).  The cell is floor(w) per axis; bound.cu
-// pads every cell by one voxel, which absorbs the rounding difference between this arithmetic and
-// fetch_taps' i0 = floor(p * dim - 0.5).  No conversion instructions: clamp (fmaxf maps NaN to 0), then the
-// 1.5 * 2^23 addition rounded down leaves floor(w) + 0x4B400000 in the bits; the three biases leave the index
-// with one wrapping subtraction.
+// w(t) = wo + t * wd, the ray in NORMALISED cell coordinates (cell / cells per axis; set up once per walk).  Two
+// instructions per axis: an FFMA that saturates to [0, 1] (the clamp to the grid is the .SAT modifier, and NaN becomes
+// 0), and an FFMA rounded down that scales to cells and adds 1.5 * 2^23, which leaves floor(cell) + 0x4B400000 in the
+// bits -- no min / max, no conversion instructions; the three biases leave the index with one wrapping subtraction.
+// The arithmetic differs from fetch_taps' i0 = floor(p * dim - 0.5) by a few 1e-4 voxels at most (the grid has at most
+// a few hundred cells per axis, every step is one rounding); bound.cu pads every cell by one voxel, which absorbs it.
 struct CellRay {
     float ox, oy, oz, dx, dy, dz;
 };
+// the ray in cell coordinates (raymarch.cuh: skip_transparent works in cells)
 __device__ __forceinline__ CellRay cell_ray(const BoundGrid& A, float3_ o, float3_ d) {
     return {fmaf(o.x, A.fc[0], A.hc), fmaf(o.y, A.fc[1], A.hc), fmaf(o.z, A.fc[2], A.hc),
             d.x * A.fc[0], d.y * A.fc[1], d.z * A.fc[2]};
 }
-__device__ __forceinline__ unsigned cell_bits(float w, float wmax) {
-    return __float_as_uint(__fadd_rd(fminf(fmaxf(w, 0.0f), wmax), 12582912.0f));
+// the ray in normalised cell coordinates (bound_at)
+__device__ __forceinline__ CellRay cell_ray_n(const BoundGrid& A, float3_ o, float3_ d) {
+    return {fmaf(o.x, A.fn[0], A.hn[0]), fmaf(o.y, A.fn[1], A.hn[1]), fmaf(o.z, A.fn[2], A.hn[2]),
+            d.x * A.fn[0], d.y * A.fn[1], d.z * A.fn[2]};
 }
-__device__ __forceinline__ float bound_at(const BoundGrid& A, const CellRay& R, float t) {
-    unsigned bx = cell_bits(fmaf(t, R.dx, R.ox), A.mx[0]);
-    unsigned by = cell_bits(fmaf(t, R.dy, R.oy), A.mx[1]);
-    unsigned bz = cell_bits(fmaf(t, R.dz, R.oz), A.mx[2]);
+// `magic` = 12582912.0f held in a register the compiler cannot see through (tracer.cu: ScanRegs): an FFMA takes ONE operand
+// that is not a register, and with the constant as an immediate every gs[] would cost a constant-bank load per test.
+__device__ __forceinline__ unsigned cell_bits(float t, float wd, float wo, float gs, float magic) {
+    return __float_as_uint(__fmaf_rd(__saturatef(fmaf(t, wd, wo)), gs, magic));
+}
+__device__ __forceinline__ float bound_at(const BoundGrid& A, const CellRay& R, float t, float magic) {
+    unsigned bx = cell_bits(t, R.dx, R.ox, A.gs[0], magic);
+    unsigned by = cell_bits(t, R.dy, R.oy, A.gs[1], magic);
+    unsigned bz = cell_bits(t, R.dz, R.oz, A.gs[2], magic);
     return __ldg(A.g + (bx + by * (unsigned)A.nx + bz * (unsigned)A.nxy - A.bias));
 }
 

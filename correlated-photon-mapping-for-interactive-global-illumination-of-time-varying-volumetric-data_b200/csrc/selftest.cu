@@ -3,6 +3,7 @@
 #include "sampling.cuh"
 
 namespace {
+__device__ const float g_nlog[64] = {CPM_NLOG_TABLE};
 __global__ void math_kernel(int fn, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
                             size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -19,6 +20,7 @@ __global__ void math_kernel(int fn, const float* __restrict__ x, const float* __
         case 7: r = cpm_powf(a, b); break;
         case 8: r = cpm_cbrtf(a); break;
         case 9: r = cpm_expf_sym(a); break;
+        case 10: r = cpm_native_logf_tab(a, g_nlog); break;
         default: r = 0.0f;
     }
     out[i] = r;
@@ -27,7 +29,7 @@ __global__ void math_kernel(int fn, const float* __restrict__ x, const float* __
 
 extern "C" int cpm_selftest_math(cpm_ctx* ctx, int fn, const float* x, const float* y, float* out, size_t n) {
     if (!ctx) return CPM_E_INVALID;
-    CPM_REQUIRE(ctx, fn >= 0 && fn <= 9, "unknown function id");
+    CPM_REQUIRE(ctx, fn >= 0 && fn <= 10, "unknown function id");
     if (n == 0) return CPM_OK;
     CPM_REQUIRE(ctx, x && out, "null buffer");
     CPM_LAUNCH(ctx, math_kernel, cpm_div_up(n, 256), 256, 0, fn, x, y, out, n);

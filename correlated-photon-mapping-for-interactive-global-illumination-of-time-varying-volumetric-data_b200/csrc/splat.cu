@@ -109,7 +109,39 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
     }
 }
 
+// copyIndexPhotonsKernel (ppm/cl/photonstolightvolume.cl:225-247): the records of the listed ids, every interaction,
+// power times `multiplier`, packed as out[out_offset + g + k * n] -- the "mem-aligned changed photons" of
+// PhotonToLightVolumeProcessorCL (alignChangedPhotons).  One thread per (id, interaction): 2 x LDG.128 gathered,
+// 2 x STG.128 coalesced.
+__global__ void __launch_bounds__(256) copy_index_photons_kernel(const float4* __restrict__ photons, const uint32_t* __restrict__ indices,
+                                                                 int n, float multiplier, int per_interaction, int n_interactions,
+                                                                 float4* __restrict__ out, size_t out_offset) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)n * n_interactions) return;
+    const int k = (int)(g / (size_t)n);
+    const size_t i = g - (size_t)k * n;
+    const size_t pid = (size_t)k * per_interaction + indices[i];
+    float4 p0 = photons[2 * pid], p1 = photons[2 * pid + 1];
+    p0.w *= multiplier;
+    p1.x *= multiplier;
+    p1.y *= multiplier;
+    out[2 * (out_offset + g)] = p0;
+    out[2 * (out_offset + g) + 1] = p1;
+}
+
 }  // namespace
+
+extern "C" int cpm_copy_index_photons(cpm_ctx* ctx, const float* photons, const uint32_t* indices, int n, float multiplier,
+                                      int photons_per_interaction, int n_interactions, float* aligned_photons, size_t out_offset) {
+    if (!ctx) return CPM_E_INVALID;
+    CPM_REQUIRE(ctx, n >= 0 && n_interactions >= 1 && photons_per_interaction >= 0, "negative size");
+    if (n == 0) return CPM_OK;
+    CPM_REQUIRE(ctx, photons && indices && aligned_photons, "null argument");
+    const size_t total = (size_t)n * n_interactions;
+    CPM_LAUNCH(ctx, copy_index_photons_kernel, cpm_div_up(total, 256), 256, 0, (const float4*)photons, indices, n, multiplier,
+               photons_per_interaction, n_interactions, (float4*)aligned_photons, out_offset);
+    return CPM_OK;
+}
 
 static int splat_common(cpm_ctx* ctx, float* light_volume, int channels, const float texture_to_index[16],
                         const float index_to_texture[16], const int out_dims[3], const float* photons,

@@ -36,7 +36,9 @@ struct TraceArgs {
     uint2* rng;
     unsigned long long* tests;
     BoundGrid bound;  // per-cell opacity bound (cpm_opacity_bound); bound.g == null: off
+    cudaTextureObject_t btex;  // the same grid as a point-sampled 3-D texture (cpm_bound_tex), or 0
     int scan;  // cheap tests a lane scans before the warp reconverges for the candidate fetches
+    int zero;  // 0, unknown to the compiler (ScanRegs)
 };
 
 __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x, float y, float z, float pr, float pg,
@@ -49,6 +51,34 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 #ifndef CPM_SCAN
 #define CPM_SCAN 8  // cheap tests a lane scans before the warp reconverges for the candidate fetches
 #endif
+#ifndef CPM_TRACE_MIN_CTAS
+#define CPM_TRACE_MIN_CTAS 9  // __launch_bounds__(128, .): register cap 56 (tools/build_variant.sh sweeps it)
+#endif
+#ifndef CPM_TRACE_OPAQUE_RD
+#define CPM_TRACE_OPAQUE_RD 0  // 1: also hide d * fc from the compiler's rematerialisation (measured slower: 0.596 vs 0.561 ms)
+#endif
+
+// native_log(u) for u = (float)k * 2^-32, k the raw 32-bit draw (what random_01 returns): cpm_native_logf_tab
+// (include/cpm_detmath.h) with its table in shared memory, without the rare-argument exits such values never take,
+// and with the 2^-32 folded into the bit constants (the product is exact, so bits((float)k * 2^-32) =
+// bits((float)k) - 0x10000000 for k != 0); k == 0 becomes a select.  Same bits as the header function.
+__device__ __forceinline__ float log_unit(uint32_t k, const float2* __restrict__ s_nlog, float c02 = 0.2f) {
+    const uint32_t fb = __float_as_uint(__uint2float_rn(k));
+    const uint32_t jx = fb + (0x00400000u - 0x10000000u);
+    const float fe = __uint_as_float((jx >> 23) + (0x4B400000u - 127u)) - 12582912.0f;
+    const float2 T = s_nlog[(jx >> 18) & 31u];
+    const float m = __uint_as_float(fb + (0x3f800000u - 0x10000000u) - (jx & 0xff800000u));
+    const float r = fmaf(m, T.x, -1.0f);
+    float q = fmaf(r, c02, -0.25f);
+    q = fmaf(r, q, 0.3333333432674407958984375f);
+    q = fmaf(r, q, -0.5f);
+    const float lp = fmaf(r * r, q, r);
+    const float y = fmaf(fe, 0.693147182464599609375f, T.y) + lp;
+    return k == 0u ? __uint_as_float(0xff800000u) : y;
+}
+// the table of cpm_native_logf_tab, staged in shared memory by every CTA
+__device__ const float g_nlog_table[64] = {CPM_NLOG_TABLE};
+#define CPM_SMEM_NLOG_FLOATS 64
 
 // woodcockTracking (ppm/cl/transmittance.cl:126-144).  The step length of test k+1 depends only on the
 // random stream, not on the outcome of test k, so the taps of sample k+1 are requested BEFORE sample k is
@@ -57,12 +87,12 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 // stream is left exactly after the second number of test k), so the result is bit-identical to the
 // sequential loop.
 template <int FMT, int LAYOUT>
-__device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_alpha, int tfw, float ftfw, float3_ o,
+__device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_alpha, const float2* s_nlog, int tfw, float ftfw, float3_ o,
                                           float3_ d, float tStart, float tEnd, cpm_rng& rng, unsigned& tests) {
     // tauMax = 1 (photontracer.cl:160): invTauMaxSampleBaseInterval = 1/(1*150), invTauMax = 1
     const float inv = 1.0f / 150.0f;
     cpm_rng spec = rng;
-    float tA = advance_t(tStart, cpm_logf(cpm_rng_01(spec)), inv), tB;
+    float tA = advance_t(tStart, log_unit(cpm_rng_next(spec), s_nlog), inv), tB;
     float3_ pA = ray_at(o, tA, d);
     Taps A = fetch_taps<FMT, LAYOUT>(V, pA.x, pA.y, pA.z), B;
     float t;
@@ -73,7 +103,7 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
         rng = spec;                 /* commit the first number of this test */                             \
         float u2 = cpm_rng_01(rng); /* second number of this test */                                       \
         spec = rng;                                                                                        \
-        TNXT = advance_t(TCUR, cpm_logf(cpm_rng_01(spec)), inv);                                           \
+        TNXT = advance_t(TCUR, log_unit(cpm_rng_next(spec), s_nlog), inv);                                        \
         const float3_ pn = ray_at(o, TNXT, d);                                                             \
         NXT = fetch_taps<FMT, LAYOUT>(V, pn.x, pn.y, pn.z);                                                \
         float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, blend_taps<FMT>(V, CUR));                      \
@@ -91,30 +121,6 @@ __device__ __forceinline__ float woodcock(const VolumeView& V, const float* s_al
     return t;
 }
 
-// log(u) for u = k * 2^-32, k a 32-bit integer (the values cpm_rng_01 returns): cpm_logf without its
-// subnormal / inf / NaN exits, which such arguments never take; the zero case becomes a select.
-__device__ __forceinline__ float log_unit(float x) {
-    uint32_t ix = __float_as_uint(x);
-    uint32_t jx = ix + (0x3f800000u - 0x3f3504f3u);
-    float fe = __uint_as_float((jx >> 23) + (0x4B400000u - 127u)) - 12582912.0f;
-    float f = __uint_as_float((jx & 0x007fffffu) + 0x3f3504f3u) - 1.0f;
-    float z = f * f;
-    float p = 7.0376836292E-2f;
-    p = fmaf(p, f, -1.1514610310E-1f);
-    p = fmaf(p, f, 1.1676998740E-1f);
-    p = fmaf(p, f, -1.2420140846E-1f);
-    p = fmaf(p, f, 1.4249322787E-1f);
-    p = fmaf(p, f, -1.6668057665E-1f);
-    p = fmaf(p, f, 2.0000714765E-1f);
-    p = fmaf(p, f, -2.4999993993E-1f);
-    p = fmaf(p, f, 3.3333331174E-1f);
-    float y = (f * z) * p;
-    y = fmaf(fe, -2.12194440e-4f, y);
-    y = fmaf(-0.5f, z, y);
-    float r = fmaf(fe, 0.693359375f, f + y);
-    return ix == 0u ? __uint_as_float(0xff800000u) : r;
-}
-
 // The same walk with the per-cell opacity bound (bound.cu).  A test continues the walk iff
 // `u2 >= opacity && t <= tEnd`; with m >= opacity known for the cell, `u2 >= m` decides "continue" without the
 // voxel and transfer-function fetches, and `!(t <= tEnd)` ends the walk whatever the opacity is.  Only the
@@ -124,22 +130,48 @@ __device__ __forceinline__ float log_unit(float x) {
 // until it holds a candidate, leaves the volume, or has done A.scan tests; the warp then reconverges and all
 // lanes holding a candidate fetch their taps together, so the expensive path runs warp-coherently instead of
 // once per lane and iteration.
-template <int FMT, int LAYOUT>
-__device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const float* s_alpha, int tfw, float ftfw,
-                                                  float3_ o, float3_ d, float tStart, float tEnd, cpm_rng& rng,
+// Values the scan loop wants in REGISTERS.  sm_100 ALU instructions take no constant-bank operands and uniform registers
+// do not live across the divergent loop, so whatever the compiler can trace back to a kernel argument or a literal it
+// re-loads (LDC / LDCU) or re-builds (d * fc) every test.  Or-ing the bits with a kernel argument that is zero at run
+// time hides the origin: the values are computed once per thread and stay put.
+struct ScanRegs {
+    float fcx, fcy, fcz;   // BoundGrid::fc (texture look-up) or ::fn (linear look-up)
+    float c02;             // 0.2f, the leading coefficient of log_unit's polynomial
+    float magic;           // 1.5 * 2^23 (bound_at)
+};
+__device__ __forceinline__ float opaque(float v, int zero) { return __uint_as_float(__float_as_uint(v) | (unsigned)zero); }
+template <bool BTEX>
+__device__ __forceinline__ ScanRegs scan_regs(const TraceArgs& A) {
+    const float* f = BTEX ? A.bound.fc : A.bound.fn;
+    return {opaque(f[0], A.zero), opaque(f[1], A.zero), opaque(f[2], A.zero), opaque(0.2f, A.zero), opaque(12582912.0f, A.zero)};
+}
+
+// BTEX: the bound comes from the 3-D texture -- the ray in cell coordinates (three FFMA) and one TEX whose unit floors,
+// clamps and addresses; otherwise from the linear grid (bound_at).
+template <int FMT, int LAYOUT, bool BTEX>
+__device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const ScanRegs& C, const float* s_alpha, const float2* s_nlog,
+                                                  int tfw, float ftfw, float3_ o, float3_ d, float tStart, float tEnd, cpm_rng& rng,
                                                   unsigned& tests, unsigned& fetched) {
     const VolumeView& V = A.vol;
     const float inv = 1.0f / 150.0f;
-    const CellRay R = cell_ray(A.bound, o, d);
+    const float hx = BTEX ? A.bound.hc : A.bound.hn[0], hy = BTEX ? A.bound.hc : A.bound.hn[1], hz = BTEX ? A.bound.hc : A.bound.hn[2];
+    const CellRay R = {fmaf(o.x, C.fcx, hx), fmaf(o.y, C.fcy, hy), fmaf(o.z, C.fcz, hz),
+#if CPM_TRACE_OPAQUE_RD
+                       opaque(d.x * C.fcx, A.zero), opaque(d.y * C.fcy, A.zero), opaque(d.z * C.fcz, A.zero)};
+#else
+                       d.x * C.fcx, d.y * C.fcy, d.z * C.fcz};
+#endif
     float t = tStart;
+    unsigned k = 0u;                              // tests of this walk; a scan round ends when k reaches a multiple of A.scan
+    const unsigned mask = (unsigned)A.scan - 1u;  // (a power of two)
     while (true) {
         bool cand = false, done = false;
-        float u2 = 0.0f;
+        uint32_t k2 = 0u;
 #pragma unroll 1
-        for (int k = 0; k < A.scan; ++k) {
-            t = advance_t(t, log_unit(cpm_rng_01(rng)), inv);
-            u2 = cpm_rng_01(rng);
-            ++tests;
+        while (true) {
+            t = advance_t(t, log_unit(cpm_rng_next(rng), s_nlog, C.c02), inv);
+            k2 = cpm_rng_next(rng);
+            ++k;
             if (!(t <= tEnd)) {
                 done = true;
                 break;
@@ -147,31 +179,38 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const floa
             // (a bound <= 0 -- transparent cell, negative when cpm_opacity_bound_clearance annotated it -- never
             // makes a candidate.  Using the clearance to skip look-ups was measured: lanes leave their transparent
             // stretches at different tests, the warp splits, and the walk gets slower, not faster.)
-            float m = bound_at(A.bound, R, t);
-            if (!(u2 >= m)) {
+            float m = BTEX ? tex3DLod<float>(A.btex, fmaf(t, R.dx, R.ox), fmaf(t, R.dy, R.oy), fmaf(t, R.dz, R.oz), 0.0f)
+                           : bound_at(A.bound, R, t, C.magic);
+            if (!(cpm_u01(k2) >= m)) {
                 cand = true;
                 break;
             }
+            if ((k & mask) == 0u) break;
         }
         if (cand) {
             ++fetched;
             const float3_ pc = ray_at(o, t, d);
             float v = sample_volume<FMT, LAYOUT>(V, pc.x, pc.y, pc.z);
             float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
-            done = !(u2 >= opacity);
+            done = !(cpm_u01(k2) >= opacity);
         }
         if (done) break;
     }
+    tests += k;
     return t;
 }
 
-template <int FMT, int LAYOUT, bool BOUNDED>
-__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
-    extern __shared__ float s_alpha[];
+// BOUNDED: 0 = every test fetches (the reference's loop), 1 = opacity bound from the linear grid, 2 = from the texture
+template <int FMT, int LAYOUT, int BOUNDED>
+__global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) trace_kernel(const TraceArgs A) {
+    extern __shared__ float2 s_nlog[];   // 32 x (rc, lc) of native_log, then the alpha column of the transfer function
+    float* s_alpha = reinterpret_cast<float*>(s_nlog) + CPM_SMEM_NLOG_FLOATS;
+    if (threadIdx.x < CPM_SMEM_NLOG_FLOATS) reinterpret_cast<float*>(s_nlog)[threadIdx.x] = g_nlog_table[threadIdx.x];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
     __syncthreads();
 
     const cpm_trace_params& P = A.p;
+    const ScanRegs C = scan_regs<BOUNDED == 2>(A);
     unsigned tests = 0, fetched = 0;
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int tid = -1;
@@ -201,8 +240,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
 
         if (P.flags & CPM_TRACE_NO_SINGLE_SCATTERING) {
             // photontracer.cl:143-157: the walk is executed even when the ray misses
-            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT>(A, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
-                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT, BOUNDED == 2>(A, C, s_alpha, s_nlog, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
+                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, s_nlog, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             if (scatter) {
                 o = ray_at(o, t, d);
                 tStart = 0.0f;
@@ -218,8 +257,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs A) {
             }
         }
         while (scatter) {
-            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT>(A, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
-                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
+            float t = BOUNDED ? woodcock_bounded<FMT, LAYOUT, BOUNDED == 2>(A, C, s_alpha, s_nlog, tfw, ftfw, o, d, tStart, tEnd, rng, tests, fetched)
+                              : woodcock<FMT, LAYOUT>(A.vol, s_alpha, s_nlog, tfw, ftfw, o, d, tStart, tEnd, rng, tests);
             scatter = t <= tEnd;
             if (scatter) {
                 o = ray_at(o, t, d);
@@ -285,7 +324,9 @@ struct RefillArgs {
 
 template <int FMT, int LAYOUT>
 __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, const RefillArgs Q) {
-    extern __shared__ float s_alpha[];
+    extern __shared__ float2 s_nlog[];   // 32 x (rc, lc) of native_log, then the alpha column of the transfer function
+    float* s_alpha = reinterpret_cast<float*>(s_nlog) + CPM_SMEM_NLOG_FLOATS;
+    if (threadIdx.x < CPM_SMEM_NLOG_FLOATS) reinterpret_cast<float*>(s_nlog)[threadIdx.x] = g_nlog_table[threadIdx.x];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
     __syncthreads();
     const cpm_trace_params& P = A.p;
@@ -303,6 +344,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, co
     unsigned n = 0, tests = 0, fetched = 0;
     cpm_rng rng{0u, 0u};
     CellRay R = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const ScanRegs C = scan_regs<false>(A);
 
     while (true) {
         const unsigned walking = __ballot_sync(0xffffffffu, state == WALK);
@@ -340,7 +382,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, co
                     }
                 }
                 if (scatter) {
-                    R = cell_ray(A.bound, o, d);
+                    R = cell_ray_n(A.bound, o, d);
                     state = WALK;
                 } else {
                     float2 ang = encode_direction(d);
@@ -383,7 +425,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, co
                                 tEnd = ip.y;
                                 n = 0;
                                 if (ip.x < ip.y) {
-                                    R = cell_ray(A.bound, o, d);
+                                    R = cell_ray_n(A.bound, o, d);
                                     state = WALK;
                                 } else {
                                     // the ray misses the volume: empty slots only (t > tEnd makes step (1) write them)
@@ -404,14 +446,14 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, co
             float u2 = 0.0f;
 #pragma unroll 1
             for (int k = 0; k < A.scan; ++k) {
-                t = advance_t(t, log_unit(cpm_rng_01(rng)), inv);
+                t = advance_t(t, log_unit(cpm_rng_next(rng), s_nlog, C.c02), inv);
                 u2 = cpm_rng_01(rng);
                 ++tests;
                 if (!(t <= tEnd)) {
                     done = true;
                     break;
                 }
-                float m = bound_at(A.bound, R, t);
+                float m = bound_at(A.bound, R, t, C.magic);
                 if (!(u2 >= m)) {
                     cand = true;
                     break;
@@ -439,9 +481,9 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, co
     }
 }
 
-template <int FMT, int LAYOUT, bool BOUNDED>
+template <int FMT, int LAYOUT, int BOUNDED>
 int launch2(cpm_ctx* ctx, const TraceArgs& a) {
-    size_t smem = (size_t)a.tf_width * sizeof(float);
+    size_t smem = ((size_t)a.tf_width + CPM_SMEM_NLOG_FLOATS) * sizeof(float);
     if (smem > 48 * 1024)
         CPM_CUDA(ctx, cudaFuncSetAttribute(trace_kernel<FMT, LAYOUT, BOUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT, BOUNDED>), cpm_div_up(a.n_work, 128), 128, smem, a);
@@ -449,7 +491,7 @@ int launch2(cpm_ctx* ctx, const TraceArgs& a) {
 }
 template <int FMT, int LAYOUT>
 int launch_refill(cpm_ctx* ctx, const TraceArgs& a, int refill_min) {
-    size_t smem = (size_t)a.tf_width * sizeof(float);
+    size_t smem = ((size_t)a.tf_width + CPM_SMEM_NLOG_FLOATS) * sizeof(float);
     if (smem > 48 * 1024)
         CPM_CUDA(ctx, cudaFuncSetAttribute(trace_refill_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static int per_sm = 0;
@@ -475,9 +517,10 @@ int launch(cpm_ctx* ctx, const TraceArgs& a) {
     // differently and stay on trace_kernel.
     static const int refill_env = getenv("CPM_TRACE_REFILL") ? atoi(getenv("CPM_TRACE_REFILL")) : 0;
     const int refill = refill_env > 0 ? refill_env : ((a.p.flags & CPM_TRACE_LANE_REFILL) ? 12 : 0);
-    if (a.bound.g && refill > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING))
+    if (a.bound.g && !a.btex && refill > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING))
         return launch_refill<FMT, LAYOUT>(ctx, a, std::min(refill, 32));
-    return a.bound.g ? launch2<FMT, LAYOUT, true>(ctx, a) : launch2<FMT, LAYOUT, false>(ctx, a);
+    if (a.btex) return launch2<FMT, LAYOUT, 2>(ctx, a);
+    return a.bound.g ? launch2<FMT, LAYOUT, 1>(ctx, a) : launch2<FMT, LAYOUT, 0>(ctx, a);
 }
 
 }  // namespace
@@ -508,8 +551,23 @@ extern "C" int cpm_trace_photons(cpm_ctx* ctx, const cpm_volume* vol, const floa
     a.tests = collision_tests;
     static const int scan_env = getenv("CPM_TRACE_SCAN") ? atoi(getenv("CPM_TRACE_SCAN")) : 0;   // tuning sweeps only
     a.scan = scan_env > 0 ? scan_env : CPM_SCAN;
+    while (a.scan & (a.scan - 1)) a.scan &= a.scan - 1;   // a power of two (woodcock_bounded masks with scan - 1)
+    a.zero = 0;
     CPM_REQUIRE(ctx, make_bound_grid(a.bound, params->opacity_bound, vol->dims, params->bound_cell_log2),
                 "bound_cell_log2 must be in 0..8 and the bound grid smaller than 2^31 cells");
+    a.btex = 0;
+    if (params->opacity_bound_tex) {
+        const cpm_bound_tex* bt = params->opacity_bound_tex;
+        // the texture needs the cell geometry only: a placeholder pointer switches the grid parameters on
+        CPM_REQUIRE(ctx, make_bound_grid(a.bound, params->opacity_bound ? params->opacity_bound : (const float*)bt, vol->dims,
+                                         params->bound_cell_log2), "bound_cell_log2 must be in 0..8");
+        int gd[3];
+        cpm_bound_grid_dims(vol->dims, params->bound_cell_log2, gd);
+        CPM_REQUIRE(ctx, gd[0] == bt->dims[0] && gd[1] == bt->dims[1] && gd[2] == bt->dims[2],
+                    "opacity_bound_tex was created for another grid");
+        static const bool tex_off = getenv("CPM_TRACE_BOUND_TEX") && atoi(getenv("CPM_TRACE_BOUND_TEX")) == 0;   // A/B runs
+        if (!(tex_off && params->opacity_bound)) a.btex = bt->tex;
+    }
     if (a.n_work == 0) return CPM_OK;
 #define CPM_DISPATCH(F)                                                                  \
     return vol->layout == CPM_VOLUME_TEXTURE ? launch<F, CPM_VOLUME_TEXTURE>(ctx, a)      \

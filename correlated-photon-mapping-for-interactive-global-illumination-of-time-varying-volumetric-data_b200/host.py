@@ -3,12 +3,13 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-HOST_LIB_PATH = _HERE / "libcpm_host.so"
+HOST_LIB_PATH = Path(os.environ.get("CPM_HOST_LIB", _HERE / "libcpm_host.so"))   # override: tuning sweeps only
 _lib = None
 
 
@@ -113,6 +114,13 @@ def runtime_set_comm(comm_handle, sharded_ingest=True):
     rc = lib().cpmh_runtime_set_comm(C.c_void_p(comm_handle or 0), int(bool(sharded_ingest)))
     if rc < 0:
         raise HostError(f"cpm host error {rc}: {lib().cpmh_last_error().decode()}")
+
+
+def runtime_set_global_budget(on=True):
+    """re-trace budget over the photons of all shards (cpm_comm_select_global) instead of per shard"""
+    rc = lib().cpmh_runtime_set_global_budget(int(bool(on)))
+    if rc != 0:
+        raise RuntimeError(lib().cpmh_last_error().decode())
 
 
 def profile_enable(on=True):

@@ -94,6 +94,13 @@ int cpmh_runtime_set_comm(void* comm, int sharded_ingest) {
     });
 }
 
+int cpmh_runtime_set_global_budget(int on) {
+    return guarded([&]() {
+        CpmRuntime::get().globalBudget = on != 0;
+        return (int)CPM_OK;
+    });
+}
+
 int cpmh_network_sum_light_volume(cpmh_network* net, float* out_host, size_t n_floats, void** sum_device) {
     return guarded([&]() {
         auto v = std::const_pointer_cast<Volume>(net->toLightVolume.outport_.getData());

@@ -53,6 +53,10 @@ CPMH_API int cpmh_runtime_set_photon_shard_offset(uint64_t photon_shard_offset);
  * communicator. */
 CPMH_API void* cpmh_runtime_ctx(void);
 CPMH_API int cpmh_runtime_set_comm(void* cpm_comm_handle, int sharded_ingest);
+/* on != 0 (and a communicator set): `maxIncrementalPhotonsToUpdate` is a budget over the photons of ALL shards, selected in one
+ * global importance order (cpm_comm_select_global); every rank must then evaluate its network the same number of times.
+ * Default off: the budget applies per shard (SURVEY.md 8e offers both). */
+CPMH_API int cpmh_runtime_set_global_budget(int on);
 /* frame result across GPUs: sum over ranks of the networks' light volumes (cpm_allreduce_lightvol) into a device buffer
  * owned by the network (*sum_device, valid until the next call); out_host != NULL: also read back into it (n_floats),
  * synchronously -- typically on rank 0 only */

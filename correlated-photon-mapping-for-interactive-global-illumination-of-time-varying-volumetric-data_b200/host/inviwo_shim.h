@@ -112,6 +112,7 @@ public:
     // rank r uploads slab r of a time step and the slabs are all-gathered over NVLink (cpm_comm_upload_volume_sharded)
     cpm_comm* comm = nullptr;
     bool shardedIngest = false;
+    bool globalBudget = false;   // re-trace budget over the photons of all shards (cpm_comm_select_global) instead of per shard
     // slab upload possible for a volume of `bytes`?
     bool shardedUpload(size_t bytes) const {
         if (!comm || !shardedIngest) return false;

@@ -697,6 +697,20 @@ void PhotonTracerCL::prepareOpacityBound(const Volume* volume, TransferFunction&
         opacityBound_.setSize(nCells);
         float* bound = static_cast<float*>(opacityBound_.deviceWrite());
         rt.check(cpm_opacity_bound(rt.ctx(), range, nCells, scale, offset, tf.deviceData(), (int)tf.getTextureSize(), bound));
+        if (useBoundTexture) {
+            // the tracer reads the grid as a point-sampled 3-D texture (one TEX per collision test)
+            const size3_t vd = volume->getDimensions();
+            const int vdims[3] = {(int)vd.x, (int)vd.y, (int)vd.z};
+            int gd[3];
+            cpm_bound_grid_dims(vdims, boundCellLog2, gd);
+            if (!boundTex_ || gd[0] != boundTexDims_[0] || gd[1] != boundTexDims_[1] || gd[2] != boundTexDims_[2]) {
+                if (boundTex_) cpm_bound_tex_destroy(boundTex_);
+                boundTex_ = nullptr;
+                rt.check(cpm_bound_tex_create(rt.ctx(), gd, &boundTex_));
+                for (int k = 0; k < 3; ++k) boundTexDims_[k] = gd[k];
+            }
+            rt.check(cpm_bound_tex_update(rt.ctx(), boundTex_, bound));
+        }
         boundVolumeVersion_ = volume->dataVersion();
         boundTfVersion_ = tf.version();
     }
@@ -739,6 +753,7 @@ void PhotonTracerCL::tracePhotons(const Volume* volume, TransferFunction& tf, co
         prepareOpacityBound(volume, tf);
         p.opacity_bound = static_cast<const float*>(opacityBound_.deviceRead());
         p.bound_cell_log2 = boundCellLog2;
+        p.opacity_bound_tex = useBoundTexture ? boundTex_ : nullptr;
     }
     rt.check(cpm_trace_photons(rt.ctx(), vh, tfData, (int)tf.getTextureSize(), &p, ls, ip, idx, nInvalidPhotons, photons,
                                rng, collisionCounter));
@@ -1015,6 +1030,7 @@ void ProgressivePhotonTracerCL::process() {
             recomputedPhotonIndices_->indicesToRecomputedPhotons.setSize(N);
         auto& indices = recomputedPhotonIndices_->indicesToRecomputedPhotons;
         auto& rt = CpmRuntime::get();
+        const bool globalBudget = rt.globalBudget && rt.comm && cpm_comm_world(rt.comm) > 1;
 
         if (flag & (static_cast<int>(R::TransferFunction) | static_cast<int>(R::Volume))) {
             auto grid = dynamic_cast<const ImportanceUniformGrid3D*>(recomputationImportanceGrid_.getData().get());
@@ -1046,6 +1062,23 @@ void ProgressivePhotonTracerCL::process() {
             rt.check(cpm_select_below_end(rt.ctx(), &nInvalid));
             const long long budget = static_cast<long long>((maxIncrementalPhotonsToUpdate_.get() / 100.f) * (float)N);
             selectionIsSorted_ = spatialSorting_.get() && nInvalid <= budget;
+            if (globalBudget) {
+                // SURVEY 8e "select globally": the budget max% * N_total is applied to the photons of ALL shards in one
+                // importance order.  Every decision below derives from all-gathered values, so the ranks stay in lockstep.
+                const int W = cpm_comm_world(rt.comm);
+                unsigned long long mine[2] = {(unsigned long long)N, (unsigned long long)nInvalid};
+                std::vector<unsigned long long> all((size_t)2 * W);
+                rt.check(cpm_comm_allgather_u64(rt.comm, mine, 2, all.data()));
+                unsigned long long nTotal = 0, invalidTotal = 0;
+                for (int r = 0; r < W; ++r) {
+                    nTotal += all[2 * r];
+                    invalidTotal += all[2 * r + 1];
+                }
+                globalBudget_ = static_cast<long long>((maxIncrementalPhotonsToUpdate_.get() / 100.f) * (float)nTotal);
+                selectionIsSorted_ = spatialSorting_.get() && (long long)invalidTotal <= globalBudget_;
+                remainingGlobal_ = (long long)invalidTotal;
+                globalOffset_ = 0;
+            }
             if (!selectionIsSorted_) {
                 // 3. the budget cuts the list (or the importance order is wanted): sort all photon ids by importance key.
                 //    The keys are sorted on a COPY so that key[i] keeps belonging to photon i (the reference permutes
@@ -1064,6 +1097,20 @@ void ProgressivePhotonTracerCL::process() {
         }
         int maxPhotonsToUpdate = static_cast<int>((maxIncrementalPhotonsToUpdate_.get() / 100.f) * (float)N);
         nPhotonsToCompute = (size_t)std::max(0, std::min(remainingPhotonsToUpdate_, maxPhotonsToUpdate));
+        long long takeGlobal = 0;
+        if (globalBudget) {
+            takeGlobal = std::max(0LL, std::min(remainingGlobal_, globalBudget_));
+            if (selectionIsSorted_) {
+                nPhotonsToCompute = (size_t)std::max(0, remainingPhotonsToUpdate_);   // nothing is cut: every invalid photon of this shard
+            } else {
+                // this shard's part of the next `takeGlobal` photons of the global importance order: the sorted id list is
+                // consumed front to back, remainingPhotonsOffset_ entries are already done
+                unsigned long long upTo = 0;
+                rt.check(cpm_comm_select_global(rt.comm, static_cast<const uint32_t*>(sortedImportance_.deviceRead()), N,
+                                                (unsigned long long)(globalOffset_ + takeGlobal), &upTo));
+                nPhotonsToCompute = (size_t)std::max(0LL, (long long)upTo - (long long)remainingPhotonsOffset_);
+            }
+        }
         if (remainingPhotonsOffset_ > 0 && nPhotonsToCompute > 0) {
             // continue a budgeted batch: slide the next slice of the sorted id list to the front
             uint32_t* idx = static_cast<uint32_t*>(const_cast<void*>(indices.deviceRead()));
@@ -1099,6 +1146,12 @@ void ProgressivePhotonTracerCL::process() {
         }
         remainingPhotonsOffset_ += (int)nPhotonsToCompute;
         remainingPhotonsToUpdate_ -= (int)nPhotonsToCompute;
+        if (globalBudget) {
+            globalOffset_ += takeGlobal;
+            remainingGlobal_ -= takeGlobal;
+            // batches continue while ANY shard has photons left (the selection above is a collective)
+            remainingPhotonsToUpdate_ = (int)std::min<long long>(remainingGlobal_, 2147483647LL);
+        }
         if (remainingPhotonsToUpdate_ > 0 && enableProgressivePhotonRecomputation_.get()) {
             enableProgressiveRefinement_.set(true);
         } else {
@@ -1361,12 +1414,26 @@ void PhotonToLightVolumeProcessorCL::process() {
         lightVolume_->deviceWrite();
         ScopedStage st("splat");
         beforeWrite();
+        if (alignChangedPhotons_.get()) {
+            // :207-244 -- gather the old (power * -1) and the new (power * +1) records of the listed ids into one packed
+            // buffer (copyIndexPhotonsKernel twice) and splat its 2 * n * I records as plain photons.  The reference sizes
+            // the buffer for one interaction (maxRecomputationPhotons * 4 vec4); here it holds every interaction.
+            const size_t need = (size_t)nRecomputed * (size_t)I * 4;
+            if (changedAlignedPhotons_.getSize() < need) changedAlignedPhotons_.setSize(std::max(need, (size_t)maxRecomputationPhotons * 4));
+            float* packed = reinterpret_cast<float*>(changedAlignedPhotons_.deviceWrite());
+            rt.check(cpm_copy_index_photons(rt.ctx(), static_cast<const float*>(prevPhotons_.deviceRead()), idx, nRecomputed, -1.f, N, I, packed, 0));
+            rt.check(cpm_copy_index_photons(rt.ctx(), photonsDev, idx, nRecomputed, 1.f, N, I, packed, (size_t)nRecomputed * (size_t)I));
+            rt.check(cpm_splat_photons(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim, packed, nullptr, 2 * nRecomputed * I, N, I,
+                                       radius, scale, 1.f));
+            lastPath = "incremental-aligned";
+        } else {
         // (the kernel leaves prevPhotons_ equal to the new records of the listed ids: no whole-buffer copy below)
         rt.check(cpm_splat_photons_update_sync(rt.ctx(), lv, channels, t2i.data(), i2t.data(), outDim,
                                                static_cast<float*>(prevPhotons_.deviceWrite()), photonsDev, idx, nRecomputed, N, I,
                                                radius, scale));
         lastPath = "incremental";
         prevInSync = true;
+        }
     } else if (prevPhotons_.getSize() != photonData->photons_.getSize() || nRecomputed < 0 || nRecomputed >= maxRecomputationPhotons) {
         float* lv = static_cast<float*>(lightVolume_->deviceWrite());
         ScopedStage st("splat");

@@ -3,6 +3,7 @@
 // (include/cpm_b200.h).  Class identifiers, port identifiers, property identifiers, defaults and
 // ranges are the reference's so that a saved workspace keeps working.
 #pragma once
+#include <cstdlib>
 #include "inviwo_shim.h"
 
 namespace inviwo {
@@ -236,8 +237,14 @@ public:
     // per-cell opacity bound (cpm_opacity_bound): collision tests it decides skip the voxel fetch, results unchanged
     bool useOpacityBound = true;
     int boundCellLog2 = 3;
+    // the bound grid also as a 3-D texture for the tracer (cpm_bound_tex): CPM_BOUND_TEXTURE=0 in the environment
+    // keeps the linear look-up (A/B runs)
+    bool useBoundTexture = getenv("CPM_BOUND_TEXTURE") ? atoi(getenv("CPM_BOUND_TEXTURE")) != 0 : true;
+    ~PhotonTracerCL() { if (boundTex_) cpm_bound_tex_destroy(boundTex_); }
 private:
     Buffer<float> opacityBound_;
+    cpm_bound_tex* boundTex_ = nullptr;
+    int boundTexDims_[3] = {0, 0, 0};
     uint64_t boundVolumeVersion_ = 0, boundTfVersion_ = 0;
     Buffer<uvec2> randomState_;
     bool onlyMultipleScattering_ = false, progressive_ = false;
@@ -365,6 +372,8 @@ private:
     Radixsort recomputationImportanceSorter_{true};
     Radixsort recomputationIndexSorter_{false};
     int remainingPhotonsToUpdate_ = -1;
+    // global (cross-shard) budget, CpmRuntime::globalBudget: budget and photons left over ALL shards, position in the global order
+    long long globalBudget_ = 0, remainingGlobal_ = 0, globalOffset_ = 0;
     int remainingPhotonsOffset_ = 0;
     bool selectionIsSorted_ = false;   // the id list came from cpm_select_below: ascending, complete
 };
@@ -397,6 +406,7 @@ private:
     void volumeSizeOptionChanged();
     std::shared_ptr<Volume> lightVolume_;
     Buffer<vec4> prevPhotons_;
+    Buffer<vec4> changedAlignedPhotons_;   // packed -old / +new records of the `alignChangedPhotons` path
 };
 
 // org.inviwo.VolumeMinMaxCLProcessor -- ugc/processors/volumeminmaxclprocessor.cpp:45-184

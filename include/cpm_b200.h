@@ -198,6 +198,10 @@ typedef struct cpm_trace_params {
     const float* opacity_bound;
     int32_t bound_cell_log2; /* the cell_log2 the bound grid was built with */
     int32_t reserved_;
+    /* Optional: the same bound grid as a point-sampled 3-D texture (cpm_bound_tex_create / _update; bound_cell_log2
+     * applies).  When set it is used instead of opacity_bound: one TEX per collision test instead of the index
+     * arithmetic and the load.  Results are identical. */
+    const struct cpm_bound_tex* opacity_bound_tex;
 } cpm_trace_params;
 
 /* photonTracerKernel (ppm/cl/photontracer.cl:69-216) incl. woodcockTracking
@@ -238,6 +242,14 @@ CPM_API int cpm_volume_value_range(cpm_ctx* ctx, const cpm_volume* vol, int cell
  * when the volume (range) or the transfer function changes. */
 CPM_API int cpm_opacity_bound(cpm_ctx* ctx, const float* range, size_t n_cells, float format_scale, float format_offset,
                               const float* tf_rgba, int tf_width, float* bound);
+
+/* The bound grid as a point-sampled 3-D texture for cpm_trace_params::opacity_bound_tex.  grid_dims =
+ * cpm_bound_grid_dims; cpm_bound_tex_update copies `bound` (device memory, the layout cpm_opacity_bound writes) into
+ * the texture on the context stream -- call it after every cpm_opacity_bound.  Not in the reference. */
+typedef struct cpm_bound_tex cpm_bound_tex;
+CPM_API int cpm_bound_tex_create(cpm_ctx* ctx, const int grid_dims[3], cpm_bound_tex** out);
+CPM_API int cpm_bound_tex_update(cpm_ctx* ctx, cpm_bound_tex* tex, const float* bound);
+CPM_API void cpm_bound_tex_destroy(cpm_bound_tex* tex);
 
 /* Clearance of transparent cells, in place: a cell whose bound is exactly 0 (every transfer-function texel it can
  * reach is 0) and whose surrounding cube of radius R >= 1 cells (R <= max_radius) holds only such cells gets the
@@ -374,6 +386,13 @@ CPM_API int cpm_splat_photons_update_sync(cpm_ctx* ctx, float* light_volume, int
                                           const uint32_t* indices, int n, int photons_per_interaction, int n_interactions,
                                           float radius, float relative_irradiance_scale);
 
+/* copyIndexPhotonsKernel (ppm/cl/photonstolightvolume.cl:225-247; host: photontolightvolumeprocessorcl.cpp:207-244, the
+ * `alignChangedPhotons` path): aligned_photons[out_offset + g + k * n] = record k * photons_per_interaction + indices[g]
+ * with its power multiplied by `multiplier` (-1 for the previous records, +1 for the new ones), g < n, k < n_interactions.
+ * The packed buffer is then splatted as plain records (cpm_splat_photons, indices == NULL). */
+CPM_API int cpm_copy_index_photons(cpm_ctx* ctx, const float* photons, const uint32_t* indices, int n, float multiplier,
+                                   int photons_per_interaction, int n_interactions, float* aligned_photons, size_t out_offset);
+
 /* ---- multi-GPU exchange (option B) --------------------------------------------------------------- */
 /* Sum of the per-GPU light volumes over NVLink peer memory, in place: peer_buffers[r] (r < world; host array of device
  * pointers, this GPU's mapping of rank r's buffer, all n_floats long) each hold one rank's volume on entry and the sum
@@ -436,6 +455,16 @@ CPM_API int cpm_allgather_volume(cpm_comm* comm, void* volume, size_t slab_bytes
 CPM_API int cpm_comm_upload_volume_sharded(cpm_comm* comm, void* volume, const void* src_host, size_t total_bytes,
                                            int on_transfer_stream, cpm_event** done);
 CPM_API int cpm_comm_barrier(cpm_comm* comm);
+/* Host-value all-gather: all_out[r * count + i] = values[i] of rank r (count <= 64).  SYNCHRONOUS (returns the values). */
+CPM_API int cpm_comm_allgather_u64(cpm_comm* comm, const unsigned long long* values, int count, unsigned long long* all_out);
+/* Global (cross-shard) selection, SURVEY.md 8e: "all-gather the (key, idx) of candidates and select globally".  Every rank
+ * holds its own keys sorted ascending (device memory, what cpm_radix_sort_u32 leaves); the global order is (key, rank,
+ * local index), i.e. one stable sort over the concatenated shards.  *local_count = how many of THIS rank's sorted keys
+ * are among the first `position` elements of that order: the re-trace budget max% * N_total applied to the whole photon
+ * set instead of per shard (ppm/processor/progressivephotontracercl.cpp:419-431 on one GPU).  Four rounds of a 256-ary
+ * search over the key bits, each one all-gather of 257 counts: no keys travel.  COLLECTIVE and SYNCHRONOUS. */
+CPM_API int cpm_comm_select_global(cpm_comm* comm, const uint32_t* sorted_keys, size_t n_local, unsigned long long position,
+                                   unsigned long long* local_count);
 
 /* ---- (5)(6)(7) photon map for gathering: cell keys, cell-sorted records, ray-march gather ------ */
 /* Not launched anywhere in the reference; the estimator is the reference's

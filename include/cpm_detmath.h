@@ -113,6 +113,52 @@ CPM_HD float cpm_logf(float x) {
     return fmaf(fe, 0.693359375f, r);
 }
 
+/* native_log (ppm/cl/transmittance.cl:135 `t += -native_log(random_01(...)) * ...`): the delta-tracking step evaluates one
+ * logarithm per collision test, so this one is built for instruction count.  x = 2^e * m with m in [0.75, 1.5)
+ * (adding 0x00400000 to the bits moves mantissas >= 1.5 to the next exponent), the top five bits of the shifted
+ * mantissa field select one of 32 intervals with a tabulated reciprocal rc of its centre and lc = -log(rc) (exact
+ * reciprocal, so r = m * rc - 1 carries no table error; one fma), and
+ *     log x = e ln2 + lc + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5),     |r| < 2^-5: next term < 5e-9 relative.
+ * The two intervals touching m = 1 use rc = 1, lc = 0, so log(x) -> x - 1 keeps its relative accuracy near 1 and
+ * log(1) == 0 exactly.  Measured against float64 log on the tracer's arguments k * 2^-32: <= 2 ulp.
+ * `tab` = CPM_NLOG_TABLE (64 floats: rc, lc per interval): a static array on the host, shared memory in the tracer.
+ * Zero, subnormal, infinite, NaN and negative arguments take cpm_logf's exits. */
+#define CPM_NLOG_TABLE \
+    0x1.51d07e0000000p+0f, -0x1.1bf9940000000p-2f, 0x1.4afd6a0000000p+0f, -0x1.0713860000000p-2f, \
+    0x1.446f860000000p+0f, -0x1.e530ee0000000p-3f, 0x1.3e22cc0000000p+0f, -0x1.bd08740000000p-3f, \
+    0x1.3813820000000p+0f, -0x1.95a5b20000000p-3f, 0x1.323e340000000p+0f, -0x1.6f01240000000p-3f, \
+    0x1.2c9fb40000000p+0f, -0x1.4913d20000000p-3f, 0x1.27350c0000000p+0f, -0x1.23d7160000000p-3f, \
+    0x1.21fb780000000p+0f, -0x1.fe89120000000p-4f, 0x1.1cf06a0000000p+0f, -0x1.b6ac7c0000000p-4f, \
+    0x1.1811820000000p+0f, -0x1.700d3e0000000p-4f, 0x1.135c820000000p+0f, -0x1.2aa0580000000p-4f, \
+    0x1.0ecf560000000p+0f, -0x1.ccb7260000000p-5f, 0x1.0a68100000000p+0f, -0x1.466ada0000000p-5f, \
+    0x1.0624de0000000p+0f, -0x1.8492860000000p-6f, 0x1.0000000000000p+0f, 0x0p+0f, \
+    0x1.0000000000000p+0f, 0x0p+0f, 0x1.e9131a0000000p-1f, 0x1.77459c0000000p-5f, \
+    0x1.dae6080000000p-1f, 0x1.341d740000000p-4f, 0x1.cd85680000000p-1f, 0x1.a926d80000000p-4f, \
+    0x1.c0e0700000000p-1f, 0x1.0d77e80000000p-3f, 0x1.b4e81c0000000p-1f, 0x1.44d2b40000000p-3f, \
+    0x1.a98ef60000000p-1f, 0x1.7ab8900000000p-3f, 0x1.9ec8ea0000000p-1f, 0x1.af3c920000000p-3f, \
+    0x1.948b100000000p-1f, 0x1.e270760000000p-3f, 0x1.8acb900000000p-1f, 0x1.0a32500000000p-2f, \
+    0x1.8181820000000p-1f, 0x1.22941e0000000p-2f, 0x1.78a4c80000000p-1f, 0x1.3a64c60000000p-2f, \
+    0x1.702e060000000p-1f, 0x1.51aad80000000p-2f, 0x1.6816820000000p-1f, 0x1.686c800000000p-2f, \
+    0x1.6058160000000p-1f, 0x1.7eaf840000000p-2f, 0x1.58ed240000000p-1f, 0x1.94793e0000000p-2f
+
+CPM_HD float cpm_native_logf_tab(float x, const float* tab) {
+    uint32_t ix = cpm_f2u(x);
+    if (ix - 0x00800000u >= 0x7f000000u) return cpm_logf(x);
+    uint32_t jx = ix + 0x00400000u;
+    float fe = cpm_u2f((jx >> 23) + (0x4B400000u - 127u)) - 12582912.0f;
+    uint32_t i = (jx >> 18) & 31u;
+    float m = cpm_u2f(ix + 0x3f800000u - (jx & 0xff800000u));
+    float r = fmaf(m, tab[2 * i], -1.0f);
+    float q = fmaf(r, 0.2f, -0.25f);
+    q = fmaf(r, q, 0.3333333432674407958984375f);
+    q = fmaf(r, q, -0.5f);
+    float lp = fmaf(r * r, q, r);
+    return fmaf(fe, 0.693147182464599609375f, tab[2 * i + 1]) + lp;
+}
+/* host form (the oracle, the OpenCL-on-host shim of oracle/_ref) */
+static const float cpm_nlog_table_host[64] = {CPM_NLOG_TABLE};
+static inline float cpm_native_logf(float x) { return cpm_native_logf_tab(x, cpm_nlog_table_host); }
+
 /* exp(x) for x in [-87, 0] (the path uses it for the transmittance of one ray-march step).
  * k = rint(x log2 e), r = x - k ln2 (two fma steps with the 16-bit-exact LN2_HI), degree-6 Taylor kernel
  * on |r| <= 0.347 (next term r^7/5040 < 1.2e-7 relative), scaled by 2^k through the exponent field.

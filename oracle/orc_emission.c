@@ -254,6 +254,7 @@ void orc_selftest_math(int fn, const float* x, const float* y, float* out, size_
             case 7: r = cpm_powf(a, b); break;
             case 8: r = cpm_cbrtf(a); break;
             case 9: r = cpm_expf_sym(a); break;
+            case 10: r = cpm_native_logf(a); break;
             default: r = 0.0f;
         }
         out[i] = r;

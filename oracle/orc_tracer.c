@@ -67,7 +67,7 @@ static float woodcockTracking(const orc_volume* vol, const float* tf, int tfw, v
     float opacity;
     float r;
     do {
-        t += -cpm_logf(random_01(rs)) * invTauMaxSampleBaseInterval;
+        t += -cpm_native_logf(random_01(rs)) * invTauMaxSampleBaseInterval;
         v3 pos = v3_ray(origin, t, direction);
         float volumeSample = orc_sample_volume(vol, pos.x, pos.y, pos.z);
         opacity = orc_sample_tf_alpha(tf, tfw, volumeSample);

@@ -354,7 +354,7 @@ inline float max(float a, float b) { return cpm_fmax(a, b); }
 inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 inline float mix(float x, float y, float a) { return fmaf(y - x, a, x); }   // x + (y - x) a
 inline float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
-inline float native_log(float x) { return cpm_logf(x); }
+inline float native_log(float x) { return cpm_native_logf(x); }
 inline float native_exp(float x) { return cpm_expf_sym(x); }
 #define CLC_FCOMMON(V, N)                                                                                         \
     inline V min(const V& a, const V& b) { V r; for (int i = 0; i < N; ++i) r.s[i] = min(a.s[i], b.s[i]); return r; } \

@@ -146,7 +146,17 @@ def _bounded_trace(cpm, ctx, torch, vol, tf, L, layout, s, clearance=True, **kw)
     ctx.opacity_bound(rng, n_cells, torch.from_numpy(tf).cuda(), bound)
     if clearance:
         ctx.opacity_bound_clearance(bound, gd, 6)
-    return cuda_trace(cpm, ctx, torch, vol, tf, L, layout, opacity_bound=bound, bound_cell_log2=s, **kw)
+    out = cuda_trace(cpm, ctx, torch, vol, tf, L, layout, opacity_bound=bound, bound_cell_log2=s, **kw)
+    # the same grid as a point-sampled 3-D texture (cpm_bound_tex: one TEX per test instead of the index arithmetic):
+    # same photons, same random states, same counters -- with and without the linear grid beside it
+    btex = ctx.bound_texture(gd, bound)
+    for lin in (bound, None):
+        kw2 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+        out_t = cuda_trace(cpm, ctx, torch, vol, tf, L, layout, opacity_bound=lin, bound_cell_log2=s, opacity_bound_tex=btex, **kw2)
+        assert np.array_equal(out_t[0].view(np.uint32), out[0].view(np.uint32)), "texture bound: photons differ"
+        assert np.array_equal(out_t[1], out[1]) and out_t[2:] == out[2:], "texture bound: rng / counters differ"
+    btex.close()
+    return out
 
 
 @pytest.mark.gpu

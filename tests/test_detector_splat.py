@@ -192,3 +192,47 @@ def test_cuda_splat_update_equals_remove_then_add(cpm, orc, ctx, torch_cuda, syn
                              torch.from_numpy(idx.view(np.int32)).cuda(), idx.size, n, 2, radius, scale)
     ctx.sync()
     assert np.array_equal(lv2.cpu().numpy(), base.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels", [1, 4])
+def test_cuda_copy_index_photons_then_splat_equals_update(cpm, orc, ctx, torch_cuda, synth, channels):
+    """copyIndexPhotonsKernel (ppm/cl/photonstolightvolume.cl:225-247): packed[off + g + k * n] = record (k, ids[g]) with
+    its power times the multiplier, bit for bit; splatting the packed -old / +new records as plain photons is the
+    `alignChangedPhotons` update (photontolightvolumeprocessorcl.cpp:207-244)"""
+    torch = torch_cuda
+    c = make_case(orc, synth, cpm, I=2, n_side=64)
+    n = c["L"]["n"]
+    old = c["photons"]
+    new = old.copy()
+    ph = new.reshape(2, n, 8)
+    moved = np.arange(1, n, 3)
+    stored = ph[0, moved, 0] != np.float32(3.4028234663852886e38)
+    ph[0, moved[stored], 0:3] = np.clip(ph[0, moved[stored], 0:3] - np.float32(0.02), 0, 1)
+    idx = np.arange(1, n, 2, dtype=np.uint32)
+    m = idx.size
+    packed = torch.zeros(4 * m * 8, dtype=torch.float32, device="cuda")
+    d_idx = torch.from_numpy(idx.view(np.int32)).cuda()
+    ctx.copy_index_photons(torch.from_numpy(old).cuda(), d_idx, m, -1.0, n, 2, packed, 0)
+    ctx.copy_index_photons(torch.from_numpy(new).cuda(), d_idx, m, 1.0, n, 2, packed, 2 * m)
+    ctx.sync()
+    got = packed.cpu().numpy().reshape(2, 2, m, 8)                 # (old/new, interaction, listed id, field)
+    for half, (src, mul) in enumerate(((old, np.float32(-1)), (new, np.float32(1)))):
+        want = src.reshape(2, n, 8)[:, idx].copy()
+        want[:, :, 3:6] *= mul
+        assert np.array_equal(got[half].view(np.uint32), want.view(np.uint32))
+    od = (32, 32, 32)
+    nvox = od[0] * od[1] * od[2]
+    t2i, i2t = cpm.capi.texture_to_index_matrix(od), cpm.capi.index_to_texture_matrix(od)
+    radius, scale = 1.3 / 32, 0.37
+    want = np.zeros(nvox * channels, np.float64)
+    orc.splat(want, channels, t2i, i2t, od, old, None, n, n, 2, radius, scale)
+    base = want.copy()
+    orc.splat(want, channels, t2i, i2t, od, old, idx, m, n, 2, radius, scale, -1.0)
+    orc.splat(want, channels, t2i, i2t, od, new, idx, m, n, 2, radius, scale, 1.0)
+    lv = torch.from_numpy(base.astype(np.float32)).cuda()
+    ctx.splat_photons(lv, channels, t2i, i2t, od, packed, None, 4 * m, n, 2, radius, scale)
+    ctx.sync()
+    g = lv.cpu().numpy().astype(np.float64)
+    assert np.abs(want - base).max() > 0
+    assert np.sqrt(((g - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5

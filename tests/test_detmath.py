@@ -26,6 +26,10 @@ def _ulps(got, want64):
 def test_accuracy_against_libm(orc):
     u, ang, cz, y, x = _inputs()
     assert _ulps(orc.selftest_math(0, u), np.log(u.astype(np.float64))).max() <= 2.0
+    # native_log of the delta-tracking step (table-driven cpm_native_logf)
+    assert _ulps(orc.selftest_math(10, u), np.log(u.astype(np.float64))).max() <= 2.0
+    nl = orc.selftest_math(10, np.array([0.0, 1.0], np.float32))
+    assert np.isneginf(nl[0]) and nl[1] == 0.0
     assert np.abs(orc.selftest_math(1, ang) - np.sin(ang.astype(np.float64))).max() <= 1.5e-7
     assert np.abs(orc.selftest_math(2, ang) - np.cos(ang.astype(np.float64))).max() <= 1.5e-7
     assert np.abs(orc.selftest_math(3, cz) - np.arccos(cz.astype(np.float64))).max() <= 4e-7
@@ -51,7 +55,8 @@ def test_accuracy_against_libm(orc):
 def test_host_and_device_agree_bitwise(orc, ctx, torch_cuda):
     torch = torch_cuda
     u, ang, cz, y, x = _inputs()
-    cases = [(0, u, None), (1, ang, None), (2, ang, None), (3, cz, None), (4, y, x),
+    cases = [(0, u, None), (10, u, None), (10, np.concatenate([np.float32(10.0) ** np.linspace(-44, 38, 50_000, dtype=np.float32), np.zeros(3, np.float32)]), None),
+             (1, ang, None), (2, ang, None), (3, cz, None), (4, y, x),
              (5, np.arange(256, dtype=np.float32), None), (6, np.arange(65536, dtype=np.float32), None)]
     rng = np.random.default_rng(5)
     base = rng.uniform(0.0, 1.5, 200_000).astype(np.float32)

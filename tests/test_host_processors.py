@@ -419,3 +419,33 @@ def test_network_data_range_change_reaches_sampling_and_bound(host, cpm, orc, sy
     stored = (want[:, 0] != FLT_MAX).sum()
     assert stored > 500
     net.close()
+
+
+@pytest.mark.gpu
+def test_network_align_changed_photons_path(host, cpm, synth, torch_cuda):
+    """`alignChangedPhotons` (photontolightvolumeprocessorcl.cpp:207-244): the incremental update through the packed
+    -old / +new buffer gives the light volume of the default (index-list) update up to the order of the float adds, and
+    keeps doing so over consecutive updates (the copy of the previous records is refreshed after every frame)."""
+    dims, ns, I = (64, 64, 64), 96, 2
+    vol = synth.volume_u8(dims, 8)
+    kw = dict(max_scattering_events=I, light_volume_option=2, with_importance_grid=True, reference_full_splat_bound=False,
+              incremental_threshold=100.0)
+    nets = [host.Network(dims, cpm.CPM_FMT_U8, ns, [(0.2, 0.3, 0.9)], **kw) for _ in range(2)]
+    nets[1].set_property("org.inviwo.PhotonToLightVolumeProcessorCL", "alignChangedPhotons", 1)
+    for net in nets:
+        net.set_transfer_function(synth.WS_TF_POINTS)
+        net.set_volume_host(vol)
+        net.evaluate()
+    pts = list(synth.WS_TF_POINTS)
+    for alpha in (0.9, 0.35, 0.6):
+        pts[-1] = (pts[-1][0], (0.1, 0.6, 0.65, alpha))
+        for net in nets:
+            net.set_transfer_function(pts)
+            net.evaluate()
+        assert nets[0].last_splat_path == "incremental" and nets[1].last_splat_path == "incremental-aligned"
+        assert 0 < nets[0].n_recomputed == nets[1].n_recomputed
+        a, b = (net.read_light_volume().astype(np.float64) for net in nets)
+        rmse = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((a ** 2).mean())
+        assert rmse < 1e-5, rmse
+    for net in nets:
+        net.close()

@@ -90,5 +90,8 @@ def test_volume_player_interpolates(host, cpm, synth, torch_cuda, fmt):
         else:
             m = a.astype(np.float64) / 255 + (b.astype(np.float64) / 255 - a.astype(np.float64) / 255) * float(w)
             want = np.rint(np.clip(m, 0, 1) * 255)
+            # float32 on the device, float64 here: they may round differently only where the mix lands on a tie (x.5)
             assert np.abs(out[k].astype(np.int32) - want.astype(np.int32)).max() <= 1
-            assert (out[k] == want).mean() > 0.999
+            mism = out[k] != want
+            assert np.all(np.abs(np.abs(m * 255 - np.floor(m * 255)) - 0.5)[mism] < 1e-3)
+            assert mism.mean() < 0.1

@@ -91,7 +91,7 @@ def test_replay_property(orc, synth):
 # ------------------------------------------------------------------ GPU: CUDA vs oracle ------
 def cuda_trace(cpm, ctx, torch, vol_np, tf, L, layout, max_interactions=1, flags=0, phase=0, material=(0, 0, 0, 0),
                rng=None, recompute=None, photons=None, step_size=1.0 / 64, aabb=((0, 0, 0), (1, 1, 1)),
-               total_photons=None, photon_offset=0, opacity_bound=None, bound_cell_log2=3):
+               total_photons=None, photon_offset=0, opacity_bound=None, bound_cell_log2=3, opacity_bound_tex=None):
     """returns (photons, rng, collision tests) and, with an opacity bound, the number of tests that fetched voxels"""
     n = L["n"]
     total = total_photons or n
@@ -114,13 +114,13 @@ def cuda_trace(cpm, ctx, torch, vol_np, tf, L, layout, max_interactions=1, flags
     p = cpm.make_trace_params(n, total_photons=total, photon_offset=photon_offset, max_interactions=max_interactions,
                               flags=flags | cpm.CPM_TRACE_STATS, phase=phase, material=material, step_size=step_size,
                               aabb_min=aabb[0], aabb_max=aabb[1], opacity_bound=opacity_bound,
-                              bound_cell_log2=bound_cell_log2)
+                              bound_cell_log2=bound_cell_log2, opacity_bound_tex=opacity_bound_tex)
     didx = None if recompute is None else torch.from_numpy(recompute.view(np.int32)).cuda()
     ctx.trace_photons(V, dtf, p, dls, dis, dph, drng, didx, 0 if recompute is None else len(recompute), dcount)
     ctx.sync()
     counts = dcount.cpu().numpy()
     out = dph.cpu().numpy().reshape(-1, 8), drng.cpu().numpy().view(np.uint32), int(counts[0])
-    if opacity_bound is None:
+    if opacity_bound is None and opacity_bound_tex is None:
         assert counts[1] == counts[0]
     else:
         out = out + (int(counts[1]),)

@@ -45,3 +45,26 @@ print("asin max rel err", np.max(np.abs((x + x*z*horner(fit(q_asin,1e-9,0.25,5),
 z = np.linspace(1e-9, T*T, 100001)
 t = np.sqrt(z)
 print("atan max rel err", np.max(np.abs((t + t*z*horner(fit(r_atan,1e-9,T*T,5), z))/np.arctan(t) - 1)))
+
+
+# ---- cpm_native_logf: 32-interval table over m in [0.75, 1.5) ------------------------------------------------------------
+# interval i = top five bits of the mantissa field after the "+0x00400000" shift (see cpm_detmath.h); rc = fl(1 / centre),
+# lc = fl(-log(rc)) -- the logarithm of the EXACT reciprocal of rc, so that m * rc - 1 carries no table rounding error.
+# The two intervals that touch m = 1 use rc = 1, lc = 0: log(x) near 1 keeps its relative accuracy.
+def nlog_table():
+    import math
+    rows = []
+    for i in range(32):
+        if i in (15, 16):
+            c = 1.0
+        elif i < 15:
+            c = 0.75 + (i + 0.5) / 64
+        else:
+            c = 1.0 + (i - 15.5) / 32
+        rc = np.float32(1.0 / c)
+        lc = np.float32(-math.log(float(rc)))
+        rows.append((rc, lc))
+    print("/* CPM_NLOG_TABLE: {rc, lc} x 32 (tools/fit_detmath.py: nlog_table) */")
+    for i in range(0, 32, 2):
+        print("    " + " ".join(f"{float(a).hex()}f, {float(b).hex()}f," for a, b in rows[i:i + 2]))
+nlog_table()
