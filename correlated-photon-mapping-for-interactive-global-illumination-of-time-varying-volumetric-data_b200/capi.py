@@ -606,6 +606,20 @@ class Comm:
     def barrier(self):
         self.ctx._check(lib().cpm_comm_barrier(self.h))
 
+    def allgather_u64(self, values):
+        """host values of every rank: list of `world` lists (synchronous)"""
+        n = len(values)
+        mine = (C.c_ulonglong * n)(*[int(v) for v in values])
+        out = (C.c_ulonglong * (n * self.world))()
+        self.ctx._check(lib().cpm_comm_allgather_u64(self.h, mine, n, out))
+        return [list(out[r * n:(r + 1) * n]) for r in range(self.world)]
+
+    def select_global(self, sorted_keys, n_local, position):
+        """how many of this rank's ascending keys are among the first `position` of the global (key, rank, index) order"""
+        c = C.c_ulonglong()
+        self.ctx._check(lib().cpm_comm_select_global(self.h, _p(sorted_keys), C.c_size_t(n_local), C.c_ulonglong(int(position)), C.byref(c)))
+        return int(c.value)
+
     def close(self):
         if self.h:
             lib().cpm_comm_destroy(self.h)

@@ -23,7 +23,9 @@ struct cpm_ctx {
     void* comm = nullptr;  // ncclComm_t when multi-GPU is initialised
     cudaStream_t xfer_stream = nullptr;  // transfer stream of cpm_mem_prefetch_h2d (lazy)
     cudaEvent_t xfer_fence = nullptr;
-    unsigned* trace_cursor = nullptr;    // work cursor of trace_refill_kernel
+    unsigned* trace_cursor = nullptr;    // work cursor of walk_kernel (tracer.cu)
+    void* walk_buf = nullptr;            // walk entries + power of the wavefront tracer
+    size_t walk_bytes = 0;
     cudaStream_t d2h_stream = nullptr;   // read-back stream of cpm_mem_readback_d2h (lazy)
     cudaEvent_t d2h_fence = nullptr;
     cudaEvent_t select_done = nullptr;   // cpm_select_below_begin / _end

@@ -96,6 +96,7 @@ void cpm_ctx_destroy(cpm_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->select_done) cudaEventDestroy(ctx->select_done);
     if (ctx->trace_cursor) cudaFree(ctx->trace_cursor);
+    if (ctx->walk_buf) cudaFree(ctx->walk_buf);
     if (ctx->d2h_stream) {
         cudaStreamSynchronize(ctx->d2h_stream);
         cudaStreamDestroy(ctx->d2h_stream);

@@ -54,6 +54,9 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 #ifndef CPM_TRACE_MIN_CTAS
 #define CPM_TRACE_MIN_CTAS 9  // __launch_bounds__(128, .): register cap 56 (tools/build_variant.sh sweeps it)
 #endif
+#ifndef CPM_TRACE_WAVEFRONT_DEFAULT
+#define CPM_TRACE_WAVEFRONT_DEFAULT 0  // 1: bounded traces take the wavefront form unless CPM_TRACE_WAVEFRONT=0
+#endif
 #ifndef CPM_TRACE_OPAQUE_RD
 #define CPM_TRACE_OPAQUE_RD 0  // 1: also hide d * fc from the compiler's rematerialisation (measured slower: 0.596 vs 0.561 ms)
 #endif
@@ -200,6 +203,11 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const Scan
     return t;
 }
 
+// (Measured and rejected: the same loop software-pipelined -- draws, logarithm and bound look-up of test k+1 issued
+// before test k is decided, the speculative test dropped when k ends the walk or is a candidate.  Bit-identical, but
+// the second set of pending values costs 8 registers and ~10 copies per test: 0.562 -> 0.624 ms with the texture
+// look-up, 0.592 -> 0.696 ms with the linear one.)
+
 // BOUNDED: 0 = every test fetches (the reference's loop), 1 = opacity bound from the linear grid, 2 = from the texture
 template <int FMT, int LAYOUT, int BOUNDED>
 __global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) trace_kernel(const TraceArgs A) {
@@ -308,177 +316,235 @@ __global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) trace_kernel(const Tr
     }
 }
 
-// ---- the bounded walk with LANE REFILL ---------------------------------------------------------------------------------
+// ---- the bounded walk as a WAVEFRONT: set-up | walk | interaction -------------------------------------------------------
 // trace_kernel gives every photon a thread for its whole life: a warp runs until its longest walk ends, and the scan
-// loop -- 98 % of the instructions -- executes with 19.6 of 32 lanes on C4 (ncu).  Photons are independent (per-photon
-// RNG stream, result independent of lane / warp / GPU), so here warps are PERSISTENT and lanes are re-used: a lane
-// whose walk has ended waits until REFILL lanes of its warp are in that state, then the warp handles all of them
-// together -- store the interaction (or the empty slots), start the next walk of a scattered photon, or fetch a new
-// photon from a global cursor -- and returns to the scan loop with (almost) all lanes walking.  Batching matters: the
-// end-of-walk / set-up code is ~300 instructions per photon and would otherwise run with one or two lanes at a time.
+// loop executes with about half of its lanes on C4 (ncu: 18.8 lanes per instruction over the kernel).  Photons are
+// independent (per-photon RNG stream, result independent of lane / warp / GPU), so lanes can be re-used -- but only if
+// taking the next photon is CHEAP: with set-up (two sincos, divisions) and the interaction (acos, atan2, voxel taps,
+// divisions, stores) inside the refill, those ~800 instructions per photon run at the few lanes that happen to be idle
+// and eat the gain (measured: 0.59 -> 0.70 ms).  Here the three phases are three kernels:
+//   walk_setup_kernel   one thread per work item, full warps: light sample -> walk entry (origin, direction, t, tEnd,
+//                       stream state), 48 bytes; rays that miss the volume are finalised here
+//   walk_kernel         persistent warps; an idle lane takes the next entry from a global cursor (a 48-byte load), walks
+//                       it with the scan loop of woodcock_bounded and writes back t and the stream state (12 bytes)
+//   walk_finish_kernel  one thread per entry, full warps: the interaction at t (store the record, scatter or absorb); a
+//                       photon that scatters again rewrites its entry for the next round, up to maxInteractions rounds
 // Same draws, same positions, same records as trace_kernel and the oracle (tests/test_bound.py runs both).
-struct RefillArgs {
-    unsigned* cursor;      // next unclaimed work item (device counter, zeroed before the launch)
-    int refill_min;        // lanes that must be waiting before the warp leaves the scan loop for them
+// Measured on C4 (2 M re-traced photons): walk_kernel runs with 23.9 lanes per instruction instead of 18.8 and takes
+// 0.47 ms, but the two streaming kernels around it move 216 B per photon and cost 0.12 ms: 0.594 ms against 0.559 ms for
+// trace_kernel.  OPT-IN (CPM_TRACE_LANE_REFILL / CPM_TRACE_WAVEFRONT=<batch>); it pays where walks are long compared
+// with the interaction, i.e. thin media and several scattering events.
+struct WalkEntry {
+    float4 a;   // origin, t (start of the walk; after walk_kernel: where it ended)
+    float4 b;   // direction, tEnd
+    uint4 c;    // stream state (x, c), photon id within the light (tid), interactions so far | WALK_ACTIVE
+};
+constexpr unsigned WALK_ACTIVE = 0x80000000u;
+struct WaveArgs {
+    WalkEntry* entries;
+    float4* power;       // (r, g, b, -) carried between interactions
+    unsigned* cursor;    // next unclaimed entry (zeroed before every walk_kernel launch)
+    int refill_min;      // idle lanes a warp collects before it fetches entries for them
 };
 
-template <int FMT, int LAYOUT>
-__global__ void __launch_bounds__(128) trace_refill_kernel(const TraceArgs A, const RefillArgs Q) {
-    extern __shared__ float2 s_nlog[];   // 32 x (rc, lc) of native_log, then the alpha column of the transfer function
+// empty slots n .. maxI-1, and the stream state of a progressive trace (photontracer.cl:199-214)
+__device__ __forceinline__ void finalize_photon(const TraceArgs& A, int tid, unsigned n, float pr, float3_ d, cpm_rng rng) {
+    const cpm_trace_params& P = A.p;
+    const unsigned maxI = (unsigned)P.max_interactions;
+    float2 ang = encode_direction(d);
+    for (unsigned i = n; i < maxI; ++i) {
+        size_t pid = (size_t)P.photon_offset + (size_t)i * P.total_photons + tid;
+        store_photon(A.photons, pid, CPM_FLT_MAX, CPM_FLT_MAX, CPM_FLT_MAX, pr, CPM_FLT_MAX, CPM_FLT_MAX, ang.x, ang.y);
+    }
+    if (P.flags & CPM_TRACE_PROGRESSIVE) A.rng[P.photon_offset + tid] = make_uint2(rng.x, rng.c);
+}
+
+__global__ void __launch_bounds__(128) walk_setup_kernel(const TraceArgs A, const WaveArgs W) {
+    const cpm_trace_params& P = A.p;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n_work) return;
+    int tid = gid;
+    if (A.recompute) {
+        int t = (int)A.recompute[gid] - P.photon_offset;
+        tid = (t >= 0 && t < P.n_light_samples) ? t : -1;   // not this light's photon
+    }
+    if (tid < 0) {
+        W.entries[gid].c = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    uint2 st = A.rng[P.photon_offset + tid];
+    float4 l0 = A.light_samples[2 * (size_t)tid], l1 = A.light_samples[2 * (size_t)tid + 1];
+    float fmaxi = (float)P.max_interactions;
+    float pr = l0.w / fmaxi, pg = l1.x / fmaxi, pb = l1.y / fmaxi;
+    float3_ d = decode_direction(l1.z, l1.w);
+    float2 ip = A.isect[tid];
+    if (ip.x < ip.y) {
+        W.entries[gid].a = make_float4(l0.x, l0.y, l0.z, ip.x);
+        W.entries[gid].b = make_float4(d.x, d.y, d.z, ip.y);
+        W.entries[gid].c = make_uint4(st.x, st.y, (unsigned)tid, WALK_ACTIVE);
+        W.power[gid] = make_float4(pr, pg, pb, 0.0f);
+    } else {
+        W.entries[gid].c = make_uint4(0u, 0u, 0u, 0u);
+        finalize_photon(A, tid, 0u, pr, d, cpm_rng{st.x, st.y});   // the ray misses the volume
+    }
+}
+
+template <int FMT, int LAYOUT, bool BTEX>
+__global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) walk_kernel(const TraceArgs A, const WaveArgs W) {
+    extern __shared__ float2 s_nlog[];
     float* s_alpha = reinterpret_cast<float*>(s_nlog) + CPM_SMEM_NLOG_FLOATS;
     if (threadIdx.x < CPM_SMEM_NLOG_FLOATS) reinterpret_cast<float*>(s_nlog)[threadIdx.x] = g_nlog_table[threadIdx.x];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha[i] = A.tf[i].w;
     __syncthreads();
-    const cpm_trace_params& P = A.p;
     const VolumeView& V = A.vol;
+    const ScanRegs C = scan_regs<BTEX>(A);
     const int tfw = A.tf_width;
     const float ftfw = (float)tfw;
     const float inv = 1.0f / 150.0f;
-    const unsigned maxI = (unsigned)P.max_interactions;
+    const float hx = BTEX ? A.bound.hc : A.bound.hn[0], hy = BTEX ? A.bound.hc : A.bound.hn[1], hz = BTEX ? A.bound.hc : A.bound.hn[2];
     const unsigned lane = threadIdx.x & 31u;
-    enum { EMPTY = 0, WALK = 1, ENDED = 2 };
-    int state = EMPTY, tid = -1;
-    bool exhausted = false;                 // warp-uniform: the cursor has passed n_work
+    const unsigned n_work = (unsigned)A.n_work;
+    bool walking = false, exhausted = false;   // exhausted is warp-uniform: the cursor has passed the last entry
+    unsigned g = 0u;                           // entry this lane walks
     float3_ o = {0.f, 0.f, 0.f}, d = {0.f, 0.f, 1.f};
-    float t = 0.f, tEnd = 0.f, pr = 0.f, pg = 0.f, pb = 0.f;
-    unsigned n = 0, tests = 0, fetched = 0;
-    cpm_rng rng{0u, 0u};
     CellRay R = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const ScanRegs C = scan_regs<false>(A);
-
+    float t = 0.f, tEnd = 0.f;
+    cpm_rng rng{0u, 0u};
+    unsigned tests = 0, fetched = 0;
     while (true) {
-        const unsigned walking = __ballot_sync(0xffffffffu, state == WALK);
-        const unsigned todo = __ballot_sync(0xffffffffu, state == ENDED || (state == EMPTY && !exhausted));
-        if (walking == 0u && todo == 0u) break;
-        if (__popc(todo) >= Q.refill_min || walking == 0u) {
-            // ---- (1) walks that ended: photontracer.cl:161-197 ------------------------------------------------------
-            if (state == ENDED) {
-                bool scatter = t <= tEnd;
-                if (scatter) {
-                    o = ray_at(o, t, d);
-                    size_t pid = (size_t)P.photon_offset + (size_t)n * P.total_photons + tid;
-                    float2 ang = encode_direction(d);
-                    float vs = sample_volume<FMT, LAYOUT>(V, o.x, o.y, o.z);
-                    float ca = sample_tf_alpha(s_alpha, tfw, ftfw, vs);   // color.w == scattering.w
-                    float albedo = ca / (ca + ca);
-                    float den = cpm_fmax(ca, 0.01f);
-                    pr = pr / den; pg = pg / den; pb = pb / den;
-                    ++n;
-                    if (n < maxI && cpm_rng_01(rng) < albedo) {
-                        pr *= albedo; pg *= albedo; pb *= albedo;
-                        store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
-                        float tStart = 0.0f;
-                        tEnd = CPM_FLT_MAX;
-                        float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
-                        d = (P.phase_function == CPM_PHASE_HENYEY_GREENSTEIN) ? sample_henyey_greenstein(d, P.material[0], u1, u2)
-                                                                              : uniform_sample_sphere(u1, u2);
-                        scatter = ray_box(P.aabb_min, P.aabb_max, o, d, tStart, tEnd);
-                        tStart += 0.5f * P.step_size;
-                        t = tStart;
-                    } else {
-                        store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
-                        pr = pg = pb = CPM_FLT_MAX;
-                        scatter = false;
-                    }
-                }
-                if (scatter) {
-                    R = cell_ray_n(A.bound, o, d);
-                    state = WALK;
-                } else {
-                    float2 ang = encode_direction(d);
-                    for (unsigned i = n; i < maxI; ++i) {
-                        size_t pid = (size_t)P.photon_offset + (size_t)i * P.total_photons + tid;
-                        store_photon(A.photons, pid, CPM_FLT_MAX, CPM_FLT_MAX, CPM_FLT_MAX, pr, CPM_FLT_MAX, CPM_FLT_MAX, ang.x, ang.y);
-                    }
-                    if (P.flags & CPM_TRACE_PROGRESSIVE) A.rng[P.photon_offset + tid] = make_uint2(rng.x, rng.c);
-                    state = EMPTY;
-                    tid = -1;
-                }
-            }
-            // ---- (2) free lanes take new photons --------------------------------------------------------------------------
-            if (!exhausted) {
-                const unsigned freem = __ballot_sync(0xffffffffu, state == EMPTY);
-                if (freem) {
-                    unsigned base = 0;
-                    if (lane == (unsigned)(__ffs(freem) - 1)) base = atomicAdd(Q.cursor, (unsigned)__popc(freem));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(freem) - 1);
-                    exhausted = base + (unsigned)__popc(freem) >= (unsigned)A.n_work;
-                    if (state == EMPTY) {
-                        const unsigned g = base + (unsigned)__popc(freem & ((1u << lane) - 1u));
-                        if (g < (unsigned)A.n_work) {
-                            int cand = (int)g;
-                            if (A.recompute) {
-                                cand = (int)A.recompute[g] - P.photon_offset;
-                                if (cand < 0 || cand >= P.n_light_samples) cand = -1;   // not this light's photon
-                            }
-                            if (cand >= 0) {
-                                tid = cand;
-                                uint2 st = A.rng[P.photon_offset + tid];
-                                rng = cpm_rng{st.x, st.y};
-                                float4 l0 = A.light_samples[2 * (size_t)tid], l1 = A.light_samples[2 * (size_t)tid + 1];
-                                o = {l0.x, l0.y, l0.z};
-                                float fmaxi = (float)P.max_interactions;
-                                pr = l0.w / fmaxi; pg = l1.x / fmaxi; pb = l1.y / fmaxi;
-                                d = decode_direction(l1.z, l1.w);
-                                float2 ip = A.isect[tid];
-                                t = ip.x;
-                                tEnd = ip.y;
-                                n = 0;
-                                if (ip.x < ip.y) {
-                                    R = cell_ray_n(A.bound, o, d);
-                                    state = WALK;
-                                } else {
-                                    // the ray misses the volume: empty slots only (t > tEnd makes step (1) write them)
-                                    state = ENDED;
-                                    t = CPM_FLT_MAX;
-                                    tEnd = -CPM_FLT_MAX;
-                                }
-                            }
-                        }
+        const unsigned idle = __ballot_sync(0xffffffffu, !walking);
+        if (!exhausted && ((int)__popc(idle) >= W.refill_min || idle == 0xffffffffu)) {
+            // ---- idle lanes take the next entries --------------------------------------------------------------------------
+            const int leader = __ffs(idle) - 1;
+            unsigned base = 0u;
+            if ((int)lane == leader) base = atomicAdd(W.cursor, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (unsigned)__popc(idle) >= n_work;
+            if (!walking) {
+                const unsigned e = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (e < n_work) {
+                    const uint4 c = W.entries[e].c;
+                    if (c.w & WALK_ACTIVE) {
+                        const float4 a = W.entries[e].a, b = W.entries[e].b;
+                        g = e;
+                        o = {a.x, a.y, a.z};
+                        d = {b.x, b.y, b.z};
+                        t = a.w;
+                        tEnd = b.w;
+                        rng = cpm_rng{c.x, c.y};
+                        R = {fmaf(o.x, C.fcx, hx), fmaf(o.y, C.fcy, hy), fmaf(o.z, C.fcz, hz), d.x * C.fcx, d.y * C.fcy, d.z * C.fcz};
+                        walking = true;
                     }
                 }
             }
             continue;
         }
-        // ---- (3) the scan loop of woodcock_bounded for the walking lanes --------------------------------------------------
-        if (state == WALK) {
-            bool cand = false, done = false;
-            float u2 = 0.0f;
+        if (idle == 0xffffffffu) break;   // nothing walks and nothing is left
+        // ---- one scan round (woodcock_bounded) for the walking lanes; the trip count is warp-uniform -----------------------
+        bool live = walking, cand = false, done = false;
+        uint32_t k2 = 0u;
 #pragma unroll 1
-            for (int k = 0; k < A.scan; ++k) {
+        for (int j = 0; j < A.scan; ++j) {
+            if (live) {
                 t = advance_t(t, log_unit(cpm_rng_next(rng), s_nlog, C.c02), inv);
-                u2 = cpm_rng_01(rng);
+                k2 = cpm_rng_next(rng);
                 ++tests;
                 if (!(t <= tEnd)) {
                     done = true;
-                    break;
-                }
-                float m = bound_at(A.bound, R, t, C.magic);
-                if (!(u2 >= m)) {
-                    cand = true;
-                    break;
+                    live = false;
+                } else {
+                    float m = BTEX ? tex3DLod<float>(A.btex, fmaf(t, R.dx, R.ox), fmaf(t, R.dy, R.oy), fmaf(t, R.dz, R.oz), 0.0f)
+                                   : bound_at(A.bound, R, t, C.magic);
+                    if (!(cpm_u01(k2) >= m)) {
+                        cand = true;
+                        live = false;
+                    }
                 }
             }
-            if (cand) {
-                ++fetched;
-                const float3_ pc = ray_at(o, t, d);
-                float v = sample_volume<FMT, LAYOUT>(V, pc.x, pc.y, pc.z);
-                float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
-                done = !(u2 >= opacity);
-            }
-            if (done) state = ENDED;
+        }
+        if (cand) {
+            ++fetched;
+            const float3_ pc = ray_at(o, t, d);
+            float v = sample_volume<FMT, LAYOUT>(V, pc.x, pc.y, pc.z);
+            float opacity = sample_tf_alpha(s_alpha, tfw, ftfw, v);
+            done = !(cpm_u01(k2) >= opacity);
+        }
+        if (done) {
+            W.entries[g].a.w = t;
+            *reinterpret_cast<uint2*>(&W.entries[g].c) = make_uint2(rng.x, rng.c);
+            walking = false;
         }
     }
     if (A.tests) {
         unsigned long long v = tests;
         for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0 && v) atomicAdd(A.tests, v);
-        if (P.flags & CPM_TRACE_STATS) {
+        if (A.p.flags & CPM_TRACE_STATS) {
             unsigned long long f = fetched;
             for (int off = 16; off; off >>= 1) f += __shfl_xor_sync(0xffffffffu, f, off);
             if (lane == 0 && f) atomicAdd(A.tests + 1, f);
         }
     }
+}
+
+// photontracer.cl:161-197 for the walk that just ended
+template <int FMT, int LAYOUT>
+__global__ void __launch_bounds__(128) walk_finish_kernel(const TraceArgs A, const WaveArgs W) {
+    extern __shared__ float s_alpha_f[];
+    for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_alpha_f[i] = A.tf[i].w;
+    __syncthreads();
+    const cpm_trace_params& P = A.p;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= A.n_work) return;
+    const uint4 c = W.entries[gid].c;
+    if (!(c.w & WALK_ACTIVE)) return;
+    const float4 a = W.entries[gid].a, b = W.entries[gid].b;
+    const float4 pw = W.power[gid];
+    const int tfw = A.tf_width;
+    const float ftfw = (float)tfw;
+    const int tid = (int)c.z;
+    unsigned n = c.w & ~WALK_ACTIVE;
+    const unsigned maxI = (unsigned)P.max_interactions;
+    float3_ o = {a.x, a.y, a.z}, d = {b.x, b.y, b.z};
+    const float t = a.w;
+    float tEnd = b.w;
+    cpm_rng rng{c.x, c.y};
+    float pr = pw.x, pg = pw.y, pb = pw.z;
+    bool scatter = t <= tEnd;
+    if (scatter) {
+        o = ray_at(o, t, d);
+        size_t pid = (size_t)P.photon_offset + (size_t)n * P.total_photons + tid;
+        float2 ang = encode_direction(d);
+        float vs = sample_volume<FMT, LAYOUT>(A.vol, o.x, o.y, o.z);
+        float ca = sample_tf_alpha(s_alpha_f, tfw, ftfw, vs);  // color.w == scattering.w
+        float albedo = ca / (ca + ca);                        // 0.5, or NaN when alpha == 0
+        float den = cpm_fmax(ca, 0.01f);
+        pr = pr / den; pg = pg / den; pb = pb / den;
+        ++n;
+        if (n < maxI && cpm_rng_01(rng) < albedo) {
+            pr *= albedo; pg *= albedo; pb *= albedo;
+            store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+            float tStart = 0.0f;
+            tEnd = CPM_FLT_MAX;
+            float u1 = cpm_rng_01(rng), u2 = cpm_rng_01(rng);
+            d = (P.phase_function == CPM_PHASE_HENYEY_GREENSTEIN) ? sample_henyey_greenstein(d, P.material[0], u1, u2)
+                                                                  : uniform_sample_sphere(u1, u2);
+            scatter = ray_box(P.aabb_min, P.aabb_max, o, d, tStart, tEnd);
+            tStart += 0.5f * P.step_size;
+            if (scatter) {   // walks again in the next round
+                W.entries[gid].a = make_float4(o.x, o.y, o.z, tStart);
+                W.entries[gid].b = make_float4(d.x, d.y, d.z, tEnd);
+                W.entries[gid].c = make_uint4(rng.x, rng.c, (unsigned)tid, n | WALK_ACTIVE);
+                W.power[gid] = make_float4(pr, pg, pb, 0.0f);
+                return;
+            }
+        } else {
+            store_photon(A.photons, pid, o.x, o.y, o.z, pr, pg, pb, ang.x, ang.y);
+            pr = pg = pb = CPM_FLT_MAX;  // "absorbed" marker read by the detector
+        }
+    }
+    W.entries[gid].c.w = 0u;
+    finalize_photon(A, tid, n, pr, d, rng);
 }
 
 template <int FMT, int LAYOUT, int BOUNDED>
@@ -489,36 +555,57 @@ int launch2(cpm_ctx* ctx, const TraceArgs& a) {
     CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT, BOUNDED>), cpm_div_up(a.n_work, 128), 128, smem, a);
     return CPM_OK;
 }
-template <int FMT, int LAYOUT>
-int launch_refill(cpm_ctx* ctx, const TraceArgs& a, int refill_min) {
-    size_t smem = ((size_t)a.tf_width + CPM_SMEM_NLOG_FLOATS) * sizeof(float);
-    if (smem > 48 * 1024)
-        CPM_CUDA(ctx, cudaFuncSetAttribute(trace_refill_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int FMT, int LAYOUT, bool BTEX>
+int launch_wave2(cpm_ctx* ctx, const TraceArgs& a, const WaveArgs& w) {
+    const size_t smem = ((size_t)a.tf_width + CPM_SMEM_NLOG_FLOATS) * sizeof(float), smem_f = (size_t)a.tf_width * sizeof(float);
+    if (smem > 48 * 1024) {
+        CPM_CUDA(ctx, cudaFuncSetAttribute(walk_kernel<FMT, LAYOUT, BTEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPM_CUDA(ctx, cudaFuncSetAttribute(walk_finish_kernel<FMT, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    }
     static int per_sm = 0;
     if (!per_sm) {
-        CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_refill_kernel<FMT, LAYOUT>, 128, smem));
+        CPM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_kernel<FMT, LAYOUT, BTEX>, 128, smem));
         per_sm = per_sm > 0 ? per_sm : 1;
     }
-    if (!ctx->trace_cursor) CPM_CUDA(ctx, cudaMalloc((void**)&ctx->trace_cursor, 256));
-    RefillArgs q;
-    q.cursor = ctx->trace_cursor;
-    q.refill_min = refill_min;
-    CPM_CUDA(ctx, cudaMemsetAsync(q.cursor, 0, sizeof(unsigned), ctx->stream));
-    // persistent grid: every resident CTA slot of the device, but no more warps than work items / 32
-    unsigned grid = (unsigned)(ctx->sm_count * per_sm);
-    grid = std::max(1u, std::min(grid, cpm_div_up(a.n_work, 128)));
-    CPM_LAUNCH(ctx, (trace_refill_kernel<FMT, LAYOUT>), grid, 128, smem, a, q);
+    // persistent grid: every resident CTA slot of the device, but no more warps than entries / 32
+    const unsigned grid = std::max(1u, std::min((unsigned)(ctx->sm_count * per_sm), cpm_div_up(a.n_work, 128)));
+    const unsigned blocks = cpm_div_up(a.n_work, 128);
+    CPM_LAUNCH(ctx, walk_setup_kernel, blocks, 128, 0, a, w);
+    for (int round = 0; round < a.p.max_interactions; ++round) {
+        CPM_CUDA(ctx, cudaMemsetAsync(w.cursor, 0, sizeof(unsigned), ctx->stream));
+        CPM_LAUNCH(ctx, (walk_kernel<FMT, LAYOUT, BTEX>), grid, 128, smem, a, w);
+        CPM_LAUNCH(ctx, (walk_finish_kernel<FMT, LAYOUT>), blocks, 128, smem_f, a, w);
+    }
     return CPM_OK;
 }
 template <int FMT, int LAYOUT>
+int launch_wave(cpm_ctx* ctx, const TraceArgs& a, int refill_min) {
+    const size_t need = (size_t)a.n_work * (sizeof(WalkEntry) + sizeof(float4));
+    if (need > ctx->walk_bytes) {
+        CPM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->walk_buf) CPM_CUDA(ctx, cudaFree(ctx->walk_buf));
+        ctx->walk_buf = nullptr;
+        ctx->walk_bytes = 0;
+        CPM_CUDA(ctx, cudaMalloc(&ctx->walk_buf, need));
+        ctx->walk_bytes = need;
+    }
+    if (!ctx->trace_cursor) CPM_CUDA(ctx, cudaMalloc((void**)&ctx->trace_cursor, 256));
+    WaveArgs w;
+    w.entries = (WalkEntry*)ctx->walk_buf;
+    w.power = (float4*)((char*)ctx->walk_buf + (size_t)a.n_work * sizeof(WalkEntry));
+    w.cursor = ctx->trace_cursor;
+    w.refill_min = refill_min;
+    return a.btex ? launch_wave2<FMT, LAYOUT, true>(ctx, a, w) : launch_wave2<FMT, LAYOUT, false>(ctx, a, w);
+}
+template <int FMT, int LAYOUT>
 int launch(cpm_ctx* ctx, const TraceArgs& a) {
-    // lane refill (trace_refill_kernel): opt-in through CPM_TRACE_LANE_REFILL or CPM_TRACE_REFILL=<batch> in the
-    // environment (A/B runs).  Bounded walks that start at the light sample only: NO_SINGLE_SCATTERING walks start
-    // differently and stay on trace_kernel.
-    static const int refill_env = getenv("CPM_TRACE_REFILL") ? atoi(getenv("CPM_TRACE_REFILL")) : 0;
-    const int refill = refill_env > 0 ? refill_env : ((a.p.flags & CPM_TRACE_LANE_REFILL) ? 12 : 0);
-    if (a.bound.g && !a.btex && refill > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING))
-        return launch_refill<FMT, LAYOUT>(ctx, a, std::min(refill, 32));
+    // the wavefront form (set-up | persistent walk with lane refill | interaction): bounded walks that start at the light
+    // sample.  NO_SINGLE_SCATTERING walks start differently and stay on trace_kernel.  CPM_TRACE_WAVEFRONT=0 / =<refill
+    // batch> in the environment overrides the default (A/B runs); the CPM_TRACE_LANE_REFILL flag asks for it explicitly.
+    static const int wave_env = getenv("CPM_TRACE_WAVEFRONT") ? atoi(getenv("CPM_TRACE_WAVEFRONT")) : -1;
+    const int refill = wave_env >= 0 ? wave_env : (((a.p.flags & CPM_TRACE_LANE_REFILL) || CPM_TRACE_WAVEFRONT_DEFAULT) ? 8 : 0);
+    if (a.bound.g && refill > 0 && !(a.p.flags & CPM_TRACE_NO_SINGLE_SCATTERING))
+        return launch_wave<FMT, LAYOUT>(ctx, a, std::min(refill, 32));
     if (a.btex) return launch2<FMT, LAYOUT, 2>(ctx, a);
     return a.bound.g ? launch2<FMT, LAYOUT, 1>(ctx, a) : launch2<FMT, LAYOUT, 0>(ctx, a);
 }

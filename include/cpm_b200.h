@@ -173,10 +173,11 @@ enum {
     CPM_TRACE_NO_SINGLE_SCATTERING = 2, /* -D NO_SINGLE_SCATTERING */
     CPM_TRACE_STATS = 4,                /* collision_tests points to TWO counters: [0] collision tests,
                                            [1] tests that fetched voxels (== [0] without an opacity bound) */
-    CPM_TRACE_LANE_REFILL = 8           /* scheduling only (same photons): persistent warps whose lanes take new
-                                           photons as walks end (trace_refill_kernel).  Measured slower than the
-                                           static grid on C4 (0.71 vs 0.59 ms); kept as a tested
-                                           option.  Needs an opacity bound; ignored with NO_SINGLE_SCATTERING */
+    CPM_TRACE_LANE_REFILL = 8           /* scheduling only (same photons): the wavefront form -- set-up kernel, persistent
+                                           walk kernel whose idle lanes take the next walk from a cursor, interaction
+                                           kernel, one round per scattering event.  On C4 0.594 vs 0.559 ms for the
+                                           one-kernel form; a tested option for long walks.  Needs an
+                                           opacity bound; ignored with NO_SINGLE_SCATTERING */
 };
 enum { CPM_PHASE_ISOTROPIC = 0, CPM_PHASE_HENYEY_GREENSTEIN = 1 };
 

@@ -127,6 +127,28 @@ def main():
             e.close()
     except (RuntimeError, ImportError) as e:       # no symmetric memory on this node: reported, not a failure of the ABI
         log.append(f"torch symmetric memory unavailable: {type(e).__name__}: {e}")
+    # ---- 2b. global (cross-shard) selection: this rank's share of the first P elements of the (key, rank, index) order --
+    gk = torch.Generator().manual_seed(500 + rank)
+    n_loc = 5000 + 137 * rank
+    raw = torch.cat([torch.randint(0, 40, (n_loc - 900,), generator=gk), torch.randint(0, 2 ** 31 - 1, (600,), generator=gk),
+                     torch.full((300,), 2 ** 31 - 1, dtype=torch.int64)])           # many ties, a tail of "valid" photons
+    keys_loc = torch.sort(raw).values.to(torch.int32).to(dev)
+    sizes = comm.allgather_u64([n_loc])
+    assert [v[0] for v in sizes] == [5000 + 137 * r for r in range(world)], "allgather_u64"
+    padded = torch.full((5000 + 137 * world,), -1, dtype=torch.int32, device=dev)
+    padded[:n_loc] = keys_loc
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    glob = np.concatenate([np.stack([p.cpu().numpy()[:sizes[r][0]].astype(np.int64), np.full(sizes[r][0], r), np.arange(sizes[r][0])], 1)
+                           for r, p in enumerate(parts)])
+    order = np.lexsort((glob[:, 2], glob[:, 1], glob[:, 0]))
+    ranks_in_order = glob[order, 1]
+    total = len(order)
+    for P in (0, 1, 17, total // 3, total // 2, total - 301 * world, total - 1, total, total + 5):
+        want_c = int((ranks_in_order[:min(P, total)] == rank).sum())
+        got_c = comm.select_global(keys_loc, n_loc, P)
+        assert got_c == want_c, ("select_global", P, got_c, want_c)
+    log.append("global selection == one stable sort over the concatenated shards")
     comm.close()
     ctx.close()
 
@@ -166,6 +188,53 @@ def main():
     if rank == 0:
         assert torch.equal(sb.to(dev).view(torch.int32), want.view(torch.int32)), "cpmh_network_sum_light_volume"
     log.append(f"sharded ingest: h2d bytes {ha} -> {hb} per rank over {T + 1} steps, photons identical")
+    # ---- 4. global budget: max% of the photons of ALL shards per evaluation, most important first --------------------
+    for mode in (False, True):
+        host.runtime_set_comm(hcomm.h.value, False)
+        host.runtime_set_global_budget(mode)
+        net = host.Network((D, D, D), cpm.CPM_FMT_F32, 128, [(0.3, -0.5, 0.8)], light_volume_option=2, with_importance_grid=True,
+                           reference_full_splat_bound=False, device=local, max_incremental_percent=10.0)
+        net.set_transfer_function(synth.WS_TF_POINTS)
+        net.set_volume_host(vols[0].numpy())
+        net.evaluate()
+        pts = [(p, (c[0], c[1], c[2], min(1.0, c[3] * (1.3 + 0.4 * rank)))) for p, c in synth.WS_TF_POINTS]   # shards differ in how much changes
+        net.set_transfer_function(pts)
+        n_tot = net.n_photons * world
+        budget = int(np.float32(0.10) * np.float32(n_tot))
+        done_ids, rounds, left, keys_prev = [], 0, None, None
+        VALID = 2 ** 31 - 1
+        while True:
+            net.evaluate()
+            rounds += 1
+            n_rec = max(net.n_recomputed, 0)
+            ids = net.read_recomputed_indices()[:n_rec]
+            keys_after = net.read_importance_keys().copy()        # re-traced photons are valid again, the rest keep their keys
+            if mode:
+                cnt = torch.tensor([n_rec, int((keys_after < VALID).sum())], device=dev)
+                dist.all_reduce(cnt)          # (lockstep: in global mode every rank evaluates the same number of times)
+                if left is None:
+                    left = int(cnt[0]) + int(cnt[1])
+                assert int(cnt[0]) == min(left, budget), ("global budget per evaluation", int(cnt[0]), left, budget)
+                left -= int(cnt[0])
+                assert left == int(cnt[1])
+                if keys_prev is not None:
+                    # importance order across shards: nothing selected now is less important than anything left anywhere
+                    still = keys_after < VALID
+                    ext = torch.tensor([int(keys_prev[ids].max()) if n_rec else -1, -(int(keys_prev[still].min()) if still.any() else VALID)],
+                                       device=dev)
+                    dist.all_reduce(ext, op=dist.ReduceOp.MAX)
+                    assert int(ext[0]) <= -int(ext[1]), ("global importance order", int(ext[0]), -int(ext[1]))
+            else:
+                assert n_rec <= int(np.float32(0.10) * np.float32(net.n_photons))
+            keys_prev = keys_after
+            done_ids.append(ids.copy())
+            if net.remaining_photons <= 0 or rounds > 60:
+                break
+        allids = np.concatenate(done_ids)
+        assert len(np.unique(allids)) == len(allids), "a photon was re-traced twice"
+        log.append(f"{'global' if mode else 'per-shard'} budget: {rounds} evaluations")
+        net.close()
+    host.runtime_set_global_budget(False)
     host.runtime_set_comm(None, False)
     hcomm.close()
     dist.barrier()
