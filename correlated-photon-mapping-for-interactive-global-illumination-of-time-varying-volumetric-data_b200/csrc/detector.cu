@@ -72,30 +72,53 @@ __device__ float uniform_grid_importance(const GridArgs& G, float3_ x1, float3_ 
         // d1 == dt1.  The loop is branch-free apart from its exit: lanes of a warp step along different axes in the same
         // iteration, and with a branch per axis every iteration would run all three paths.
         // Written in PTX: from the C++ form of this loop the compiler builds 34 instructions per step (predicate
-        // shuffles, copies, two-instruction conditional decrements); this is 25, one per line.
+        // shuffles, copies, two-instruction conditional decrements); this is 24 per step (two steps per trip, so that the previous parameter needs no copy).
         asm volatile(
             "{\n\t"
             ".reg .pred ax, ay, axy, go;\n\t"
-            ".reg .f32 dt0, dt1, c, w, val;\n\t"
+            ".reg .f32 dta, dtb, c, w, val;\n\t"
             ".reg .s32 r, st;\n\t"
             ".reg .u64 addr;\n\t"
-            "mov.f32 dt0, 0f00000000;\n"
+            "mov.f32 dta, 0f00000000;\n"
             "DDA_STEP:\n\t"
             "mad.wide.s32 addr, %0, 4, %8;\n\t"
             "ld.global.nc.f32 val, [addr];\n\t"
-            "min.f32 dt1, %1, %2;\n\t"
-            "min.f32 dt1, dt1, %3;\n\t"
-            "setp.eq.f32 ax, %1, dt1;\n\t"
-            "setp.eq.and.f32 ay, %2, dt1, !ax;\n\t"
+            "min.f32 dtb, %1, %2;\n\t"
+            "min.f32 dtb, dtb, %3;\n\t"
+            "setp.eq.f32 ax, %1, dtb;\n\t"
+            "setp.eq.and.f32 ay, %2, dtb, !ax;\n\t"
             "selp.s32 r, %5, %6, ay;\n\t"
             "selp.s32 r, %4, r, ax;\n\t"
             "setp.ne.s32 go, r, 0;\n\t"
-            "min.f32 c, dt1, 0f3F800000;\n\t"
-            "sub.rn.f32 w, c, dt0;\n\t"
+            "min.f32 c, dtb, 0f3F800000;\n\t"
+            "sub.rn.f32 w, c, dta;\n\t"
             "mul.rn.f32 w, val, w;\n\t"
             "add.rn.f32 %7, %7, w;\n\t"
             "@!go bra DDA_DONE;\n\t"
-            "mov.f32 dt0, dt1;\n\t"
+            "selp.s32 st, %13, %14, ay;\n\t"
+            "selp.s32 st, %12, st, ax;\n\t"
+            "add.s32 %0, %0, st;\n\t"
+            "or.pred axy, ax, ay;\n\t"
+            "@ax add.rn.f32 %1, %1, %9;\n\t"
+            "@ay add.rn.f32 %2, %2, %10;\n\t"
+            "@!axy add.rn.f32 %3, %3, %11;\n\t"
+            "@ax sub.s32 %4, %4, 1;\n\t"
+            "@ay sub.s32 %5, %5, 1;\n\t"
+            "@!axy sub.s32 %6, %6, 1;\n\t"
+            "mad.wide.s32 addr, %0, 4, %8;\n\t"
+            "ld.global.nc.f32 val, [addr];\n\t"
+            "min.f32 dta, %1, %2;\n\t"
+            "min.f32 dta, dta, %3;\n\t"
+            "setp.eq.f32 ax, %1, dta;\n\t"
+            "setp.eq.and.f32 ay, %2, dta, !ax;\n\t"
+            "selp.s32 r, %5, %6, ay;\n\t"
+            "selp.s32 r, %4, r, ax;\n\t"
+            "setp.ne.s32 go, r, 0;\n\t"
+            "min.f32 c, dta, 0f3F800000;\n\t"
+            "sub.rn.f32 w, c, dtb;\n\t"
+            "mul.rn.f32 w, val, w;\n\t"
+            "add.rn.f32 %7, %7, w;\n\t"
+            "@!go bra DDA_DONE;\n\t"
             "selp.s32 st, %13, %14, ay;\n\t"
             "selp.s32 st, %12, st, ax;\n\t"
             "add.s32 %0, %0, st;\n\t"
