@@ -236,3 +236,49 @@ def test_cuda_copy_index_photons_then_splat_equals_update(cpm, orc, ctx, torch_c
     g = lv.cpu().numpy().astype(np.float64)
     assert np.abs(want - base).max() > 0
     assert np.sqrt(((g - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("light", ["oblique", "axis", "point"])
+def test_cuda_detector_sparse_grids_bit_exact(cpm, orc, ctx, torch_cuda, synth, light):
+    """Importance grids that are mostly zero -- isolated cells, a slab, cells on the grid's faces, a NaN cell, negative
+    zeros -- under an oblique, an axis-parallel (segments inside cell faces: the NaN-parameter path of the DDA) and a
+    point light, several interactions, both exit-point semantics, a non-cubic grid: keys bit for bit."""
+    torch = torch_cuda
+    dims = (64, 48, 40)
+    vol = synth.volume_u8(dims, 8)
+    tf = synth.rasterise_tf(width=512)
+    L = {"oblique": lambda: scenes.directional_light(72, (0.3, -0.5, 0.8)), "axis": lambda: scenes.directional_light(72, (0.0, 0.0, 1.0)),
+         "point": lambda: scenes.point_light(72)}[light]()
+    I = 3
+    photons, _, _ = oracle_trace(orc, vol, tf, L, max_interactions=I)
+    n = L["n"]
+    gd = (8, 6, 5)
+    t2i = cpm.capi.texture_to_index_matrix(dims)
+    rng = np.random.default_rng(11)
+    grids = []
+    g = np.zeros(gd[::-1], np.float32); g[2, 3, 4] = 0.7; g[0, 0, 0] = 0.2; g[4, 5, 7] = 1.5
+    grids.append(g)
+    g = np.zeros(gd[::-1], np.float32); g[:, 2, :] = 0.05
+    grids.append(g)
+    g = np.full(gd[::-1], -0.0, np.float32); g[3, 1, 6] = np.nan; g[1, 4, 2] = 0.3
+    grids.append(g)
+    g = (rng.random(gd[::-1]) < 0.06).astype(np.float32) * rng.random(gd[::-1]).astype(np.float32)
+    grids.append(g)
+    grids.append(np.zeros(gd[::-1], np.float32))
+    dph = torch.from_numpy(photons).cuda()
+    dls, dis = torch.from_numpy(L["light_samples"]).cuda(), torch.from_numpy(L["isect"]).cuda()
+    flagged = 0
+    for gi, g in enumerate(grids):
+        g = np.ascontiguousarray(g.reshape(-1))
+        for fix_exit in (False, True):
+            want = np.full(n, 0x7FFFFFFF, np.uint32)
+            orc.detect_invalid(g, gd, (8.0, 8.0, 8.0), t2i, photons, 0, L["light_samples"], L["isect"], n, I, n, want, fix_exit=fix_exit)
+            keys = torch.from_numpy(np.full(n, 0x7FFFFFFF, np.uint32).view(np.int32)).cuda()
+            ctx.detect_invalid(torch.from_numpy(g).cuda(), gd, (8.0, 8.0, 8.0), t2i, dph, 0, dls, dis, n, I, n, keys,
+                               flags=cpm.capi.CPM_DETECT_FIX_EXIT if fix_exit else 0)
+            ctx.sync()
+            got = keys.cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, want), (light, gi, fix_exit, int((got != want).sum()))
+            flagged += int((want < 0x7FFFFFFF).sum())
+    assert flagged > 0
