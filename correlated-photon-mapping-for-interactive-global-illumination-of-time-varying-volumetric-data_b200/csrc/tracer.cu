@@ -51,8 +51,11 @@ __device__ __forceinline__ void store_photon(float4* photons, size_t id, float x
 #ifndef CPM_SCAN
 #define CPM_SCAN 8  // cheap tests a lane scans before the warp reconverges for the candidate fetches
 #endif
+#ifndef CPM_TRACE_THREADS
+#define CPM_TRACE_THREADS 128  // threads per CTA of trace_kernel
+#endif
 #ifndef CPM_TRACE_MIN_CTAS
-#define CPM_TRACE_MIN_CTAS 9  // __launch_bounds__(128, .): register cap 56 (tools/build_variant.sh sweeps it)
+#define CPM_TRACE_MIN_CTAS (9 * 128 / CPM_TRACE_THREADS)  // __launch_bounds__: register cap 56 (tools/build_variant.sh sweeps it)
 #endif
 #ifndef CPM_TRACE_WAVEFRONT_DEFAULT
 #define CPM_TRACE_WAVEFRONT_DEFAULT 0  // 1: bounded traces take the wavefront form unless CPM_TRACE_WAVEFRONT=0
@@ -210,7 +213,7 @@ __device__ __forceinline__ float woodcock_bounded(const TraceArgs& A, const Scan
 
 // BOUNDED: 0 = every test fetches (the reference's loop), 1 = opacity bound from the linear grid, 2 = from the texture
 template <int FMT, int LAYOUT, int BOUNDED>
-__global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) trace_kernel(const TraceArgs A) {
+__global__ void __launch_bounds__(CPM_TRACE_THREADS, CPM_TRACE_MIN_CTAS) trace_kernel(const TraceArgs A) {
     extern __shared__ float2 s_nlog[];   // 32 x (rc, lc) of native_log, then the alpha column of the transfer function
     float* s_alpha = reinterpret_cast<float*>(s_nlog) + CPM_SMEM_NLOG_FLOATS;
     if (threadIdx.x < CPM_SMEM_NLOG_FLOATS) reinterpret_cast<float*>(s_nlog)[threadIdx.x] = g_nlog_table[threadIdx.x];
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(128) walk_setup_kernel(const TraceArgs A, cons
 }
 
 template <int FMT, int LAYOUT, bool BTEX>
-__global__ void __launch_bounds__(128, CPM_TRACE_MIN_CTAS) walk_kernel(const TraceArgs A, const WaveArgs W) {
+__global__ void __launch_bounds__(128, 9) walk_kernel(const TraceArgs A, const WaveArgs W) {
     extern __shared__ float2 s_nlog[];
     float* s_alpha = reinterpret_cast<float*>(s_nlog) + CPM_SMEM_NLOG_FLOATS;
     if (threadIdx.x < CPM_SMEM_NLOG_FLOATS) reinterpret_cast<float*>(s_nlog)[threadIdx.x] = g_nlog_table[threadIdx.x];
@@ -552,7 +555,7 @@ int launch2(cpm_ctx* ctx, const TraceArgs& a) {
     size_t smem = ((size_t)a.tf_width + CPM_SMEM_NLOG_FLOATS) * sizeof(float);
     if (smem > 48 * 1024)
         CPM_CUDA(ctx, cudaFuncSetAttribute(trace_kernel<FMT, LAYOUT, BOUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT, BOUNDED>), cpm_div_up(a.n_work, 128), 128, smem, a);
+    CPM_LAUNCH(ctx, (trace_kernel<FMT, LAYOUT, BOUNDED>), cpm_div_up(a.n_work, CPM_TRACE_THREADS), CPM_TRACE_THREADS, smem, a);
     return CPM_OK;
 }
 template <int FMT, int LAYOUT, bool BTEX>
