@@ -356,10 +356,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(const uint32_t* __restrict_
 }
 
 // ---- stable selection: ids of the elements below a threshold, ascending ---------------------------------
-// One pass: a tile (8 warps x 512 consecutive elements) ranks its hits with ballots (16 coalesced loads per
-// lane, order = element order), one thread chains the tile totals through a decoupled look-back over status
+// One pass: a tile (32 warps x 512 consecutive elements) ranks its hits with ballots (16 coalesced loads per
+// lane, order = element order), warp 0 chains the tile totals through a decoupled look-back over status
 // words (2 flag bits + 30 value bits), then every warp writes its ids to a contiguous range.
-constexpr int SEL_ROUNDS = 16, SEL_WARPS = 8, SEL_TILE = SEL_ROUNDS * 32 * SEL_WARPS;
+constexpr int SEL_ROUNDS = 16, SEL_WARPS = 32, SEL_TILE = SEL_ROUNDS * 32 * SEL_WARPS;   // 16 Ki elements per tile
 constexpr uint32_t SEL_AGG = 1u << 30, SEL_INC = 2u << 30, SEL_VAL = (1u << 30) - 1u;
 
 __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const uint32_t* __restrict__ data, size_t n, uint32_t threshold,
@@ -383,25 +383,52 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const uint32_t* 
     }
     if (lane == 0) s_warp[warp] = wtotal;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-        for (int w = 0; w < SEL_WARPS; ++w) total += s_warp[w];
+    if (warp == 0) {
+        // Warp 0 chains the tile totals.  The look-back reads a WINDOW of 32 predecessors at a time: a tile is done as
+        // soon as every predecessor up to the nearest inclusive prefix has published at least its aggregate -- which
+        // each does right after counting, so no tile waits for a chain of prefixes (with one thread and one predecessor
+        // per read, 1024 tiles of 4 Ki elements took 23 us for 16 MB of keys: 22 ns per link).
+        uint32_t v = lane < SEL_WARPS ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const uint32_t total = v;
         uint32_t excl = 0;
         if (tile > 0) {
-            status[tile] = SEL_AGG | total;
-            __threadfence();
-            for (int p = (int)tile - 1; p >= 0; --p) {
-                uint32_t st;
-                while (((st = status[p]) & (SEL_AGG | SEL_INC)) == 0) {
+            if (lane == 0) {
+                status[tile] = SEL_AGG | total;
+                __threadfence();
+            }
+            int p = (int)tile - 1;   // the window is tiles p - 31 ... p, lane l looks at p - l
+            while (true) {
+                const int q = p - lane;
+                uint32_t st = 2u << 30;                              // "before tile 0": inclusive prefix 0 (SEL_INC | 0)
+                if (q >= 0) st = status[q];
+                const unsigned ready = __ballot_sync(0xffffffffu, (st & (SEL_AGG | SEL_INC)) != 0u);
+                const unsigned inc = __ballot_sync(0xffffffffu, (st & SEL_INC) != 0u);
+                if (inc) {
+                    const int f = __ffs(inc) - 1;                    // nearest inclusive prefix
+                    const unsigned need = f == 31 ? 0xffffffffu : ((2u << f) - 1u);
+                    if ((ready & need) != need) continue;            // someone nearer has not published yet: poll again
+                    uint32_t c = lane <= f ? (st & SEL_VAL) : 0u;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    excl += c;
+                    break;
                 }
-                excl += st & SEL_VAL;
-                if (st & SEL_INC) break;
+                if (ready != 0xffffffffu) continue;
+                uint32_t c = st & SEL_VAL;                           // 32 aggregates: take them all, look further back
+#pragma unroll
+                for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                p -= 32;
             }
         }
-        status[tile] = SEL_INC | (excl + total);
-        __threadfence();
-        s_base = excl;
-        if (tile == n_tiles - 1) *result = (unsigned long long)(excl + total);
+        if (lane == 0) {
+            status[tile] = SEL_INC | (excl + total);
+            __threadfence();
+            s_base = excl;
+            if (tile == n_tiles - 1) *result = (unsigned long long)(excl + total);
+        }
     }
     __syncthreads();
     uint32_t wbase = s_base;

@@ -127,6 +127,11 @@ def profile_enable(on=True):
     lib().cpmh_profile_enable(int(on))
 
 
+def profile_only(stage=None):
+    """while profiling is on, time only this stage (None: every stage)"""
+    lib().cpmh_profile_only(stage.encode() if stage else None)
+
+
 def profile_reset():
     lib().cpmh_profile_reset()
 

@@ -627,6 +627,7 @@ float cpmh_network_stage_ms(cpmh_network*, const char* stage) {
     return v;
 }
 void cpmh_profile_enable(int on) { StageProfiler::get().enabled = on != 0; }
+void cpmh_profile_only(const char* stage) { StageProfiler::get().only = stage ? stage : ""; }
 void cpmh_profile_reset(void) { guarded([&]() { StageProfiler::get().reset(); return (int)CPM_OK; }); }
 double cpmh_profile_total_ms(const char* stage) {
     double v = 0;

@@ -150,6 +150,8 @@ CPMH_API float cpmh_network_stage_ms(cpmh_network* net, const char* stage);
  * "seed","emission","h2d","texcopy","minmax","voldiff","classify","detector","count+iota","sort",
  * "indexsort","trace","splat","copyprev" */
 CPMH_API void cpmh_profile_enable(int on);
+/* time only this stage while profiling is on (NULL or "": every stage): two event records per frame instead of two per stage */
+CPMH_API void cpmh_profile_only(const char* stage);
 CPMH_API void cpmh_profile_reset(void);
 CPMH_API double cpmh_profile_total_ms(const char* stage);
 CPMH_API int cpmh_profile_count(const char* stage);

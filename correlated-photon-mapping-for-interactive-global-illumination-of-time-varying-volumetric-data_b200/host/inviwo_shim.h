@@ -135,6 +135,7 @@ class StageProfiler {
 public:
     static StageProfiler& get();
     bool enabled = false;
+    std::string only;   // non-empty: only this stage is timed (two event records per frame instead of two per stage)
     void begin(const char* stage);
     void end();
     void resolve();

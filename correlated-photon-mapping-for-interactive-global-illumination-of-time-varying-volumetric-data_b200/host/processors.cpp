@@ -80,12 +80,20 @@ cpm_event* StageProfiler::take() {
 }
 void StageProfiler::begin(const char* stage) {
     if (!enabled) return;
+    if (!only.empty() && only != stage) {   // filtered out: keep the nesting, record nothing
+        open_.emplace_back(stage, nullptr);
+        return;
+    }
     cpm_event* e = take();
     CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), e));
     open_.emplace_back(stage, e);
 }
 void StageProfiler::end() {
     if (!enabled || open_.empty()) return;
+    if (!open_.back().second) {
+        open_.pop_back();
+        return;
+    }
     cpm_event* b = take();
     CPM_CHECK(cpm_event_record(CpmRuntime::get().ctx(), b));
     pending_.push_back({open_.back().first, open_.back().second, b});
@@ -108,7 +116,8 @@ void StageProfiler::resolve() {
 }
 void StageProfiler::reset() {
     resolve();
-    for (auto& o : open_) pool_.push_back(o.second);   // stages left open by an exception
+    for (auto& o : open_)
+        if (o.second) pool_.push_back(o.second);   // stages left open by an exception
     open_.clear();
     acc_.clear();
 }
