@@ -39,7 +39,7 @@ struct SplatArgs {
 // evaluated from the squared distance (no square root, no division) and the voxel centre is built per loop level
 // (3 fma per voxel instead of a full matrix product): a few ulp from the reference's operation order, far
 // inside the order-dependence of the float adds themselves (tests: relative RMSE <= 1e-5 vs a double sum).
-template <int CH>
+template <int CH, bool DIAG>
 __device__ __forceinline__ void splat_one(const SplatArgs& A, float4 p0, float pr, float pg, float pb) {
     if (p0.x == CPM_FLT_MAX_ || p0.y == CPM_FLT_MAX_ || p0.z == CPM_FLT_MAX_) return;
     const float r = A.radius;
@@ -61,10 +61,18 @@ __device__ __forceinline__ void splat_one(const SplatArgs& A, float4 p0, float p
             const float fy = (float)y;
             const float yx = fmaf(M[4], fy, zx), yy = fmaf(M[5], fy, zy), yz = fmaf(M[6], fy, zz);
             float* row = A.vol + ((size_t)y + (size_t)z * A.dim[1]) * A.dim[0] * CH;
+            // axis-aligned volumes (the index-to-texture matrix is diagonal): dy and dz do not change along the row
+            const float s_yz = fmaf(yz, yz, yy * yy);
             for (int x = sx; x < ex; ++x) {
                 const float fx = (float)x;
-                float dx = fmaf(M[0], fx, yx), dy = fmaf(M[1], fx, yy), dz = fmaf(M[2], fx, yz);
-                float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                float d2;
+                if (DIAG) {
+                    const float dx = fmaf(M[0], fx, yx);
+                    d2 = fmaf(dx, dx, s_yz);
+                } else {
+                    float dx = fmaf(M[0], fx, yx), dy = fmaf(M[1], fx, yy), dz = fmaf(M[2], fx, yz);
+                    d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                }
                 float w = d2 <= r2 ? fmaf(-k, d2, 0.75f) : 0.0f;
                 float fr = pr * w;
                 if (CH == 1) {
@@ -80,14 +88,14 @@ __device__ __forceinline__ void splat_one(const SplatArgs& A, float4 p0, float p
     }
 }
 
-template <int CH>
+template <int CH, bool DIAG>
 __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= A.n) return;
     const float s = CPM_INV_4PI_F * A.scale;
     if (!A.indices) {
         float4 p0 = A.photons[2 * (size_t)g], p1 = A.photons[2 * (size_t)g + 1];
-        splat_one<CH>(A, p0, p0.w * s, p1.x * s, p1.y * s);
+        splat_one<CH, DIAG>(A, p0, p0.w * s, p1.x * s, p1.y * s);
     } else {
         uint32_t id = A.indices[g];
         for (int k = 0; k < A.n_interactions; ++k) {
@@ -102,9 +110,9 @@ __global__ void __launch_bounds__(128) splat_kernel(const SplatArgs A) {
                     A.old_sync[2 * pid + 1] = p1;
                 }
                 if (q0.x == p0.x && q0.y == p0.y && q0.z == p0.z && q0.w == p0.w && q1.x == p1.x && q1.y == p1.y) continue;
-                splat_one<CH>(A, q0, -(q0.w * s * A.multiplier), -(q1.x * s * A.multiplier), -(q1.y * s * A.multiplier));
+                splat_one<CH, DIAG>(A, q0, -(q0.w * s * A.multiplier), -(q1.x * s * A.multiplier), -(q1.y * s * A.multiplier));
             }
-            splat_one<CH>(A, p0, p0.w * s * A.multiplier, p1.x * s * A.multiplier, p1.y * s * A.multiplier);
+            splat_one<CH, DIAG>(A, p0, p0.w * s * A.multiplier, p1.x * s * A.multiplier, p1.y * s * A.multiplier);
         }
     }
 }
@@ -170,10 +178,16 @@ static int splat_common(cpm_ctx* ctx, float* light_volume, int channels, const f
     a.radius = radius;
     a.scale = relative_irradiance_scale;
     a.multiplier = multiplier;
-    if (channels == 1)
-        CPM_LAUNCH(ctx, splat_kernel<1>, cpm_div_up(n, 128), 128, 0, a);
-    else
-        CPM_LAUNCH(ctx, splat_kernel<4>, cpm_div_up(n, 128), 128, 0, a);
+    // diagonal index-to-texture matrix (an axis-aligned light volume, the usual case): the kernel's row loop is shorter
+    const float* m = index_to_texture;
+    const bool diag = m[1] == 0.f && m[2] == 0.f && m[4] == 0.f && m[6] == 0.f && m[8] == 0.f && m[9] == 0.f;
+    if (channels == 1) {
+        if (diag) CPM_LAUNCH(ctx, (splat_kernel<1, true>), cpm_div_up(n, 128), 128, 0, a);
+        else CPM_LAUNCH(ctx, (splat_kernel<1, false>), cpm_div_up(n, 128), 128, 0, a);
+    } else {
+        if (diag) CPM_LAUNCH(ctx, (splat_kernel<4, true>), cpm_div_up(n, 128), 128, 0, a);
+        else CPM_LAUNCH(ctx, (splat_kernel<4, false>), cpm_div_up(n, 128), 128, 0, a);
+    }
     return CPM_OK;
 }
 

@@ -282,3 +282,29 @@ def test_cuda_detector_sparse_grids_bit_exact(cpm, orc, ctx, torch_cuda, synth, 
             assert np.array_equal(got, want), (light, gi, fix_exit, int((got != want).sum()))
             flagged += int((want < 0x7FFFFFFF).sum())
     assert flagged > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels", [1, 4])
+def test_cuda_splat_sheared_light_volume(cpm, orc, ctx, torch_cuda, synth, channels):
+    """a light volume whose index-to-texture matrix is NOT diagonal (the general row loop of splat_kernel; axis-aligned
+    volumes take the shorter one): same estimate as the double-precision oracle"""
+    torch = torch_cuda
+    c = make_case(orc, synth, cpm, I=2, n_side=64)
+    n = c["L"]["n"]
+    od = (32, 28, 24)
+    A = np.eye(4)
+    A[:3, :3] = np.array([[1 / 32, 0.0021, 0.0], [0.0, 1 / 28, 0.0013], [0.0017, 0.0, 1 / 24]])
+    A[:3, 3] = A[:3, :3] @ np.array([0.5, 0.5, 0.5]) + np.array([0.01, -0.02, 0.015])
+    i2t = [float(np.float32(v)) for v in A.T.reshape(-1)]                       # column-major, as the C ABI takes it
+    t2i = [float(np.float32(v)) for v in np.linalg.inv(A).T.reshape(-1)]
+    nvox = od[0] * od[1] * od[2]
+    radius, scale = 1.4 / 28, 0.21
+    want = np.zeros(nvox * channels, np.float64)
+    orc.splat(want, channels, t2i, i2t, od, c["photons"], None, n, n, 2, radius, scale)
+    lv = torch.zeros(nvox * channels, dtype=torch.float32, device="cuda")
+    ctx.splat_photons(lv, channels, t2i, i2t, od, torch.from_numpy(c["photons"]).cuda(), None, n, n, 2, radius, scale)
+    ctx.sync()
+    got = lv.cpu().numpy().astype(np.float64)
+    assert want.sum() > 0
+    assert np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()) < 1e-5
