@@ -284,3 +284,21 @@ def test_cuda_bounded_tracer_with_and_without_clearance(cpm, orc, ctx, torch_cud
             assert gt == wt
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (s, clearance)
             assert np.array_equal(got_rng, want_rng)
+
+
+@pytest.mark.gpu
+def test_bound_texture_errors(cpm, ctx, torch_cuda, synth):
+    """cpm_bound_tex_*: a texture made for another grid is refused by the tracer (CPM_E_INVALID, message names the reason),
+    non-positive dims are refused at creation"""
+    torch = torch_cuda
+    with pytest.raises(cpm.capi.CpmError):
+        ctx.bound_texture((0, 4, 4))
+    vol = scenes.make_volume((32, 32, 32), "u8", 3)
+    tf = synth.rasterise_tf(width=64)
+    L = scenes.directional_light(16)
+    gd = cpm.capi.bound_grid_dims((32, 32, 32), 3)
+    wrong = ctx.bound_texture((gd[0] + 1, gd[1], gd[2]), torch.zeros((gd[0] + 1) * gd[1] * gd[2], dtype=torch.float32, device="cuda"))
+    with pytest.raises(cpm.capi.CpmError) as e:
+        cuda_trace(cpm, ctx, torch, vol, tf, L, cpm.CPM_VOLUME_LINEAR, opacity_bound_tex=wrong, bound_cell_log2=3)
+    assert "another grid" in str(e.value)
+    wrong.close()
