@@ -113,9 +113,12 @@ __device__ __forceinline__ void gather_point(const GatherArgs& A, float x, float
 //    the ray (|q|^2 - (q.d)^2) rejects most candidates, and the survivors update the batch's estimates through
 //    d_k^2 = d_perp^2 + (t_k - q.d)^2 -- instead of once per sample through 8 cells.
 constexpr int GATHER_S = 12;
+#ifndef CPM_GATHER_MIN_CTAS
+#define CPM_GATHER_MIN_CTAS 4   // __launch_bounds__(128, .): register cap 128 (5 -> 102 and 6 -> 85 spill and measure slower)
+#endif
 
 template <int FMT, int LAYOUT>
-__global__ void __launch_bounds__(128, 4) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
+__global__ void __launch_bounds__(128, CPM_GATHER_MIN_CTAS) gather_kernel(const GatherArgs A, unsigned* __restrict__ tile_counter) {
     extern __shared__ float4 s_tf[];
     for (int i = threadIdx.x; i < A.tf_width; i += blockDim.x) s_tf[i] = A.tf[i];
     __syncthreads();
