@@ -427,7 +427,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const uint32_t* 
             status[tile] = SEL_INC | (excl + total);
             __threadfence();
             s_base = excl;
-            if (tile == n_tiles - 1) *result = (unsigned long long)(excl + total);
+            if (tile == n_tiles - 1) {
+                *result = (unsigned long long)(excl + total);   // device scratch, or the mapped pinned host word
+                __threadfence_system();
+            }
         }
     }
     __syncthreads();
@@ -555,10 +558,20 @@ int cpm_select_below_begin(cpm_ctx* ctx, const uint32_t* data, size_t n, uint32_
     uint32_t* ticket = (uint32_t*)((char*)scratch + 2048 + 8);
     uint32_t* status = (uint32_t*)((char*)scratch + 4096);
     CPM_CUDA(ctx, cudaMemsetAsync((char*)scratch + 2048, 0, 2048 + tiles * sizeof(uint32_t), ctx->stream));
-    CPM_LAUNCH(ctx, select_kernel, (unsigned)tiles, SEL_WARPS * 32, 0, data, n, threshold, ids_out, status, ticket, acc,
-               (unsigned)tiles);
-    unsigned long long* pinned = (unsigned long long*)ctx->pinned;
-    CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
+    // The count goes straight into the context's pinned host word: the last tile stores it through the mapped
+    // address.  A cudaMemcpyAsync of 8 bytes would queue on the device-to-host copy engine -- behind a 64 MB read-back
+    // of the previous frame's light volume when the caller streams results out (1 ms of the frame at N = 8).
+    unsigned long long* pinned_dev = nullptr;
+    if (cudaHostGetDevicePointer((void**)&pinned_dev, ctx->pinned, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        pinned_dev = nullptr;
+    }
+    CPM_LAUNCH(ctx, select_kernel, (unsigned)tiles, SEL_WARPS * 32, 0, data, n, threshold, ids_out, status, ticket,
+               pinned_dev ? pinned_dev : acc, (unsigned)tiles);
+    if (!pinned_dev) {
+        unsigned long long* pinned = (unsigned long long*)ctx->pinned;
+        CPM_CUDA(ctx, cudaMemcpyAsync(pinned, acc, sizeof(*acc), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (!ctx->select_done) CPM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->select_done, cudaEventDisableTiming));
     CPM_CUDA(ctx, cudaEventRecord(ctx->select_done, ctx->stream));
     ctx->select_pending = true;
