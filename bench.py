@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--bound-log2", type=int, default=0,
                     help="tracer opacity-bound cells: 0 = default (8^3 voxels), n = 2^n voxels per axis, -1 = off")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pageable", action="store_true",
+                    help="e2e leg from PAGEABLE host buffers (an unregistered Inviwo VolumeRAM) instead of pinned ones: a data point, "
+                         "not the default line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU (A/B)")
@@ -663,9 +666,13 @@ def run_b200(a):
             out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
             e2e_k = [0]
 
+            src = pinned
+            if a.e2e_pageable:
+                src = [torch.empty(h.shape, dtype=h.dtype).copy_(h) for h in pinned]   # plain malloc'ed memory
+
             def step_e2e(t):
-                net.stream_timestep_host(pinned[t % T])            # adopts the upload announced one step earlier
-                net.prefetch_timestep_host(pinned[(t + 1) % T])    # next step's 512 MB (N > 1: this rank's slab + NVLink all-gather)
+                net.stream_timestep_host(src[t % T])            # adopts the upload announced one step earlier
+                net.prefetch_timestep_host(src[(t + 1) % T])    # next step's 512 MB (N > 1: this rank's slab + NVLink all-gather)
                 net.evaluate()
                 # frame result -> host: the sum over ranks (cpm_allreduce_lightvol through the host layer's communicator) is
                 # read back by rank 0 -- the process that shows the image -- on the read-back stream; the copy of frame k
@@ -710,7 +717,8 @@ def run_b200(a):
                               "all-gathered over NVLink on the transfer stream (cpm_comm_upload_volume_sharded); rank 0 reads "
                               "the summed light volume back" if (world > 1 and not a.no_sharded_ingest) else
                               "every rank uploads the whole step from pinned host memory" if world > 1 else
-                              "whole step from pinned (cudaHostAlloc) host memory"),
+                              "whole step from pinned (cudaHostAlloc) host memory") +
+                             (" -- THIS RUN: --e2e-pageable, plain pageable source buffers" if a.e2e_pageable else ""),
                    "frames_per_sec": a.steps / (wall_e * 1e-3),
                    "h2d_gbs": (h2d / a.steps) / (wall_e / a.steps * 1e-3) / 1e9,   # per rank: the step is PCIe bound
                    "stages_ms_per_step": {s: v[0] / a.steps for s, v in sorted(st_e.items())},
