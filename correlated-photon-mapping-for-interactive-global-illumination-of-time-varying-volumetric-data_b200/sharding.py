@@ -324,3 +324,37 @@ def sum_over_ranks(values, device="cpu"):
     if is_distributed():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [float(x) for x in t]
+
+
+# ---- global (cross-shard) selection: the algorithm of cpm_comm_select_global over torch.distributed -----------------------
+def select_global(sorted_keys: torch.Tensor, position: int, group=None) -> int:
+    """How many of THIS rank's ascending uint32 keys (an int64 / int32 tensor holding 0 .. 2^32-1) are among the first
+    `position` elements of the global (key, rank, local index) order -- one stable sort over the concatenated shards.
+    The same four rounds of a 256-ary search over the key bits as csrc/comm.cu (`cpm_comm_select_global`), each one
+    all-gather of 257 counts; no keys travel.  Used by the gloo tests and as the checker of the C entry point."""
+    keys = sorted_keys.to(torch.int64) & 0xFFFFFFFF
+    world = dist.get_world_size(group) if is_distributed() else 1
+    rank = dist.get_rank(group) if is_distributed() else 0
+    prefix, less, leq = 0, [0] * world, [0] * world
+    for shift in (24, 16, 8, 0):
+        probes = prefix + (torch.arange(257, dtype=torch.int64) << shift)
+        mine = torch.searchsorted(keys.cpu().contiguous(), probes, right=False).to(torch.int64)
+        mine[probes > 0xFFFFFFFF] = keys.numel()
+        if world > 1:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+        else:
+            parts = [mine]
+        total = torch.stack(parts).sum(0)
+        pick = int((total[:256] <= position).nonzero().max())     # total[0] <= position by induction
+        prefix += pick << shift
+        less = [int(p[pick]) for p in parts]
+        leq = [int(p[pick + 1]) for p in parts]
+    left = max(position - sum(less), 0)
+    count = 0
+    for r in range(world):
+        take = min(leq[r] - less[r], left)
+        if r == rank:
+            count = less[r] + take
+        left -= take
+    return count

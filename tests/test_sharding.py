@@ -56,6 +56,24 @@ def _worker(rank, world, port, q):
     tot = sh.allreduce_image(part)
     k = float(sum(range(1, world + 1)))
     ok = ok and bool(torch.equal(tot, torch.tensor([[k, 2 * k, 3 * k, 0.5], [0.0, 0.25 * k, 0.0, 0.75]]))) and tot.data_ptr() != part.data_ptr()
+    # global (cross-shard) selection: this rank's share of the first P elements of the (key, rank, index) order
+    g = torch.Generator().manual_seed(40 + rank)
+    n_loc = 3000 + 111 * rank
+    raw = torch.cat([torch.randint(0, 30, (n_loc - 500,), generator=g), torch.randint(0, 2 ** 32 - 1, (300,), generator=g, dtype=torch.int64),
+                     torch.full((200,), 2 ** 31 - 1, dtype=torch.int64)])
+    mykeys = torch.sort(raw).values
+    sizes = [3000 + 111 * r for r in range(world)]
+    padded = torch.full((max(sizes),), -1, dtype=torch.int64)
+    padded[:n_loc] = mykeys
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    glob = np.concatenate([np.stack([p.numpy()[:sizes[r]], np.full(sizes[r], r), np.arange(sizes[r])], 1) for r, p in enumerate(parts)])
+    order = np.lexsort((glob[:, 2], glob[:, 1], glob[:, 0]))
+    ranks_in_order = glob[order, 1]
+    total = len(order)
+    for P in (0, 1, 29, total // 3, total // 2, total - 250, total - 1, total, total + 7):
+        want_c = int((ranks_in_order[:min(P, total)] == rank).sum())
+        ok = ok and sh.select_global(mykeys, P) == want_c
     mx = sh.max_over_ranks([float(rank), 5.0 - rank])
     sm = sh.sum_over_ranks([float(rank + 1)])
     first, count = sh.photon_shard(rank, world, 4096)
